@@ -1,0 +1,120 @@
+// common.cuh -- shared definitions of libcsp_b200.so (sm_100a only; no CPU fallback, no multi-backend dispatch).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/csp_b200.h"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device-resident flattened tree (SoA).  Ids: node = preorder rank, internal = preorder rank among non-leaves,
+// leaf = rank in leaves(root).  See DESIGN.md "Data layout in HBM".
+// ---------------------------------------------------------------------------------------------------------------
+
+// Descent record, degree 2 (48 B, three 16-B vector loads).  Decision rule of src/tree.jl:383:
+//   bit_j = (x[sd] >= (xself+xother)/2) xor (xother < xself);  fictive dims contribute 0.
+// dj: bits 0..30 = 0-based dimension, bit 31 = flip (xother < xself); CSP_DIM_FICTIVE marks a fictive dimension.
+// child[k]: >= 0 internal id of the child;  < 0: leaf, leaf id = -child-2 (fake leaves encode leaf id -1 and are never reached).
+#define CSP_DIM_FICTIVE 0x7fffffff
+struct __align__(16) DRec2 {
+    double mid0, mid1;
+    int child[4];
+    int d0, d1, pad0, pad1;
+};
+// degree 1 (32 B, two 16-B loads)
+struct __align__(16) DRec1 {
+    double mid;
+    int d, pad0;
+    int child[2];
+    int pad1, pad2;
+};
+
+// per-node record: x = parent node id, y = istart (number of internal nodes before this node in preorder; the node's
+// own internal id when it is internal), z = icount (internal nodes in the subtree, itself included), w = flags
+#define CSP_NF_CHILDINDEX(w) ((w)&0xff)
+#define CSP_NF_LEAF 0x100
+#define CSP_NF_FAKE 0x200
+
+struct TreeView {
+    int n, p, n_nodes, n_internal, n_leaves;
+    const double* lower;   // [n]
+    const double* upper;   // [n]
+    const void* drec;      // [n_internal] DRec1 / DRec2
+    const int4* ninfo;     // [n_nodes]
+    const int* nleaf;      // [n_nodes] leaf id or -1
+    const int* inode;      // [n_internal] node id
+    const int* idims;      // [n_internal*p]   1-based, > n fictive
+    const double* ixs;     // [n_internal*p]   split.xs
+    const double* ixself;  // [n_internal*p]   position(split.self, dims[k])
+    const double* icval;   // [n_internal*2^p] value(getchild(split, k))
+    const int* ichild;     // [n_internal*2^p] node ids of the children
+    const double* ipos;    // [n_internal*n]   position(box)
+    const int* lnode;      // [n_leaves] node id of each leaf
+};
+
+// Per-leaf canonical models, one record of `stride` doubles per leaf:
+//   [ b[n] | g[n] | Qp[n(n+1)/2] (upper triangle, row-major: (0,0),(0,1)..(0,n-1),(1,1).. ) | c | pad ]   (degree 2)
+//   [ b[n] | g[n] | c | pad ]                                                                            (degree 1)
+struct ModelsView {
+    int n, degree, stride;
+    long long n_models;
+    const double* data;
+};
+static inline int csp_model_stride(int n, int degree) {
+    long long s = 2LL * n + 1 + (degree == 2 ? (long long)n * (n + 1) / 2 : 0);
+    return (int)((s + 3) / 4 * 4);  // whole 32-B sectors per record
+}
+
+struct csp_tree {
+    int device = 0;
+    TreeView v{};
+    int max_depth = 0;
+    size_t bytes = 0;
+    std::vector<void*> allocs;
+    int n_sm = 0;
+};
+struct csp_models {
+    int device = 0;
+    int n = 0, degree = 2, stride = 0;
+    long long n_models = 0;
+    double* data = nullptr;    // device, n_models*stride
+    uint8_t* status = nullptr; // device, n_models (CSP_FIT_*)
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// error plumbing / launch accounting
+// ---------------------------------------------------------------------------------------------------------------
+int csp_set_error(int code, const char* fmt, ...);
+extern std::atomic<long long> g_csp_launches;
+int csp_current_device();
+int csp_require_device();  // CSP_OK or CSP_ERR_NO_DEVICE
+
+#define CSP_CUDA(call)                                                                                         \
+    do {                                                                                                       \
+        cudaError_t _e = (call);                                                                               \
+        if (_e != cudaSuccess)                                                                                 \
+            return csp_set_error(CSP_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+    } while (0)
+#define CSP_CHECK(call)            \
+    do {                           \
+        int _rc = (call);          \
+        if (_rc != CSP_OK) return _rc; \
+    } while (0)
+#define CSP_LAUNCHED() (g_csp_launches.fetch_add(1, std::memory_order_relaxed))
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};

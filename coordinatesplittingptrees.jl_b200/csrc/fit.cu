@@ -1,0 +1,673 @@
+// fit.cu -- K2: batched per-box model fits for sm_100a.  COMPILED WITH -fmad=false: the reference (Julia) performs no
+// FMA contraction on this path and its formulas are cancellation-heavy, so every floating-point expression below is
+// evaluated in the reference's order with separate multiplies and adds; results are bit-identical to the oracle.
+//
+// Replaces, per box (reference paths):
+//   chaintop                src/polynomials.jl:22-98
+//   fit_poly1               src/cs2.jl:162-205
+//   coefficients_p!         src/polynomials.jl:182-230  (dense output, p = 1 or 2)
+//   fit_poly2_diag!         src/cs2.jl:208-274  (+ Qcoef_lineq :314-325)
+//   canonicalize / chi      src/cs2.jl:132-140, 277-280
+//
+// Work decomposition: one warp per box.  The reference's `splits(box)` traversal (src/tree.jl:461-540) is replaced by
+// the preorder identity: for each ancestor a of the box, bottom-up, coming from child c, the iterator
+// yields the internal-node id ranges [I_a+1, I_c) and [I_c+S_c, I_a+S_a) in ascending order, then I_a itself.  So the
+// traversal is a list of contiguous, coalesced range scans over the per-split SoA arrays; "first split in iteration
+// order wins" becomes an integer atomicMin on the scan position per coefficient slot (shared memory), and the
+// reference's early exit becomes "stop when every slot is filled".  The O(n) / O(n^2) floating-point work is then done
+// one lane per output entry, sequentially in the reference's order.
+#include <climits>
+
+#include "common.cuh"
+
+#define FIT_MODE_FULL 0   // fit_quadratic (p == 2)
+#define FIT_MODE_COEF 1   // coefficients_p only
+#define FIT_MODE_LIN 2    // degree-1 model for CS1 trees: c = value(box), g = coefficients_p(box), b = position(box)
+
+struct FitParams {
+    TreeView t;
+    const int* node_ids;  // null: every leaf in leaves(root) order
+    long long nb;
+    int skip, mode;
+    // strided outputs (doubles); *_stride in doubles per box
+    double* c; long long c_stride;
+    double* g; long long g_stride;
+    double* Q; long long Q_stride; int q_packed;  // dense n*n .data layout, or packed upper triangle (row-major)
+    double* b; long long b_stride;
+    double* gnat; double* y; uint8_t* prec;       // optional native-form extras (dense, box-major)
+    uint8_t* status;
+    long long* visited;
+    int* scratch;            // global pair tables when they do not fit in shared memory
+    int pairs_in_smem;
+    int warp_smem_bytes;
+};
+
+__device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+__device__ __forceinline__ bool newinfo(double x, double b, double y) { return (x != b) & (x != y); }
+
+// src/cs2.jl:314-325, including the operator-precedence quirk of line 317 (case A falls through)
+__device__ __forceinline__ double qcoef_lineq(bool same, double dxi, double xk, double bk, double yk, bool precik) {
+    if (same) {
+        if (xk == bk && dxi == yk - bk) {
+        } else if (xk == yk && dxi == bk - yk) {
+            return 0.0;
+        }
+        return dxi / 2 + xk - (bk + yk) / 2;
+    }
+    if (precik) {
+        if (xk == bk) return 0.0;
+        return 0.0 + (xk - bk);
+    }
+    return 0.0 + (xk - yk);
+}
+
+struct QIndex {
+    int n, packed;
+    __device__ __forceinline__ long long operator()(int i, int j) const {  // 0-based; order-insensitive (SymmetricArray)
+        if (i > j) { int tmp = i; i = j; j = tmp; }
+        return packed ? ((long long)i * n - (long long)i * (i - 1) / 2 + (j - i)) : ((long long)j * n + i);
+    }
+};
+
+// per-warp state shared by the helpers
+struct WarpCtx {
+    int lane, n, npairs;
+    double *sb, *sy, *sg;
+    int *sstep, *dkey, *did, *pkey, *pid;
+};
+
+// chaintop (src/polynomials.jl:22-98) on the flat arrays; executed by one lane.  Returns CSP_FIT_* and the top NODE id.
+__device__ int chaintop_dev(const TreeView& t, int box, int* covered, int* top_out) {
+    const int n = t.n;
+    for (int i = 0; i < n; ++i) covered[i] = 0;
+    int nremaining = n;
+    auto process = [&](int I, bool& did) {
+        const int d0 = t.idims[2 * I], d1 = t.idims[2 * I + 1];
+        int nnovel = 2, ntarget = 2;
+        nnovel -= (d0 > n || covered[d0 - 1]) ? 1 : 0; ntarget -= (d0 > n) ? 1 : 0;
+        nnovel -= (d1 > n || covered[d1 - 1]) ? 1 : 0; ntarget -= (d1 > n) ? 1 : 0;
+        if (!(nnovel == ntarget || nnovel == nremaining)) { did = false; return; }
+        if (d0 <= n) covered[d0 - 1] = 1;
+        if (d1 <= n) covered[d1 - 1] = 1;
+        nremaining -= nnovel;
+        did = true;
+    };
+    const int4 bi = t.ninfo[box];
+    const int pb = bi.x;
+    if (t.ninfo[pb].w & CSP_NF_LEAF) return CSP_FIT_CHAIN_UNDEF;  // root that is a leaf: box.parent.split undefined
+    int I = t.ninfo[pb].y;
+    bool did = false;
+    while (nremaining > 0) {  // go down
+        process(I, did);
+        if (!did) break;
+        const int bottom = t.ichild[4 * I + 3];
+        const int4 bo = t.ninfo[bottom];
+        if (bo.w & CSP_NF_LEAF) break;
+        if (t.idims[2 * I] > n || t.idims[2 * I + 1] > n) break;
+        I = bo.y;
+    }
+    int top = pb;
+    if (nremaining == 0) { *top_out = top; return CSP_FIT_OK; }
+    if (pb == box) return CSP_FIT_NO_CHAIN;  // isroot(box)
+    int ptop = t.ninfo[top].x;
+    I = t.ninfo[ptop].y;
+    while (nremaining > 0) {  // go up
+        process(I, did);
+        if (ptop == top) return CSP_FIT_NO_CHAIN;  // isroot(top)
+        top = ptop;
+        ptop = t.ninfo[top].x;
+        I = t.ninfo[ptop].y;
+    }
+    *top_out = top;
+    return CSP_FIT_OK;
+}
+
+// Drives `fn(lo, hi)` over the id ranges of splits(box) in iteration order until fn returns true (done).
+template <class F>
+__device__ __forceinline__ void for_split_ranges(const TreeView& t, int box, F&& fn) {
+    int cnode = box;
+    int4 ci = t.ninfo[box];
+    if (!(ci.w & CSP_NF_LEAF))
+        if (fn(ci.y, ci.y + ci.z)) return;
+    while (ci.x != cnode) {
+        const int a = ci.x;
+        const int4 ai = t.ninfo[a];
+        if (fn(ai.y + 1, ci.y)) return;
+        if (fn(ci.y + ci.z, ai.y + ai.z)) return;
+        if (fn(ai.y, ai.y + 1)) return;
+        cnode = a;
+        ci = ai;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ double coef_value(const TreeView& t, int id) {
+    if (P == 2) {  // src/polynomials.jl:212-224 with p = 2: s = +1, signs (+,-,-,+)
+        const double x0 = t.ixs[2 * id], x1 = t.ixs[2 * id + 1];
+        const double s0 = t.ixself[2 * id], s1 = t.ixself[2 * id + 1];
+        double denom = 1.0;
+        denom = denom * (x0 - s0);
+        denom = denom * (x1 - s1);
+        double num = 0.0;
+        num = num + 1.0 * t.icval[4 * id + 0];
+        num = num + -1.0 * t.icval[4 * id + 1];
+        num = num + -1.0 * t.icval[4 * id + 2];
+        num = num + 1.0 * t.icval[4 * id + 3];
+        return num / denom;
+    } else {  // p = 1: s = -1, signs (-,+)
+        double denom = 1.0;
+        denom = denom * (t.ixs[id] - t.ixself[id]);
+        double num = 0.0;
+        num = num + -1.0 * t.icval[2 * id + 0];
+        num = num + 1.0 * t.icval[2 * id + 1];
+        return num / denom;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TreeView& t = prm.t;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int n = t.n;
+    const int npairs = P == 2 ? n * (n - 1) / 2 : n;
+    const unsigned FULL = 0xffffffffu;
+
+    unsigned char* wbase = smem_raw + (size_t)wib * prm.warp_smem_bytes;
+    WarpCtx w;
+    w.lane = lane; w.n = n; w.npairs = npairs;
+    w.sb = (double*)wbase; w.sy = w.sb + n; w.sg = w.sy + n;
+    w.sstep = (int*)(w.sg + n); w.dkey = w.sstep + n; w.did = w.dkey + n;
+    if (prm.pairs_in_smem) { w.pkey = w.did + n; w.pid = w.pkey + npairs; }
+    else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 2 * (size_t)npairs; w.pid = w.pkey + npairs; }
+
+    for (long long bi = (long long)blockIdx.x * W + wib; bi < prm.nb; bi += (long long)gridDim.x * W) {
+        const int box = prm.node_ids ? prm.node_ids[bi] : t.lnode[bi];
+        double* Qo = prm.Q + bi * prm.Q_stride;
+        const QIndex qi{n, prm.q_packed};
+        const long long qlen = P == 1 ? n : (prm.q_packed ? (long long)n * (n + 1) / 2 : (long long)n * n);
+        for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
+        for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
+        for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
+        __syncwarp();
+
+        int status = CSP_FIT_OK, top = -1;
+        double cval = dnan();
+        if (prm.mode == FIT_MODE_FULL) {
+            // ---- fit_poly1: getleaf, chaintop, walk the chain (src/cs2.jl:162-205)
+            if (lane == 0) {
+                int leaf = box;
+                while (!(t.ninfo[leaf].w & CSP_NF_LEAF)) leaf = leaf + 1;  // split.self is the next node in preorder
+                status = chaintop_dev(t, leaf, w.did, &top);
+            }
+            status = __shfl_sync(FULL, status, 0);
+            top = __shfl_sync(FULL, top, 0);
+            if (status == CSP_FIT_OK) {
+                const int Itop = t.ninfo[top].y;
+                for (int e = lane; e < n; e += 32) w.sb[e] = t.ipos[(size_t)Itop * n + e];
+                __syncwarp();
+                if (lane == 0) {
+                    cval = t.icval[4 * Itop];  // value(top) == value(top.split.self)
+                    int cur = top;
+                    const int nch = (n + 1) / 2;
+                    for (int k = 1; k <= nch; ++k) {
+                        const int4 cinfo = t.ninfo[cur];
+                        if (cinfo.w & CSP_NF_LEAF) { status = CSP_FIT_CHAIN_UNDEF; break; }
+                        const int I = cinfo.y;
+                        const int d1 = t.idims[2 * I], d2 = t.idims[2 * I + 1];
+                        if (d1 == d2 || d1 > n || w.sstep[d1 - 1] != 0 || (d2 <= n && w.sstep[d2 - 1] != 0)) {
+                            status = CSP_FIT_CHAIN_ASSERT;
+                            break;
+                        }
+                        const double x1 = t.ixs[2 * I], x2 = t.ixs[2 * I + 1];
+                        const double f0 = t.icval[4 * I], f1 = t.icval[4 * I + 1], f2 = t.icval[4 * I + 2];
+                        w.sy[d1 - 1] = x1; w.sstep[d1 - 1] = k;
+                        if (d2 <= n) { w.sy[d2 - 1] = x2; w.sstep[d2 - 1] = k; }
+                        w.sg[d1 - 1] = (f1 - f0) / (x1 - w.sb[d1 - 1]);
+                        if (d2 <= n) w.sg[d2 - 1] = (f2 - f0) / (x2 - w.sb[d2 - 1]);
+                        cur = t.ichild[4 * I + 3];
+                    }
+                }
+                status = __shfl_sync(FULL, status, 0);
+                cval = __shfl_sync(FULL, cval, 0);
+            }
+            for (int e = lane; e < n; e += 32) w.dkey[e] = INT_MAX;  // w.did was chaintop's scratch; keys stay clean
+            __syncwarp();
+        }
+
+        long long nvisited = 0;
+        if (status == CSP_FIT_OK) {
+            // ---- the splits(box) scan: first occurrence per coefficient slot
+            int tpos = 0, foundp = 0, foundd = 0;
+            bool need_pairs = npairs > 0, need_diag = prm.mode == FIT_MODE_FULL;
+            const int skip = prm.skip;
+            for_split_ranges(t, box, [&](int lo, int hi) -> bool {
+                for (int base = lo; base < hi; base += 32) {
+                    const int id = base + lane;
+                    const int pos = tpos + lane;
+                    const bool act = id < hi && pos >= skip;
+                    int pidx = -1, dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
+                    bool newp = false, newd0 = false, newd1 = false;
+                    if (act) {
+                        if (P == 2) {
+                            const int2 dd = __ldg((const int2*)t.idims + id);
+                            dd0 = dd.x; dd1 = dd.y;
+                            if (need_pairs && dd0 <= n && dd1 <= n && dd0 != dd1) {
+                                const int i = min(dd0, dd1) - 1, j = max(dd0, dd1) - 1;
+                                pidx = i * n - i * (i + 1) / 2 + (j - i - 1);
+                                newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                            }
+                            if (need_diag) {
+                                const double2 xs = __ldg((const double2*)t.ixs + id);
+                                const double2 xf = __ldg((const double2*)t.ixself + id);
+                                if (dd0 <= n && w.dkey[dd0 - 1] > 2 * pos &&
+                                    (newinfo(xs.x, w.sb[dd0 - 1], w.sy[dd0 - 1]) || newinfo(xf.x, w.sb[dd0 - 1], w.sy[dd0 - 1]))) {
+                                    dk0 = 2 * pos;
+                                    newd0 = atomicMin(&w.dkey[dd0 - 1], dk0) == INT_MAX;
+                                }
+                                if (dd1 <= n && w.dkey[dd1 - 1] > 2 * pos + 1 &&
+                                    (newinfo(xs.y, w.sb[dd1 - 1], w.sy[dd1 - 1]) || newinfo(xf.y, w.sb[dd1 - 1], w.sy[dd1 - 1]))) {
+                                    dk1 = 2 * pos + 1;
+                                    newd1 = atomicMin(&w.dkey[dd1 - 1], dk1) == INT_MAX;
+                                }
+                            }
+                        } else {
+                            dd0 = __ldg(t.idims + id);
+                            if (need_pairs && dd0 <= n) {
+                                pidx = dd0 - 1;
+                                newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
+                    if (dk0 >= 0 && w.dkey[dd0 - 1] == dk0) w.did[dd0 - 1] = 2 * id;
+                    if (dk1 >= 0 && w.dkey[dd1 - 1] == dk1) w.did[dd1 - 1] = 2 * id + 1;
+                    foundp += __popc(__ballot_sync(FULL, newp));
+                    foundd += __popc(__ballot_sync(FULL, newd0)) + __popc(__ballot_sync(FULL, newd1));
+                    tpos += min(32, hi - base);
+                    need_pairs = foundp < npairs;
+                    need_diag = prm.mode == FIT_MODE_FULL && foundd < n;
+                    if (!need_pairs && !need_diag) return true;
+                }
+                return false;
+            });
+            __syncwarp();
+            // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
+            {
+                int mx = -1;
+                for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
+                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+                nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - skip : max(0, tpos - skip);
+            }
+
+            // ---- coefficients_p values (src/polynomials.jl:211-226), one lane per slot
+            bool sawnan = false;
+            if (P == 2) {
+                for (int e = lane; e < n * n; e += 32) {
+                    const int i = e / n, j = e - i * n;
+                    if (i >= j) continue;
+                    const int pidx = i * n - i * (i + 1) / 2 + (j - i - 1);
+                    if (w.pkey[pidx] == INT_MAX) continue;
+                    const double v = coef_value<2>(t, w.pid[pidx]);
+                    sawnan |= (v != v);
+                    Qo[qi(i, j)] = v;
+                }
+            } else {
+                for (int e = lane; e < n; e += 32) {
+                    if (w.pkey[e] == INT_MAX) continue;
+                    const double v = coef_value<1>(t, w.pid[e]);
+                    sawnan |= (v != v);
+                    Qo[e] = v;
+                }
+            }
+            sawnan = __any_sync(FULL, sawnan);
+            __syncwarp();
+            if (sawnan) {
+                // A computed coefficient was NaN (non-finite samples or a vanishing denominator).  The reference then keeps
+                // overwriting that slot from later splits while still counting it towards `nremaining`; reproduce that
+                // sequential behaviour exactly with one lane (rare path).
+                if (lane == 0) {
+                    for (long long e = 0; e < qlen; ++e) Qo[e] = dnan();
+                    long long nrem = npairs, tp = 0, examined = 0;
+                    for_split_ranges(t, box, [&](int lo, int hi) -> bool {
+                        for (int id = lo; id < hi; ++id, ++tp) {
+                            if (tp < prm.skip) continue;
+                            ++examined;
+                            long long slot;
+                            if (P == 2) {
+                                const int d0 = t.idims[2 * id], d1 = t.idims[2 * id + 1];
+                                if (d0 > n || d1 > n) continue;
+                                slot = qi(d0 - 1, d1 - 1);
+                            } else {
+                                const int d0 = t.idims[id];
+                                if (d0 > n) continue;
+                                slot = d0 - 1;
+                            }
+                            const double cur = Qo[slot];
+                            if (cur != cur) {
+                                Qo[slot] = P == 2 ? coef_value<2>(t, id) : coef_value<1>(t, id);
+                                nrem -= 1;
+                            }
+                            if (nrem <= 0) return true;
+                        }
+                        return false;
+                    });
+                    nvisited = examined;
+                }
+                nvisited = __shfl_sync(FULL, nvisited, 0);
+                __syncwarp();
+            }
+
+            if (prm.mode == FIT_MODE_FULL) {
+                // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per diagonal entry, sequential over k
+                for (int d = lane; d < n; d += 32) {
+                    if (w.dkey[d] == INT_MAX) continue;
+                    const int code = w.did[d];
+                    const int id = code >> 1, dimidx = code & 1;  // 0-based dimidx
+                    const double* xpos = t.ipos + (size_t)id * n;
+                    const double bd = w.sb[d], yd = w.sy[d];
+                    const double xsd = t.ixs[2 * id + dimidx];
+                    const int d2 = t.idims[2 * id + (1 - dimidx)] - 1;  // the split's other dimension (0-based; may be fictive)
+                    const double xs2 = t.ixs[2 * id + (1 - dimidx)];
+                    double xnew, xd, fchild, fref;
+                    bool swapped;
+                    if (newinfo(xsd, bd, yd)) {
+                        swapped = false;
+                        xnew = xsd; xd = xpos[d];
+                        fchild = t.icval[4 * id + (1 + dimidx)];  // split.others.children[dimidx]
+                        fref = t.icval[4 * id];                   // split.self
+                    } else {
+                        swapped = true;  // evaluate from children[3]'s position instead
+                        xnew = xpos[d]; xd = xsd;
+                        fchild = t.icval[4 * id + (2 - dimidx)];  // split.others.children[3-dimidx]
+                        fref = t.icval[4 * id + 3];
+                    }
+                    const double dxi = xnew - xd;
+                    const double coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
+                    double consts = -w.sg[d];
+                    const int sd = w.sstep[d];
+                    for (int k = 0; k < n; ++k) {
+                        if (k == d) continue;
+                        double xk = xpos[k];
+                        if (swapped && k == d2) xk = xs2;
+                        const bool precdk = sd <= w.sstep[k];  // prec[d,k]: d split before-or-with k
+                        const double xc = qcoef_lineq(false, dxi, xk, w.sb[k], w.sy[k], precdk);
+                        consts = consts - Qo[qi(d, k)] * xc;
+                    }
+                    Qo[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- outputs
+        if (prm.mode == FIT_MODE_FULL) {
+            const bool ok = status == CSP_FIT_OK;
+            if (!ok) for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
+            for (int i = lane; i < n; i += 32) {
+                double gc = dnan(), bb = dnan();
+                if (ok) {  // canonicalize (src/cs2.jl:132-140): sequential over j
+                    gc = w.sg[i];
+                    const int si = w.sstep[i];
+                    for (int j = 0; j < n; ++j) {
+                        const double chi = (i == j) ? w.sy[j] : (si <= w.sstep[j] ? w.sb[j] : 2 * w.sy[j] - w.sb[j]);
+                        gc = gc + (w.sb[j] - chi) * Qo[qi(i, j)] / 2;
+                    }
+                    bb = w.sb[i];
+                }
+                if (prm.g) prm.g[bi * prm.g_stride + i] = gc;
+                if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
+                if (prm.gnat) prm.gnat[bi * n + i] = ok ? w.sg[i] : dnan();
+                if (prm.y) prm.y[bi * n + i] = ok ? w.sy[i] : dnan();
+            }
+            if (prm.prec)
+                for (int e = lane; e < n * n; e += 32) {
+                    const int j = e / n, i = e - j * n;  // column-major: prec[i,j]
+                    prm.prec[bi * (long long)n * n + e] = ok && (w.sstep[i] <= w.sstep[j]) ? 1 : 0;
+                }
+            if (lane == 0 && prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
+        } else if (prm.mode == FIT_MODE_LIN) {
+            // degree-1 model of a CS1 box: c = value(box), b = position(box), g = Cp (already in Qo == g slot)
+            const int4 binfo = t.ninfo[box];
+            const bool isroot = binfo.x == box;
+            const int Ip = t.ninfo[binfo.x].y, ci = CSP_NF_CHILDINDEX(binfo.w);
+            const bool internal = !(binfo.w & CSP_NF_LEAF);
+            for (int i = lane; i < n; i += 32) {
+                double bb;
+                if (internal) bb = t.ipos[(size_t)binfo.y * n + i];
+                else if (isroot) bb = dnan();  // a tree without splits carries no positions on the device
+                else {
+                    bb = t.ipos[(size_t)Ip * n + i];
+                    if (P == 1) { if (ci == 1 && t.idims[Ip] - 1 == i) bb = t.ixs[Ip]; }
+                    else {
+                        if ((ci & 1) && t.idims[2 * Ip] - 1 == i) bb = t.ixs[2 * Ip];
+                        if ((ci & 2) && t.idims[2 * Ip + 1] - 1 == i) bb = t.ixs[2 * Ip + 1];
+                    }
+                }
+                if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
+            }
+            if (lane == 0 && prm.c) {
+                double cv;
+                if (internal) cv = t.icval[(size_t)binfo.y << P];
+                else if (isroot) cv = dnan();
+                else cv = t.icval[((size_t)Ip << P) + ci];
+                prm.c[bi * prm.c_stride] = cv;
+            }
+        }
+        if (lane == 0) {
+            if (prm.status) prm.status[bi] = (uint8_t)status;
+            if (prm.visited) prm.visited[bi] = nvisited;
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void** scratch_out) {
+    *scratch_out = nullptr;
+    if (prm.nb == 0) return CSP_OK;
+    const int n = t->v.n, P = t->v.p;
+    const long long npairs = P == 2 ? (long long)n * (n - 1) / 2 : n;
+    size_t base = (size_t)n * 8 * 3 + (size_t)n * 4 * 3;
+    size_t withpairs = base + (size_t)npairs * 8;
+    prm.pairs_in_smem = withpairs <= 200 * 1024;
+    size_t per_warp = prm.pairs_in_smem ? withpairs : base;
+    per_warp = (per_warp + 15) & ~size_t(15);
+    int W = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / per_warp));
+    if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
+    prm.warp_smem_bytes = (int)per_warp;
+    size_t smem = per_warp * W;
+    auto launch = [&](auto kern) -> int {
+        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
+        if (occ < 1) return csp_set_error(CSP_ERR_CUDA, "fit kernel does not fit on an SM (smem %zu)", smem);
+        long long grid = std::min<long long>((prm.nb + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
+        if (!prm.pairs_in_smem) {
+            CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 2 * npairs * sizeof(int)));
+            prm.scratch = (int*)*scratch_out;
+        }
+        kern<<<(unsigned)grid, W * 32, smem, st>>>(prm);
+        CSP_LAUNCHED();
+        CSP_CUDA(cudaGetLastError());
+        return CSP_OK;
+    };
+    return P == 2 ? launch(k_fit<2>) : launch(k_fit<1>);
+}
+
+// dense NaN-filled status helper for node id validation
+static int check_nodes(const csp_tree* t, const int32_t* node_ids, int64_t nb) {
+    if (!t) return csp_set_error(CSP_ERR_INVALID, "tree is NULL");
+    if (nb < 0) return csp_set_error(CSP_ERR_INVALID, "nb < 0");
+    if (!node_ids && nb != t->v.n_leaves)
+        return csp_set_error(CSP_ERR_INVALID, "node_ids == NULL means all leaves: nb must be %d (got %lld)", t->v.n_leaves, (long long)nb);
+    if (node_ids)
+        for (int64_t i = 0; i < nb; ++i)
+            if (node_ids[i] < 0 || node_ids[i] >= t->v.n_nodes)
+                return csp_set_error(CSP_ERR_INVALID, "node id %d out of range at %lld", node_ids[i], (long long)i);
+    return CSP_OK;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t bytes) {
+        CSP_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
+        return CSP_OK;
+    }
+};
+
+extern "C" {
+
+int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q, double* b,
+                  double* g_native, double* y, uint8_t* prec, uint8_t* status) {
+    CSP_CHECK(check_nodes(t, node_ids, nb));
+    if (t->v.p != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "fit_quadratic is defined for Box{2} only (reference src/cs2.jl:89); tree has p=%d", t->v.p);
+    if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
+    if (nb == 0) return CSP_OK;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    const int n = t->v.n;
+    // chunk the boxes so that the dense Q workspace stays below ~2 GiB
+    const long long per = (long long)n * n * 8;
+    const long long chunk = std::max<long long>(1, std::min<long long>(nb, (2LL << 30) / per));
+    DevBuf dids, dc, dg_, dQ, db, dgn, dy, dprec, dst;
+    if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
+    CSP_CHECK(dc.alloc(chunk * 8)); CSP_CHECK(dg_.alloc(chunk * n * 8)); CSP_CHECK(dQ.alloc(chunk * per)); CSP_CHECK(db.alloc(chunk * n * 8));
+    if (g_native) CSP_CHECK(dgn.alloc(chunk * n * 8));
+    if (y) CSP_CHECK(dy.alloc(chunk * n * 8));
+    if (prec) CSP_CHECK(dprec.alloc(chunk * (long long)n * n));
+    CSP_CHECK(dst.alloc(chunk));
+    for (long long off = 0; off < nb; off += chunk) {
+        const long long cnt = std::min(chunk, nb - off);
+        FitParams prm{};
+        prm.t = t->v;
+        prm.nb = cnt; prm.skip = skip; prm.mode = FIT_MODE_FULL;
+        if (node_ids) {
+            CSP_CUDA(cudaMemcpy(dids.p, node_ids + off, cnt * 4, cudaMemcpyHostToDevice));
+            prm.node_ids = (const int*)dids.p;
+        } else {
+            prm.node_ids = t->v.lnode + off;
+        }
+        prm.c = (double*)dc.p; prm.c_stride = 1;
+        prm.g = (double*)dg_.p; prm.g_stride = n;
+        prm.Q = (double*)dQ.p; prm.Q_stride = (long long)n * n; prm.q_packed = 0;
+        prm.b = (double*)db.p; prm.b_stride = n;
+        prm.gnat = (double*)dgn.p; prm.y = (double*)dy.p; prm.prec = (uint8_t*)dprec.p; prm.status = (uint8_t*)dst.p;
+        void* scratch = nullptr;
+        int rc = launch_fit(t, prm, 0, &scratch);
+        if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "fit kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (scratch) cudaFree(scratch);
+        CSP_CHECK(rc);
+        if (c) CSP_CUDA(cudaMemcpy(c + off, dc.p, cnt * 8, cudaMemcpyDeviceToHost));
+        if (g) CSP_CUDA(cudaMemcpy(g + off * n, dg_.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+        if (Q) CSP_CUDA(cudaMemcpy(Q + off * (long long)n * n, dQ.p, cnt * per, cudaMemcpyDeviceToHost));
+        if (b) CSP_CUDA(cudaMemcpy(b + off * n, db.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+        if (g_native) CSP_CUDA(cudaMemcpy(g_native + off * n, dgn.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+        if (y) CSP_CUDA(cudaMemcpy(y + off * n, dy.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+        if (prec) CSP_CUDA(cudaMemcpy(prec + off * (long long)n * n, dprec.p, cnt * (long long)n * n, cudaMemcpyDeviceToHost));
+        if (status) CSP_CUDA(cudaMemcpy(status + off, dst.p, cnt, cudaMemcpyDeviceToHost));
+    }
+    return CSP_OK;
+}
+
+int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited) {
+    CSP_CHECK(check_nodes(t, node_ids, nb));
+    if (skip < 0 || !Cp) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    if (nb == 0) return CSP_OK;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    const int n = t->v.n;
+    const long long per = (t->v.p == 2 ? (long long)n * n : n) * 8;
+    const long long chunk = std::max<long long>(1, std::min<long long>(nb, (2LL << 30) / per));
+    DevBuf dids, dQ, dvis;
+    if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
+    CSP_CHECK(dQ.alloc(chunk * per));
+    CSP_CHECK(dvis.alloc(chunk * 8));
+    for (long long off = 0; off < nb; off += chunk) {
+        const long long cnt = std::min(chunk, nb - off);
+        FitParams prm{};
+        prm.t = t->v;
+        prm.nb = cnt; prm.skip = skip; prm.mode = FIT_MODE_COEF;
+        if (node_ids) {
+            CSP_CUDA(cudaMemcpy(dids.p, node_ids + off, cnt * 4, cudaMemcpyHostToDevice));
+            prm.node_ids = (const int*)dids.p;
+        } else {
+            prm.node_ids = t->v.lnode + off;
+        }
+        prm.Q = (double*)dQ.p; prm.Q_stride = per / 8; prm.q_packed = 0;
+        prm.visited = (long long*)dvis.p;
+        void* scratch = nullptr;
+        int rc = launch_fit(t, prm, 0, &scratch);
+        if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (scratch) cudaFree(scratch);
+        CSP_CHECK(rc);
+        CSP_CUDA(cudaMemcpy(Cp + off * (per / 8), dQ.p, cnt * per, cudaMemcpyDeviceToHost));
+        if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
+    }
+    return CSP_OK;
+}
+
+static int models_fit_launch(const csp_tree* t, int32_t skip, csp_models* mo, cudaStream_t st, void** scratch) {
+    const int n = t->v.n;
+    FitParams prm{};
+    prm.t = t->v;
+    prm.node_ids = nullptr; prm.nb = mo->n_models; prm.skip = skip;
+    prm.mode = mo->degree == 2 ? FIT_MODE_FULL : FIT_MODE_LIN;
+    prm.b = mo->data; prm.b_stride = mo->stride;
+    prm.g = mo->data + n; prm.g_stride = mo->stride;
+    prm.status = mo->status;
+    if (mo->degree == 2) {
+        prm.Q = mo->data + 2 * n; prm.Q_stride = mo->stride; prm.q_packed = 1;
+        prm.c = mo->data + 2 * n + (size_t)n * (n + 1) / 2; prm.c_stride = mo->stride;
+    } else {
+        prm.Q = mo->data + n; prm.Q_stride = mo->stride; prm.q_packed = 0;  // Cp (the gradient) lands in the g slot
+        prm.g = nullptr;
+        prm.c = mo->data + 2 * n; prm.c_stride = mo->stride;
+    }
+    return launch_fit(t, prm, st, scratch);
+}
+
+int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
+    if (!t || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    const int n = t->v.n;
+    csp_models* mo = new csp_models();
+    mo->device = t->device; mo->n = n; mo->degree = t->v.p == 2 ? 2 : 1;
+    mo->stride = csp_model_stride(n, mo->degree);
+    mo->n_models = t->v.n_leaves;
+    auto fail = [&](int rc) { csp_models_free(mo); return rc; };
+    if (cudaMalloc(&mo->data, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess || cudaMalloc(&mo->status, (size_t)mo->n_models) != cudaSuccess)
+        return fail(csp_set_error(CSP_ERR_NOMEM, "cannot allocate %lld model records of %d doubles", mo->n_models, mo->stride));
+    if (cudaMemset(mo->data, 0, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess) return fail(csp_set_error(CSP_ERR_CUDA, "memset failed"));
+    void* scratch = nullptr;
+    int rc = models_fit_launch(t, skip, mo, 0, &scratch);
+    if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "fit kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (scratch) cudaFree(scratch);
+    if (rc != CSP_OK) return fail(rc);
+    *out = mo;
+    return CSP_OK;
+}
+
+int csp_models_refit(const csp_tree* t, int32_t skip, csp_models* mo, void* stream) {
+    if (!t || !mo) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
+    if (mo->device != t->device || mo->n != t->v.n || mo->n_models != t->v.n_leaves || mo->degree != (t->v.p == 2 ? 2 : 1))
+        return csp_set_error(CSP_ERR_INVALID, "models handle does not belong to this tree");
+    DeviceGuard dg(t->device);
+    void* scratch = nullptr;
+    int rc = models_fit_launch(t, skip, mo, (cudaStream_t)stream, &scratch);
+    if (scratch) {  // large-n path uses a global scratch table: wait before releasing it
+        cudaStreamSynchronize((cudaStream_t)stream);
+        cudaFree(scratch);
+    }
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,301 @@
+// tree.cu -- residency of the flattened CSp-tree: validation, derived arrays, upload, blob (wire) format.
+// Replaces the Box/Split/World object graph (reference src/types.jl:7-23,155-192) by SoA arrays in HBM.
+#include <cstring>
+
+#include "common.cuh"
+
+std::atomic<long long> g_csp_launches{0};
+static thread_local std::string g_last_error;
+static thread_local int g_device = 0;
+
+int csp_set_error(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+int csp_current_device() { return g_device; }
+int csp_require_device() {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt <= 0) {
+        cudaGetLastError();
+        return csp_set_error(CSP_ERR_NO_DEVICE, "no CUDA device available (%s); libcsp_b200 has no CPU fallback",
+                             e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return CSP_OK;
+}
+
+extern "C" {
+int csp_version(void) { return 100; }
+const char* csp_last_error(void) { return g_last_error.c_str(); }
+int csp_device_count(int* count) {
+    if (!count) return csp_set_error(CSP_ERR_INVALID, "count is NULL");
+    int cnt = 0;
+    if (cudaGetDeviceCount(&cnt) != cudaSuccess) { cudaGetLastError(); cnt = 0; }
+    *count = cnt;
+    return CSP_OK;
+}
+int csp_set_device(int device) {
+    CSP_CHECK(csp_require_device());
+    int cnt = 0;
+    CSP_CUDA(cudaGetDeviceCount(&cnt));
+    if (device < 0 || device >= cnt) return csp_set_error(CSP_ERR_INVALID, "device %d out of range (have %d)", device, cnt);
+    g_device = device;
+    return CSP_OK;
+}
+int64_t csp_kernel_launches(void) { return g_csp_launches.load(); }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// blob format: 64-byte header followed by the desc arrays in declaration order, each padded to 16 bytes
+// ---------------------------------------------------------------------------------------------------------------
+struct BlobHeader {
+    char magic[8];  // "CSPB200\0"
+    int32_t version, n, p, n_nodes, n_internal, n_leaves;
+    int32_t reserved[8];
+};
+static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
+
+struct Section { size_t off, bytes; };
+static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+static size_t blob_layout(int n, int p, int nn, int ni, Section s[12]) {
+    size_t C = size_t(1) << p;
+    size_t sz[12] = {size_t(n) * 8, size_t(n) * 8, size_t(nn) * 4, size_t(nn), size_t(nn) * 4, size_t(nn) * 4, size_t(nn) * 8,
+                     size_t(ni) * 4, size_t(ni) * p * 4, size_t(ni) * p * 8, size_t(ni) * C * 4, size_t(ni) * n * 8};
+    size_t off = sizeof(BlobHeader);
+    for (int i = 0; i < 12; ++i) { s[i] = {off, sz[i]}; off = align16(off + sz[i]); }
+    return off;
+}
+
+static int validate_desc(const csp_tree_desc* d) {
+    if (!d) return csp_set_error(CSP_ERR_INVALID, "desc is NULL");
+    if (d->n < 1) return csp_set_error(CSP_ERR_INVALID, "n must be >= 1 (got %d)", d->n);
+    if (d->p != 1 && d->p != 2)
+        return csp_set_error(CSP_ERR_UNSUPPORTED, "degree p=%d is not supported by the sm_100a kernels (p must be 1 or 2)", d->p);
+    if (d->n_nodes < 1 || d->n_internal < 0 || d->n_leaves < 1 || d->n_internal >= d->n_nodes)
+        return csp_set_error(CSP_ERR_INVALID, "inconsistent counts: nodes=%d internal=%d leaves=%d", d->n_nodes, d->n_internal, d->n_leaves);
+    const void* ptrs[] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val};
+    for (const void* q : ptrs)
+        if (!q) return csp_set_error(CSP_ERR_INVALID, "a per-node array of the tree descriptor is NULL");
+    if (d->n_internal > 0 && (!d->inode || !d->dims || !d->xs || !d->child || !d->pos))
+        return csp_set_error(CSP_ERR_INVALID, "a per-internal-node array of the tree descriptor is NULL");
+    const int C = 1 << d->p;
+    if ((long long)d->n_nodes != 1 + (long long)d->n_internal * C)
+        return csp_set_error(CSP_ERR_INVALID, "n_nodes=%d is not 1 + n_internal*2^p = %lld", d->n_nodes, 1 + (long long)d->n_internal * C);
+    if (d->parent[0] != 0) return csp_set_error(CSP_ERR_INVALID, "node 0 must be the root (parent[0] == 0)");
+    int ni = 0, nl = 0;
+    for (int v = 0; v < d->n_nodes; ++v) {
+        int I = d->internal_id[v];
+        if (I >= 0) {
+            if (I != ni || I >= d->n_internal || d->inode[I] != v)
+                return csp_set_error(CSP_ERR_INVALID, "internal ids are not preorder ranks at node %d", v);
+            ++ni;
+            if (d->leaf_id[v] != -1) return csp_set_error(CSP_ERR_INVALID, "internal node %d has a leaf id", v);
+            if (d->child[(size_t)I * C] != v + 1)
+                return csp_set_error(CSP_ERR_INVALID, "node %d: child 0 must follow its parent in preorder", v);
+            for (int k = 0; k < C; ++k) {
+                int c = d->child[(size_t)I * C + k];
+                if (c <= v || c >= d->n_nodes || d->parent[c] != v || d->childindex[c] != k)
+                    return csp_set_error(CSP_ERR_INVALID, "node %d: child %d (%d) is inconsistent with parent/childindex", v, k, c);
+            }
+            for (int k = 0; k < d->p; ++k) {
+                int dim = d->dims[(size_t)I * d->p + k];
+                int maxdim = (d->n + d->p - 1) / d->p * d->p;
+                if (dim < 1 || dim > maxdim) return csp_set_error(CSP_ERR_INVALID, "node %d: split dimension %d out of range", v, dim);
+            }
+        } else {
+            int L = d->leaf_id[v];
+            if (L >= 0) {
+                if (L != nl) return csp_set_error(CSP_ERR_INVALID, "leaf ids are not preorder ranks at node %d", v);
+                ++nl;
+            }
+        }
+    }
+    if (ni != d->n_internal || nl != d->n_leaves)
+        return csp_set_error(CSP_ERR_INVALID, "counted %d internal / %d leaves, descriptor says %d / %d", ni, nl, d->n_internal, d->n_leaves);
+    return CSP_OK;
+}
+
+template <class T>
+static int to_device(csp_tree* t, const std::vector<T>& h, const T** out) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
+    CSP_CUDA(cudaMalloc(&p, bytes));
+    t->allocs.push_back(p);
+    t->bytes += bytes;
+    if (!h.empty()) CSP_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)p;
+    return CSP_OK;
+}
+
+static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
+    const int n = d->n, p = d->p, C = 1 << p, nn = d->n_nodes, ni = d->n_internal, nl = d->n_leaves;
+    // derived per-node arrays
+    std::vector<int4> ninfo(nn);
+    std::vector<int> icount(nn), depth(nn, 0), nleaf(d->leaf_id, d->leaf_id + nn), lnode(nl);
+    for (int v = 0; v < nn; ++v) icount[v] = d->internal_id[v] >= 0 ? 1 : 0;
+    for (int v = nn - 1; v >= 1; --v) icount[d->parent[v]] += icount[v];
+    int before = 0, maxdepth = 0;
+    for (int v = 0; v < nn; ++v) {
+        bool internal = d->internal_id[v] >= 0;
+        int flags = d->childindex[v];
+        if (!internal) flags |= CSP_NF_LEAF;
+        if (!internal && d->leaf_id[v] < 0) flags |= CSP_NF_FAKE;
+        ninfo[v] = make_int4(d->parent[v], before, icount[v], flags);
+        if (internal) ++before;
+        if (v > 0) depth[v] = depth[d->parent[v]] + 1;
+        if (d->leaf_id[v] >= 0) { lnode[d->leaf_id[v]] = v; maxdepth = std::max(maxdepth, depth[v]); }
+    }
+    // derived per-internal arrays
+    std::vector<double> ixself((size_t)ni * p), icval((size_t)ni * C);
+    std::vector<DRec1> r1(p == 1 ? ni : 0);
+    std::vector<DRec2> r2(p == 2 ? ni : 0);
+    auto enc_child = [&](int c) { return d->internal_id[c] >= 0 ? d->internal_id[c] : -d->leaf_id[c] - 2; };
+    for (int I = 0; I < ni; ++I) {
+        double mid[2] = {0, 0};
+        int dj[2] = {CSP_DIM_FICTIVE, CSP_DIM_FICTIVE};
+        for (int k = 0; k < p; ++k) {
+            int dim = d->dims[(size_t)I * p + k];
+            double xo = d->xs[(size_t)I * p + k];
+            double xself = dim <= n ? d->pos[(size_t)I * n + dim - 1] : 0.0;
+            ixself[(size_t)I * p + k] = xself;
+            if (dim <= n) {
+                mid[k] = (xself + xo) / 2;  // src/tree.jl:383, same IEEE operations as the reference
+                dj[k] = (dim - 1) | (xo < xself ? (int)0x80000000 : 0);
+            }
+        }
+        for (int k = 0; k < C; ++k) icval[(size_t)I * C + k] = d->val[d->child[(size_t)I * C + k]];
+        if (p == 1) {
+            DRec1 r{};
+            r.mid = mid[0]; r.d = dj[0];
+            r.child[0] = enc_child(d->child[(size_t)I * 2]); r.child[1] = enc_child(d->child[(size_t)I * 2 + 1]);
+            r1[I] = r;
+        } else {
+            DRec2 r{};
+            r.mid0 = mid[0]; r.mid1 = mid[1]; r.d0 = dj[0]; r.d1 = dj[1];
+            for (int k = 0; k < 4; ++k) r.child[k] = enc_child(d->child[(size_t)I * 4 + k]);
+            r2[I] = r;
+        }
+    }
+    TreeView& v = t->v;
+    v.n = n; v.p = p; v.n_nodes = nn; v.n_internal = ni; v.n_leaves = nl;
+    CSP_CHECK(to_device(t, std::vector<double>(d->lower, d->lower + n), &v.lower));
+    CSP_CHECK(to_device(t, std::vector<double>(d->upper, d->upper + n), &v.upper));
+    if (p == 1) { const DRec1* q; CSP_CHECK(to_device(t, r1, &q)); v.drec = q; }
+    else { const DRec2* q; CSP_CHECK(to_device(t, r2, &q)); v.drec = q; }
+    CSP_CHECK(to_device(t, ninfo, &v.ninfo));
+    CSP_CHECK(to_device(t, nleaf, &v.nleaf));
+    CSP_CHECK(to_device(t, std::vector<int>(d->inode, d->inode + ni), &v.inode));
+    CSP_CHECK(to_device(t, std::vector<int>(d->dims, d->dims + (size_t)ni * p), &v.idims));
+    CSP_CHECK(to_device(t, std::vector<double>(d->xs, d->xs + (size_t)ni * p), &v.ixs));
+    CSP_CHECK(to_device(t, ixself, &v.ixself));
+    CSP_CHECK(to_device(t, icval, &v.icval));
+    CSP_CHECK(to_device(t, std::vector<int>(d->child, d->child + (size_t)ni * C), &v.ichild));
+    CSP_CHECK(to_device(t, std::vector<double>(d->pos, d->pos + (size_t)ni * n), &v.ipos));
+    CSP_CHECK(to_device(t, lnode, &v.lnode));
+    t->max_depth = maxdepth;
+    return CSP_OK;
+}
+
+extern "C" {
+
+int csp_tree_free(csp_tree* tree) {
+    if (!tree) return CSP_OK;
+    {
+        DeviceGuard g(tree->device);
+        for (void* p : tree->allocs) cudaFree(p);
+    }
+    delete tree;
+    return CSP_OK;
+}
+
+int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out) {
+    if (!out) return csp_set_error(CSP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    CSP_CHECK(validate_desc(desc));
+    CSP_CHECK(csp_require_device());
+    csp_tree* t = new csp_tree();
+    t->device = csp_current_device();
+    DeviceGuard g(t->device);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, t->device) == cudaSuccess) t->n_sm = prop.multiProcessorCount;
+    int rc = upload_impl(desc, t);
+    if (rc != CSP_OK) { csp_tree_free(t); return rc; }
+    *out = t;
+    return CSP_OK;
+}
+
+int csp_tree_blob_size(const csp_tree_desc* d, size_t* bytes) {
+    if (!d || !bytes) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    Section s[12];
+    *bytes = blob_layout(d->n, d->p, d->n_nodes, d->n_internal, s);
+    return CSP_OK;
+}
+
+int csp_tree_pack(const csp_tree_desc* d, void* blob, size_t bytes) {
+    if (!blob) return csp_set_error(CSP_ERR_INVALID, "blob is NULL");
+    CSP_CHECK(validate_desc(d));
+    Section s[12];
+    size_t need = blob_layout(d->n, d->p, d->n_nodes, d->n_internal, s);
+    if (bytes < need) return csp_set_error(CSP_ERR_INVALID, "blob buffer too small: %zu < %zu", bytes, need);
+    memset(blob, 0, need);
+    BlobHeader h{};
+    memcpy(h.magic, "CSPB200", 8);
+    h.version = 1; h.n = d->n; h.p = d->p; h.n_nodes = d->n_nodes; h.n_internal = d->n_internal; h.n_leaves = d->n_leaves;
+    memcpy(blob, &h, sizeof h);
+    const void* src[12] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val,
+                           d->inode, d->dims, d->xs, d->child, d->pos};
+    for (int i = 0; i < 12; ++i)
+        if (s[i].bytes) memcpy((char*)blob + s[i].off, src[i], s[i].bytes);
+    return CSP_OK;
+}
+
+int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out) {
+    if (!blob || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    if (bytes < sizeof(BlobHeader)) return csp_set_error(CSP_ERR_INVALID, "blob shorter than its header");
+    CSP_CHECK(csp_require_device());
+    std::vector<char> host;
+    const char* base = (const char*)blob;
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, blob) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+        host.resize(bytes);  // e.g. the buffer an NCCL broadcast landed in
+        CSP_CUDA(cudaMemcpy(host.data(), blob, bytes, cudaMemcpyDeviceToHost));
+        base = host.data();
+    } else {
+        cudaGetLastError();
+    }
+    BlobHeader h;
+    memcpy(&h, base, sizeof h);
+    if (memcmp(h.magic, "CSPB200", 8) != 0 || h.version != 1) return csp_set_error(CSP_ERR_INVALID, "not a CSPB200 v1 blob");
+    Section s[12];
+    size_t need = blob_layout(h.n, h.p, h.n_nodes, h.n_internal, s);
+    if (bytes < need) return csp_set_error(CSP_ERR_INVALID, "blob truncated: %zu < %zu", bytes, need);
+    csp_tree_desc d{};
+    d.n = h.n; d.p = h.p; d.n_nodes = h.n_nodes; d.n_internal = h.n_internal; d.n_leaves = h.n_leaves;
+    d.lower = (const double*)(base + s[0].off);
+    d.upper = (const double*)(base + s[1].off);
+    d.parent = (const int32_t*)(base + s[2].off);
+    d.childindex = (const uint8_t*)(base + s[3].off);
+    d.internal_id = (const int32_t*)(base + s[4].off);
+    d.leaf_id = (const int32_t*)(base + s[5].off);
+    d.val = (const double*)(base + s[6].off);
+    d.inode = (const int32_t*)(base + s[7].off);
+    d.dims = (const int32_t*)(base + s[8].off);
+    d.xs = (const double*)(base + s[9].off);
+    d.child = (const int32_t*)(base + s[10].off);
+    d.pos = (const double*)(base + s[11].off);
+    return csp_tree_upload(&d, out);
+}
+
+int csp_tree_info(const csp_tree* t, int64_t info[8]) {
+    if (!t || !info) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    info[0] = t->v.n; info[1] = t->v.p; info[2] = t->v.n_nodes; info[3] = t->v.n_internal; info[4] = t->v.n_leaves;
+    info[5] = t->device; info[6] = t->max_depth; info[7] = (int64_t)(t->bytes >> 10);
+    return CSP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,263 @@
+"""Device-side objects: the flattened tree resident in HBM, per-leaf models, and the batched operations.
+
+Everything here calls libcsp_b200.so through the C ABI of include/csp_b200.h.  Host buffers are numpy arrays; resident
+buffers are torch CUDA tensors (torch is used only for device memory and streams -- plumbing, not compute).  There is
+no CPU fallback: without the built library or without a CUDA device these calls raise.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+from ._native import TreeDesc, c_f64p, c_i32p, c_i64p, c_u8p
+
+Q_OK, Q_OUTSIDE = 0, 1
+FIT_OK, FIT_NO_CHAIN, FIT_CHAIN_ASSERT, FIT_CHAIN_UNDEF = 0, 1, 2, 3
+
+
+def _is_cuda_tensor(x):
+    return hasattr(x, "data_ptr") and getattr(x, "is_cuda", False)
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if _is_cuda_tensor(a):
+        return a.data_ptr()
+    return a.ctypes.data
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        try:
+            import torch
+            return torch.cuda.current_stream().cuda_stream
+        except Exception:
+            return None
+    return getattr(stream, "cuda_stream", stream)
+
+
+def make_desc(flat):
+    """csp_tree_desc over the arrays of a flat dict (tree._Tree.flat() or the oracle's export_flat)."""
+    d = TreeDesc()
+    d.n, d.p, d.n_nodes, d.n_internal, d.n_leaves = flat["n"], flat["p"], flat["n_nodes"], flat["n_internal"], flat["n_leaves"]
+    keep = {}
+    for name, dt, ct in (("lower", np.float64, c_f64p), ("upper", np.float64, c_f64p), ("parent", np.int32, c_i32p),
+                         ("childindex", np.uint8, c_u8p), ("internal_id", np.int32, c_i32p), ("leaf_id", np.int32, c_i32p),
+                         ("val", np.float64, c_f64p), ("inode", np.int32, c_i32p), ("dims", np.int32, c_i32p),
+                         ("xs", np.float64, c_f64p), ("child", np.int32, c_i32p), ("pos", np.float64, c_f64p)):
+        a = np.ascontiguousarray(flat[name], dt)
+        keep[name] = a
+        setattr(d, name, a.ctypes.data_as(ct) if a.size else C.cast(None, ct))
+    return d, keep
+
+
+def pack_blob(flat):
+    """The flattened tree as one relocatable byte blob (numpy uint8): the wire / on-disk format."""
+    d, keep = make_desc(flat)
+    sz = C.c_size_t()
+    N.dchk(N.dev().csp_tree_blob_size(C.byref(d), C.byref(sz)))
+    blob = np.zeros(sz.value, np.uint8)
+    N.dchk(N.dev().csp_tree_pack(C.byref(d), blob.ctypes.data, sz.value))
+    return blob
+
+
+class DeviceTree:
+    """Flattened CSp-tree resident on one GPU (csp_tree)."""
+
+    def __init__(self, flat=None, blob=None, device=None):
+        L = N.dev()
+        if device is not None:
+            N.dchk(L.csp_set_device(int(device)))
+        h = C.c_void_p()
+        if blob is not None:
+            nbytes = blob.numel() if _is_cuda_tensor(blob) else blob.nbytes
+            N.dchk(L.csp_tree_upload_blob(_ptr(blob), nbytes, C.byref(h)))
+        else:
+            d, keep = make_desc(flat)
+            N.dchk(L.csp_tree_upload(C.byref(d), C.byref(h)))
+        self.h = h
+        info = (C.c_int64 * 8)()
+        N.dchk(L.csp_tree_info(h, info))
+        self.n, self.p, self.n_nodes, self.n_internal, self.n_leaves, self.device, self.max_depth, self.kib = [int(v) for v in info]
+
+    def close(self):
+        if self.h:
+            N.dev().csp_tree_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- K1 -------------------------------------------------------------------------------------------------
+    def find_leaf(self, X, leaf=None, status=None, stream=None):
+        """Batched find_leaf_at.  X: (m, n) float64 numpy array (host path) or torch CUDA tensor (resident path).
+        Returns (leaf ids int32, status uint8)."""
+        m = self._check_X(X)
+        if _is_cuda_tensor(X):
+            import torch
+            leaf = torch.empty(m, dtype=torch.int32, device=X.device) if leaf is None else leaf
+            status = torch.empty(m, dtype=torch.uint8, device=X.device) if status is None else status
+            N.dchk(N.dev().csp_find_leaf_dev(self.h, _ptr(X), m, _ptr(leaf), _ptr(status), _stream_ptr(stream)))
+        else:
+            X = np.ascontiguousarray(X, np.float64)
+            leaf = np.empty(m, np.int32) if leaf is None else leaf
+            status = np.empty(m, np.uint8) if status is None else status
+            N.dchk(N.dev().csp_find_leaf(self.h, _ptr(X), m, _ptr(leaf), _ptr(status)))
+        return leaf, status
+
+    def _check_X(self, X):
+        shape = tuple(X.shape)
+        if len(shape) != 2 or shape[1] != self.n:
+            raise N.DimensionMismatch(f"tree has {self.n} dimensions, got a query array of shape {shape}")
+        if _is_cuda_tensor(X):
+            import torch
+            if X.dtype != torch.float64 or not X.is_contiguous():
+                raise TypeError("resident queries must be a contiguous float64 CUDA tensor")
+        return shape[0]
+
+    # ---- K2 -------------------------------------------------------------------------------------------------
+    def fit_boxes(self, node_ids=None, skip=0, native=False):
+        """fit_quadratic for the listed node ids (None: every leaf).  Returns a dict of host arrays:
+        c (nb,), g (nb,n), Q (nb,n,n) with Q[l,i,j] = SymmetricArray .data[i,j], b (nb,n), status (nb,);
+        with native=True also gnat, y, prec (nb,n,n bool)."""
+        n = self.n
+        if node_ids is None:
+            nb, ids = self.n_leaves, None
+        else:
+            ids = np.ascontiguousarray(node_ids, np.int32)
+            nb = len(ids)
+        c, g, Q, b = np.empty(nb), np.empty((nb, n)), np.empty((nb, n * n)), np.empty((nb, n))
+        st = np.empty(nb, np.uint8)
+        gn = np.empty((nb, n)) if native else None
+        y = np.empty((nb, n)) if native else None
+        prec = np.empty((nb, n * n), np.uint8) if native else None
+        N.dchk(N.dev().csp_fit_boxes(self.h, _ptr(ids), nb, skip, _ptr(c), _ptr(g), _ptr(Q), _ptr(b), _ptr(gn), _ptr(y), _ptr(prec),
+                                     _ptr(st)))
+        out = dict(c=c, g=g, Q=Q.reshape(nb, n, n).transpose(0, 2, 1), b=b, status=st)
+        if native:
+            out.update(gnat=gn, y=y, prec=prec.reshape(nb, n, n).transpose(0, 2, 1).astype(bool))
+        return out
+
+    def coefficients_p(self, node_ids=None, skip=0):
+        """coefficients_p for the listed node ids (None: every leaf): (Cp, visited); Cp is (nb,n) for p=1 and (nb,n,n)
+        (.data layout, Cp[l,i,j] = data[i,j]) for p=2."""
+        n = self.n
+        if node_ids is None:
+            nb, ids = self.n_leaves, None
+        else:
+            ids = np.ascontiguousarray(node_ids, np.int32)
+            nb = len(ids)
+        per = n * n if self.p == 2 else n
+        Cp = np.empty((nb, per))
+        vis = np.empty(nb, np.int64)
+        N.dchk(N.dev().csp_coefficients_p(self.h, _ptr(ids), nb, skip, _ptr(Cp), _ptr(vis)))
+        if self.p == 2:
+            Cp = Cp.reshape(nb, n, n).transpose(0, 2, 1)
+        return Cp, vis
+
+    def fit_models(self, skip=0):
+        """Fit every leaf and keep the canonical models on the device (csp_models_fit)."""
+        h = C.c_void_p()
+        N.dchk(N.dev().csp_models_fit(self.h, skip, C.byref(h)))
+        return LeafModels(h)
+
+    def refit_models(self, models, skip=0, stream=None):
+        """Re-fit every leaf into an existing LeafModels (asynchronous, no allocation)."""
+        N.dchk(N.dev().csp_models_refit(self.h, skip, models.h, _stream_ptr(stream)))
+        return models
+
+    # ---- K3 -------------------------------------------------------------------------------------------------
+    def locate_eval(self, models, X, leaf=None, val=None, status=None, stream=None):
+        """Fused find_leaf_at + modelvalue.  Returns (leaf ids, values, status)."""
+        m = self._check_X(X)
+        if _is_cuda_tensor(X):
+            import torch
+            leaf = torch.empty(m, dtype=torch.int32, device=X.device) if leaf is None else leaf
+            val = torch.empty(m, dtype=torch.float64, device=X.device) if val is None else val
+            status = torch.empty(m, dtype=torch.uint8, device=X.device) if status is None else status
+            N.dchk(N.dev().csp_locate_eval_dev(self.h, models.h, _ptr(X), m, _ptr(leaf), _ptr(val), _ptr(status), _stream_ptr(stream)))
+        else:
+            X = np.ascontiguousarray(X, np.float64)
+            leaf = np.empty(m, np.int32) if leaf is None else leaf
+            val = np.empty(m, np.float64) if val is None else val
+            status = np.empty(m, np.uint8) if status is None else status
+            N.dchk(N.dev().csp_locate_eval(self.h, models.h, _ptr(X), m, _ptr(leaf), _ptr(val), _ptr(status)))
+        return leaf, val, status
+
+
+class LeafModels:
+    """Per-leaf canonical models (c, g, Q, b) resident on one GPU (csp_models)."""
+
+    def __init__(self, h):
+        self.h = h
+        info = (C.c_int64 * 4)()
+        N.dchk(N.dev().csp_models_info(h, info))
+        self.n, self.n_models, self.degree, self.device = [int(v) for v in info]
+
+    @classmethod
+    def upload(cls, c, g, Q, b, device=None):
+        """Caller-supplied models: c (nl,), g (nl,n), Q (nl,n,n) with Q[l,i,j] = .data[i,j] (upper triangle used) or None
+        for degree-1 models, b (nl,n)."""
+        if device is not None:
+            N.dchk(N.dev().csp_set_device(int(device)))
+        c = np.ascontiguousarray(c, np.float64)
+        g = np.ascontiguousarray(g, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        nl, n = g.shape
+        Qf = None if Q is None else np.ascontiguousarray(np.asarray(Q, np.float64).transpose(0, 2, 1))
+        h = C.c_void_p()
+        N.dchk(N.dev().csp_models_upload(n, nl, _ptr(c), _ptr(g), _ptr(Qf), _ptr(b), C.byref(h)))
+        return cls(h)
+
+    def download(self):
+        nl, n = self.n_models, self.n
+        c, g, b = np.empty(nl), np.empty((nl, n)), np.empty((nl, n))
+        Q = np.empty((nl, n * n)) if self.degree == 2 else None
+        st = np.empty(nl, np.uint8)
+        N.dchk(N.dev().csp_models_download(self.h, _ptr(c), _ptr(g), _ptr(Q), _ptr(b), _ptr(st)))
+        out = dict(c=c, g=g, b=b, status=st)
+        if Q is not None:
+            out["Q"] = Q.reshape(nl, n, n).transpose(0, 2, 1)
+        return out
+
+    def evaluate(self, X, leaf, val=None, stream=None):
+        """modelvalue of model leaf[i] at X[i] (K3, leaf ids supplied)."""
+        shape = tuple(X.shape)
+        if len(shape) != 2 or shape[1] != self.n:
+            raise N.DimensionMismatch(f"models have {self.n} dimensions, got a query array of shape {shape}")
+        m = shape[0]
+        if _is_cuda_tensor(X):
+            import torch
+            val = torch.empty(m, dtype=torch.float64, device=X.device) if val is None else val
+            N.dchk(N.dev().csp_eval_dev(self.h, _ptr(X), _ptr(leaf), m, _ptr(val), _stream_ptr(stream)))
+        else:
+            X = np.ascontiguousarray(X, np.float64)
+            leaf = np.ascontiguousarray(leaf, np.int32)
+            val = np.empty(m, np.float64) if val is None else val
+            N.dchk(N.dev().csp_eval(self.h, _ptr(X), _ptr(leaf), m, _ptr(val)))
+        return val
+
+    def close(self):
+        if self.h:
+            N.dev().csp_models_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def kernel_launches():
+    return int(N.dev().csp_kernel_launches())
+
+
+def device_count():
+    c = C.c_int()
+    N.dchk(N.dev().csp_device_count(C.byref(c)))
+    return c.value

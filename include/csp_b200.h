@@ -1,0 +1,147 @@
+/* csp_b200.h -- C ABI of libcsp_b200.so: the B200 (sm_100a) accelerator for the data-parallel hot path of
+ * timholy/CoordinateSplittingPTrees.jl (batched find_leaf_at, per-box quadratic model fit, batched model evaluation).
+ *
+ * The reference is pure Julia and has no FFI of its own; the boundary below is what a Julia `ccall` binding for this
+ * path would bind (see INTEGRATION.md for the Julia stub).  Each entry point cites the reference function it
+ * replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - every function returns CSP_OK (0) or a negative CSP_ERR_* code; csp_last_error() returns the message of the last
+ *     failure on the calling thread.  No exceptions cross this boundary; the host wrapper re-raises the reference's
+ *     exception types from the status codes documented below.
+ *   - the caller owns every host buffer; the library owns device memory behind the opaque handles.
+ *   - one caller thread per handle at a time; concurrent readers of one csp_tree are safe.
+ *   - a query matrix X holds m queries of n doubles each, each query contiguous (Julia: an n x m column-major Matrix).
+ *   - `*_dev` variants take DEVICE pointers on the handle's device plus a cudaStream_t (as void*; NULL = default stream),
+ *     are asynchronous, and are what a caller with resident data uses.  The plain variants take HOST buffers, move them
+ *     with chunked, double-buffered copies and return when the results are in the caller's buffers.
+ *   - dimensions are 1-based in every array that holds them (as in the reference); node / leaf ids are 0-based.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with CSP_ERR_NO_DEVICE.
+ */
+#ifndef CSP_B200_H
+#define CSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSP_OK 0
+#define CSP_ERR_INVALID (-1)     /* bad argument; DimensionMismatch / ArgumentError on the host side */
+#define CSP_ERR_CUDA (-2)        /* a CUDA runtime call failed */
+#define CSP_ERR_NOMEM (-3)
+#define CSP_ERR_UNSUPPORTED (-4) /* degree / dimension outside what the kernels cover (p in {1,2}; fits need p == 2) */
+#define CSP_ERR_NO_DEVICE (-5)
+
+/* per-query status written by csp_find_leaf* / csp_locate_eval* */
+#define CSP_Q_OK 0
+#define CSP_Q_OUTSIDE 1 /* src/tree.jl:357-360 throws ErrorException("... not within ... along dimension ...") */
+
+/* per-box status written by csp_fit_boxes / csp_models_fit */
+#define CSP_FIT_OK 0
+#define CSP_FIT_NO_CHAIN 1     /* src/cs2.jl:166-167  error("no chain found at ...") */
+#define CSP_FIT_CHAIN_ASSERT 2 /* src/cs2.jl:186-187  AssertionError (chain repeats a dimension) */
+#define CSP_FIT_CHAIN_UNDEF 3  /* src/cs2.jl:184      UndefRefError (chain runs into a leaf before covering n dims) */
+
+typedef struct csp_tree csp_tree;     /* device-resident flattened CSp-tree */
+typedef struct csp_models csp_models; /* device-resident per-leaf models (c, g, Q, b) */
+
+/* Flattened tree, as produced by walking `collect(root)` (preorder, src/tree.jl:393-415).
+ * Node ids are preorder ranks; internal ids are preorder ranks among non-leaf boxes; leaf ids are ranks in
+ * `leaves(root)` (src/tree.jl:423, fake boxes excluded).  Replaces the Box/Split/Children/World object graph of
+ * src/types.jl:7-23,155-192.  Everything derivable (split midpoints, subtree sizes, child values ...) is computed by
+ * the library at upload. */
+typedef struct csp_tree_desc {
+    int32_t n;          /* ndims(root) */
+    int32_t p;          /* degree(root): 1 or 2 */
+    int32_t n_nodes;    /* length(root) */
+    int32_t n_internal; /* number of non-leaf boxes */
+    int32_t n_leaves;   /* length(leaves(root)) */
+    const double* lower;        /* [n]  world.lower */
+    const double* upper;        /* [n]  world.upper */
+    /* per node, preorder */
+    const int32_t* parent;      /* [n_nodes] node id of box.parent (root: itself) */
+    const uint8_t* childindex;  /* [n_nodes] box.childindex (0 = self) */
+    const int32_t* internal_id; /* [n_nodes] internal id, or -1 for leaves */
+    const int32_t* leaf_id;     /* [n_nodes] leaf id, or -1 for non-leaves and fake leaves (src/tree.jl:430-442) */
+    const double* val;          /* [n_nodes] value(box) (src/CoordinateSplittingPTrees.jl:61, src/tree.jl:316-323) */
+    /* per internal node, preorder */
+    const int32_t* inode;       /* [n_internal] node id */
+    const int32_t* dims;        /* [n_internal*p] split.dims, 1-based, > n = fictive */
+    const double* xs;           /* [n_internal*p] split.xs */
+    const int32_t* child;       /* [n_internal*2^p] node ids of getchild(split, 0..2^p-1) (src/tree.jl:325) */
+    const double* pos;          /* [n_internal*n] position(box) (src/tree.jl:71,103-129) */
+} csp_tree_desc;
+
+int csp_version(void);
+const char* csp_last_error(void);
+int csp_device_count(int* count);
+int csp_set_device(int device); /* device used by subsequent uploads on this thread (default 0) */
+
+/* ---- tree residency ------------------------------------------------------------------------------------------- */
+int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out);
+/* The same tree as one relocatable byte blob (the wire / on-disk format: header + the desc arrays, little endian),
+ * so that it can be broadcast across GPUs or saved.  `blob` for csp_tree_upload_blob may be a host or a device pointer. */
+int csp_tree_blob_size(const csp_tree_desc* desc, size_t* bytes);
+int csp_tree_pack(const csp_tree_desc* desc, void* blob, size_t bytes);
+int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out);
+/* info[0..7] = n, p, n_nodes, n_internal, n_leaves, device, max leaf depth, bytes resident (KiB) */
+int csp_tree_info(const csp_tree* tree, int64_t info[8]);
+int csp_tree_free(csp_tree* tree);
+
+/* ---- K1: batched point location; replaces find_leaf_at (src/tree.jl:351-388) ------------------------------------ */
+/* leaf[i] = leaf id of the leaf containing X[:,i], or -1 with status[i] = CSP_Q_OUTSIDE.  status may be NULL. */
+int csp_find_leaf(const csp_tree* tree, const double* X, int64_t m, int32_t* leaf, uint8_t* status);
+int csp_find_leaf_dev(const csp_tree* tree, const double* dX, int64_t m, int32_t* dleaf, uint8_t* dstatus, void* stream);
+
+/* ---- K2: batched model fits ------------------------------------------------------------------------------------- */
+/* fit_quadratic(value, box; skip) for each listed box (src/cs2.jl:89-93: fit_poly1 :162-205, coefficients_p
+ * src/polynomials.jl:182-230, fit_poly2_diag! src/cs2.jl:208-274, canonicalize :132-140).  node_ids == NULL means
+ * "every leaf, in leaves(root) order" (then nb must equal n_leaves).  Outputs (any may be NULL), box-major:
+ *   c[nb], g[nb*n] canonical gradient, Q[nb*n*n] in the layout of SymmetricArray .data (column-major, values at
+ *   [i,j] with i<=j, the strictly lower triangle keeps the NaN fill; src/types.jl:432-454, src/polynomials.jl:232-233),
+ *   b[nb*n]; native-form extras of fit_quadratic_native (src/cs2.jl:115-121): g_native[nb*n], y[nb*n],
+ *   prec[nb*n*n] (column-major Bool matrix, prec[i,j] <=> i was split before-or-with j); status[nb] CSP_FIT_*.
+ * Boxes whose status is not CSP_FIT_OK get NaN outputs.  Requires p == 2. */
+int csp_fit_boxes(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q,
+                  double* b, double* g_native, double* y, uint8_t* prec, uint8_t* status);
+/* coefficients_p(value, box; skip) (src/polynomials.jl:127-230), dense output Cp[nb*n^p]: p == 2 gives the
+ * off-diagonal Hessian entries (.data layout as above, diagonal NaN), p == 1 the gradient vector.
+ * visited[nb] (may be NULL) = number of splits the traversal examined. */
+int csp_coefficients_p(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited);
+
+/* ---- per-leaf models resident on the device ---------------------------------------------------------------------- */
+/* Fit every leaf and keep the canonical models (c, g, Q, b) on the device for evaluation.  p == 2: fit_quadratic;
+ * p == 1: the degree-1 model c = value(leaf), g = coefficients_p(leaf), b = position(leaf). */
+int csp_models_fit(const csp_tree* tree, int32_t skip, csp_models** out);
+/* Re-fit into an existing handle obtained from csp_models_fit on the same tree (asynchronous on `stream`; no allocation):
+ * what a caller that re-fits every iteration uses. */
+int csp_models_refit(const csp_tree* tree, int32_t skip, csp_models* models, void* stream);
+/* Models supplied by the caller (host arrays, layouts as in csp_fit_boxes; Q may be NULL for degree-1 models). */
+int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double* g, const double* Q, const double* b,
+                      csp_models** out);
+int csp_models_download(const csp_models* models, double* c, double* g, double* Q, double* b, uint8_t* status);
+/* info[0..3] = n, n_models, degree (1|2), device */
+int csp_models_info(const csp_models* models, int64_t info[4]);
+int csp_models_free(csp_models* models);
+
+/* ---- K3: batched evaluation; replaces modelvalue(c, g, Q, b, x) (src/cs2.jl:155-159) ----------------------------- */
+/* val[i] = c_l + g_l'(x_i - b_l) + (x_i - b_l)' Q_l (x_i - b_l) / 2 with l = leaf[i] (leaf[i] < 0 gives NaN). */
+int csp_eval(const csp_models* models, const double* X, const int32_t* leaf, int64_t m, double* val);
+int csp_eval_dev(const csp_models* models, const double* dX, const int32_t* dleaf, int64_t m, double* dval, void* stream);
+/* find_leaf_at followed by modelvalue of that leaf's model, fused.  leaf / status may be NULL. */
+int csp_locate_eval(const csp_tree* tree, const csp_models* models, const double* X, int64_t m, int32_t* leaf, double* val,
+                    uint8_t* status);
+int csp_locate_eval_dev(const csp_tree* tree, const csp_models* models, const double* dX, int64_t m, int32_t* dleaf,
+                        double* dval, uint8_t* dstatus, void* stream);
+
+/* ---- instrumentation -------------------------------------------------------------------------------------------- */
+/* Number of kernels this library has launched in this process since load (bench.py reports it as gpu_launches). */
+int64_t csp_kernel_launches(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSP_B200_H */

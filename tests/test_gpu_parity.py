@@ -1,0 +1,376 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against the CPU oracle
+on the same seeded inputs.  Bars: leaf ids / status / fitted coefficients BIT-EXACT (the fit kernels evaluate every
+expression in the reference's order with FMA contraction off); evaluated values within 1e-12 relative (the reference
+does not pin the summation order of modelvalue, src/cs2.jl:155-159)."""
+import numpy as np
+import pytest
+
+import csp_b200 as cb
+from csp_b200.device import DeviceTree, LeafModels
+from oracle import oracle as O
+from helpers import grow_both
+
+pytestmark = pytest.mark.gpu
+
+EVAL_RTOL = 1e-12
+
+
+def same(a, b):
+    return np.array_equal(np.asarray(a), np.asarray(b), equal_nan=True)
+
+
+def edge_queries(root, oroot, rng, m):
+    """Random queries plus the reference's edge cases: split midpoints (ties), leaf positions, world corners/edges,
+    out-of-world rows and NaN."""
+    w = root.world
+    n = root.n
+    X = w.lower + (w.upper - w.lower) * rng.random((m, n))
+    f = root.tree.flat()
+    ni = f["n_internal"]
+    if ni:
+        # rows sitting exactly on a split midpoint along one split dimension, elsewhere at the split's own position
+        k = min(ni, m // 4)
+        I = rng.integers(0, ni, k)
+        pos = f["pos"].reshape(ni, n)[I].copy()
+        for r, i in enumerate(I):
+            d = f["dims"][i * f["p"]]
+            if d <= n:
+                pos[r, d - 1] = (pos[r, d - 1] + f["xs"][i * f["p"]]) / 2
+        X[:k] = pos
+        X[k:2 * k] = f["pos"].reshape(ni, n)[I]  # exact evaluation points
+    X[-1] = w.lower
+    X[-2] = w.upper
+    X[-3] = w.upper
+    X[-3, 0] = np.nextafter(w.upper[0], np.inf)  # just outside
+    X[-4] = w.lower
+    X[-4, n - 1] = np.nextafter(w.lower[n - 1], -np.inf)
+    X[-5, 0] = np.nan
+    return np.ascontiguousarray(X)
+
+
+TREES = [  # (n, p, npoints)
+    (1, 1, 50), (2, 1, 500), (5, 1, 200), (1, 2, 30), (2, 2, 200), (3, 2, 150), (7, 2, 200), (10, 2, 400), (20, 2, 120),
+]
+
+
+@pytest.mark.parametrize("n,p,npoints", TREES)
+def test_find_leaf_bit_exact(n, p, npoints):
+    root, oroot, _ = grow_both(n, p, npoints, seed=100 + n + p)
+    rng = np.random.default_rng(n * 7 + p)
+    X = edge_queries(root, oroot, rng, 20000)
+    oleaf, ostatus, _ = O.find_leaf_batch(oroot, X, nthreads=O.max_threads())
+    dt = cb.device_tree(root)
+    leaf, status = dt.find_leaf(X)  # host-buffer path
+    assert same(leaf, oleaf) and same(status, ostatus)
+    assert (ostatus == 1).sum() >= 3 and (ostatus == 0).sum() > 19000
+    import torch
+    Xd = torch.from_numpy(X).cuda()
+    leafd, statusd = dt.find_leaf(Xd)  # resident path
+    torch.cuda.synchronize()
+    assert same(leafd.cpu().numpy(), oleaf) and same(statusd.cpu().numpy(), ostatus)
+    # ragged / unaligned / tiny batches (odd row counts defeat the 16-byte TMA granularity; offset base pointer)
+    for m in (0, 1, 3, 127, 129, 1001):
+        l2, s2 = dt.find_leaf(Xd[5:5 + m].contiguous() if m else Xd[:0])
+        torch.cuda.synchronize()
+        assert same(l2.cpu().numpy(), oleaf[5:5 + m])
+    flat = Xd.reshape(-1)
+    if n % 2 == 1:  # a view starting at an odd element offset is only 8-byte aligned
+        Xo = flat[n:n + 999 * n].view(999, n)
+        l3, _ = dt.find_leaf(Xo)
+        torch.cuda.synchronize()
+        assert same(l3.cpu().numpy(), oleaf[1:1000])
+
+
+def test_find_leaf_reference_goldens_on_gpu():  # runtests.jl:87-96, 110-114, 242-251 through the public API
+    world = cb.World([0], [1], [0], 10)
+    root = cb.Box(world, 1)
+    box = cb.split(root, 1, 1, 20)[0]
+    box1 = cb.split(box, 1, 0.5, 30)[0]
+    assert cb.find_leaf_at(root, [0.3]) == cb.getleaf(root)
+    assert cb.find_leaf_at(root, [0.5]) == box1
+    assert cb.find_leaf_at(root, [0.8]) == cb.getleaf(box)
+    with pytest.raises(cb.ErrorException):
+        cb.find_leaf_at(root, [1.2])
+    with pytest.raises(cb.DimensionMismatch):
+        cb.find_leaf_at(root, [0.1, 0.2])
+    world = cb.World([0], [1], [1], 10)
+    root = cb.Box(world, 1)
+    cb.split(root, 1, 0, 20)
+    assert cb.find_leaf_at(root, 0.5) == cb.getleaf(root)  # scalar x; tie goes to the closed-below side
+    root = cb.Box(cb.World([0], [1], [0], 10), 1)
+    b1 = cb.split(root, 1, 1, 20)[0]
+    assert cb.find_leaf_at(root, 0.5) == b1
+    # a tree without splits: the root is the only leaf
+    root = cb.Box(cb.World([0, 0], [1, 1], [0.5, 0.5], 1.0), 2)
+    assert cb.find_leaf_at(root, [0.2, 0.9]) == root
+    # staleness: growing the tree re-flattens the device copy
+    leaf = cb.addpoint(root, [0.25, 0.75], [(1, 2)], lambda y: float(y.sum()))
+    assert cb.find_leaf_at(root, [0.2, 0.9]) == leaf
+
+
+FIT_TREES = [(2, 60), (3, 80), (4, 100), (7, 200), (8, 200), (10, 400), (20, 150), (33, 70)]
+
+
+@pytest.mark.parametrize("n,npoints", FIT_TREES)
+@pytest.mark.parametrize("skip", [0, 3])
+def test_fit_leaves_bit_exact(n, npoints, skip):
+    root, oroot, _ = grow_both(n, 2, npoints, seed=200 + n)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    fit = dt.fit_boxes(skip=skip, native=True)
+    ofit = O.fit_boxes_batch(olv, skip=skip, nthreads=O.max_threads(), native=True)
+    assert same(fit["status"], ofit["status"])
+    assert (ofit["status"] == 0).sum() > 0.5 * len(olv)
+    for k in ("c", "g", "Q", "b", "gnat", "y"):
+        assert same(fit[k], ofit[k]), k
+    ok = ofit["status"] == 0
+    assert same(fit["prec"][ok], ofit["prec"][ok])
+    # off-diagonals alone (coefficients_p) and the number of splits the traversal examined
+    Cp, vis = dt.coefficients_p(skip=skip)
+    oCp, ovis, _ = O.coefficients_p_batch(olv, skip=skip, nthreads=O.max_threads())
+    assert same(Cp, oCp.reshape(len(olv), n, n).transpose(0, 2, 1))
+    assert same(vis, ovis)
+
+
+def test_fit_internal_boxes_and_failures():
+    """Boxes that are not leaves (fit_poly1 uses getleaf(box), the traversals start at the box itself), and trees grown
+    with random pairings where chaintop fails: status codes must match the oracle's exceptions."""
+    rng = np.random.default_rng(5)
+    n = 6
+    cycle = []
+    for _ in range(40):
+        perm = rng.permutation(n) + 1
+        cycle.append([(int(perm[i]), int(perm[i + 1])) for i in range(0, n, 2)])
+    root, oroot, _ = grow_both(n, 2, 160, seed=9, cycle=cycle)
+    dt = cb.device_tree(root)
+    oall = O.collect(oroot)
+    ids = np.arange(len(oall), dtype=np.int32)
+    keep = [i for i in ids if not O.isfake(oall[i])]
+    fit = dt.fit_boxes(node_ids=keep, native=True)
+    ofit = O.fit_boxes_batch([oall[i] for i in keep], nthreads=O.max_threads(), native=True)
+    assert same(fit["status"], ofit["status"])
+    assert set(np.unique(ofit["status"])) >= {0, 1}
+    for k in ("c", "g", "Q", "b", "gnat", "y"):
+        assert same(fit[k], ofit[k]), k
+    Cp, vis = dt.coefficients_p(node_ids=keep)
+    oCp, ovis, _ = O.coefficients_p_batch([oall[i] for i in keep], nthreads=O.max_threads())
+    assert same(Cp, oCp.reshape(len(keep), n, n).transpose(0, 2, 1)) and same(vis, ovis)
+
+
+def test_fit_underdetermined_nan_pattern():
+    """few addpoint!s at larger n leave most pairs unseen -> NaN pattern identical to the reference's."""
+    root, oroot, _ = grow_both(40, 2, 5, seed=11, sigma=0.0)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    fit = dt.fit_boxes()
+    ofit = O.fit_boxes_batch(olv, nthreads=O.max_threads())
+    assert np.isnan(ofit["Q"]).any() and same(fit["status"], ofit["status"])
+    for k in ("c", "g", "Q", "b"):
+        assert same(fit[k], ofit[k]), k
+
+
+def test_fit_nonfinite_samples_sequential_path():
+    """Non-finite objective values make computed coefficients NaN; the reference then re-fills those slots from later
+    splits while counting them (polynomials.jl:211-227).  The kernel's exact sequential path must reproduce that."""
+    n = 6
+    calls = [0]
+    base = cb.synthetic.quad_objective(n, 3, sigma=0.0)
+
+    def f(y):
+        calls[0] += 1
+        return float("nan") if calls[0] % 17 == 0 else base(y)
+    rng = np.random.default_rng(1)
+    lo, up = -np.ones(n), np.ones(n)
+    X = lo + (up - lo) * rng.random((60, n))
+    cycle = cb.synthetic.round_robin_dimlists(n)
+    root = cb.Box(cb.World(lo, up, np.zeros(n), 0.0), 2)
+    oroot = O.Box(O.World(lo, up, np.zeros(n), 0.0), 2)
+    for i, x in enumerate(X):
+        calls[0] = 1000 * i
+        cb.addpoint(root, x, cycle[i % len(cycle)], f)
+        calls[0] = 1000 * i
+        O.addpoint(oroot, x, cycle[i % len(cycle)], f)
+    O.index_tree(oroot)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    Cp, vis = dt.coefficients_p()
+    oCp, ovis, _ = O.coefficients_p_batch(olv)
+    assert np.isnan(root.tree.flat()["val"]).any()
+    assert same(Cp, oCp.reshape(len(olv), n, n).transpose(0, 2, 1)) and same(vis, ovis)
+    fit = dt.fit_boxes()
+    ofit = O.fit_boxes_batch(olv)
+    for k in ("status", "c", "g", "Q", "b"):
+        assert same(fit[k], ofit[k]), k
+
+
+@pytest.mark.parametrize("n,npoints", [(1, 40), (2, 500), (6, 100), (100, 12)])
+def test_cs1_gradient_bit_exact(n, npoints):
+    """CS1 trees: coefficients_p returns the gradient (polynomials.jl:216,232-233)."""
+    root, oroot, _ = grow_both(n, 1, npoints, seed=300 + n)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    Cp, vis = dt.coefficients_p()
+    oCp, ovis, _ = O.coefficients_p_batch(olv, nthreads=O.max_threads())
+    assert same(Cp, oCp) and same(vis, ovis)
+    # degree-1 models: c = value(leaf), g = gradient, b = position(leaf)
+    mo = dt.fit_models().download()
+    assert same(mo["g"], oCp)
+    assert same(mo["c"], np.array([O.value(b) for b in olv]))
+    assert same(mo["b"], np.array([O.position(b) for b in olv]))
+
+
+@pytest.mark.parametrize("n,p,npoints", [(2, 2, 200), (3, 2, 150), (10, 2, 400), (20, 2, 120), (2, 1, 300)])
+def test_locate_eval_parity(n, p, npoints):
+    root, oroot, _ = grow_both(n, p, npoints, seed=400 + n)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    rng = np.random.default_rng(n)
+    X = edge_queries(root, oroot, rng, 30000)
+    models = dt.fit_models()
+    mo = models.download()
+    if p == 2:
+        ofit = O.fit_boxes_batch(olv, nthreads=O.max_threads())
+        for k in ("status", "c", "g", "Q", "b"):
+            assert same(mo[k], ofit[k]), k
+        Q = ofit["Q"]
+    else:
+        Q = np.zeros((len(olv), n, n))
+    oleaf, oval, ostatus, _ = O.locate_eval_batch(oroot, X, mo["c"], mo["g"], Q, mo["b"], nthreads=O.max_threads())
+    leaf, val, status = dt.locate_eval(models, X)
+    assert same(leaf, oleaf) and same(status, ostatus)
+    fin = np.isfinite(oval)
+    assert same(np.isfinite(val), fin)
+    # condition-aware scale: |c| + |g|.|dx| + |dx|'|Q||dx|/2 bounds the magnitude of the summed terms
+    dx = np.abs(X[fin] - mo["b"][oleaf[fin]])
+    Qs = np.abs(np.nan_to_num(np.triu(Q) + np.triu(Q, 1).transpose(0, 2, 1)))[oleaf[fin]]
+    scale = np.abs(mo["c"][oleaf[fin]]) + (np.abs(mo["g"][oleaf[fin]]) * dx).sum(1) + np.einsum("qi,qij,qj->q", dx, Qs, dx) / 2
+    err = np.abs(val[fin] - oval[fin])
+    assert (err <= EVAL_RTOL * np.maximum(scale, 1e-300)).all(), (err / scale).max()
+    # resident path and eval-only path give the same bits as the host path
+    import torch
+    Xd = torch.from_numpy(X).cuda()
+    leafd, vald, _ = dt.locate_eval(models, Xd)
+    torch.cuda.synchronize()
+    assert same(leafd.cpu().numpy(), leaf) and same(vald.cpu().numpy(), val)
+    ok = oleaf >= 0
+    v2 = models.evaluate(X[ok], oleaf[ok])
+    assert (np.abs(v2[fin[ok]] - oval[ok][fin[ok]]) <= EVAL_RTOL * np.maximum(scale, 1e-300)).all()
+
+
+def test_models_upload_roundtrip_and_supplied_eval():
+    """Config-C4 style: models (c, g, Q, b) supplied per leaf; only the evaluation arithmetic is pinned."""
+    rng = np.random.default_rng(3)
+    n, nl, m = 12, 50, 5000
+    c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), rng.standard_normal((nl, n))
+    Q = rng.standard_normal((nl, n, n))
+    Qu = np.triu(Q) + np.tril(np.full((n, n), np.nan), -1)  # SymmetricArray .data: lower triangle is fill
+    mo = LeafModels.upload(c, g, Qu, b)
+    d = mo.download()
+    assert same(d["c"], c) and same(d["g"], g) and same(d["b"], b) and same(d["Q"], Qu)
+    X = rng.standard_normal((m, n))
+    leaf = rng.integers(0, nl, m).astype(np.int32)
+    val = mo.evaluate(X, leaf)
+    oval, _ = O.eval_batch(c, g, Qu, b, X, leaf)
+    assert np.allclose(val, oval, rtol=1e-12, atol=1e-12)
+    Qs = np.triu(Q) + np.triu(Q, 1).transpose(0, 2, 1)
+    dx = X - b[leaf]
+    direct = c[leaf] + (g[leaf] * dx).sum(1) + np.einsum("qi,qij,qj->q", dx, Qs[leaf], dx) / 2
+    assert np.allclose(val, direct, rtol=1e-11, atol=1e-11)
+    assert cb.modelvalue(c[0], g[0], cb.SymmetricArray(Qu[0]), b[0], X[0]) == pytest.approx(
+        c[0] + g[0] @ (X[0] - b[0]) + (X[0] - b[0]) @ Qs[0] @ (X[0] - b[0]) / 2, rel=1e-12)
+
+
+def test_blob_broadcast_format_on_device():
+    """The wire format: pack on the host, upload from a host pointer and from a DEVICE pointer (as after an NCCL
+    broadcast); all three trees answer identically."""
+    import torch
+    root, oroot, _ = grow_both(5, 2, 100, seed=21)
+    flat = root.tree.flat()
+    blob = cb.pack_blob(flat)
+    X = cb.synthetic.uniform_queries(root, 5000, seed=2)
+    ref, _ = cb.device_tree(root).find_leaf(X)
+    t1 = DeviceTree(blob=blob)
+    t2 = DeviceTree(blob=torch.from_numpy(blob).cuda())
+    for t in (t1, t2):
+        leaf, _ = t.find_leaf(X)
+        assert same(leaf, ref)
+        assert (t.n, t.p, t.n_leaves) == (5, 2, flat["n_leaves"])
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 8])
+def test_cs2_full_models_like_reference(n):
+    """runtests.jl:824-859 through the public API on the GPU: Q ~ B, g ~ Q*b, value identities."""
+    rng = np.random.default_rng(60 + n)
+    B = rng.standard_normal((n, n))
+    B = (B + B.T) / 2
+    f = cb.quadnoise_objective(B, sigma=0.0)
+    x0 = rng.standard_normal(n)
+    world = cb.World(np.full(n, -np.inf), np.full(n, np.inf), x0, f)
+    root = cb.Box(world, 2)
+    cycle = cb.synthetic.round_robin_dimlists(n)
+    for i in range(2 * len(cycle) + 2):
+        box = cb.addpoint(root, rng.standard_normal(n), cycle[i % len(cycle)], f)
+    Cp = cb.coefficients_p(box)
+    assert not np.isnan(Cp.data[np.triu_indices(n, 1)]).any()
+    c, g, Q, b = cb.fit_quadratic(box)
+    Qf = Q.full()
+    assert np.allclose(Qf, f.B, rtol=1e-6, atol=1e-8)
+    assert np.allclose(g, Qf @ b, rtol=1e-6, atol=1e-8)
+    x = cb.position(box)
+    assert cb.modelvalue(c, g, Q, b, x) == pytest.approx(f(x), rel=1e-8, abs=1e-10)
+    assert abs(c - g @ b + b @ Qf @ b / 2) < 1e-8
+    cn, gn, Qn, bn, y, prec, firstmatch = cb.fit_quadratic_native(box)
+    oc, og, oQ, ob, oy, oprec, ofm = None, None, None, None, None, None, None
+    assert same(Qn.data, Q.data) and same(bn, b) and cn == c
+    assert Q[1, n] == Q[n, 1] == Qf[0, n - 1]  # SymmetricArray indexing, 1-based, order-insensitive
+    full = cb.polynomial_full(box)
+    assert same(full[2].data, Q.data)
+    mn = cb.polynomial_minimal(box)
+    assert np.isnan(np.diag(mn[2].data)).all()
+    with pytest.raises(TypeError):
+        cb.fit_quadratic(cb.Box(cb.World([0.0], [1.0], [0.5], 0.0), 1))
+
+
+def test_full_size_properties_c2():
+    """BASELINE config C2 (CS2, n=10, 1e5 leaves) at full tree size through size-independent properties:
+    every leaf's own evaluation point is located in that leaf; the fitted model reproduces the stored value there;
+    leaf ids are a valid range; locate is idempotent under re-query; sharded batches agree with one big batch."""
+    import torch
+    root, obj = cb.synthetic.config_tree("C2")
+    f = root.tree.flat()
+    assert f["n_leaves"] == 100006
+    dt = cb.device_tree(root)
+    # leaf positions: parent's position with the displaced dims replaced
+    n, p = 10, 2
+    par = f["parent"][f["leaf_nodes"]]
+    I = f["internal_id"][par]
+    P = f["pos"].reshape(-1, n)[I].copy()
+    ci = f["childindex"][f["leaf_nodes"]]
+    for k in range(p):
+        d = f["dims"].reshape(-1, p)[I, k] - 1
+        sel = ((ci >> k) & 1).astype(bool)
+        P[np.flatnonzero(sel), d[sel]] = f["xs"].reshape(-1, p)[I, k][sel]
+    leaf, status = dt.find_leaf(P)
+    assert (status == 0).all() and same(leaf, np.arange(f["n_leaves"], dtype=np.int32))
+    models = dt.fit_models()
+    mo = models.download()
+    okfit = mo["status"] == 0
+    assert okfit.mean() > 0.95
+    leaf2, val, _ = dt.locate_eval(models, P)
+    assert same(leaf2, leaf)
+    # the canonical model interpolates the data it was built from up to the noise level sigma = 1e-3
+    truth = f["val"][f["leaf_nodes"]]
+    fin = np.isfinite(val) & okfit
+    assert np.median(np.abs(val[fin] - truth[fin])) < 0.05
+    Xd = (torch.rand(2_000_000, n, dtype=torch.float64, device="cuda") * 2 - 1)
+    l_all, v_all, s_all = dt.locate_eval(models, Xd)
+    torch.cuda.synchronize()
+    assert int(l_all.min()) >= 0 and int(l_all.max()) < f["n_leaves"] and int(s_all.max()) == 0
+    halves = [dt.locate_eval(models, Xd[i::2].contiguous()) for i in range(2)]
+    torch.cuda.synchronize()
+    for i in range(2):
+        assert torch.equal(halves[i][0], l_all[i::2]) and torch.equal(halves[i][1].nan_to_num(), v_all[i::2].nan_to_num())
+    sub = slice(0, 20000)
+    v_again = models.evaluate(Xd[sub].contiguous(), l_all[sub].contiguous())
+    torch.cuda.synchronize()
+    assert torch.allclose(v_again.nan_to_num(), v_all[sub].nan_to_num(), rtol=1e-12, atol=1e-12)
