@@ -389,9 +389,7 @@ int cspo_locate_eval_batch(void* root, const double* X, long m, int n, const dou
             Box* leaf = find_leaf_at(r, x, n);
             int l = leaf->leaf_rank;
             leaf_out[i] = l;
-            SymArray S(n, 2, 0.0);
-            std::copy(Q + (size_t)l * n * n, Q + (size_t)(l + 1) * n * n, S.data.begin());
-            val_out[i] = modelvalue_canonical(c[l], g + (size_t)l * n, S, b + (size_t)l * n, x, n);
+            val_out[i] = modelvalue_canonical(c[l], g + (size_t)l * n, Q + (size_t)l * n * n, b + (size_t)l * n, x, n);
             if (status) status[i] = 0;
         } catch (const JlError&) {
             leaf_out[i] = -1;
@@ -411,9 +409,7 @@ int cspo_eval_batch(int n, const double* c, const double* g, const double* Q, co
 #pragma omp parallel for schedule(static) num_threads(nthreads)
     for (long i = 0; i < m; ++i) {
         int l = leaf[i];
-        SymArray S(n, 2, 0.0);
-        std::copy(Q + (size_t)l * n * n, Q + (size_t)(l + 1) * n * n, S.data.begin());
-        val_out[i] = modelvalue_canonical(c[l], g + (size_t)l * n, S, b + (size_t)l * n, X + (size_t)i * n, n);
+        val_out[i] = modelvalue_canonical(c[l], g + (size_t)l * n, Q + (size_t)l * n * n, b + (size_t)l * n, X + (size_t)i * n, n);
     }
     if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     CSPO_CATCH

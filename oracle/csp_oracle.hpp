@@ -843,18 +843,22 @@ inline double modelvalue_chi(double c, const double* g, const SymArray& Q, const
 }
 // cs2.jl:155-159:  dx = x-b;  c + g'dx + (dx'Q dx)/2.  The reference's summation order is whatever LinearAlgebra's
 // dot / generic matvec use (not pinned); this restatement forms (dx'Q) column by column and then dots with dx.
-inline double modelvalue_canonical(double c, const double* g, const SymArray& Q, const double* b, const double* x, int n) {
-    std::vector<double> dx(n);
+inline double modelvalue_canonical(double c, const double* g, const double* Qdata, const double* b, const double* x, int n) {
+    // Qdata: SymmetricArray .data (column-major n x n); Q[i,j] reads data[min,max] (types.jl:440-443)
+    std::vector<double> dx(n);  // `dx = x - b` allocates in the reference too
     for (int i = 0; i < n; ++i) dx[i] = x[i] - b[i];
     double gd = 0;
     for (int i = 0; i < n; ++i) gd += g[i] * dx[i];
     double quad = 0;
-    for (int j = 1; j <= n; ++j) {
+    for (int j = 0; j < n; ++j) {
         double s = 0;
-        for (int i = 1; i <= n; ++i) s += dx[i - 1] * Q.get2(i, j);
-        quad += s * dx[j - 1];
+        for (int i = 0; i < n; ++i) s += dx[i] * (i > j ? Qdata[(size_t)i * n + j] : Qdata[(size_t)j * n + i]);
+        quad += s * dx[j];
     }
     return c + gd + quad / 2;
+}
+inline double modelvalue_canonical(double c, const double* g, const SymArray& Q, const double* b, const double* x, int n) {
+    return modelvalue_canonical(c, g, Q.data.data(), b, x, n);
 }
 
 // ---- fit_quadratic_gdiag!, src/cs2.jl:332-384 ("next" row; restated for completeness of the checker)
