@@ -9,4 +9,4 @@ from .tree import (Box, World, addpoint, addpoints, boxbounds, collect, degree, 
 from .device import DeviceTree, LeafModels, device_count, kernel_launches, pack_blob
 from .api import (SymmetricArray, coefficients_p, device_tree, find_leaf_at, fit_leaves, fit_quadratic, fit_quadratic_native,
                   locate_eval, modelvalue, polynomial_full, polynomial_minimal)
-from . import synthetic
+from . import shard, synthetic

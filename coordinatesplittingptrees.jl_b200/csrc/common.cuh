@@ -16,23 +16,26 @@
 // leaf = rank in leaves(root).  See DESIGN.md "Data layout in HBM".
 // ---------------------------------------------------------------------------------------------------------------
 
-// Descent record, degree 2 (48 B, three 16-B vector loads).  Decision rule of src/tree.jl:383:
-//   bit_j = (x[sd] >= (xself+xother)/2) xor (xother < xself);  fictive dims contribute 0.
-// dj: bits 0..30 = 0-based dimension, bit 31 = flip (xother < xself); CSP_DIM_FICTIVE marks a fictive dimension.
-// child[k]: >= 0 internal id of the child;  < 0: leaf, leaf id = -child-2 (fake leaves encode leaf id -1 and are never reached).
-#define CSP_DIM_FICTIVE 0x7fffffff
-struct __align__(16) DRec2 {
+// Descent records.  The descent kernel uses its own numbering: internal nodes in BFS order ("descent ids"), so that the
+// top levels of the tree are the contiguous prefix [0, T) of the record array (staged in shared memory), and the
+// internal children of a node -- as well as its leaf children, numbered by a parallel BFS "descent leaf id" -- are
+// consecutive.  A record therefore needs only the first internal child F, the first leaf child G and a 4-bit mask.
+// Decision rule of reference src/tree.jl:383:  bit_j = (x[sd] >= (xself+xother)/2) xor (xother < xself); fictive dims -> 0.
+//
+// degree 2: 32 bytes, one 256-bit load (LDG.E.256).  meta: d0 bits 0-11, d1 bits 12-23 (0-based dims), flip0 24, flip1 25,
+// fictive0 26, fictive1 27, internal-children mask bits 28-31.
+struct __align__(32) DRec2 {
     double mid0, mid1;
-    int child[4];
-    int d0, d1, pad0, pad1;
+    int F, G;
+    unsigned meta, pad;
 };
-// degree 1 (32 B, two 16-B loads)
+// degree 1: 16 bytes, one 128-bit load.  w0 = F (24 bits) | G low 8 bits << 24;  w1 = G >> 8 (16 bits) | d << 16 (12 bits)
+// | flip << 28 | internal-children mask << 29 (2 bits).  Limits CS1 trees to 2^24 internal nodes / leaves.
 struct __align__(16) DRec1 {
     double mid;
-    int d, pad0;
-    int child[2];
-    int pad1, pad2;
+    unsigned w0, w1;
 };
+#define CSP_MAX_DIM 4096
 
 // per-node record: x = parent node id, y = istart (number of internal nodes before this node in preorder; the node's
 // own internal id when it is internal), z = icount (internal nodes in the subtree, itself included), w = flags
@@ -44,7 +47,8 @@ struct TreeView {
     int n, p, n_nodes, n_internal, n_leaves;
     const double* lower;   // [n]
     const double* upper;   // [n]
-    const void* drec;      // [n_internal] DRec1 / DRec2
+    const void* drec;      // [n_internal] DRec1 / DRec2, BFS order
+    const int* dleaf;      // [n_internal*(2^p-1)+1] descent leaf id -> leaf id (-1 for fake leaves)
     const int4* ninfo;     // [n_nodes]
     const int* nleaf;      // [n_nodes] leaf id or -1
     const int* inode;      // [n_internal] node id

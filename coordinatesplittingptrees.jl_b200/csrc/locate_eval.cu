@@ -4,11 +4,14 @@
 // (:362-386) with the decision rule of :383 evaluated on precomputed split midpoints.
 // K3a adds modelvalue(c, g, Q, b, x) (reference src/cs2.jl:155-159) of the located leaf's model.
 //
-// Shape of the work: an HBM stream of queries (8n B each) against a tree that lives in L2/L1 (48 B per split).
-// One CTA processes tiles of `tile` queries; a tile is ONE contiguous block of tile*n doubles in HBM and is brought
-// into shared memory by a single TMA bulk copy (cp.async.bulk + mbarrier), double buffered so the next tile streams in
-// while the current one is being descended.  One thread owns one query: its coordinates are read from shared memory at
-// the data-dependent split dimensions, node records are fetched with 16-byte read-only loads.
+// Shape of the work: an HBM stream of queries (8n B each) against a tree that lives in L2 / L1 / shared memory
+// (32 B per split).  One CTA processes tiles of `tile` queries; a tile is ONE contiguous block of tile*n doubles in HBM
+// and is brought into shared memory by a single TMA bulk copy (cp.async.bulk + mbarrier), double buffered so the next
+// tile streams in while the current one is being processed.
+//   locate:   one thread owns one query; its coordinates are read from shared memory at the data-dependent split
+//             dimensions; one 256-bit record load per level -- from shared memory for the BFS-first `top` records (the top
+//             levels of the tree), from L1/L2 below that.
+//   evaluate: warp-cooperative; the 32 lanes of a warp read each located leaf's model record with coalesced loads.
 #include "common.cuh"
 
 // ---- mbarrier / bulk-copy PTX wrappers ---------------------------------------------------------------------------
@@ -47,54 +50,202 @@ struct LocateParams {
     int tile;         // queries per tile == blockDim.x
     int stages;       // 1 or 2
     int bulk;         // X is 16-byte aligned: TMA bulk copies allowed
+    int top;          // number of BFS-first descent records staged in shared memory
 };
 
+__device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// 256-bit read-only load of one degree-2 descent record (LDG.E.256)
+__device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid1, int& F, int& G, unsigned& meta) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    mid0 = __longlong_as_double((long long)a);
+    mid1 = __longlong_as_double((long long)b);
+    F = (int)(unsigned)(c & 0xffffffffu);
+    G = (int)(unsigned)(c >> 32);
+    meta = (unsigned)(d & 0xffffffffu);
+}
+
+// Descent (reference src/tree.jl:362-386).  Returns the leaf id.  s_top: the first `top` records, in shared memory.
 template <int P>
-__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr) {
-    if (t.n_internal == 0) return -2;  // the root is the only leaf (leaf id 0)
-    int cur = 0;
+__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr, const void* s_top, int top) {
+    if (t.n_internal == 0) return 0;  // the root is the only leaf
+    int cur = 0, dl;
     if (P == 2) {
         const DRec2* __restrict__ recs = (const DRec2*)t.drec;
-        while (cur >= 0) {
-            const double2 mid = __ldg((const double2*)&recs[cur].mid0);
-            const int4 ch = __ldg((const int4*)&recs[cur].child[0]);
-            const int2 dd = __ldg((const int2*)&recs[cur].d0);
-            const bool f0 = dd.x == CSP_DIM_FICTIVE, f1 = dd.y == CSP_DIM_FICTIVE;
-            const double x0 = xr[f0 ? 0 : (dd.x & 0x7fffffff)];
-            const double x1 = xr[f1 ? 0 : (dd.y & 0x7fffffff)];
-            const bool b0 = !f0 && ((x0 >= mid.x) != (dd.x < 0));
-            const bool b1 = !f1 && ((x1 >= mid.y) != (dd.y < 0));
-            const int lo = b0 ? ch.y : ch.x, hi = b0 ? ch.w : ch.z;
-            cur = b1 ? hi : lo;
+        const DRec2* stop = (const DRec2*)s_top;
+        while (true) {
+            double mid0, mid1;
+            int F, G;
+            unsigned meta;
+            if (cur < top) {
+                const double2 mm = *(const double2*)&stop[cur].mid0;
+                const int4 w = *(const int4*)&stop[cur].F;
+                mid0 = mm.x; mid1 = mm.y; F = w.x; G = w.y; meta = (unsigned)w.z;
+            } else {
+                ldg256(recs + cur, mid0, mid1, F, G, meta);
+            }
+            const double x0 = xr[meta & 0xfffu];
+            const double x1 = xr[(meta >> 12) & 0xfffu];
+            const unsigned b0 = (unsigned)(x0 >= mid0) ^ ((meta >> 24) & 1u);
+            const unsigned b1 = (unsigned)(x1 >= mid1) ^ ((meta >> 25) & 1u);
+            const unsigned idx = (b0 & ~(meta >> 26) & 1u) | ((b1 & ~(meta >> 27) & 1u) << 1);
+            const unsigned mask = meta >> 28, below = (1u << idx) - 1u;
+            if ((mask >> idx) & 1u) {
+                cur = F + __popc(mask & below);
+            } else {
+                dl = G + __popc(~mask & below);
+                break;
+            }
         }
     } else {
         const DRec1* __restrict__ recs = (const DRec1*)t.drec;
-        while (cur >= 0) {
-            const int4 a = __ldg((const int4*)&recs[cur].mid);  // mid (2 words), d, pad
-            const int2 ch = __ldg((const int2*)&recs[cur].child[0]);
+        const DRec1* stop = (const DRec1*)s_top;
+        while (true) {
+            int4 a;
+            if (cur < top) a = *(const int4*)&stop[cur];
+            else a = __ldg((const int4*)&recs[cur]);
             const double mid = __hiloint2double(a.y, a.x);
-            const bool f0 = a.z == CSP_DIM_FICTIVE;
-            const double x0 = xr[f0 ? 0 : (a.z & 0x7fffffff)];
-            const bool b0 = !f0 && ((x0 >= mid) != (a.z < 0));
-            cur = b0 ? ch.y : ch.x;
+            const unsigned w0 = (unsigned)a.z, w1 = (unsigned)a.w;
+            const int F = (int)(w0 & 0xffffffu), G = (int)((w0 >> 24) | ((w1 & 0xffffu) << 8));
+            const double x0 = xr[(w1 >> 16) & 0xfffu];
+            const unsigned idx = (unsigned)(x0 >= mid) ^ ((w1 >> 28) & 1u);
+            const unsigned mask = (w1 >> 29) & 3u, below = (1u << idx) - 1u;
+            if ((mask >> idx) & 1u) {
+                cur = F + __popc(mask & below);
+            } else {
+                dl = G + __popc(~mask & below);
+                break;
+            }
         }
     }
-    return cur;
+    return __ldg(t.dleaf + dl);
 }
 
-template <int P, bool EVAL>
+// Warp-cooperative canonical model evaluation (reference src/cs2.jl:155-159) of the 32 queries a warp has just located.
+// Query q of the warp: the 32 lanes read the leaf's model record with coalesced 8-byte loads (element lane + 32 s),
+// lanes holding b_k turn the query row in shared memory into dx = x - b in place, every lane then multiplies its
+// record elements with the dx factors they belong to, and a shuffle tree adds the 32 partial sums.
+// NS > 0: ceil(stride/32) <= NS, slots unrolled with per-slot (i,j) decoded once per kernel; NS == 0: any stride.
+template <int NS>
+__device__ __forceinline__ double warp_eval(const ModelsView& mv, double* __restrict__ rows, int lane, int lf_mine) {
+    const unsigned FULL = 0xffffffffu;
+    const int n = mv.n, stride = mv.stride;
+    const int npk = mv.degree == 2 ? n * (n + 1) / 2 : 0;
+    const int cpos = 2 * n + npk;
+    double myval = dnan_le();
+    if constexpr (NS > 0) {
+        // role of element k = lane + 32 s:  [0,n) b  |  [n,2n) g  |  [2n,2n+npk) packed Q(i,j)  |  cpos: c
+        int ij[NS];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            const int k = lane + 32 * s;
+            int code = -1;  // nothing
+            if (k < n) code = -2;                         // b_k
+            else if (k < 2 * n) code = ((k - n) << 16) | 0xffff;  // g_i
+            else if (k < cpos) {
+                int e = k - 2 * n, i = 0;
+                while (e >= n - i) { e -= n - i; ++i; }
+                code = (i << 16) | (i + e);
+            } else if (k == cpos) code = -3;              // c
+            ij[s] = code;
+        }
+        double cur[NS], nxt[NS];
+        auto load = [&](double* r, int lf) {
+            const double* __restrict__ M = mv.data + (size_t)lf * stride;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int k = lane + 32 * s;
+                r[s] = (k < stride) ? __ldg(M + k) : 0.0;
+            }
+        };
+        int q = 0;
+        unsigned live = __ballot_sync(FULL, lf_mine >= 0);
+        if (live == 0) return myval;
+        q = __ffs(live) - 1;
+        live &= live - 1;
+        load(cur, __shfl_sync(FULL, lf_mine, q));
+        while (true) {
+            const int qn = live ? __ffs(live) - 1 : -1;
+            if (qn >= 0) load(nxt, __shfl_sync(FULL, lf_mine, qn));  // prefetch the next query's model
+            double* xr = rows + (size_t)q * n;
+#pragma unroll
+            for (int s = 0; s < NS; ++s)
+                if (ij[s] == -2) xr[lane + 32 * s] -= cur[s];  // dx = x - b, in place
+            __syncwarp();
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                const int code = ij[s];
+                if (code >= 0) {
+                    const int i = code >> 16, j = code & 0xffff;
+                    const double di = xr[i];
+                    if (j == 0xffff) acc += cur[s] * di;
+                    else acc += (i == j ? 0.5 * cur[s] * di : cur[s] * xr[j]) * di;
+                } else if (code == -3) acc += cur[s];
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (lane == q) myval = acc;
+            if (qn < 0) break;
+            live &= live - 1;
+            q = qn;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) cur[s] = nxt[s];
+        }
+    } else {
+        unsigned live = __ballot_sync(FULL, lf_mine >= 0);
+        while (live) {
+            const int q = __ffs(live) - 1;
+            live &= live - 1;
+            const int lf = __shfl_sync(FULL, lf_mine, q);
+            const double* __restrict__ M = mv.data + (size_t)lf * stride;
+            double* xr = rows + (size_t)q * n;
+            for (int k = lane; k < n; k += 32) xr[k] -= __ldg(M + k);
+            __syncwarp();
+            double acc = lane == 0 ? __ldg(M + cpos) : 0.0;
+            for (int k = lane; k < n; k += 32) acc += __ldg(M + n + k) * xr[k];
+            if (npk) {
+                // packed upper triangle, row-major: walk (i, j) forward by 32 entries per step
+                int i = 0, e = lane;
+                while (i < n && e >= n - i) { e -= n - i; ++i; }
+                for (int k = lane; k < npk; k += 32) {
+                    const int j = i + e;
+                    const double qv = __ldg(M + 2 * n + k), di = xr[i];
+                    acc += (e == 0 ? 0.5 * qv * di : qv * xr[j]) * di;
+                    e += 32;
+                    while (i < n && e >= n - i) { e -= n - i; ++i; }
+                }
+            }
+            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            if (lane == q) myval = acc;
+        }
+    }
+    return myval;
+}
+
+template <int P, int NS_EVAL>  // NS_EVAL: -1 = locate only, 0 = generic evaluation, > 0 = unrolled evaluation slots
 __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool EVAL = NS_EVAL >= 0;
     const int n = prm.t.n, tile = prm.tile, stages = prm.stages;
     const size_t tile_doubles = (size_t)tile * n;
-    double* bufs = (double*)smem_raw;
+    const size_t rec_bytes = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    unsigned char* s_top = smem_raw;                                     // [top] descent records (32-B aligned)
+    double* bufs = (double*)(smem_raw + (((size_t)prm.top * rec_bytes + 127) & ~(size_t)127));
     double* s_lower = bufs + stages * tile_doubles;
     double* s_upper = s_lower + n;
     uint64_t* bars = (uint64_t*)(s_upper + n);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const long long ntiles = (prm.m + tile - 1) / tile;
 
     for (int i = tid; i < n; i += blockDim.x) { s_lower[i] = prm.t.lower[i]; s_upper[i] = prm.t.upper[i]; }
+    {   // stage the top of the tree: contiguous prefix of the BFS-ordered record array, 16 bytes per thread-step
+        const int4* src = (const int4*)prm.t.drec;
+        int4* dst = (int4*)s_top;
+        const int n16 = (int)((size_t)prm.top * rec_bytes / 16);
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -105,12 +256,11 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
     auto tile_bulk = [&](long long tl) -> bool { return prm.bulk && (((size_t)tile_rows(tl) * n * 8) % 16 == 0); };
     auto issue = [&](long long tl, int s) {  // thread 0 only
         uint32_t bytes = (uint32_t)((size_t)tile_rows(tl) * n * 8);
-        fence_proxy_async();
         mbar_expect_tx(&bars[s], bytes);
         bulk_g2s(bufs + s * tile_doubles, prm.X + (size_t)tl * tile_doubles, bytes, &bars[s]);
     };
 
-    uint32_t phase[2] = {0, 0};
+    uint32_t phase0 = 0, phase1 = 0;
     long long tl = blockIdx.x;
     if (tl < ntiles && tile_bulk(tl) && tid == 0) issue(tl, 0);
     for (int it = 0; tl < ntiles; ++it, tl += gridDim.x) {
@@ -120,55 +270,33 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
         double* buf = bufs + s * tile_doubles;
         const int rows = tile_rows(tl);
         if (tile_bulk(tl)) {
-            mbar_wait(&bars[s], phase[s]);
-            phase[s] ^= 1;
+            if (s == 0) { mbar_wait(&bars[0], phase0); phase0 ^= 1; }
+            else { mbar_wait(&bars[1], phase1); phase1 ^= 1; }
         } else {  // unaligned base or odd-sized tail: plain coalesced copy
             const double* src = prm.X + (size_t)tl * tile_doubles;
             for (int e = tid; e < rows * n; e += blockDim.x) buf[e] = src[e];
             __syncthreads();
         }
+        int lf = -1;
+        const long long q = tl * tile + tid;
         if (tid < rows) {
-            double* xr = buf + (size_t)tid * n;
+            const double* xr = buf + (size_t)tid * n;
             bool ok = true;
             for (int i = 0; i < n; ++i) {  // reference src/tree.jl:357-360 at the true root: lower <= x <= upper (NaN fails)
                 const double xi = xr[i];
                 ok &= (xi >= s_lower[i]) & (xi <= s_upper[i]);
             }
-            int lf = -1;
-            if (ok) lf = -descend<P>(prm.t, xr) - 2;
-            const long long q = tl * tile + tid;
+            if (ok) lf = descend<P>(prm.t, xr, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (EVAL) {
-                double v = __longlong_as_double(0x7ff8000000000000LL);
-                if (ok) {
-                    const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
-                    double lin = 0.0;
-                    for (int i = 0; i < n; ++i) {
-                        const double dx = xr[i] - __ldg(M + i);
-                        xr[i] = dx;
-                        lin += __ldg(M + n + i) * dx;
-                    }
-                    double quad = 0.0;
-                    int cpos = 2 * n;
-                    if (prm.mv.degree == 2) {
-                        const double* __restrict__ Qp = M + 2 * n;
-                        int k = 0;
-                        for (int i = 0; i < n; ++i) {
-                            const double di = xr[i];
-                            double sacc = 0.5 * __ldg(Qp + k) * di;
-                            ++k;
-                            for (int j = i + 1; j < n; ++j, ++k) sacc += __ldg(Qp + k) * xr[j];
-                            quad += di * sacc;
-                        }
-                        cpos += k;
-                    }
-                    v = __ldg(M + cpos) + lin + quad;
-                }
-                prm.val[q] = v;
-            }
         }
-        __syncthreads();  // the buffer may be refilled by the next-but-one issue
+        if constexpr (EVAL) {
+            __syncwarp();
+            const double v = warp_eval<(NS_EVAL > 0 ? NS_EVAL : 0)>(prm.mv, buf + (size_t)(tid - lane) * n, lane, lf);
+            if (tid < rows) prm.val[q] = v;
+            fence_proxy_async();  // the in-place dx writes (generic proxy) precede the next bulk copy into this buffer
+        }
+        __syncthreads();  // the buffer may be refilled by the next issue
         if (stages == 1 && nxt < ntiles && tile_bulk(nxt) && tid == 0) issue(nxt, 0);
     }
 }
@@ -207,21 +335,32 @@ __global__ void __launch_bounds__(256) k_eval(const ModelsView mv, const double*
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
-static int pick_tile(int n, int* tile, int* stages, size_t* smem) {
-    int tl = 128, st = 2;
-    auto need = [&](int t, int s) { return (size_t)s * t * n * 8 + (size_t)2 * n * 8 + 16; };
-    while (need(tl, st) > 96 * 1024 && tl > 32) tl /= 2;
-    if (need(tl, st) > 96 * 1024) st = 1;
-    if (need(tl, st) > 200 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the tiled descent kernel", n);
-    *tile = tl; *stages = st; *smem = need(tl, st);
+// Launch geometry: tile (== block) size, pipeline stages, number of tree-top records staged in shared memory.
+static int pick_geometry(const csp_tree* t, LocateParams& prm, size_t* smem) {
+    const int n = prm.t.n;
+    const size_t rec = prm.t.p == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    const char* env = getenv("CSP_TOP_RECORDS");
+    int top = env ? atoi(env) : 1024;
+    top = std::max(0, std::min(top, prm.t.n_internal));
+    int tl = 256, st = 2;
+    auto need = [&](int tile, int stages, int tp) {
+        return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)stages * tile * n * 8 + (size_t)2 * n * 8 + 16;
+    };
+    const size_t budget = 100 * 1024;  // two CTAs per SM
+    while (need(tl, st, top) > budget && tl > 32) tl /= 2;
+    if (need(tl, st, top) > budget) st = 1;
+    while (need(tl, st, top) > 200 * 1024 && top > 0) top /= 2;
+    if (need(tl, st, top) > 200 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the tiled descent kernel", n);
+    prm.tile = tl; prm.stages = st; prm.top = top;
+    *smem = need(tl, st, top);
     return CSP_OK;
 }
 
-template <int P, bool EVAL>
+template <int P, int NS>
 static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st) {
     size_t smem;
-    CSP_CHECK(pick_tile(prm.t.n, &prm.tile, &prm.stages, &smem));
-    auto kern = k_locate<P, EVAL>;
+    CSP_CHECK(pick_geometry(t, prm, &smem));
+    auto kern = k_locate<P, NS>;
     CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, prm.tile, smem));
@@ -234,6 +373,15 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
     return CSP_OK;
 }
 
+template <int P>
+static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams& prm, cudaStream_t st) {
+    if (!mo) return launch_locate_t<P, -1>(t, prm, st);
+    const int slots = (mo->stride + 31) / 32;
+    if (slots <= 3) return launch_locate_t<P, 3>(t, prm, st);   // n <= 10 (degree 2)
+    if (slots <= 8) return launch_locate_t<P, 8>(t, prm, st);   // n <= 20
+    return launch_locate_t<P, 0>(t, prm, st);
+}
+
 static int launch_locate(const csp_tree* t, const csp_models* mo, const double* dX, long long m, int* dleaf, double* dval,
                          uint8_t* dstatus, cudaStream_t st) {
     if (m == 0) return CSP_OK;
@@ -241,11 +389,8 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
     prm.t = t->v;
     prm.X = dX; prm.m = m; prm.leaf = dleaf; prm.val = dval; prm.status = dstatus;
     prm.bulk = ((uintptr_t)dX % 16 == 0) ? 1 : 0;
-    if (mo) {
-        prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data;
-        return t->v.p == 2 ? launch_locate_t<2, true>(t, prm, st) : launch_locate_t<1, true>(t, prm, st);
-    }
-    return t->v.p == 2 ? launch_locate_t<2, false>(t, prm, st) : launch_locate_t<1, false>(t, prm, st);
+    if (mo) { prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data; }
+    return t->v.p == 2 ? launch_locate_p<2>(t, mo, prm, st) : launch_locate_p<1>(t, mo, prm, st);
 }
 
 static int check_pair(const csp_tree* t, const csp_models* mo) {

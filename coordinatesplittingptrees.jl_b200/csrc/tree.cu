@@ -74,6 +74,9 @@ static size_t blob_layout(int n, int p, int nn, int ni, Section s[12]) {
 static int validate_desc(const csp_tree_desc* d) {
     if (!d) return csp_set_error(CSP_ERR_INVALID, "desc is NULL");
     if (d->n < 1) return csp_set_error(CSP_ERR_INVALID, "n must be >= 1 (got %d)", d->n);
+    if (d->n > CSP_MAX_DIM) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d exceeds the supported maximum %d", d->n, CSP_MAX_DIM);
+    if (d->p == 1 && d->n_internal >= (1 << 24))
+        return csp_set_error(CSP_ERR_UNSUPPORTED, "CS1 trees are limited to 2^24 splits by the 16-byte descent record");
     if (d->p != 1 && d->p != 2)
         return csp_set_error(CSP_ERR_UNSUPPORTED, "degree p=%d is not supported by the sm_100a kernels (p must be 1 or 2)", d->p);
     if (d->n_nodes < 1 || d->n_internal < 0 || d->n_leaves < 1 || d->n_internal >= d->n_nodes)
@@ -150,35 +153,56 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
         if (v > 0) depth[v] = depth[d->parent[v]] + 1;
         if (d->leaf_id[v] >= 0) { lnode[d->leaf_id[v]] = v; maxdepth = std::max(maxdepth, depth[v]); }
     }
-    // derived per-internal arrays
+    // derived per-internal arrays (preorder ids)
     std::vector<double> ixself((size_t)ni * p), icval((size_t)ni * C);
-    std::vector<DRec1> r1(p == 1 ? ni : 0);
-    std::vector<DRec2> r2(p == 2 ? ni : 0);
-    auto enc_child = [&](int c) { return d->internal_id[c] >= 0 ? d->internal_id[c] : -d->leaf_id[c] - 2; };
     for (int I = 0; I < ni; ++I) {
-        double mid[2] = {0, 0};
-        int dj[2] = {CSP_DIM_FICTIVE, CSP_DIM_FICTIVE};
         for (int k = 0; k < p; ++k) {
             int dim = d->dims[(size_t)I * p + k];
-            double xo = d->xs[(size_t)I * p + k];
-            double xself = dim <= n ? d->pos[(size_t)I * n + dim - 1] : 0.0;
-            ixself[(size_t)I * p + k] = xself;
-            if (dim <= n) {
-                mid[k] = (xself + xo) / 2;  // src/tree.jl:383, same IEEE operations as the reference
-                dj[k] = (dim - 1) | (xo < xself ? (int)0x80000000 : 0);
-            }
+            ixself[(size_t)I * p + k] = dim <= n ? d->pos[(size_t)I * n + dim - 1] : 0.0;
         }
         for (int k = 0; k < C; ++k) icval[(size_t)I * C + k] = d->val[d->child[(size_t)I * C + k]];
-        if (p == 1) {
-            DRec1 r{};
-            r.mid = mid[0]; r.d = dj[0];
-            r.child[0] = enc_child(d->child[(size_t)I * 2]); r.child[1] = enc_child(d->child[(size_t)I * 2 + 1]);
-            r1[I] = r;
-        } else {
-            DRec2 r{};
-            r.mid0 = mid[0]; r.mid1 = mid[1]; r.d0 = dj[0]; r.d1 = dj[1];
-            for (int k = 0; k < 4; ++k) r.child[k] = enc_child(d->child[(size_t)I * 4 + k]);
-            r2[I] = r;
+    }
+    // descent records in BFS order (see common.cuh)
+    std::vector<DRec1> r1(p == 1 ? ni : 0);
+    std::vector<DRec2> r2(p == 2 ? ni : 0);
+    std::vector<int> dleaf;
+    dleaf.reserve((size_t)ni * (C - 1) + 1);
+    if (ni == 0) dleaf.push_back(0);  // the root is the only leaf
+    {
+        std::vector<int> bfs;  // preorder internal ids in BFS order
+        bfs.reserve(ni);
+        if (ni > 0) bfs.push_back(0);
+        for (size_t head = 0; head < bfs.size(); ++head) {
+            const int I = bfs[head];
+            const int F = (int)bfs.size(), G = (int)dleaf.size();
+            unsigned mask = 0;
+            for (int k = 0; k < C; ++k) {
+                const int c = d->child[(size_t)I * C + k];
+                if (d->internal_id[c] >= 0) { mask |= 1u << k; bfs.push_back(d->internal_id[c]); }
+                else dleaf.push_back(d->leaf_id[c]);
+            }
+            double mid[2] = {0, 0};
+            unsigned dim0[2] = {0, 0}, flip[2] = {0, 0}, fict[2] = {1, 1};
+            for (int k = 0; k < p; ++k) {
+                const int dim = d->dims[(size_t)I * p + k];
+                const double xo = d->xs[(size_t)I * p + k], xself = ixself[(size_t)I * p + k];
+                if (dim <= n) {
+                    mid[k] = (xself + xo) / 2;  // src/tree.jl:383, the same IEEE operations as the reference
+                    dim0[k] = (unsigned)(dim - 1); flip[k] = xo < xself ? 1u : 0u; fict[k] = 0;
+                }
+            }
+            if (p == 2) {
+                DRec2 r{};
+                r.mid0 = mid[0]; r.mid1 = mid[1]; r.F = F; r.G = G;
+                r.meta = dim0[0] | (dim0[1] << 12) | (flip[0] << 24) | (flip[1] << 25) | (fict[0] << 26) | (fict[1] << 27) | (mask << 28);
+                r2[head] = r;
+            } else {
+                DRec1 r{};
+                r.mid = mid[0];
+                r.w0 = (unsigned)F | (((unsigned)G & 0xffu) << 24);
+                r.w1 = ((unsigned)G >> 8) | (dim0[0] << 16) | (flip[0] << 28) | (mask << 29);
+                r1[head] = r;
+            }
         }
     }
     TreeView& v = t->v;
@@ -187,6 +211,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     CSP_CHECK(to_device(t, std::vector<double>(d->upper, d->upper + n), &v.upper));
     if (p == 1) { const DRec1* q; CSP_CHECK(to_device(t, r1, &q)); v.drec = q; }
     else { const DRec2* q; CSP_CHECK(to_device(t, r2, &q)); v.drec = q; }
+    CSP_CHECK(to_device(t, dleaf, &v.dleaf));
     CSP_CHECK(to_device(t, ninfo, &v.ninfo));
     CSP_CHECK(to_device(t, nleaf, &v.nleaf));
     CSP_CHECK(to_device(t, std::vector<int>(d->inode, d->inode + ni), &v.inode));
