@@ -61,17 +61,26 @@ struct TreeView {
     const int* lnode;      // [n_leaves] node id of each leaf
 };
 
-// Per-leaf canonical models, one record of `stride` doubles per leaf:
-//   [ b[n] | g[n] | Qp[n(n+1)/2] (upper triangle, row-major: (0,0),(0,1)..(0,n-1),(1,1).. ) | c | pad ]   (degree 2)
-//   [ b[n] | g[n] | c | pad ]                                                                            (degree 1)
+// Per-leaf canonical models, one record of `stride` doubles per leaf.  With z = (x - b, 1) the canonical model
+// c + g'dx + dx'Q dx/2 (reference src/cs2.jl:155-159) is the single quadratic form  sum_{i<=j} A[i][j] z_i z_j  with
+//   A[i][j] = Q[i][j] (i < j < n),   A[i][i] = Q[i][i]/2,   A[i][n] = g[i],   A[n][n] = c,
+// so every stored coefficient is used the same way (no per-element roles in the evaluation kernels):
+//   degree 2: [ b[n] | A, packed upper triangle of the (n+1)x(n+1) matrix, row-major | pad ]
+//   degree 1: [ b[n] | g[n] | c | pad ]                          (the last column of A only)
 struct ModelsView {
     int n, degree, stride;
     long long n_models;
     const double* data;
 };
+static inline long long csp_model_len(int n, int degree) {
+    return n + (degree == 2 ? (long long)(n + 1) * (n + 2) / 2 : (long long)n + 1);
+}
 static inline int csp_model_stride(int n, int degree) {
-    long long s = 2LL * n + 1 + (degree == 2 ? (long long)n * (n + 1) / 2 : 0);
-    return (int)((s + 3) / 4 * 4);  // whole 32-B sectors per record
+    return (int)((csp_model_len(n, degree) + 3) / 4 * 4);  // whole 32-B sectors per record
+}
+// offset of A[i][j] (i <= j <= n) inside the packed triangle
+__host__ __device__ static inline long long csp_a_index(int n, int i, int j) {
+    return (long long)i * (n + 1) - (long long)i * (i - 1) / 2 + (j - i);
 }
 
 struct csp_tree {

@@ -32,7 +32,7 @@ struct FitParams {
     // strided outputs (doubles); *_stride in doubles per box
     double* c; long long c_stride;
     double* g; long long g_stride;
-    double* Q; long long Q_stride; int q_packed;  // dense n*n .data layout, or packed upper triangle (row-major)
+    double* Q; long long Q_stride; int q_packed;  // 0: dense n*n .data layout; 2: the model record's packed A (common.cuh)
     double* b; long long b_stride;
     double* gnat; double* y; uint8_t* prec;       // optional native-form extras (dense, box-major)
     uint8_t* status;
@@ -65,7 +65,7 @@ struct QIndex {
     int n, packed;
     __device__ __forceinline__ long long operator()(int i, int j) const {  // 0-based; order-insensitive (SymmetricArray)
         if (i > j) { int tmp = i; i = j; j = tmp; }
-        return packed ? ((long long)i * n - (long long)i * (i - 1) / 2 + (j - i)) : ((long long)j * n + i);
+        return packed ? csp_a_index(n, i, j) : ((long long)j * n + i);
     }
 };
 
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
         const int box = prm.node_ids ? prm.node_ids[bi] : t.lnode[bi];
         double* Qo = prm.Q + bi * prm.Q_stride;
         const QIndex qi{n, prm.q_packed};
-        const long long qlen = P == 1 ? n : (prm.q_packed ? (long long)n * (n + 1) / 2 : (long long)n * n);
+        const long long qlen = P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n);
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
         for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
         for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
@@ -416,7 +416,12 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     }
                     bb = w.sb[i];
                 }
-                if (prm.g) prm.g[bi * prm.g_stride + i] = gc;
+                if (prm.q_packed) {  // model record: g is A's last column, the diagonal is stored halved (exact scaling)
+                    Qo[qi(i, n)] = gc;
+                    if (ok) Qo[qi(i, i)] = Qo[qi(i, i)] * 0.5;
+                } else if (prm.g) {
+                    prm.g[bi * prm.g_stride + i] = gc;
+                }
                 if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
                 if (prm.gnat) prm.gnat[bi * n + i] = ok ? w.sg[i] : dnan();
                 if (prm.y) prm.y[bi * n + i] = ok ? w.sy[i] : dnan();
@@ -426,7 +431,10 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     const int j = e / n, i = e - j * n;  // column-major: prec[i,j]
                     prm.prec[bi * (long long)n * n + e] = ok && (w.sstep[i] <= w.sstep[j]) ? 1 : 0;
                 }
-            if (lane == 0 && prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
+            if (lane == 0) {
+                if (prm.q_packed) Qo[qi(n, n)] = ok ? cval : dnan();
+                else if (prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
+            }
         } else if (prm.mode == FIT_MODE_LIN) {
             // degree-1 model of a CS1 box: c = value(box), b = position(box), g = Cp (already in Qo == g slot)
             const int4 binfo = t.ninfo[box];
@@ -618,14 +626,12 @@ static int models_fit_launch(const csp_tree* t, int32_t skip, csp_models* mo, cu
     prm.node_ids = nullptr; prm.nb = mo->n_models; prm.skip = skip;
     prm.mode = mo->degree == 2 ? FIT_MODE_FULL : FIT_MODE_LIN;
     prm.b = mo->data; prm.b_stride = mo->stride;
-    prm.g = mo->data + n; prm.g_stride = mo->stride;
     prm.status = mo->status;
+    prm.Q = mo->data + n; prm.Q_stride = mo->stride;
     if (mo->degree == 2) {
-        prm.Q = mo->data + 2 * n; prm.Q_stride = mo->stride; prm.q_packed = 1;
-        prm.c = mo->data + 2 * n + (size_t)n * (n + 1) / 2; prm.c_stride = mo->stride;
+        prm.q_packed = 2;  // g, c and Q all live inside the packed A (common.cuh)
     } else {
-        prm.Q = mo->data + n; prm.Q_stride = mo->stride; prm.q_packed = 0;  // Cp (the gradient) lands in the g slot
-        prm.g = nullptr;
+        prm.q_packed = 0;  // Cp (the gradient) lands in the g slot
         prm.c = mo->data + 2 * n; prm.c_stride = mo->stride;
     }
     return launch_fit(t, prm, st, scratch);

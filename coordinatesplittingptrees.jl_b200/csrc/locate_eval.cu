@@ -122,112 +122,116 @@ __device__ __forceinline__ int descend(const TreeView& t, const double* __restri
     return __ldg(t.dleaf + dl);
 }
 
+// Index pair (i, j) of coefficient e of a model record's coefficient block (everything after b): value = sum coef*z_i*z_j.
+__device__ __forceinline__ int coef_pair(int n, int degree, int e) {
+    if (degree == 2) {  // packed upper triangle of the (n+1)x(n+1) matrix A, row-major
+        int i = 0;
+        while (e >= n + 1 - i) { e -= n + 1 - i; ++i; }
+        return (i << 16) | (i + e);
+    }
+    return (e << 16) | n;  // [g | c]: (i, n) for i < n, (n, n) for c
+}
+
 // Warp-cooperative canonical model evaluation (reference src/cs2.jl:155-159) of the 32 queries a warp has just located.
-// Query q of the warp: the 32 lanes read the leaf's model record with coalesced 8-byte loads (element lane + 32 s),
-// lanes holding b_k turn the query row in shared memory into dx = x - b in place, every lane then multiplies its
-// record elements with the dx factors they belong to, and a shuffle tree adds the 32 partial sums.
-// NS > 0: ceil(stride/32) <= NS, slots unrolled with per-slot (i,j) decoded once per kernel; NS == 0: any stride.
-template <int NS>
-__device__ __forceinline__ double warp_eval(const ModelsView& mv, double* __restrict__ rows, int lane, int lf_mine) {
+// G lanes work on one query (32/G queries per pass): they read the leaf's record with coalesced 8-byte loads (element
+// gl + G*s), the lanes holding b_k write z_k = x_k - b_k into a per-group scratch row whose entry n is the constant 1,
+// every lane multiplies its coefficients with their two z factors, and a log2(G)-step shuffle tree adds the partial sums.
+// NS = ceil(len / G) record slots per lane, unrolled, with the per-slot (i, j) decoded once.
+template <int G, int NS>
+__device__ __forceinline__ double warp_eval(const ModelsView& mv, const double* __restrict__ rows, double* __restrict__ zs,
+                                            int lane, int lf_mine) {
+    const unsigned FULL = 0xffffffffu;
+    constexpr int NQ = 32 / G;  // queries per pass
+    const int n = mv.n, stride = mv.stride;
+    const int len = (int)(n + (mv.degree == 2 ? (n + 1) * (n + 2) / 2 : n + 1));
+    const int grp = lane / G, gl = lane % G;
+    double myval = dnan_le();
+    if (__ballot_sync(FULL, lf_mine >= 0) == 0) return myval;
+    double* zq = zs + (size_t)grp * (n + 1);
+    if (gl == 0) zq[n] = 1.0;
+    int code[NS];  // -2: b_k (k = gl + G*s < n)   -1: padding   >= 0: (i << 16) | j
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const int k = gl + G * s;
+        code[s] = k < n ? -2 : (k < len ? coef_pair(n, mv.degree, k - n) : -1);
+    }
+    auto load = [&](double (&r)[NS], int pass) {
+        const int lf = __shfl_sync(FULL, lf_mine, pass * NQ + grp);
+        const double* __restrict__ M = mv.data + (size_t)(lf < 0 ? 0 : lf) * stride;
+#pragma unroll
+        for (int s = 0; s < NS; ++s) r[s] = (gl + G * s < stride) ? __ldg(M + gl + G * s) : 0.0;
+    };
+    auto process = [&](const double (&r)[NS], int pass) {
+        const int q = pass * NQ + grp;
+        const double* xr = rows + (size_t)q * n;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (code[s] == -2) zq[gl + G * s] = xr[gl + G * s] - r[s];
+        __syncwarp();
+        double acc = 0.0;
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+            if (code[s] >= 0) acc = fma(r[s] * zq[code[s] >> 16], zq[code[s] & 0xffff], acc);
+#pragma unroll
+        for (int o = G / 2; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        // lane L owns query L, which was evaluated in pass L / NQ by group L % NQ
+        const double got = __shfl_sync(FULL, acc, (lane % NQ) * G);
+        if (lane / NQ == pass) myval = got;
+        __syncwarp();  // z scratch is rewritten by the next pass
+    };
+    double ra[NS], rb[NS];
+    load(ra, 0);
+#pragma unroll 1
+    for (int pass = 0; pass < G; pass += 2) {  // software pipeline: the next pass's record is in flight during this one
+        load(rb, pass + 1);
+        process(ra, pass);
+        if (pass + 2 < G) load(ra, pass + 2);
+        process(rb, pass + 1);
+    }
+    return lf_mine >= 0 ? myval : dnan_le();
+}
+
+// any record length: 32 lanes per query, strided loop with an incrementally decoded (i, j)
+__device__ __forceinline__ double warp_eval_generic(const ModelsView& mv, const double* __restrict__ rows, double* __restrict__ zq,
+                                                    int lane, int lf_mine) {
     const unsigned FULL = 0xffffffffu;
     const int n = mv.n, stride = mv.stride;
-    const int npk = mv.degree == 2 ? n * (n + 1) / 2 : 0;
-    const int cpos = 2 * n + npk;
+    const int ncoef = mv.degree == 2 ? (n + 1) * (n + 2) / 2 : n + 1;
     double myval = dnan_le();
-    if constexpr (NS > 0) {
-        // role of element k = lane + 32 s:  [0,n) b  |  [n,2n) g  |  [2n,2n+npk) packed Q(i,j)  |  cpos: c
-        int ij[NS];
-#pragma unroll
-        for (int s = 0; s < NS; ++s) {
-            const int k = lane + 32 * s;
-            int code = -1;  // nothing
-            if (k < n) code = -2;                         // b_k
-            else if (k < 2 * n) code = ((k - n) << 16) | 0xffff;  // g_i
-            else if (k < cpos) {
-                int e = k - 2 * n, i = 0;
-                while (e >= n - i) { e -= n - i; ++i; }
-                code = (i << 16) | (i + e);
-            } else if (k == cpos) code = -3;              // c
-            ij[s] = code;
-        }
-        double cur[NS], nxt[NS];
-        auto load = [&](double* r, int lf) {
-            const double* __restrict__ M = mv.data + (size_t)lf * stride;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int k = lane + 32 * s;
-                r[s] = (k < stride) ? __ldg(M + k) : 0.0;
-            }
-        };
-        int q = 0;
-        unsigned live = __ballot_sync(FULL, lf_mine >= 0);
-        if (live == 0) return myval;
-        q = __ffs(live) - 1;
+    unsigned live = __ballot_sync(FULL, lf_mine >= 0);
+    if (lane == 0) zq[n] = 1.0;
+    while (live) {
+        const int q = __ffs(live) - 1;
         live &= live - 1;
-        load(cur, __shfl_sync(FULL, lf_mine, q));
-        while (true) {
-            const int qn = live ? __ffs(live) - 1 : -1;
-            if (qn >= 0) load(nxt, __shfl_sync(FULL, lf_mine, qn));  // prefetch the next query's model
-            double* xr = rows + (size_t)q * n;
-#pragma unroll
-            for (int s = 0; s < NS; ++s)
-                if (ij[s] == -2) xr[lane + 32 * s] -= cur[s];  // dx = x - b, in place
-            __syncwarp();
-            double acc = 0.0;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                const int code = ij[s];
-                if (code >= 0) {
-                    const int i = code >> 16, j = code & 0xffff;
-                    const double di = xr[i];
-                    if (j == 0xffff) acc += cur[s] * di;
-                    else acc += (i == j ? 0.5 * cur[s] * di : cur[s] * xr[j]) * di;
-                } else if (code == -3) acc += cur[s];
+        const int lf = __shfl_sync(FULL, lf_mine, q);
+        const double* __restrict__ M = mv.data + (size_t)lf * stride;
+        const double* xr = rows + (size_t)q * n;
+        for (int k = lane; k < n; k += 32) zq[k] = xr[k] - __ldg(M + k);
+        __syncwarp();
+        double acc = 0.0;
+        if (mv.degree == 2) {
+            int i = 0, e = lane;  // e: offset inside row i of the packed triangle (row length n + 1 - i)
+            while (i <= n && e >= n + 1 - i) { e -= n + 1 - i; ++i; }
+            for (int k = lane; k < ncoef; k += 32) {
+                acc = fma(__ldg(M + n + k) * zq[i], zq[i + e], acc);
+                e += 32;
+                while (i <= n && e >= n + 1 - i) { e -= n + 1 - i; ++i; }
             }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (lane == q) myval = acc;
-            if (qn < 0) break;
-            live &= live - 1;
-            q = qn;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) cur[s] = nxt[s];
+        } else {
+            for (int k = lane; k < ncoef; k += 32) acc = fma(__ldg(M + n + k), zq[k], acc);
         }
-    } else {
-        unsigned live = __ballot_sync(FULL, lf_mine >= 0);
-        while (live) {
-            const int q = __ffs(live) - 1;
-            live &= live - 1;
-            const int lf = __shfl_sync(FULL, lf_mine, q);
-            const double* __restrict__ M = mv.data + (size_t)lf * stride;
-            double* xr = rows + (size_t)q * n;
-            for (int k = lane; k < n; k += 32) xr[k] -= __ldg(M + k);
-            __syncwarp();
-            double acc = lane == 0 ? __ldg(M + cpos) : 0.0;
-            for (int k = lane; k < n; k += 32) acc += __ldg(M + n + k) * xr[k];
-            if (npk) {
-                // packed upper triangle, row-major: walk (i, j) forward by 32 entries per step
-                int i = 0, e = lane;
-                while (i < n && e >= n - i) { e -= n - i; ++i; }
-                for (int k = lane; k < npk; k += 32) {
-                    const int j = i + e;
-                    const double qv = __ldg(M + 2 * n + k), di = xr[i];
-                    acc += (e == 0 ? 0.5 * qv * di : qv * xr[j]) * di;
-                    e += 32;
-                    while (i < n && e >= n - i) { e -= n - i; ++i; }
-                }
-            }
-            for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-            if (lane == q) myval = acc;
-        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+        if (lane == q) myval = acc;
+        __syncwarp();
     }
     return myval;
 }
 
-template <int P, int NS_EVAL>  // NS_EVAL: -1 = locate only, 0 = generic evaluation, > 0 = unrolled evaluation slots
+// EG: lanes per query in the evaluation (8/16/32), 0 = generic evaluation, -1 = locate only.  ENS: record slots per lane.
+template <int P, int EG, int ENS>
 __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr bool EVAL = NS_EVAL >= 0;
+    constexpr bool EVAL = EG >= 0;
     const int n = prm.t.n, tile = prm.tile, stages = prm.stages;
     const size_t tile_doubles = (size_t)tile * n;
     const size_t rec_bytes = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
@@ -236,6 +240,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
     double* s_lower = bufs + stages * tile_doubles;
     double* s_upper = s_lower + n;
     uint64_t* bars = (uint64_t*)(s_upper + n);
+    double* s_z = (double*)(bars + 2);  // evaluation scratch: per warp, 32/EG rows of n + 1 doubles
     const int tid = threadIdx.x, lane = tid & 31;
     const long long ntiles = (prm.m + tile - 1) / tile;
 
@@ -292,41 +297,45 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
         }
         if constexpr (EVAL) {
             __syncwarp();
-            const double v = warp_eval<(NS_EVAL > 0 ? NS_EVAL : 0)>(prm.mv, buf + (size_t)(tid - lane) * n, lane, lf);
+            const double* wrows = buf + (size_t)(tid - lane) * n;
+            double v;
+            if constexpr (EG > 0) v = warp_eval<EG, ENS>(prm.mv, wrows, s_z + (size_t)(tid >> 5) * (32 / EG) * (n + 1), lane, lf);
+            else v = warp_eval_generic(prm.mv, wrows, s_z + (size_t)(tid >> 5) * (n + 1), lane, lf);
             if (tid < rows) prm.val[q] = v;
-            fence_proxy_async();  // the in-place dx writes (generic proxy) precede the next bulk copy into this buffer
         }
         __syncthreads();  // the buffer may be refilled by the next issue
         if (stages == 1 && nxt < ntiles && tile_bulk(nxt) && tid == 0) issue(nxt, 0);
     }
 }
 
-// eval-only kernel: leaf ids supplied (scattered models), one thread per query, coalesced-by-row reads via L1
+// eval-only kernel: leaf ids supplied (scattered models); one thread per query
 __global__ void __launch_bounds__(256) k_eval(const ModelsView mv, const double* __restrict__ X, const int* __restrict__ leaf,
                                              long long m, double* __restrict__ val) {
     const int n = mv.n;
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
         const int lf = leaf[q];
-        double v = __longlong_as_double(0x7ff8000000000000LL);
+        double v = dnan_le();
         if (lf >= 0 && lf < mv.n_models) {
             const double* __restrict__ M = mv.data + (size_t)lf * mv.stride;
             const double* __restrict__ x = X + (size_t)q * n;
-            double lin = 0.0, quad = 0.0;
-            for (int i = 0; i < n; ++i) lin += __ldg(M + n + i) * (x[i] - __ldg(M + i));
-            int cpos = 2 * n;
+            const double* __restrict__ A = M + n;
+            double acc = 0.0;
             if (mv.degree == 2) {
-                const double* __restrict__ Qp = M + 2 * n;
                 int k = 0;
                 for (int i = 0; i < n; ++i) {
-                    const double di = x[i] - __ldg(M + i);
-                    double sacc = 0.5 * __ldg(Qp + k) * di;
+                    const double zi = x[i] - __ldg(M + i);
+                    double row = 0.0;
+                    for (int j = i; j < n; ++j, ++k) row = fma(__ldg(A + k), x[j] - __ldg(M + j), row);
+                    row += __ldg(A + k);  // A[i][n] * 1
                     ++k;
-                    for (int j = i + 1; j < n; ++j, ++k) sacc += __ldg(Qp + k) * (x[j] - __ldg(M + j));
-                    quad += di * sacc;
+                    acc = fma(row, zi, acc);
                 }
-                cpos += k;
+                acc += __ldg(A + k);  // A[n][n] = c
+            } else {
+                for (int i = 0; i < n; ++i) acc = fma(__ldg(A + i), x[i] - __ldg(M + i), acc);
+                acc += __ldg(A + n);
             }
-            v = __ldg(M + cpos) + lin + quad;
+            v = acc;
         }
         val[q] = v;
     }
@@ -343,8 +352,9 @@ static int pick_geometry(const csp_tree* t, LocateParams& prm, size_t* smem) {
     int top = env ? atoi(env) : 1024;
     top = std::max(0, std::min(top, prm.t.n_internal));
     int tl = 256, st = 2;
-    auto need = [&](int tile, int stages, int tp) {
-        return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)stages * tile * n * 8 + (size_t)2 * n * 8 + 16;
+    auto need = [&](int tile, int stages, int tp) {  // + evaluation scratch: <= 4 rows of n + 1 doubles per warp
+        return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)stages * tile * n * 8 + (size_t)2 * n * 8 + 16 +
+               (size_t)(tile / 32) * 4 * (n + 1) * 8;
     };
     const size_t budget = 100 * 1024;  // two CTAs per SM
     while (need(tl, st, top) > budget && tl > 32) tl /= 2;
@@ -356,11 +366,11 @@ static int pick_geometry(const csp_tree* t, LocateParams& prm, size_t* smem) {
     return CSP_OK;
 }
 
-template <int P, int NS>
+template <int P, int EG, int ENS>
 static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st) {
     size_t smem;
     CSP_CHECK(pick_geometry(t, prm, &smem));
-    auto kern = k_locate<P, NS>;
+    auto kern = k_locate<P, EG, ENS>;
     CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, prm.tile, smem));
@@ -375,11 +385,12 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
 
 template <int P>
 static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams& prm, cudaStream_t st) {
-    if (!mo) return launch_locate_t<P, -1>(t, prm, st);
-    const int slots = (mo->stride + 31) / 32;
-    if (slots <= 3) return launch_locate_t<P, 3>(t, prm, st);   // n <= 10 (degree 2)
-    if (slots <= 8) return launch_locate_t<P, 8>(t, prm, st);   // n <= 20
-    return launch_locate_t<P, 0>(t, prm, st);
+    if (!mo) return launch_locate_t<P, -1, 1>(t, prm, st);
+    const long long len = csp_model_len(mo->n, mo->degree);
+    if (len <= 80) return launch_locate_t<P, 8, 10>(t, prm, st);    // degree 2: n <= 10
+    if (len <= 128) return launch_locate_t<P, 16, 8>(t, prm, st);   // n <= 13
+    if (len <= 256) return launch_locate_t<P, 32, 8>(t, prm, st);   // n <= 20
+    return launch_locate_t<P, 0, 1>(t, prm, st);
 }
 
 static int launch_locate(const csp_tree* t, const csp_models* mo, const double* dX, long long m, int* dleaf, double* dval,

@@ -47,14 +47,19 @@ int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double
         for (long long l = 0; l < cnt; ++l) {
             double* r = stage.data() + (size_t)l * S;
             const long long L = off + l;
-            for (int i = 0; i < n; ++i) { r[i] = b[L * n + i]; r[n + i] = g[L * n + i]; }
-            size_t k = 2 * (size_t)n;
+            for (int i = 0; i < n; ++i) r[i] = b[L * n + i];
             if (Q) {
+                double* A = r + n;
                 const double* q = Q + (size_t)L * n * n;
-                for (int i = 0; i < n; ++i)
-                    for (int j = i; j < n; ++j) r[k++] = q[(size_t)j * n + i];  // .data[i,j], i <= j
+                for (int i = 0; i < n; ++i) {
+                    for (int j = i; j < n; ++j) A[csp_a_index(n, i, j)] = (i == j ? 0.5 : 1.0) * q[(size_t)j * n + i];  // .data[i,j], i <= j
+                    A[csp_a_index(n, i, n)] = g[L * n + i];
+                }
+                A[csp_a_index(n, n, n)] = c[L];
+            } else {
+                for (int i = 0; i < n; ++i) r[n + i] = g[L * n + i];
+                r[2 * n] = c[L];
             }
-            r[k] = c[L];
         }
         if (cudaMemcpy(mo->data + (size_t)off * S, stage.data(), (size_t)cnt * S * 8, cudaMemcpyHostToDevice) != cudaSuccess)
             return fail(csp_set_error(CSP_ERR_CUDA, "model upload failed: %s", cudaGetErrorString(cudaGetLastError())));
@@ -77,22 +82,24 @@ int csp_models_download(const csp_models* mo, double* c, double* g, double* Q, d
         for (long long l = 0; l < cnt; ++l) {
             const double* r = stage.data() + (size_t)l * S;
             const long long L = off + l;
-            for (int i = 0; i < n; ++i) {
+            for (int i = 0; i < n; ++i)
                 if (b) b[L * n + i] = r[i];
-                if (g) g[L * n + i] = r[n + i];
-            }
-            size_t k = 2 * (size_t)n;
             if (mo->degree == 2) {
+                const double* A = r + n;
                 if (Q) {
                     double* q = Q + (size_t)L * n * n;
                     for (size_t e = 0; e < (size_t)n * n; ++e) q[e] = NaN;  // the SymmetricArray fill value below the diagonal
                     for (int i = 0; i < n; ++i)
-                        for (int j = i; j < n; ++j) q[(size_t)j * n + i] = r[k++];
-                } else {
-                    k += (size_t)n * (n + 1) / 2;
+                        for (int j = i; j < n; ++j) q[(size_t)j * n + i] = (i == j ? 2.0 : 1.0) * A[csp_a_index(n, i, j)];
                 }
+                for (int i = 0; i < n; ++i)
+                    if (g) g[L * n + i] = A[csp_a_index(n, i, n)];
+                if (c) c[L] = A[csp_a_index(n, n, n)];
+            } else {
+                for (int i = 0; i < n; ++i)
+                    if (g) g[L * n + i] = r[n + i];
+                if (c) c[L] = r[2 * n];
             }
-            if (c) c[L] = r[k];
         }
     }
     if (status) CSP_CUDA(cudaMemcpy(status, mo->status, (size_t)mo->n_models, cudaMemcpyDeviceToHost));
