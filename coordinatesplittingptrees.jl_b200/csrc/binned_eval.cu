@@ -1,0 +1,251 @@
+// binned_eval.cu -- K3a, large-batch form: model-stationary evaluation after binning the located queries by leaf.
+//
+// The fused kernel of locate_eval.cu fetches a model record (8(n+1)(n+2)/2 + 8n bytes) from L2 for EVERY query; with
+// many queries per leaf that traffic (and the per-query reduction work) dominates.  Here the located queries are
+// counting-sorted by leaf id, so that consecutive evaluation threads share a leaf: the record is read once per warp as
+// uniform (broadcast) loads that hit L1, each thread owns one query with its z = (x - b, 1) vector in registers, and
+// there is no cross-lane reduction at all.  Pipeline (all on the caller's stream):
+//   k_locate<P,-1> + histogram   leaf ids in query order, count per leaf (global reductions)   [locate_eval.cu]
+//   k_scan_*                     exclusive prefix sum over the per-leaf counts -> segment offsets
+//   k_scatter                    slot = offsets[leaf]++ ; perm[slot] = (query, leaf)
+//   k_eval_binned<NPAD>          thread s: (q, leaf) = perm[s]; gather x[q]; value = sum A_ij z_i z_j; val[q] = value
+// Evaluation arithmetic: reference src/cs2.jl:155-159 (summation order not pinned by the reference).
+#include "common.cuh"
+
+__device__ __forceinline__ double dnan_b() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+// ---- exclusive scan of cnt[0..nl) into off[0..nl] (off[nl] = total), three small kernels ----------------------------
+#define SCAN_T 256
+#define SCAN_PER 8  // elements per thread => 2048 per block
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_partials(const int* __restrict__ cnt, int nl, int* __restrict__ partial) {
+    __shared__ int ws[SCAN_T / 32];
+    const int base = blockIdx.x * SCAN_T * SCAN_PER;
+    int s = 0;
+    for (int k = 0; k < SCAN_PER; ++k) {
+        const int i = base + k * SCAN_T + threadIdx.x;
+        if (i < nl) s += cnt[i];
+    }
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < SCAN_T / 32; ++w) t += ws[w];
+        partial[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_top(int* __restrict__ partial, int nblocks, int* __restrict__ total_out) {
+    // single block: exclusive scan of the block partials (nblocks is small: nl / 2048)
+    __shared__ int carry;
+    __shared__ int ws[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < nblocks; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < nblocks ? partial[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = ws[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += y;
+            }
+            ws[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = carry + (threadIdx.x >= 32 ? ws[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (i < nblocks) partial[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int* __restrict__ cnt, int nl, const int* __restrict__ partial,
+                                                       int* __restrict__ off, int* __restrict__ cursor) {
+    // block-local exclusive scan in the same element order as k_scan_partials (k-major), plus the block's base
+    __shared__ int ws[SCAN_T / 32];
+    __shared__ int carry;
+    const int base = blockIdx.x * SCAN_T * SCAN_PER;
+    if (threadIdx.x == 0) carry = partial[blockIdx.x];
+    __syncthreads();
+    for (int k = 0; k < SCAN_PER; ++k) {
+        const int i = base + k * SCAN_T + threadIdx.x;
+        const int v = i < nl ? cnt[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
+        __syncthreads();
+        int wbefore = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbefore += ws[w];
+        const int before = carry + wbefore + x - v;
+        if (i < nl) { off[i] = before; cursor[i] = before; }
+        __syncthreads();
+        if (threadIdx.x == SCAN_T - 1) carry = before + v;
+        __syncthreads();
+    }
+}
+
+// ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
+                                                 int2* __restrict__ perm, double* __restrict__ val) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
+        const int lf = leaf[q];
+        if (lf >= 0) {
+            const int slot = atomicAdd(cursor + lf, 1);
+            perm[slot] = make_int2((int)q, lf);
+        } else {
+            val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359); value undefined
+        }
+    }
+}
+
+// ---- model-stationary evaluation ---------------------------------------------------------------------------------
+// One thread per binned query.  NPAD >= n is a compile-time bound so that z stays in registers (loops fully unrolled and
+// guarded by i < n); record loads are warp-uniform whenever the warp's queries share a leaf.
+template <int NPAD>
+__global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const double* __restrict__ X, const int2* __restrict__ perm,
+                                                    const int* __restrict__ total, double* __restrict__ val) {
+    const int n = mv.n;
+    const long long tot = *total;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < tot; s += (long long)gridDim.x * blockDim.x) {
+        const int2 ql = perm[s];
+        const double* __restrict__ M = mv.data + (size_t)ql.y * mv.stride;
+        const double* __restrict__ x = X + (size_t)(unsigned)ql.x * n;
+        double z[NPAD];
+        if ((n & 1) == 0) {  // rows are 16-byte aligned when n is even and X is (checked by the host): 128-bit gathers
+#pragma unroll
+            for (int i = 0; i < NPAD; i += 2)
+                if (i < n) {
+                    const double2 xv = __ldg((const double2*)(x + i));
+                    z[i] = xv.x - __ldg(M + i);
+                    if (i + 1 < NPAD) z[i + 1] = xv.y - __ldg(M + i + 1);
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPAD; ++i)
+                if (i < n) z[i] = __ldg(x + i) - __ldg(M + i);
+        }
+        const double* __restrict__ A = M + n;
+        double acc = 0.0;
+        if (mv.degree == 2) {
+#pragma unroll
+            for (int i = 0; i < NPAD; ++i)
+                if (i < n) {
+                    const double* __restrict__ Ar = A + (i * (n + 1) - i * (i - 1) / 2);  // row i of the packed triangle
+                    double row = __ldg(Ar + (n - i));                                     // A[i][n] * 1
+#pragma unroll
+                    for (int j = i; j < NPAD; ++j)
+                        if (j < n) row = fma(__ldg(Ar + (j - i)), z[j], row);
+                    acc = fma(row, z[i], acc);
+                }
+            acc += __ldg(A + ((n + 1) * (n + 2) / 2 - 1));  // A[n][n] = c
+        } else {
+#pragma unroll
+            for (int i = 0; i < NPAD; ++i)
+                if (i < n) acc = fma(__ldg(A + i), z[i], acc);
+            acc += __ldg(A + n);
+        }
+        val[(unsigned)ql.x] = acc;
+    }
+}
+
+// any n: z recomputed on the fly (two extra loads per term)
+__global__ void __launch_bounds__(256) k_eval_binned_generic(const ModelsView mv, const double* __restrict__ X,
+                                                            const int2* __restrict__ perm, const int* __restrict__ total,
+                                                            double* __restrict__ val) {
+    const int n = mv.n;
+    const long long tot = *total;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < tot; s += (long long)gridDim.x * blockDim.x) {
+        const int2 ql = perm[s];
+        const double* __restrict__ M = mv.data + (size_t)ql.y * mv.stride;
+        const double* __restrict__ x = X + (size_t)(unsigned)ql.x * n;
+        const double* __restrict__ A = M + n;
+        double acc = 0.0;
+        if (mv.degree == 2) {
+            long long k = 0;
+            for (int i = 0; i < n; ++i) {
+                double row = 0.0;
+                for (int j = i; j < n; ++j, ++k) row = fma(__ldg(A + k), __ldg(x + j) - __ldg(M + j), row);
+                row += __ldg(A + k);
+                ++k;
+                acc = fma(row, __ldg(x + i) - __ldg(M + i), acc);
+            }
+            acc += __ldg(A + k);
+        } else {
+            for (int i = 0; i < n; ++i) acc = fma(__ldg(A + i), __ldg(x + i) - __ldg(M + i), acc);
+            acc += __ldg(A + n);
+        }
+        val[(unsigned)ql.x] = acc;
+    }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------------------
+struct BinWorkspace {
+    int* cnt = nullptr;      // [nl]
+    int* off = nullptr;      // [nl + 1]; off[nl] = number of located queries
+    int* cursor = nullptr;   // [nl]
+    int* partial = nullptr;  // [nblocks]
+    int2* perm = nullptr;    // [m]
+    int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
+};
+
+int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w) {
+    const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
+    CSP_CUDA(cudaMallocAsync(&w->cnt, (size_t)nl * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->off, (size_t)(nl + 1) * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->cursor, (size_t)nl * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
+    if (need_leaf) CSP_CUDA(cudaMallocAsync(&w->leaf, (size_t)m * 4, st));
+    CSP_CUDA(cudaMemsetAsync(w->cnt, 0, (size_t)nl * 4, st));
+    return CSP_OK;
+}
+void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
+    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
+    for (void* p : ptrs)
+        if (p) cudaFreeAsync(p, st);
+}
+
+// After k_locate<P,-1> filled leaf[] and cnt[]: scan, scatter, evaluate.
+int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
+                    cudaStream_t st) {
+    const int nl = (int)mo->n_models;
+    const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
+    k_scan_partials<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->partial);
+    CSP_LAUNCHED();
+    k_scan_top<<<1, 1024, 0, st>>>(w->partial, nblocks, w->off + nl);
+    CSP_LAUNCHED();
+    k_scan_apply<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->partial, w->off, w->cursor);
+    CSP_LAUNCHED();
+    const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
+    k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
+    CSP_LAUNCHED();
+    ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
+    const int n = mo->n;
+    const bool aligned = ((uintptr_t)dX % 16 == 0);
+    auto launch = [&](auto kern) {
+        kern<<<(unsigned)blocks, 256, 0, st>>>(mv, dX, w->perm, w->off + nl, dval);
+        CSP_LAUNCHED();
+    };
+    if (n <= 4 && (aligned || (n & 1))) launch(k_eval_binned<4>);
+    else if (n <= 8 && (aligned || (n & 1))) launch(k_eval_binned<8>);
+    else if (n <= 12 && (aligned || (n & 1))) launch(k_eval_binned<12>);
+    else if (n <= 16 && (aligned || (n & 1))) launch(k_eval_binned<16>);
+    else if (n <= 20 && (aligned || (n & 1))) launch(k_eval_binned<20>);
+    else if (n <= 24 && (aligned || (n & 1))) launch(k_eval_binned<24>);
+    else if (n <= 32 && (aligned || (n & 1))) launch(k_eval_binned<32>);
+    else launch(k_eval_binned_generic);
+    CSP_CUDA(cudaGetLastError());
+    return CSP_OK;
+}

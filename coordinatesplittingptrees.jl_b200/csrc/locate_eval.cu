@@ -12,6 +12,8 @@
 //             dimensions; one 256-bit record load per level -- from shared memory for the BFS-first `top` records (the top
 //             levels of the tree), from L1/L2 below that.
 //   evaluate: warp-cooperative; the 32 lanes of a warp read each located leaf's model record with coalesced loads.
+#include <cstring>
+
 #include "common.cuh"
 
 // ---- mbarrier / bulk-copy PTX wrappers ---------------------------------------------------------------------------
@@ -51,6 +53,7 @@ struct LocateParams {
     int stages;       // 1 or 2
     int bulk;         // X is 16-byte aligned: TMA bulk copies allowed
     int top;          // number of BFS-first descent records staged in shared memory
+    int* hist;        // optional: per-leaf query counts (binned evaluation, binned_eval.cu)
 };
 
 __device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -294,6 +297,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
             if (ok) lf = descend<P>(prm.t, xr, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
         if constexpr (EVAL) {
             __syncwarp();
@@ -393,6 +397,30 @@ static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams
     return launch_locate_t<P, 0, 1>(t, prm, st);
 }
 
+// binned_eval.cu
+struct BinWorkspace {
+    int* cnt = nullptr;
+    int* off = nullptr;
+    int* cursor = nullptr;
+    int* partial = nullptr;
+    int2* perm = nullptr;
+    int* leaf = nullptr;
+};
+int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w);
+void csp_bin_free(BinWorkspace* w, cudaStream_t st);
+int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
+                    cudaStream_t st);
+
+// Evaluation strategy: with many queries per leaf, bin the located queries by leaf and evaluate model-stationary
+// (binned_eval.cu); otherwise evaluate inside the locate kernel, fetching each query's model record.
+static bool use_binned(const csp_models* mo, long long m) {
+    const char* env = getenv("CSP_EVAL_MODE");
+    if (env && !strcmp(env, "direct")) return false;
+    if (m >= (1LL << 31)) return false;
+    if (env && !strcmp(env, "binned")) return true;
+    return m >= (1 << 18) && m >= 8 * mo->n_models;
+}
+
 static int launch_locate(const csp_tree* t, const csp_models* mo, const double* dX, long long m, int* dleaf, double* dval,
                          uint8_t* dstatus, cudaStream_t st) {
     if (m == 0) return CSP_OK;
@@ -400,6 +428,27 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
     prm.t = t->v;
     prm.X = dX; prm.m = m; prm.leaf = dleaf; prm.val = dval; prm.status = dstatus;
     prm.bulk = ((uintptr_t)dX % 16 == 0) ? 1 : 0;
+    if (mo && use_binned(mo, m)) {
+        static bool pool_ready[64] = {};
+        if (t->device < 64 && !pool_ready[t->device]) {  // keep stream-ordered allocations cached between calls
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, t->device) == cudaSuccess) {
+                unsigned long long thr = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            pool_ready[t->device] = true;
+        }
+        BinWorkspace w;
+        int rc = csp_bin_alloc((int)mo->n_models, m, dleaf == nullptr, st, &w);
+        if (rc == CSP_OK) {
+            prm.leaf = dleaf ? dleaf : w.leaf;
+            prm.hist = w.cnt;
+            rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, prm, st) : launch_locate_p<1>(t, nullptr, prm, st);
+        }
+        if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, dX, m, prm.leaf, dval, &w, st);
+        csp_bin_free(&w, st);
+        return rc;
+    }
     if (mo) { prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data; }
     return t->v.p == 2 ? launch_locate_p<2>(t, mo, prm, st) : launch_locate_p<1>(t, mo, prm, st);
 }

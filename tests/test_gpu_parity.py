@@ -2,6 +2,8 @@
 on the same seeded inputs.  Bars: leaf ids / status / fitted coefficients BIT-EXACT (the fit kernels evaluate every
 expression in the reference's order with FMA contraction off); evaluated values within 1e-12 relative (the reference
 does not pin the summation order of modelvalue, src/cs2.jl:155-159)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -219,8 +221,13 @@ def test_cs1_gradient_bit_exact(n, npoints):
     assert same(mo["b"], np.array([O.position(b) for b in olv]))
 
 
-@pytest.mark.parametrize("n,p,npoints", [(2, 2, 200), (3, 2, 150), (10, 2, 400), (20, 2, 120), (2, 1, 300)])
-def test_locate_eval_parity(n, p, npoints):
+@pytest.mark.parametrize("mode", ["direct", "binned"])
+@pytest.mark.parametrize("n,p,npoints", [(2, 2, 200), (3, 2, 150), (10, 2, 400), (13, 2, 60), (20, 2, 120), (25, 2, 40), (2, 1, 300),
+                                         (40, 1, 30)])
+def test_locate_eval_parity(n, p, npoints, mode, monkeypatch):
+    """Both evaluation strategies (model fetched per query inside the locate kernel / queries binned by leaf and evaluated
+    model-stationary) against the oracle."""
+    monkeypatch.setenv("CSP_EVAL_MODE", mode)
     root, oroot, _ = grow_both(n, p, npoints, seed=400 + n)
     dt = cb.device_tree(root)
     olv = O.leaves(oroot)
@@ -320,7 +327,6 @@ def test_cs2_full_models_like_reference(n):
     assert cb.modelvalue(c, g, Q, b, x) == pytest.approx(f(x), rel=1e-8, abs=1e-10)
     assert abs(c - g @ b + b @ Qf @ b / 2) < 1e-8
     cn, gn, Qn, bn, y, prec, firstmatch = cb.fit_quadratic_native(box)
-    oc, og, oQ, ob, oy, oprec, ofm = None, None, None, None, None, None, None
     assert same(Qn.data, Q.data) and same(bn, b) and cn == c
     assert Q[1, n] == Q[n, 1] == Qf[0, n - 1]  # SymmetricArray indexing, 1-based, order-insensitive
     full = cb.polynomial_full(box)
