@@ -99,13 +99,22 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int* __restrict__ c
 // ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
                                                  int2* __restrict__ perm, double* __restrict__ val) {
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
-        const int lf = leaf[q];
-        if (lf >= 0) {
-            const int slot = atomicAdd(cursor + lf, 1);
-            perm[slot] = make_int2((int)q, lf);
-        } else {
-            val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359); value undefined
+    // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
+        int lf[4], slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            lf[u] = q < m ? leaf[q] : -2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) slot[u] = lf[u] >= 0 ? atomicAdd(cursor + lf[u], 1) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            if (lf[u] >= 0) perm[slot[u]] = make_int2((int)q, lf[u]);
+            else if (lf[u] == -1) val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
         }
     }
 }
@@ -157,6 +166,59 @@ __global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const 
             acc += __ldg(A + n);
         }
         val[(unsigned)ql.x] = acc;
+    }
+}
+
+// Compile-time n: every index is static, the record and the query row are read with 128-bit loads (n even).
+template <int N>
+__global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, const double* __restrict__ X,
+                                                          const int2* __restrict__ perm, const int* __restrict__ total,
+                                                          double* __restrict__ val) {
+    constexpr int NC = (N + 1) * (N + 2) / 2;  // coefficients of the packed (N+1)x(N+1) triangle
+    const long long tot = *total;
+    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < tot; s += (long long)gridDim.x * blockDim.x) {
+        const int2 ql = perm[s];
+        const double* __restrict__ M = mv.data + (size_t)ql.y * mv.stride;
+        const double* __restrict__ x = X + (size_t)(unsigned)ql.x * N;
+        double z[N + 1];
+        if constexpr ((N & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < N; i += 2) {
+                const double2 xv = __ldg((const double2*)(x + i));
+                const double2 bv = __ldg((const double2*)(M + i));
+                z[i] = xv.x - bv.x;
+                z[i + 1] = xv.y - bv.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) z[i] = __ldg(x + i) - __ldg(M + i);
+        }
+        z[N] = 1.0;
+        const double* __restrict__ A = M + N;
+        double a[NC + 1];
+        if constexpr ((N & 1) == 0) {  // A is 16-byte aligned: record stride is a multiple of 4 doubles and N is even
+#pragma unroll
+            for (int k = 0; k < NC; k += 2) {
+                const double2 av = __ldg((const double2*)(A + k));  // the element after the last coefficient is record padding
+                a[k] = av.x;
+                a[k + 1] = av.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) a[k] = __ldg(A + k);
+        }
+        double acc0 = 0.0, acc1 = 0.0;
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i <= N; ++i) {
+            double row = a[k++];  // A[i][i]
+            row *= z[i];
+#pragma unroll
+            for (int j = i + 1; j <= N; ++j) row = fma(a[k++], z[j], row);
+            if (i & 1) acc1 = fma(row, z[i], acc1);
+            else acc0 = fma(row, z[i], acc0);
+        }
+        val[(unsigned)ql.x] = acc0 + acc1;
     }
 }
 
@@ -238,13 +300,32 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         kern<<<(unsigned)blocks, 256, 0, st>>>(mv, dX, w->perm, w->off + nl, dval);
         CSP_LAUNCHED();
     };
-    if (n <= 4 && (aligned || (n & 1))) launch(k_eval_binned<4>);
-    else if (n <= 8 && (aligned || (n & 1))) launch(k_eval_binned<8>);
-    else if (n <= 12 && (aligned || (n & 1))) launch(k_eval_binned<12>);
-    else if (n <= 16 && (aligned || (n & 1))) launch(k_eval_binned<16>);
-    else if (n <= 20 && (aligned || (n & 1))) launch(k_eval_binned<20>);
-    else if (n <= 24 && (aligned || (n & 1))) launch(k_eval_binned<24>);
-    else if (n <= 32 && (aligned || (n & 1))) launch(k_eval_binned<32>);
+    const bool vec_ok = aligned || (n & 1);
+    bool done = false;
+    if (mo->degree == 2 && vec_ok) {
+        done = true;
+        switch (n) {
+            case 2: launch(k_eval_binned_exact<2>); break;
+            case 3: launch(k_eval_binned_exact<3>); break;
+            case 4: launch(k_eval_binned_exact<4>); break;
+            case 5: launch(k_eval_binned_exact<5>); break;
+            case 6: launch(k_eval_binned_exact<6>); break;
+            case 8: launch(k_eval_binned_exact<8>); break;
+            case 10: launch(k_eval_binned_exact<10>); break;
+            case 12: launch(k_eval_binned_exact<12>); break;
+            case 16: launch(k_eval_binned_exact<16>); break;
+            case 20: launch(k_eval_binned_exact<20>); break;
+            default: done = false;
+        }
+    }
+    if (done) {}
+    else if (n <= 4 && vec_ok) launch(k_eval_binned<4>);
+    else if (n <= 8 && vec_ok) launch(k_eval_binned<8>);
+    else if (n <= 12 && vec_ok) launch(k_eval_binned<12>);
+    else if (n <= 16 && vec_ok) launch(k_eval_binned<16>);
+    else if (n <= 20 && vec_ok) launch(k_eval_binned<20>);
+    else if (n <= 24 && vec_ok) launch(k_eval_binned<24>);
+    else if (n <= 32 && vec_ok) launch(k_eval_binned<32>);
     else launch(k_eval_binned_generic);
     CSP_CUDA(cudaGetLastError());
     return CSP_OK;
