@@ -438,14 +438,26 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             }
             pool_ready[t->device] = true;
         }
+        // Chunks sized so that a chunk's coordinates, leaf ids, permutation and values stay L2-resident between the
+        // kernels of the pipeline: the evaluation's gather of x rows and its scattered value writes then hit L2 instead
+        // of HBM (126 MB L2; default 2^19 queries * (8n + 24) bytes).
+        const char* cenv = getenv("CSP_BIN_CHUNK");
+        long long chunk = cenv ? atoll(cenv) : std::max<long long>(1 << 16, (48LL << 20) / (8LL * t->v.n + 24));
+        chunk = std::min(std::max<long long>(chunk, 1024), m);
         BinWorkspace w;
-        int rc = csp_bin_alloc((int)mo->n_models, m, dleaf == nullptr, st, &w);
-        if (rc == CSP_OK) {
-            prm.leaf = dleaf ? dleaf : w.leaf;
-            prm.hist = w.cnt;
-            rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, prm, st) : launch_locate_p<1>(t, nullptr, prm, st);
+        int rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, st, &w);
+        for (long long off = 0; off < m && rc == CSP_OK; off += chunk) {
+            const long long cnt = std::min(chunk, m - off);
+            LocateParams cp = prm;
+            cp.X = dX + (size_t)off * t->v.n; cp.m = cnt;
+            cp.leaf = dleaf ? dleaf + off : w.leaf;
+            cp.status = dstatus ? dstatus + off : nullptr;
+            cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
+            cp.hist = w.cnt;
+            if (off > 0) rc = cudaMemsetAsync(w.cnt, 0, (size_t)mo->n_models * 4, st) == cudaSuccess ? CSP_OK : csp_set_error(CSP_ERR_CUDA, "memset failed");
+            if (rc == CSP_OK) rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, st) : launch_locate_p<1>(t, nullptr, cp, st);
+            if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w, st);
         }
-        if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, dX, m, prm.leaf, dval, &w, st);
         csp_bin_free(&w, st);
         return rc;
     }
