@@ -14,72 +14,54 @@
 
 __device__ __forceinline__ double dnan_b() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-// ---- exclusive scan of cnt[0..nl) into off[0..nl] (off[nl] = total), three small kernels ----------------------------
+// ---- exclusive scan of cnt[0..nl) into off[0..nl] (off[nl] = total) -- one launch, chained across blocks ------------
+// Block b publishes its sum with an epoch-stamped flag and adds up the sums of the blocks before it (blocks are
+// dispatched in index order, so a block only ever waits for blocks that are already running).  cnt is zeroed on the way
+// out, ready for the next chunk's histogram.
 #define SCAN_T 256
 #define SCAN_PER 8  // elements per thread => 2048 per block
 
-__global__ void __launch_bounds__(SCAN_T) k_scan_partials(const int* __restrict__ cnt, int nl, int* __restrict__ partial) {
+__device__ __forceinline__ int block_sum(int v, int* ws) {  // all threads get the sum; ws: SCAN_T/32 ints
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    int t = 0;
+    for (int w = 0; w < SCAN_T / 32; ++w) t += ws[w];
+    return t;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, int* __restrict__ cursor,
+                                                volatile int* bsum, volatile int* bflag, int epoch) {
     __shared__ int ws[SCAN_T / 32];
-    const int base = blockIdx.x * SCAN_T * SCAN_PER;
-    int s = 0;
+    __shared__ int carry;
+    const int b = blockIdx.x, base = b * SCAN_T * SCAN_PER;
+    int v[SCAN_PER], s = 0;
+#pragma unroll
     for (int k = 0; k < SCAN_PER; ++k) {
         const int i = base + k * SCAN_T + threadIdx.x;
-        if (i < nl) s += cnt[i];
+        v[k] = i < nl ? cnt[i] : 0;
+        s += v[k];
     }
-    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
-    __syncthreads();
+    const int mine = block_sum(s, ws);
     if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < SCAN_T / 32; ++w) t += ws[w];
-        partial[blockIdx.x] = t;
+        bsum[b] = mine;
+        __threadfence();
+        bflag[b] = epoch;
     }
-}
-__global__ void __launch_bounds__(1024) k_scan_top(int* __restrict__ partial, int nblocks, int* __restrict__ total_out) {
-    // single block: exclusive scan of the block partials (nblocks is small: nl / 2048)
-    __shared__ int carry;
-    __shared__ int ws[32];
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int base = 0; base < nblocks; base += 1024) {
-        const int i = base + threadIdx.x;
-        const int v = i < nblocks ? partial[i] : 0;
-        int x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, x, o);
-            if ((threadIdx.x & 31) >= o) x += y;
-        }
-        if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = x;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int w = ws[threadIdx.x];
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, w, o);
-                if (threadIdx.x >= o) w += y;
-            }
-            ws[threadIdx.x] = w;
-        }
-        __syncthreads();
-        const int before = carry + (threadIdx.x >= 32 ? ws[(threadIdx.x >> 5) - 1] : 0) + x - v;
-        if (i < nblocks) partial[i] = before;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry = before + v;
-        __syncthreads();
+    int before = 0;
+    for (int j = threadIdx.x; j < b; j += SCAN_T) {
+        while (bflag[j] != epoch) {}
+        __threadfence();
+        before += bsum[j];
     }
-    if (threadIdx.x == 0) *total_out = carry;
-}
-__global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int* __restrict__ cnt, int nl, const int* __restrict__ partial,
-                                                       int* __restrict__ off, int* __restrict__ cursor) {
-    // block-local exclusive scan in the same element order as k_scan_partials (k-major), plus the block's base
-    __shared__ int ws[SCAN_T / 32];
-    __shared__ int carry;
-    const int base = blockIdx.x * SCAN_T * SCAN_PER;
-    if (threadIdx.x == 0) carry = partial[blockIdx.x];
+    before = block_sum(before, ws);
+    if (threadIdx.x == 0) carry = before;
     __syncthreads();
-    for (int k = 0; k < SCAN_PER; ++k) {
+#pragma unroll
+    for (int k = 0; k < SCAN_PER; ++k) {  // element order: k-major, then thread
         const int i = base + k * SCAN_T + threadIdx.x;
-        const int v = i < nl ? cnt[i] : 0;
-        int x = v;
+        int x = v[k];
         for (int o = 1; o < 32; o <<= 1) {
             const int y = __shfl_up_sync(0xffffffffu, x, o);
             if ((threadIdx.x & 31) >= o) x += y;
@@ -88,12 +70,13 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_apply(const int* __restrict__ c
         __syncthreads();
         int wbefore = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbefore += ws[w];
-        const int before = carry + wbefore + x - v;
-        if (i < nl) { off[i] = before; cursor[i] = before; }
+        const int ex = carry + wbefore + x - v[k];
+        if (i < nl) { off[i] = ex; cursor[i] = ex; cnt[i] = 0; }
         __syncthreads();
-        if (threadIdx.x == SCAN_T - 1) carry = before + v;
+        if (threadIdx.x == SCAN_T - 1) carry = ex + v[k];
         __syncthreads();
     }
+    if (b == gridDim.x - 1 && threadIdx.x == 0) off[nl] = carry;
 }
 
 // ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
@@ -257,9 +240,10 @@ struct BinWorkspace {
     int* cnt = nullptr;      // [nl]
     int* off = nullptr;      // [nl + 1]; off[nl] = number of located queries
     int* cursor = nullptr;   // [nl]
-    int* partial = nullptr;  // [nblocks]
+    int* partial = nullptr;  // [2*nblocks]: block sums, then epoch flags
     int2* perm = nullptr;    // [m]
     int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
+    int epoch = 0;
 };
 
 int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w) {
@@ -267,7 +251,8 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     CSP_CUDA(cudaMallocAsync(&w->cnt, (size_t)nl * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->off, (size_t)(nl + 1) * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->cursor, (size_t)nl * 4, st));
-    CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 8, st));
+    CSP_CUDA(cudaMemsetAsync(w->partial, 0, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
     if (need_leaf) CSP_CUDA(cudaMallocAsync(&w->leaf, (size_t)m * 4, st));
     CSP_CUDA(cudaMemsetAsync(w->cnt, 0, (size_t)nl * 4, st));
@@ -284,11 +269,8 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
                     cudaStream_t st) {
     const int nl = (int)mo->n_models;
     const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
-    k_scan_partials<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->partial);
-    CSP_LAUNCHED();
-    k_scan_top<<<1, 1024, 0, st>>>(w->partial, nblocks, w->off + nl);
-    CSP_LAUNCHED();
-    k_scan_apply<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->partial, w->off, w->cursor);
+    w->epoch += 1;
+    k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
     CSP_LAUNCHED();
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
     k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/csp_b200.h"
@@ -90,6 +91,9 @@ struct csp_tree {
     size_t bytes = 0;
     std::vector<void*> allocs;
     int n_sm = 0;
+    // launch geometry cache (kernel function -> {tile, stages, top, smem, resident CTAs per SM}); one caller thread per handle
+    struct Geo { int tile, stages, top; size_t smem; int occ; };
+    mutable std::vector<std::pair<const void*, Geo>> geo;
 };
 struct csp_models {
     int device = 0;

@@ -372,16 +372,24 @@ static int pick_geometry(const csp_tree* t, LocateParams& prm, size_t* smem) {
 
 template <int P, int EG, int ENS>
 static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st) {
-    size_t smem;
-    CSP_CHECK(pick_geometry(t, prm, &smem));
     auto kern = k_locate<P, EG, ENS>;
-    CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, prm.tile, smem));
-    if (occ < 1) return csp_set_error(CSP_ERR_CUDA, "descent kernel does not fit on an SM (smem %zu)", smem);
+    const csp_tree::Geo* g = nullptr;
+    for (auto& e : t->geo)
+        if (e.first == (const void*)kern) g = &e.second;
+    if (!g) {  // first launch of this kernel for this tree: derive and cache the geometry
+        csp_tree::Geo ng{};
+        CSP_CHECK(pick_geometry(t, prm, &ng.smem));
+        ng.tile = prm.tile; ng.stages = prm.stages; ng.top = prm.top;
+        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
+        CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ng.occ, kern, ng.tile, ng.smem));
+        if (ng.occ < 1) return csp_set_error(CSP_ERR_CUDA, "descent kernel does not fit on an SM (smem %zu)", ng.smem);
+        t->geo.emplace_back((const void*)kern, ng);
+        g = &t->geo.back().second;
+    }
+    prm.tile = g->tile; prm.stages = g->stages; prm.top = g->top;
     long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
-    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * occ);
-    kern<<<(unsigned)grid, prm.tile, smem, st>>>(prm);
+    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * g->occ);
+    kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
     CSP_LAUNCHED();
     CSP_CUDA(cudaGetLastError());
     return CSP_OK;
@@ -405,6 +413,7 @@ struct BinWorkspace {
     int* partial = nullptr;
     int2* perm = nullptr;
     int* leaf = nullptr;
+    int epoch = 0;
 };
 int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w);
 void csp_bin_free(BinWorkspace* w, cudaStream_t st);
@@ -454,7 +463,6 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             cp.status = dstatus ? dstatus + off : nullptr;
             cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
             cp.hist = w.cnt;
-            if (off > 0) rc = cudaMemsetAsync(w.cnt, 0, (size_t)mo->n_models * 4, st) == cudaSuccess ? CSP_OK : csp_set_error(CSP_ERR_CUDA, "memset failed");
             if (rc == CSP_OK) rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, st) : launch_locate_p<1>(t, nullptr, cp, st);
             if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w, st);
         }
