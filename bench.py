@@ -150,7 +150,7 @@ def run_reference(args):
     lv = O.leaves(oroot)
     nl = len(lv)
     rng = np.random.default_rng(11)
-    nq = args.ref_queries
+    nq = args.ref_step_queries
     sel = rng.choice(nl, size=min(args.ref_fits, nl), replace=False)
     boxes = [lv[i] for i in sel]
     c, g, Q, b = np.zeros(nl), np.zeros((nl, n)), np.zeros((nl, n, n)), np.zeros((nl, n))
@@ -189,14 +189,15 @@ def workload_config(name, m, nl, n):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--queries", type=int, default=100_000_000)
     ap.add_argument("--e2e-queries", type=int, default=None)
-    ap.add_argument("--ref-queries", type=int, default=2_000_000)
-    ap.add_argument("--ref-fits", type=int, default=20_000)
+    ap.add_argument("--ref-queries", type=int, default=20_000_000)
+    ap.add_argument("--ref-fits", type=int, default=100_006)
+    ap.add_argument("--ref-step-queries", type=int, default=5_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -224,26 +225,22 @@ def main():
     # ---- tree: grown on rank 0 (host), flattened, broadcast once as a blob, uploaded per GPU
     name = args.config
     t0 = time.perf_counter()
+    blob = None
     if rank == 0:
         root, _ = grow_config(cb, name)
-        blob = torch.from_numpy(cb.pack_blob(root.tree.flat()))
-        nbytes = torch.tensor([blob.numel()], dtype=torch.int64, device=dev)
-    else:
-        nbytes = torch.zeros(1, dtype=torch.int64, device=dev)
+        blob = cb.pack_blob(root.tree.flat())
     bcast_ms = 0.0
     if world > 1:
-        dist.broadcast(nbytes, 0)
-        dblob = blob.to(dev) if rank == 0 else torch.empty(int(nbytes.item()), dtype=torch.uint8, device=dev)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        dist.broadcast(dblob, 0)  # C1: the one collective of the path (NCCL over NVLink)
+        dblob = cb.shard.broadcast_blob(blob, src=0, device=dev)  # C1: the one collective of the path (NCCL over NVLink)
         e1.record()
         torch.cuda.synchronize()
         bcast_ms = e0.elapsed_time(e1)
-        tree = DeviceTree(blob=dblob, device=local)
+        tree = DeviceTree(blob=dblob, device=local)  # upload straight from the device buffer the broadcast landed in
     else:
-        tree = DeviceTree(blob=blob.numpy(), device=local)
+        tree = DeviceTree(blob=blob, device=local)
     setup_s = time.perf_counter() - t0
     n, nl = tree.n, tree.n_leaves
 
@@ -301,6 +298,17 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * m / (ms_per_step * 1e-3)
 
+    # second pass, instrumented: per-kernel device times
+    from csp_b200 import device as cdev
+    cdev.timing_read()
+    cdev.timing_enable(True)
+    for k in range(args.steps):
+        step()
+    KT = cdev.timing_read()
+    cdev.timing_enable(False)
+    if world > 1:
+        dist.barrier()
+
     # distinct leaves touched (the model bytes that must cross HBM at least once per step)
     touched = int(torch.unique(leaf[: min(m, 20_000_000)]).numel())
     bad = int((status != 0).sum().item())
@@ -343,19 +351,42 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (k_locate<2,true>): algorithmic bytes per launch / measured launch time
+    # ---- roofline: algorithmic bytes / measured kernel time (CUDA events on the launching stream, library-side)
     peak, peak_src = peaks()
+    kt = KT
+    per_step = {k: (v[0] / args.steps, v[1] / args.steps) for k, v in kt.items() if v[1] > 0}
+    pipe_ms = sum(v[0] for k, v in per_step.items() if k != "fit")
+    alg_q = {"locate": 8 * n + 5, "locate_eval_fused": BYTES_PER_QUERY(n), "scan": 0, "scatter": 4 + 8, "eval_binned": 8 + 8 * n + 8,
+             "eval": 4 + 8 * n + 8}
+    kernels = {}
+    for k, (ms, cnt) in per_step.items():
+        if k == "fit":
+            continue
+        b = m * alg_q.get(k, 0) + (touched * model_bytes(n) if k in ("locate_eval_fused", "eval_binned") else 0) + \
+            (tree.kib * 1024 if k in ("locate", "locate_eval_fused") else 0)
+        kernels[k] = {"ms_per_step": ms, "launches_per_step": cnt, "share": ms / max(pipe_ms, 1e-9),
+                      "algorithmic_GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None, "frac": b / (ms * 1e-3) / 1e9 / peak if ms > 0 else None}
+    dom = max((k for k in kernels), key=lambda k: kernels[k]["ms_per_step"])
+    names = {"locate": "k_locate<2,-1> (find_leaf_at descent + per-leaf histogram)", "eval_binned": "k_eval_binned_exact<10> (model-stationary modelvalue)",
+             "locate_eval_fused": "k_locate<2,8,10> (fused find_leaf_at + modelvalue)", "scatter": "k_scatter", "scan": "k_scan", "eval": "k_eval"}
     alg_bytes = m * BYTES_PER_QUERY(n) + touched * model_bytes(n) + tree.kib * 1024
-    achieved = alg_bytes / (loc_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "k_locate<2,true> (fused find_leaf_at + modelvalue)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
-                "algorithmic_bytes_per_launch": int(alg_bytes), "ms_per_launch": loc_ms,
-                "bytes_per_query": BYTES_PER_QUERY(n), "distinct_leaves_touched": touched}
+    roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": kernels[dom]["frac"], "peak_source": peak_src, "traffic": None,
+                "ms_per_launch": kernels[dom]["ms_per_step"] / max(kernels[dom]["launches_per_step"], 1),
+                "launches_per_step": kernels[dom]["launches_per_step"], "share_of_pipeline": kernels[dom]["share"],
+                "bytes_per_query": alg_q.get(dom), "kernels": kernels,
+                "pipeline": {"what": "whole locate+evaluate pipeline of one step (all its kernels)", "algorithmic_bytes_per_step": int(alg_bytes),
+                             "bytes_per_query": BYTES_PER_QUERY(n), "distinct_leaves_touched": touched, "kernel_ms_per_step": pipe_ms,
+                             "achieved": alg_bytes / (loc_ms * 1e-3) / 1e9, "frac": alg_bytes / (loc_ms * 1e-3) / 1e9 / peak},
+                "note": "kernel times from a second, instrumented pass of the same K steps (csp_timing_*: CUDA events around "
+                        "every launch on the launching stream); value/ms_per_step come from the uninstrumented pass"}
     out = {"metric": "queries/sec (leaf lookup + quadratic eval)", "value": value, "unit": "queries/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(name, m, nl, n),
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
            "fits": {"value": world * nl / (fit_ms * 1e-3), "unit": "leaf fits/s", "ms_per_launch": fit_ms, "leaves": nl,
+                    "kernel_ms": KT["fit"][0] / max(KT["fit"][1], 1), "algorithmic_bytes_per_leaf": fit_bytes(n, 136 if n == 10 else 574),
+                    "frac": nl * fit_bytes(n, 136 if n == 10 else 574) / (max(KT["fit"][0] / max(KT["fit"][1], 1), 1e-9) * 1e-3) / 1e9 / peak,
                     "kernel": "k_fit<2> (chaintop + fit_poly1 + coefficients_p + fit_poly2_diag + canonicalize)"},
            "locate_eval_ms": loc_ms, "tree_broadcast_ms": bcast_ms, "setup_s": setup_s, "outside_world": bad, "nan_values": nanvals}
 

@@ -270,15 +270,22 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     const int nl = (int)mo->n_models;
     const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
     w->epoch += 1;
-    k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
+    {
+        CspTimed tm(CSP_K_SCAN, st);
+        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
+    }
     CSP_LAUNCHED();
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
-    k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
+    {
+        CspTimed tm(CSP_K_SCATTER, st);
+        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
+    }
     CSP_LAUNCHED();
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     auto launch = [&](auto kern) {
+        CspTimed tm(CSP_K_EVAL_BINNED, st);
         kern<<<(unsigned)blocks, 256, 0, st>>>(mv, dX, w->perm, w->off + nl, dval);
         CSP_LAUNCHED();
     };

@@ -124,6 +124,18 @@ int csp_require_device();  // CSP_OK or CSP_ERR_NO_DEVICE
     } while (0)
 #define CSP_LAUNCHED() (g_csp_launches.fetch_add(1, std::memory_order_relaxed))
 
+// Optional per-kernel timing with CUDA events on the launching stream (csp_timing_enable / csp_timing_read).
+enum { CSP_K_LOCATE = 0, CSP_K_LOCATE_EVAL, CSP_K_SCAN, CSP_K_SCATTER, CSP_K_EVAL_BINNED, CSP_K_EVAL, CSP_K_FIT, CSP_K_CLASSES };
+extern bool g_csp_timing;
+void csp_timing_begin(int cls, cudaStream_t st);
+void csp_timing_end(cudaStream_t st);
+struct CspTimed {
+    cudaStream_t st;
+    bool on;
+    CspTimed(int cls, cudaStream_t s) : st(s), on(g_csp_timing) { if (on) csp_timing_begin(cls, s); }
+    ~CspTimed() { if (on) csp_timing_end(st); }
+};
+
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev) {

@@ -498,7 +498,10 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
             CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 2 * npairs * sizeof(int)));
             prm.scratch = (int*)*scratch_out;
         }
-        kern<<<(unsigned)grid, W * 32, smem, st>>>(prm);
+        {
+            CspTimed tm(CSP_K_FIT, st);
+            kern<<<(unsigned)grid, W * 32, smem, st>>>(prm);
+        }
         CSP_LAUNCHED();
         CSP_CUDA(cudaGetLastError());
         return CSP_OK;

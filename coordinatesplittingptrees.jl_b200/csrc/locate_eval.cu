@@ -389,7 +389,10 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
     prm.tile = g->tile; prm.stages = g->stages; prm.top = g->top;
     long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
     long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * g->occ);
-    kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
+    {
+        CspTimed tm(EG >= 0 ? CSP_K_LOCATE_EVAL : CSP_K_LOCATE, st);
+        kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
+    }
     CSP_LAUNCHED();
     CSP_CUDA(cudaGetLastError());
     return CSP_OK;
@@ -531,7 +534,10 @@ int csp_eval_dev(const csp_models* mo, const double* dX, const int32_t* dleaf, i
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, mo->device);
     long long blocks = std::min<long long>((m + 255) / 256, (long long)nsm * 8);
-    k_eval<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mv, dX, dleaf, m, dval);
+    {
+        CspTimed tm(CSP_K_EVAL, (cudaStream_t)stream);
+        k_eval<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(mv, dX, dleaf, m, dval);
+    }
     CSP_LAUNCHED();
     CSP_CUDA(cudaGetLastError());
     return CSP_OK;

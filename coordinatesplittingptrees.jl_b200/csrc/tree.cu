@@ -29,7 +29,38 @@ int csp_require_device() {
     return CSP_OK;
 }
 
+bool g_csp_timing = false;
+namespace {
+struct TimedLaunch { int cls; cudaEvent_t a, b; };
+std::vector<TimedLaunch> g_timed;
+}
+void csp_timing_begin(int cls, cudaStream_t st) {
+    TimedLaunch t{cls, nullptr, nullptr};
+    cudaEventCreate(&t.a);
+    cudaEventCreate(&t.b);
+    cudaEventRecord(t.a, st);
+    g_timed.push_back(t);
+}
+void csp_timing_end(cudaStream_t st) { cudaEventRecord(g_timed.back().b, st); }
+
 extern "C" {
+int csp_timing_enable(int on) {
+    g_csp_timing = on != 0;
+    return CSP_OK;
+}
+int csp_timing_read(double* ms, int64_t* launches) {
+    if (!ms || !launches) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < CSP_K_CLASSES; ++i) { ms[i] = 0; launches[i] = 0; }
+    if (!g_timed.empty()) CSP_CUDA(cudaDeviceSynchronize());
+    for (auto& t : g_timed) {
+        float e = 0;
+        if (cudaEventElapsedTime(&e, t.a, t.b) == cudaSuccess) { ms[t.cls] += e; launches[t.cls] += 1; }
+        cudaEventDestroy(t.a);
+        cudaEventDestroy(t.b);
+    }
+    g_timed.clear();
+    return CSP_OK;
+}
 int csp_version(void) { return 100; }
 const char* csp_last_error(void) { return g_last_error.c_str(); }
 int csp_device_count(int* count) {

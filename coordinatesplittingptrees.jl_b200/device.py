@@ -261,3 +261,18 @@ def device_count():
     c = C.c_int()
     N.dchk(N.dev().csp_device_count(C.byref(c)))
     return c.value
+
+
+KERNEL_CLASSES = ("locate", "locate_eval_fused", "scan", "scatter", "eval_binned", "eval", "fit")
+
+
+def timing_enable(on=True):
+    N.dchk(N.dev().csp_timing_enable(1 if on else 0))
+
+
+def timing_read():
+    """{kernel class: (milliseconds, launches)} accumulated since the last read (synchronizes the device)."""
+    ms = (C.c_double * 7)()
+    cnt = (C.c_int64 * 7)()
+    N.dchk(N.dev().csp_timing_read(ms, cnt))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(KERNEL_CLASSES)}

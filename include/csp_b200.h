@@ -140,6 +140,12 @@ int csp_locate_eval_dev(const csp_tree* tree, const csp_models* models, const do
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process since load (bench.py reports it as gpu_launches). */
 int64_t csp_kernel_launches(void);
+/* Per-kernel device times, measured with CUDA events recorded on the launching stream around every kernel launch while
+ * enabled.  csp_timing_read synchronizes the device, returns the accumulated milliseconds and launch counts per kernel
+ * class and clears them.  Classes: 0 locate (K1, +histogram), 1 fused locate+evaluate, 2 scan, 3 scatter,
+ * 4 binned evaluation, 5 evaluate-only, 6 fit (K2); ms and launches have 7 entries. */
+int csp_timing_enable(int on);
+int csp_timing_read(double* ms, int64_t* launches);
 
 #ifdef __cplusplus
 }
