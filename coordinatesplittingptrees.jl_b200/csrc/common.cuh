@@ -90,6 +90,7 @@ struct csp_tree {
     int max_depth = 0;
     size_t bytes = 0;
     std::vector<void*> allocs;
+    std::vector<double> h_lower, h_upper;  // host copies of the world bounds (kernel parameters)
     int n_sm = 0;
     // launch geometry cache (kernel function -> {tile, stages, top, smem, resident CTAs per SM}); one caller thread per handle
     struct Geo { int tile, stages, top; size_t smem; int occ; };

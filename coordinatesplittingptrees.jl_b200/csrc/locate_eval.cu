@@ -70,8 +70,9 @@ __device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid
 }
 
 // Descent (reference src/tree.jl:362-386).  Returns the leaf id.  s_top: the first `top` records, in shared memory.
+// Coordinate d of the query is xr[d * xs] (xs = 1: row-major row; xs = tile: the thread's column of a transposed tile).
 template <int P>
-__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr, const void* s_top, int top) {
+__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr, const int xs, const void* s_top, int top) {
     if (t.n_internal == 0) return 0;  // the root is the only leaf
     int cur = 0, dl;
     if (P == 2) {
@@ -88,8 +89,8 @@ __device__ __forceinline__ int descend(const TreeView& t, const double* __restri
             } else {
                 ldg256(recs + cur, mid0, mid1, F, G, meta);
             }
-            const double x0 = xr[meta & 0xfffu];
-            const double x1 = xr[(meta >> 12) & 0xfffu];
+            const double x0 = xr[(meta & 0xfffu) * xs];
+            const double x1 = xr[((meta >> 12) & 0xfffu) * xs];
             const unsigned b0 = (unsigned)(x0 >= mid0) ^ ((meta >> 24) & 1u);
             const unsigned b1 = (unsigned)(x1 >= mid1) ^ ((meta >> 25) & 1u);
             const unsigned idx = (b0 & ~(meta >> 26) & 1u) | ((b1 & ~(meta >> 27) & 1u) << 1);
@@ -111,7 +112,7 @@ __device__ __forceinline__ int descend(const TreeView& t, const double* __restri
             const double mid = __hiloint2double(a.y, a.x);
             const unsigned w0 = (unsigned)a.z, w1 = (unsigned)a.w;
             const int F = (int)(w0 & 0xffffffu), G = (int)((w0 >> 24) | ((w1 & 0xffffu) << 8));
-            const double x0 = xr[(w1 >> 16) & 0xfffu];
+            const double x0 = xr[((w1 >> 16) & 0xfffu) * xs];
             const unsigned idx = (unsigned)(x0 >= mid) ^ ((w1 >> 28) & 1u);
             const unsigned mask = (w1 >> 29) & 3u, below = (1u << idx) - 1u;
             if ((mask >> idx) & 1u) {
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
                 const double xi = xr[i];
                 ok &= (xi >= s_lower[i]) & (xi <= s_upper[i]);
             }
-            if (ok) lf = descend<P>(prm.t, xr, s_top, prm.top);
+            if (ok) lf = descend<P>(prm.t, xr, 1, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
             if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
@@ -309,6 +310,117 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
         }
         __syncthreads();  // the buffer may be refilled by the next issue
         if (stages == 1 && nxt < ntiles && tile_bulk(nxt) && tid == 0) issue(nxt, 0);
+    }
+}
+
+// ---- K1, locate only (also the first stage of the binned pipeline) ----------------------------------------------------
+// The kernel is bound by L1/shared-memory wavefronts (random 32-byte record reads plus data-dependent coordinate reads),
+// so everything around the descent is arranged to cost as few of them as possible:
+//   * the TMA-staged row-major tile is transposed once into xT[d][thread]; a thread then reads coordinate d of ITS query
+//     at xT[d*tile + tid]: consecutive lanes hit consecutive 8-byte banks whatever d each lane needs (conflict-free);
+//   * the root bounds check (reference src/tree.jl:357-360) rides on that transpose pass, with the world bounds read from
+//     the kernel parameters (constant bank) when n <= CSP_BOUNDS_PARAM;
+//   * the raw tile is dead after the transpose, so a single raw stage is re-filled by the next TMA copy while the
+//     descent runs on the transposed copy.
+#define CSP_BOUNDS_PARAM 32
+struct LocateOnlyParams {
+    TreeView t;
+    const double* X;
+    long long m;
+    int* leaf;
+    uint8_t* status;
+    int* hist;
+    int tile, bulk, top, bounds_in_params;
+    double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
+};
+
+template <int P>
+__global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ LocateOnlyParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = prm.t.n, tile = prm.tile;
+    const size_t tile_doubles = (size_t)tile * n;
+    const size_t rec_bytes = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    unsigned char* s_top = smem_raw;
+    double* raw = (double*)(smem_raw + (((size_t)prm.top * rec_bytes + 127) & ~(size_t)127));
+    double* xT = raw + tile_doubles;
+    double* s_lower = xT + tile_doubles;
+    double* s_upper = s_lower + n;
+    uint64_t* bar = (uint64_t*)(s_upper + n);
+    const int tid = threadIdx.x;
+    const long long ntiles = (prm.m + tile - 1) / tile;
+
+    if (!prm.bounds_in_params)
+        for (int i = tid; i < n; i += blockDim.x) { s_lower[i] = prm.t.lower[i]; s_upper[i] = prm.t.upper[i]; }
+    {
+        const int4* src = (const int4*)prm.t.drec;
+        int4* dst = (int4*)s_top;
+        const int n16 = (int)((size_t)prm.top * rec_bytes / 16);
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    auto tile_rows = [&](long long tl) -> int { long long r = prm.m - tl * tile; return r < tile ? (int)r : tile; };
+    auto tile_bulk = [&](long long tl) -> bool { return prm.bulk && (((size_t)tile_rows(tl) * n * 8) % 16 == 0); };
+    auto issue = [&](long long tl) {  // thread 0 only
+        const uint32_t bytes = (uint32_t)((size_t)tile_rows(tl) * n * 8);
+        fence_proxy_async();
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(raw, prm.X + (size_t)tl * tile_doubles, bytes, bar);
+    };
+
+    uint32_t phase = 0;
+    long long tl = blockIdx.x;
+    if (tl < ntiles && tile_bulk(tl) && tid == 0) issue(tl);
+    for (; tl < ntiles; tl += gridDim.x) {
+        const long long nxt = tl + gridDim.x;
+        const int rows = tile_rows(tl);
+        if (tile_bulk(tl)) {
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            const double* src = prm.X + (size_t)tl * tile_doubles;
+            for (int e = tid; e < rows * n; e += blockDim.x) raw[e] = src[e];
+            __syncthreads();
+        }
+        // transpose own row + bounds check
+        bool ok = true;
+        if (tid < rows) {
+            const double* xr = raw + (size_t)tid * n;
+            double* col = xT + tid;
+            if ((n & 1) == 0) {
+                for (int i = 0; i < n; i += 2) {
+                    const double2 v = *(const double2*)(xr + i);
+                    col[(size_t)i * tile] = v.x;
+                    col[(size_t)(i + 1) * tile] = v.y;
+                    if (prm.bounds_in_params)
+                        ok &= (v.x >= prm.lo[i]) & (v.x <= prm.hi[i]) & (v.y >= prm.lo[i + 1]) & (v.y <= prm.hi[i + 1]);
+                    else
+                        ok &= (v.x >= s_lower[i]) & (v.x <= s_upper[i]) & (v.y >= s_lower[i + 1]) & (v.y <= s_upper[i + 1]);
+                }
+            } else {
+                for (int i = 0; i < n; ++i) {
+                    const double v = xr[i];
+                    col[(size_t)i * tile] = v;
+                    if (prm.bounds_in_params) ok &= (v >= prm.lo[i]) & (v <= prm.hi[i]);
+                    else ok &= (v >= s_lower[i]) & (v <= s_upper[i]);
+                }
+            }
+        }
+        __syncthreads();  // every row of the raw tile has been consumed
+        if (nxt < ntiles && tile_bulk(nxt) && tid == 0) issue(nxt);
+        if (tid < rows) {
+            int lf = -1;
+            if (ok) lf = descend<P>(prm.t, xT + tid, tile, s_top, prm.top);
+            const long long q = tl * tile + tid;
+            if (prm.leaf) prm.leaf[q] = lf;
+            if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+        }
+        // xT is private per thread column: no barrier needed before the next tile's transpose
     }
 }
 
@@ -399,8 +511,52 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
 }
 
 template <int P>
+static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
+    auto kern = k_locate_only<P>;
+    const int n = t->v.n;
+    const csp_tree::Geo* g = nullptr;
+    for (auto& e : t->geo)
+        if (e.first == (const void*)kern) g = &e.second;
+    if (!g) {
+        csp_tree::Geo ng{};
+        const size_t rec = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+        const char* env = getenv("CSP_TOP_RECORDS");
+        int top = env ? atoi(env) : 341;  // levels 0-4 of a CS2 tree
+        top = std::max(0, std::min(top, t->v.n_internal));
+        int tl = 256;
+        auto need = [&](int tile, int tp) {
+            return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)2 * tile * n * 8 + (size_t)2 * n * 8 + 16;
+        };
+        while (need(tl, top) > 56 * 1024 && tl > 32) tl /= 2;  // four CTAs per SM when possible
+        while (need(tl, top) > 200 * 1024 && top > 0) top /= 2;
+        if (need(tl, top) > 200 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the tiled descent kernel", n);
+        ng.tile = tl; ng.stages = 1; ng.top = top; ng.smem = need(tl, top);
+        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
+        CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ng.occ, kern, ng.tile, ng.smem));
+        if (ng.occ < 1) return csp_set_error(CSP_ERR_CUDA, "descent kernel does not fit on an SM (smem %zu)", ng.smem);
+        t->geo.emplace_back((const void*)kern, ng);
+        g = &t->geo.back().second;
+    }
+    LocateOnlyParams prm{};
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.tile = g->tile; prm.bulk = lp.bulk; prm.top = g->top;
+    prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
+    if (prm.bounds_in_params)
+        for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
+    long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
+    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * g->occ);
+    {
+        CspTimed tm(CSP_K_LOCATE, st);
+        kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
+    }
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
+    return CSP_OK;
+}
+
+template <int P>
 static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams& prm, cudaStream_t st) {
-    if (!mo) return launch_locate_t<P, -1, 1>(t, prm, st);
+    if (!mo) return launch_locate_only<P>(t, prm, st);
     const long long len = csp_model_len(mo->n, mo->degree);
     if (len <= 80) return launch_locate_t<P, 8, 10>(t, prm, st);    // degree 2: n <= 10
     if (len <= 128) return launch_locate_t<P, 16, 8>(t, prm, st);   // n <= 13

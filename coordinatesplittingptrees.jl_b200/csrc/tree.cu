@@ -236,6 +236,8 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             }
         }
     }
+    t->h_lower.assign(d->lower, d->lower + n);
+    t->h_upper.assign(d->upper, d->upper + n);
     TreeView& v = t->v;
     v.n = n; v.p = p; v.n_nodes = nn; v.n_internal = ni; v.n_leaves = nl;
     CSP_CHECK(to_device(t, std::vector<double>(d->lower, d->lower + n), &v.lower));
