@@ -7,7 +7,7 @@
 // there is no cross-lane reduction at all.  Pipeline (all on the caller's stream):
 //   k_locate<P,-1> + histogram   leaf ids in query order, count per leaf (global reductions)   [locate_eval.cu]
 //   k_scan_*                     exclusive prefix sum over the per-leaf counts -> segment offsets
-//   k_scatter                    slot = offsets[leaf]++ ; perm[slot] = (query, leaf)
+//   k_scatter                    perm[offsets[leaf] + rank] = (query, leaf)   (rank: return value of K1's histogram atomic)
 //   k_eval_binned<NPAD>          thread s: (q, leaf) = perm[s]; gather x[q]; value = sum A_ij z_i z_j; val[q] = value
 // Evaluation arithmetic: reference src/cs2.jl:155-159 (summation order not pinned by the reference).
 #include "common.cuh"
@@ -31,8 +31,8 @@ __device__ __forceinline__ int block_sum(int v, int* ws) {  // all threads get t
     return t;
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, int* __restrict__ cursor,
-                                                volatile int* bsum, volatile int* bflag, int epoch) {
+__global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, volatile int* bsum,
+                                                volatile int* bflag, int epoch) {
     __shared__ int ws[SCAN_T / 32];
     __shared__ int carry;
     const int b = blockIdx.x, base = b * SCAN_T * SCAN_PER;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
         int wbefore = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbefore += ws[w];
         const int ex = carry + wbefore + x - v[k];
-        if (i < nl) { off[i] = ex; cursor[i] = ex; cnt[i] = 0; }
+        if (i < nl) { off[i] = ex; cnt[i] = 0; }
         __syncthreads();
         if (threadIdx.x == SCAN_T - 1) carry = ex + v[k];
         __syncthreads();
@@ -79,26 +79,13 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
     if (b == gridDim.x - 1 && threadIdx.x == 0) off[nl] = carry;
 }
 
-// ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
-                                                 int2* __restrict__ perm, double* __restrict__ val) {
-    // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
-        int lf[4], slot[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long q = q0 + u * stride;
-            lf[u] = q < m ? leaf[q] : -2;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) slot[u] = lf[u] >= 0 ? atomicAdd(cursor + lf[u], 1) : -1;
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const long long q = q0 + u * stride;
-            if (lf[u] >= 0) perm[slot[u]] = make_int2((int)q, lf[u]);
-            else if (lf[u] == -1) val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
-        }
+// ---- scatter: perm[off[leaf] + rank] = (query, leaf); no atomics (the rank came back from K1's histogram atomic) -----
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, const int* __restrict__ rank, long long m,
+                                                 const int* __restrict__ off, int2* __restrict__ perm, double* __restrict__ val) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
+        const int lf = leaf[q];
+        if (lf >= 0) perm[__ldg(off + lf) + rank[q]] = make_int2((int)q, lf);
+        else val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
     }
 }
 
@@ -152,56 +139,101 @@ __global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const 
     }
 }
 
-// Compile-time n: every index is static, the record and the query row are read with 128-bit loads (n even).
+// Compile-time n.  A warp takes 32 consecutive binned positions.  The x rows are gathered straight into registers
+// (128-bit loads); the leaf's record is brought into the warp's shared-memory slot by ONE coalesced cooperative read
+// (so all of it is in flight at once, instead of a chain of register-limited batches) and then read back as broadcast
+// 128-bit shared loads.  A warp whose positions straddle several leaves repeats the staging once per distinct leaf.
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, const double* __restrict__ X,
                                                           const int2* __restrict__ perm, const int* __restrict__ total,
                                                           double* __restrict__ val) {
     constexpr int NC = (N + 1) * (N + 2) / 2;  // coefficients of the packed (N+1)x(N+1) triangle
+    constexpr bool VEC = (N & 1) == 0;         // record, A block and x rows are 16-byte aligned
+    extern __shared__ __align__(16) double s_rec[];  // [warps][stride]
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, stride = mv.stride;
+    double* rec = s_rec + (size_t)(threadIdx.x >> 5) * stride;
     const long long tot = *total;
-    for (long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x; s < tot; s += (long long)gridDim.x * blockDim.x) {
-        const int2 ql = perm[s];
-        const double* __restrict__ M = mv.data + (size_t)ql.y * mv.stride;
-        const double* __restrict__ x = X + (size_t)(unsigned)ql.x * N;
-        double z[N + 1];
-        if constexpr ((N & 1) == 0) {
+    const long long step = (long long)gridDim.x * blockDim.x;
+    long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int2 ql = s < tot ? perm[s] : make_int2(0, -1);
+    for (; s - lane < tot; s += step) {  // warp-uniform trip count
+        const bool valid = ql.y >= 0;
+        const long long sn = s + step;
+        const int2 qn = sn < tot ? perm[sn] : make_int2(0, -1);  // next iteration's position, in flight during this one
+        double x[N];
+        if (valid) {
+            const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
+            if constexpr (VEC) {
 #pragma unroll
-            for (int i = 0; i < N; i += 2) {
-                const double2 xv = __ldg((const double2*)(x + i));
-                const double2 bv = __ldg((const double2*)(M + i));
-                z[i] = xv.x - bv.x;
-                z[i + 1] = xv.y - bv.y;
+                for (int i = 0; i < N; i += 2) {
+                    const double2 v = __ldg((const double2*)(xp + i));
+                    x[i] = v.x;
+                    x[i + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < N; ++i) x[i] = __ldg(xp + i);
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < N; ++i) z[i] = __ldg(x + i) - __ldg(M + i);
         }
-        z[N] = 1.0;
-        const double* __restrict__ A = M + N;
-        double a[NC + 1];
-        if constexpr ((N & 1) == 0) {  // A is 16-byte aligned: record stride is a multiple of 4 doubles and N is even
+        unsigned todo = __ballot_sync(FULL, valid);
+        double result = 0.0;
+        while (todo) {
+            const int lf = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
+            const bool mine = valid && ql.y == lf;
+            todo &= ~__ballot_sync(FULL, mine);
+            const double* __restrict__ M = mv.data + (size_t)lf * stride;
+            for (int k = lane * 2; k < stride; k += 64) *(double2*)(rec + k) = __ldg((const double2*)(M + k));  // stride % 4 == 0
+            __syncwarp();
+            if (mine) {
+                double z[N + 1];
+                if constexpr (VEC) {
 #pragma unroll
-            for (int k = 0; k < NC; k += 2) {
-                const double2 av = __ldg((const double2*)(A + k));  // the element after the last coefficient is record padding
-                a[k] = av.x;
-                a[k + 1] = av.y;
+                    for (int i = 0; i < N; i += 2) {
+                        const double2 b = *(const double2*)(rec + i);
+                        z[i] = x[i] - b.x;
+                        z[i + 1] = x[i + 1] - b.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) z[i] = x[i] - rec[i];
+                }
+                z[N] = 1.0;
+                const double* A = rec + N;
+                double acc0 = 0.0, acc1 = 0.0, row = 0.0;
+                int i = 0, j = 0;  // all static after unrolling
+#pragma unroll
+                for (int k = 0; k < NC; k += (VEC ? 2 : 1)) {
+                    double a0, a1 = 0.0;
+                    if constexpr (VEC) {
+                        const double2 av = *(const double2*)(A + k);  // the element past the last coefficient is record padding
+                        a0 = av.x;
+                        a1 = av.y;
+                    } else {
+                        a0 = A[k];
+                    }
+#pragma unroll
+                    for (int u = 0; u < (VEC ? 2 : 1); ++u) {
+                        if (k + u < NC) {
+                            const double a = u ? a1 : a0;
+                            row = (j == i) ? a * z[j] : fma(a, z[j], row);
+                            if (j == N) {
+                                if (i & 1) acc1 = fma(row, z[i], acc1);
+                                else acc0 = fma(row, z[i], acc0);
+                                ++i;
+                                j = i;
+                            } else {
+                                ++j;
+                            }
+                        }
+                    }
+                }
+                result = acc0 + acc1;
             }
-        } else {
-#pragma unroll
-            for (int k = 0; k < NC; ++k) a[k] = __ldg(A + k);
+            __syncwarp();  // the slot is re-staged for the next distinct leaf / next iteration
         }
-        double acc0 = 0.0, acc1 = 0.0;
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i <= N; ++i) {
-            double row = a[k++];  // A[i][i]
-            row *= z[i];
-#pragma unroll
-            for (int j = i + 1; j <= N; ++j) row = fma(a[k++], z[j], row);
-            if (i & 1) acc1 = fma(row, z[i], acc1);
-            else acc0 = fma(row, z[i], acc0);
-        }
-        val[(unsigned)ql.x] = acc0 + acc1;
+        if (valid) val[(unsigned)ql.x] = result;
+        ql = qn;
     }
 }
 
@@ -239,7 +271,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_generic(const ModelsView mv
 struct BinWorkspace {
     int* cnt = nullptr;      // [nl]
     int* off = nullptr;      // [nl + 1]; off[nl] = number of located queries
-    int* cursor = nullptr;   // [nl]
+    int* rank = nullptr;     // [m] rank of each query inside its leaf (return value of the histogram atomic in K1)
     int* partial = nullptr;  // [2*nblocks]: block sums, then epoch flags
     int2* perm = nullptr;    // [m]
     int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
@@ -250,7 +282,7 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
     CSP_CUDA(cudaMallocAsync(&w->cnt, (size_t)nl * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->off, (size_t)(nl + 1) * 4, st));
-    CSP_CUDA(cudaMallocAsync(&w->cursor, (size_t)nl * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->rank, (size_t)m * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMemsetAsync(w->partial, 0, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
@@ -259,7 +291,7 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     return CSP_OK;
 }
 void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
-    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
+    void* ptrs[] = {w->cnt, w->off, w->rank, w->partial, w->perm, w->leaf};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
 }
@@ -272,13 +304,13 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     w->epoch += 1;
     {
         CspTimed tm(CSP_K_SCAN, st);
-        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
+        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->partial, w->partial + nblocks, w->epoch);
     }
     CSP_LAUNCHED();
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
     {
         CspTimed tm(CSP_K_SCATTER, st);
-        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
+        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, w->rank, m, w->off, w->perm, dval);
     }
     CSP_LAUNCHED();
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
@@ -286,7 +318,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     auto launch = [&](auto kern) {
         CspTimed tm(CSP_K_EVAL_BINNED, st);
-        kern<<<(unsigned)blocks, 256, 0, st>>>(mv, dX, w->perm, w->off + nl, dval);
+        kern<<<(unsigned)blocks, 256, (size_t)8 * mo->stride * sizeof(double), st>>>(mv, dX, w->perm, w->off + nl, dval);
         CSP_LAUNCHED();
     };
     const bool vec_ok = aligned || (n & 1);

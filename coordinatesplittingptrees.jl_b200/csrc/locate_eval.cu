@@ -54,6 +54,7 @@ struct LocateParams {
     int bulk;         // X is 16-byte aligned: TMA bulk copies allowed
     int top;          // number of BFS-first descent records staged in shared memory
     int* hist;        // optional: per-leaf query counts (binned evaluation, binned_eval.cu)
+    int* rank;        // with hist: rank of the query among the queries of its leaf (the histogram atomic's return value)
 };
 
 __device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
             if (ok) lf = descend<P>(prm.t, xr, 1, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+            if (prm.hist && lf >= 0) prm.rank[q] = atomicAdd(prm.hist + lf, 1);
         }
         if constexpr (EVAL) {
             __syncwarp();
@@ -330,6 +331,7 @@ struct LocateOnlyParams {
     int* leaf;
     uint8_t* status;
     int* hist;
+    int* rank;
     int tile, bulk, top, bounds_in_params;
     double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
 };
@@ -418,7 +420,7 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
             const long long q = tl * tile + tid;
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+            if (prm.hist && lf >= 0) prm.rank[q] = atomicAdd(prm.hist + lf, 1);
         }
         // xT is private per thread column: no barrier needed before the next tile's transpose
     }
@@ -538,7 +540,7 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
         g = &t->geo.back().second;
     }
     LocateOnlyParams prm{};
-    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist; prm.rank = lp.rank;
     prm.tile = g->tile; prm.bulk = lp.bulk; prm.top = g->top;
     prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
     if (prm.bounds_in_params)
@@ -568,7 +570,7 @@ static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams
 struct BinWorkspace {
     int* cnt = nullptr;
     int* off = nullptr;
-    int* cursor = nullptr;
+    int* rank = nullptr;
     int* partial = nullptr;
     int2* perm = nullptr;
     int* leaf = nullptr;
@@ -623,6 +625,7 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             cp.status = dstatus ? dstatus + off : nullptr;
             cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
             cp.hist = w.cnt;
+            cp.rank = w.rank;
             if (rc == CSP_OK) rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, st) : launch_locate_p<1>(t, nullptr, cp, st);
             if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w, st);
         }
