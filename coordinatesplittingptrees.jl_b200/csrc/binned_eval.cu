@@ -7,7 +7,7 @@
 // there is no cross-lane reduction at all.  Pipeline (all on the caller's stream):
 //   k_locate<P,-1> + histogram   leaf ids in query order, count per leaf (global reductions)   [locate_eval.cu]
 //   k_scan_*                     exclusive prefix sum over the per-leaf counts -> segment offsets
-//   k_scatter                    perm[offsets[leaf] + rank] = (query, leaf)   (rank: return value of K1's histogram atomic)
+//   k_scatter                    slot = offsets[leaf]++ ; perm[slot] = (query, leaf)
 //   k_eval_binned<NPAD>          thread s: (q, leaf) = perm[s]; gather x[q]; value = sum A_ij z_i z_j; val[q] = value
 // Evaluation arithmetic: reference src/cs2.jl:155-159 (summation order not pinned by the reference).
 #include "common.cuh"
@@ -31,8 +31,8 @@ __device__ __forceinline__ int block_sum(int v, int* ws) {  // all threads get t
     return t;
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, volatile int* bsum,
-                                                volatile int* bflag, int epoch) {
+__global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, int* __restrict__ cursor,
+                                                volatile int* bsum, volatile int* bflag, int epoch) {
     __shared__ int ws[SCAN_T / 32];
     __shared__ int carry;
     const int b = blockIdx.x, base = b * SCAN_T * SCAN_PER;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
         int wbefore = 0;
         for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wbefore += ws[w];
         const int ex = carry + wbefore + x - v[k];
-        if (i < nl) { off[i] = ex; cnt[i] = 0; }
+        if (i < nl) { off[i] = ex; cursor[i] = ex; cnt[i] = 0; }
         __syncthreads();
         if (threadIdx.x == SCAN_T - 1) carry = ex + v[k];
         __syncthreads();
@@ -79,13 +79,26 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
     if (b == gridDim.x - 1 && threadIdx.x == 0) off[nl] = carry;
 }
 
-// ---- scatter: perm[off[leaf] + rank] = (query, leaf); no atomics (the rank came back from K1's histogram atomic) -----
-__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, const int* __restrict__ rank, long long m,
-                                                 const int* __restrict__ off, int2* __restrict__ perm, double* __restrict__ val) {
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
-        const int lf = leaf[q];
-        if (lf >= 0) perm[__ldg(off + lf) + rank[q]] = make_int2((int)q, lf);
-        else val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
+// ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
+                                                 int2* __restrict__ perm, double* __restrict__ val) {
+    // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
+        int lf[4], slot[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            lf[u] = q < m ? leaf[q] : -2;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) slot[u] = lf[u] >= 0 ? atomicAdd(cursor + lf[u], 1) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            if (lf[u] >= 0) perm[slot[u]] = make_int2((int)q, lf[u]);
+            else if (lf[u] == -1) val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
+        }
     }
 }
 
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_generic(const ModelsView mv
 struct BinWorkspace {
     int* cnt = nullptr;      // [nl]
     int* off = nullptr;      // [nl + 1]; off[nl] = number of located queries
-    int* rank = nullptr;     // [m] rank of each query inside its leaf (return value of the histogram atomic in K1)
+    int* cursor = nullptr;   // [nl]
     int* partial = nullptr;  // [2*nblocks]: block sums, then epoch flags
     int2* perm = nullptr;    // [m]
     int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
@@ -282,7 +295,7 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
     CSP_CUDA(cudaMallocAsync(&w->cnt, (size_t)nl * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->off, (size_t)(nl + 1) * 4, st));
-    CSP_CUDA(cudaMallocAsync(&w->rank, (size_t)m * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->cursor, (size_t)nl * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMemsetAsync(w->partial, 0, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
@@ -291,7 +304,7 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     return CSP_OK;
 }
 void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
-    void* ptrs[] = {w->cnt, w->off, w->rank, w->partial, w->perm, w->leaf};
+    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
 }
@@ -304,13 +317,13 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     w->epoch += 1;
     {
         CspTimed tm(CSP_K_SCAN, st);
-        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->partial, w->partial + nblocks, w->epoch);
+        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
     }
     CSP_LAUNCHED();
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
     {
         CspTimed tm(CSP_K_SCATTER, st);
-        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, w->rank, m, w->off, w->perm, dval);
+        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
     }
     CSP_LAUNCHED();
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};

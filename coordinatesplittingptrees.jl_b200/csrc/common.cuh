@@ -95,6 +95,10 @@ struct csp_tree {
     // launch geometry cache (kernel function -> {tile, stages, top, smem, resident CTAs per SM}); one caller thread per handle
     struct Geo { int tile, stages, top; size_t smem; int occ; };
     mutable std::vector<std::pair<const void*, Geo>> geo;
+    // internal streams of the chunked binned pipeline: consecutive chunks alternate between them so that the
+    // L1-bound descent of one chunk overlaps the DRAM-bound evaluation of the previous one
+    mutable cudaStream_t pipe_st[2] = {nullptr, nullptr};
+    mutable cudaEvent_t pipe_fork = nullptr, pipe_join[2] = {nullptr, nullptr};
 };
 struct csp_models {
     int device = 0;

@@ -54,7 +54,6 @@ struct LocateParams {
     int bulk;         // X is 16-byte aligned: TMA bulk copies allowed
     int top;          // number of BFS-first descent records staged in shared memory
     int* hist;        // optional: per-leaf query counts (binned evaluation, binned_eval.cu)
-    int* rank;        // with hist: rank of the query among the queries of its leaf (the histogram atomic's return value)
 };
 
 __device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -299,7 +298,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
             if (ok) lf = descend<P>(prm.t, xr, 1, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) prm.rank[q] = atomicAdd(prm.hist + lf, 1);
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
         if constexpr (EVAL) {
             __syncwarp();
@@ -331,7 +330,6 @@ struct LocateOnlyParams {
     int* leaf;
     uint8_t* status;
     int* hist;
-    int* rank;
     int tile, bulk, top, bounds_in_params;
     double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
 };
@@ -420,7 +418,7 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
             const long long q = tl * tile + tid;
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) prm.rank[q] = atomicAdd(prm.hist + lf, 1);
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
         // xT is private per thread column: no barrier needed before the next tile's transpose
     }
@@ -540,7 +538,7 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
         g = &t->geo.back().second;
     }
     LocateOnlyParams prm{};
-    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist; prm.rank = lp.rank;
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
     prm.tile = g->tile; prm.bulk = lp.bulk; prm.top = g->top;
     prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
     if (prm.bounds_in_params)
@@ -570,7 +568,7 @@ static int launch_locate_p(const csp_tree* t, const csp_models* mo, LocateParams
 struct BinWorkspace {
     int* cnt = nullptr;
     int* off = nullptr;
-    int* rank = nullptr;
+    int* cursor = nullptr;
     int* partial = nullptr;
     int2* perm = nullptr;
     int* leaf = nullptr;
@@ -615,21 +613,47 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         const char* cenv = getenv("CSP_BIN_CHUNK");
         long long chunk = cenv ? atoll(cenv) : std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24));
         chunk = std::min(std::max<long long>(chunk, 1024), m);
-        BinWorkspace w;
-        int rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, st, &w);
-        for (long long off = 0; off < m && rc == CSP_OK; off += chunk) {
+        const long long nchunks = (m + chunk - 1) / chunk;
+        const char* senv = getenv("CSP_BIN_STREAMS");
+        const int ns = nchunks > 1 && !(senv && atoi(senv) == 1) ? 2 : 1;
+        cudaStream_t ss[2] = {st, st};
+        if (ns == 2) {
+            if (!t->pipe_st[0]) {
+                for (int i = 0; i < 2; ++i) {
+                    CSP_CUDA(cudaStreamCreateWithFlags(&t->pipe_st[i], cudaStreamNonBlocking));
+                    CSP_CUDA(cudaEventCreateWithFlags(&t->pipe_join[i], cudaEventDisableTiming));
+                }
+                CSP_CUDA(cudaEventCreateWithFlags(&t->pipe_fork, cudaEventDisableTiming));
+            }
+            CSP_CUDA(cudaEventRecord(t->pipe_fork, st));
+            for (int i = 0; i < 2; ++i) {
+                ss[i] = t->pipe_st[i];
+                CSP_CUDA(cudaStreamWaitEvent(ss[i], t->pipe_fork, 0));
+            }
+        }
+        BinWorkspace w[2];
+        int rc = CSP_OK;
+        for (int i = 0; i < ns && rc == CSP_OK; ++i) rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, ss[i], &w[i]);
+        long long ci = 0;
+        for (long long off = 0; off < m && rc == CSP_OK; off += chunk, ++ci) {
+            const int k = (int)(ci % ns);
             const long long cnt = std::min(chunk, m - off);
             LocateParams cp = prm;
             cp.X = dX + (size_t)off * t->v.n; cp.m = cnt;
-            cp.leaf = dleaf ? dleaf + off : w.leaf;
+            cp.leaf = dleaf ? dleaf + off : w[k].leaf;
             cp.status = dstatus ? dstatus + off : nullptr;
             cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
-            cp.hist = w.cnt;
-            cp.rank = w.rank;
-            if (rc == CSP_OK) rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, st) : launch_locate_p<1>(t, nullptr, cp, st);
-            if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w, st);
+            cp.hist = w[k].cnt;
+            rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
+            if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
         }
-        csp_bin_free(&w, st);
+        for (int i = 0; i < ns; ++i) {
+            csp_bin_free(&w[i], ss[i]);
+            if (ns == 2) {
+                cudaEventRecord(t->pipe_join[i], ss[i]);
+                cudaStreamWaitEvent(st, t->pipe_join[i], 0);
+            }
+        }
         return rc;
     }
     if (mo) { prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data; }

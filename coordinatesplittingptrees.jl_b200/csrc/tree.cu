@@ -266,6 +266,11 @@ int csp_tree_free(csp_tree* tree) {
     {
         DeviceGuard g(tree->device);
         for (void* p : tree->allocs) cudaFree(p);
+        for (int i = 0; i < 2; ++i) {
+            if (tree->pipe_st[i]) cudaStreamDestroy(tree->pipe_st[i]);
+            if (tree->pipe_join[i]) cudaEventDestroy(tree->pipe_join[i]);
+        }
+        if (tree->pipe_fork) cudaEventDestroy(tree->pipe_fork);
     }
     delete tree;
     return CSP_OK;
