@@ -615,7 +615,9 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         chunk = std::min(std::max<long long>(chunk, 1024), m);
         const long long nchunks = (m + chunk - 1) / chunk;
         const char* senv = getenv("CSP_BIN_STREAMS");
-        const int ns = nchunks > 1 && !(senv && atoi(senv) == 1) ? 2 : 1;
+        // Two internal streams were measured (B200, C2): no gain -- every kernel of the pipeline already fills the GPU, so
+        // concurrent chunks only time-slice (4M chunks: 11.1 ms on one stream, 12.7 ms on two).  Kept as an option.
+        const int ns = nchunks > 1 && senv && atoi(senv) == 2 ? 2 : 1;
         cudaStream_t ss[2] = {st, st};
         if (ns == 2) {
             if (!t->pipe_st[0]) {
