@@ -380,3 +380,92 @@ def test_full_size_properties_c2():
     v_again = models.evaluate(Xd[sub].contiguous(), l_all[sub].contiguous())
     torch.cuda.synchronize()
     assert torch.allclose(v_again.nan_to_num(), v_all[sub].nan_to_num(), rtol=1e-12, atol=1e-12)
+
+
+def test_c5_highdim_fits_global_pair_table():
+    """Config C5 shape (CS2, n=300, a handful of addpoint!s): the pair table (n(n-1)/2 slots) no longer fits in shared memory
+    and lives in global scratch; most pairs are unseen so the NaN pattern must match the oracle exactly."""
+    root, oroot, _ = grow_both(300, 2, 3, seed=55, sigma=0.0)
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    sel = np.linspace(0, len(olv) - 1, 40).astype(int)
+    f = root.tree.flat()
+    ids = f["leaf_nodes"][sel]
+    fit = dt.fit_boxes(node_ids=ids)
+    ofit = O.fit_boxes_batch([olv[i] for i in sel], nthreads=O.max_threads())
+    assert same(fit["status"], ofit["status"])
+    for k in ("c", "g", "Q", "b"):
+        assert same(fit[k], ofit[k]), k
+    Cp, vis = dt.coefficients_p(node_ids=ids)
+    oCp, ovis, _ = O.coefficients_p_batch([olv[i] for i in sel], nthreads=O.max_threads())
+    assert same(Cp, oCp.reshape(len(sel), 300, 300).transpose(0, 2, 1)) and same(vis, ovis)
+    # point location at n = 300 (small tiles, bounds from shared memory)
+    X = cb.synthetic.uniform_queries(root, 3000, seed=3)
+    leaf, status = dt.find_leaf(X)
+    oleaf, ostatus, _ = O.find_leaf_batch(oroot, X, nthreads=O.max_threads())
+    assert same(leaf, oleaf) and same(status, ostatus)
+
+
+def test_c4_cs1_n100_supplied_models():
+    """Config C4 shape: CS1 tree, n=100, models (c, g, Q, b) supplied per leaf; locate bit-exact, values 1e-12."""
+    n = 100
+    root, oroot, _ = grow_both(n, 1, 20, seed=77, sigma=0.0)
+    dt = cb.device_tree(root)
+    nl = dt.n_leaves
+    rng = np.random.default_rng(9)
+    c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))
+    Q = np.triu(rng.standard_normal((nl, n, n)) / n)
+    models = LeafModels.upload(c, g, Q, b)
+    X = cb.synthetic.uniform_queries(root, 4000, seed=5)
+    for mode in ("direct", "binned"):
+        os.environ["CSP_EVAL_MODE"] = mode
+        try:
+            leaf, val, status = dt.locate_eval(models, X)
+        finally:
+            os.environ.pop("CSP_EVAL_MODE")
+        oleaf, oval, ostatus, _ = O.locate_eval_batch(oroot, X, c, g, Q, b, nthreads=O.max_threads())
+        assert same(leaf, oleaf) and same(status, ostatus)
+        assert np.allclose(val, oval, rtol=1e-12, atol=1e-12 * np.abs(oval).max())
+
+
+def test_full_size_properties_c3():
+    """BASELINE config C3 (CS2, n=20, 1e6 leaves) at full tree size: every leaf's own evaluation point is located in that
+    leaf, fitted models reproduce the stored values at those points up to the noise level, both evaluation strategies
+    agree, and the fit status distribution is sane."""
+    import torch
+    root, obj = cb.synthetic.config_tree("C3")
+    f = root.tree.flat()
+    n, p = 20, 2
+    assert f["n_leaves"] == 1000021
+    dt = cb.device_tree(root)
+    par = f["parent"][f["leaf_nodes"]]
+    I = f["internal_id"][par]
+    P = f["pos"].reshape(-1, n)[I].copy()
+    ci = f["childindex"][f["leaf_nodes"]]
+    for k in range(p):
+        d = f["dims"].reshape(-1, p)[I, k] - 1
+        sel = ((ci >> k) & 1).astype(bool)
+        P[np.flatnonzero(sel), d[sel]] = f["xs"].reshape(-1, p)[I, k][sel]
+    leaf, status = dt.find_leaf(P)
+    assert (status == 0).all() and same(leaf, np.arange(f["n_leaves"], dtype=np.int32))
+    models = dt.fit_models()
+    st = models.download()["status"]
+    assert (st == 0).mean() > 0.95
+    Pd = torch.from_numpy(P).cuda()
+    out = {}
+    for mode in ("direct", "binned"):
+        os.environ["CSP_EVAL_MODE"] = mode
+        try:
+            l2, v2, _ = dt.locate_eval(models, Pd)
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("CSP_EVAL_MODE")
+        out[mode] = v2.cpu().numpy()
+        assert same(l2.cpu().numpy(), leaf)
+    fin = np.isfinite(out["direct"])
+    assert same(np.isfinite(out["binned"]), fin)
+    scale = np.abs(out["direct"][fin]).max()
+    assert np.allclose(out["binned"][fin], out["direct"][fin], rtol=1e-9, atol=1e-11 * scale)
+    truth = f["val"][f["leaf_nodes"]]
+    ok = fin & (st == 0)
+    assert np.median(np.abs(out["direct"][ok] - truth[ok])) < 0.1
