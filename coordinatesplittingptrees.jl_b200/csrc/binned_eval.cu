@@ -329,15 +329,17 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
+    size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)
     auto launch = [&](auto kern) {
         CspTimed tm(CSP_K_EVAL_BINNED, st);
-        kern<<<(unsigned)blocks, 256, (size_t)8 * mo->stride * sizeof(double), st>>>(mv, dX, w->perm, w->off + nl, dval);
+        kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, dval);
         CSP_LAUNCHED();
     };
     const bool vec_ok = aligned || (n & 1);
     bool done = false;
     if (mo->degree == 2 && vec_ok) {
         done = true;
+        dyn_smem = (size_t)8 * mo->stride * sizeof(double);
         switch (n) {
             case 2: launch(k_eval_binned_exact<2>); break;
             case 3: launch(k_eval_binned_exact<3>); break;
@@ -351,6 +353,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
             case 20: launch(k_eval_binned_exact<20>); break;
             default: done = false;
         }
+        if (!done) dyn_smem = 0;
     }
     if (done) {}
     else if (n <= 4 && vec_ok) launch(k_eval_binned<4>);
