@@ -303,6 +303,25 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     CSP_CUDA(cudaMemsetAsync(w->cnt, 0, (size_t)nl * 4, st));
     return CSP_OK;
 }
+// Persistent (synchronously allocated) workspace for the host-buffer path, which reuses it across chunks and calls.
+int csp_bin_alloc_sync(int nl, long long m, BinWorkspace* w) {
+    const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
+    CSP_CUDA(cudaMalloc(&w->cnt, (size_t)nl * 4));
+    CSP_CUDA(cudaMalloc(&w->off, (size_t)(nl + 1) * 4));
+    CSP_CUDA(cudaMalloc(&w->cursor, (size_t)nl * 4));
+    CSP_CUDA(cudaMalloc(&w->partial, (size_t)std::max(nblocks, 1) * 8));
+    CSP_CUDA(cudaMalloc(&w->perm, (size_t)m * sizeof(int2)));
+    CSP_CUDA(cudaMemset(w->cnt, 0, (size_t)nl * 4));
+    CSP_CUDA(cudaMemset(w->partial, 0, (size_t)std::max(nblocks, 1) * 8));
+    w->epoch = 0;
+    return CSP_OK;
+}
+void csp_bin_free_sync(BinWorkspace* w) {
+    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    *w = BinWorkspace();
+}
 void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
     void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
     for (void* p : ptrs)

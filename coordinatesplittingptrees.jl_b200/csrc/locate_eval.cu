@@ -13,6 +13,7 @@
 //             levels of the tree), from L1/L2 below that.
 //   evaluate: warp-cooperative; the 32 lanes of a warp read each located leaf's model record with coalesced loads.
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -575,6 +576,8 @@ struct BinWorkspace {
     int epoch = 0;
 };
 int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w);
+int csp_bin_alloc_sync(int nl, long long m, BinWorkspace* w);
+void csp_bin_free_sync(BinWorkspace* w);
 void csp_bin_free(BinWorkspace* w, cudaStream_t st);
 int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
                     cudaStream_t st);
@@ -589,8 +592,9 @@ static bool use_binned(const csp_models* mo, long long m) {
     return m >= (1 << 18) && m >= 8 * mo->n_models;
 }
 
+// preset: a caller-owned workspace valid for `preset_cap` queries per chunk on stream st (host-buffer path), or null.
 static int launch_locate(const csp_tree* t, const csp_models* mo, const double* dX, long long m, int* dleaf, double* dval,
-                         uint8_t* dstatus, cudaStream_t st) {
+                         uint8_t* dstatus, cudaStream_t st, BinWorkspace* preset = nullptr, long long preset_cap = 0) {
     if (m == 0) return CSP_OK;
     LocateParams prm{};
     prm.t = t->v;
@@ -613,11 +617,12 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         const char* cenv = getenv("CSP_BIN_CHUNK");
         long long chunk = cenv ? atoll(cenv) : std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24));
         chunk = std::min(std::max<long long>(chunk, 1024), m);
+        if (preset) chunk = std::min(chunk, preset_cap);
         const long long nchunks = (m + chunk - 1) / chunk;
         const char* senv = getenv("CSP_BIN_STREAMS");
         // Two internal streams were measured (B200, C2): no gain -- every kernel of the pipeline already fills the GPU, so
         // concurrent chunks only time-slice (4M chunks: 11.1 ms on one stream, 12.7 ms on two).  Kept as an option.
-        const int ns = nchunks > 1 && senv && atoi(senv) == 2 ? 2 : 1;
+        const int ns = !preset && nchunks > 1 && senv && atoi(senv) == 2 ? 2 : 1;
         cudaStream_t ss[2] = {st, st};
         if (ns == 2) {
             if (!t->pipe_st[0]) {
@@ -635,7 +640,8 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         }
         BinWorkspace w[2];
         int rc = CSP_OK;
-        for (int i = 0; i < ns && rc == CSP_OK; ++i) rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, ss[i], &w[i]);
+        if (preset) w[0] = *preset;
+        for (int i = 0; i < ns && rc == CSP_OK && !preset; ++i) rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, ss[i], &w[i]);
         long long ci = 0;
         for (long long off = 0; off < m && rc == CSP_OK; off += chunk, ++ci) {
             const int k = (int)(ci % ns);
@@ -649,8 +655,9 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
             if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
         }
+        if (preset) preset->epoch = w[0].epoch;
         for (int i = 0; i < ns; ++i) {
-            csp_bin_free(&w[i], ss[i]);
+            if (!preset) csp_bin_free(&w[i], ss[i]);
             if (ns == 2) {
                 cudaEventRecord(t->pipe_join[i], ss[i]);
                 cudaStreamWaitEvent(st, t->pipe_join[i], 0);
@@ -674,6 +681,8 @@ static int check_pair(const csp_tree* t, const csp_models* mo) {
 }
 
 // Host-buffer path: chunked, three streams, H2D / kernel / D2H of consecutive chunks overlap.
+// Host-buffer path: chunked, three streams, H2D / kernels / D2H of consecutive chunks overlap.  Streams, staging buffers
+// and binning workspaces are created once per device and reused by later calls (grow-only).
 struct HostPipe {
     static const int NS = 3;
     cudaStream_t st[NS]{};
@@ -681,14 +690,15 @@ struct HostPipe {
     int* dleaf[NS]{};
     double* dval[NS]{};
     uint8_t* dstat[NS]{};
-    int created = 0;
-    ~HostPipe() {
-        for (int i = 0; i < created; ++i) {
-            cudaFree(dX[i]); cudaFree(dleaf[i]); cudaFree(dval[i]); cudaFree(dstat[i]);
-            cudaStreamDestroy(st[i]);
-        }
-    }
+    BinWorkspace bin[NS];
+    long long cap_q = 0;      // queries per chunk the staging buffers hold
+    size_t cap_xbytes = 0;    // bytes of each dX buffer
+    long long bin_cap = 0;    // queries per chunk the binning workspaces hold
+    int bin_nl = 0;
+    bool streams = false;
 };
+static HostPipe g_hostpipe[64];
+static std::mutex g_hostpipe_mu;
 
 static int run_host(const csp_tree* t, const csp_models* mo, bool eval_only, const double* X, const int32_t* leaf_in, long long m,
                     int32_t* leaf, double* val, uint8_t* status);
@@ -760,14 +770,33 @@ static int run_host(const csp_tree* t, const csp_models* mo, bool eval_only, con
     // chunk: ~256 MB of queries (large enough for the binned evaluation to find many queries per leaf), at most m
     long long chunk = std::max<long long>(4096, (256LL << 20) / (8LL * n));
     chunk = std::min(chunk, m);
-    HostPipe hp;
-    for (int i = 0; i < HostPipe::NS; ++i) {
-        CSP_CUDA(cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking));
-        hp.created = i + 1;
-        CSP_CUDA(cudaMalloc(&hp.dX[i], (size_t)chunk * n * 8));
-        CSP_CUDA(cudaMalloc(&hp.dleaf[i], (size_t)chunk * 4));
-        CSP_CUDA(cudaMalloc(&hp.dval[i], (size_t)chunk * 8));
-        CSP_CUDA(cudaMalloc(&hp.dstat[i], (size_t)chunk));
+    if (dev < 0 || dev >= 64) return csp_set_error(CSP_ERR_INVALID, "device index %d not supported by the host path", dev);
+    std::lock_guard<std::mutex> lock(g_hostpipe_mu);
+    HostPipe& hp = g_hostpipe[dev];
+    if (!hp.streams) {
+        for (int i = 0; i < HostPipe::NS; ++i) CSP_CUDA(cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking));
+        hp.streams = true;
+    }
+    if (chunk > hp.cap_q || (size_t)chunk * n * 8 > hp.cap_xbytes) {
+        for (int i = 0; i < HostPipe::NS; ++i) {
+            cudaFree(hp.dX[i]); cudaFree(hp.dleaf[i]); cudaFree(hp.dval[i]); cudaFree(hp.dstat[i]);
+            hp.dX[i] = nullptr; hp.dleaf[i] = nullptr; hp.dval[i] = nullptr; hp.dstat[i] = nullptr;
+        }
+        hp.cap_q = 0; hp.cap_xbytes = 0;
+        for (int i = 0; i < HostPipe::NS; ++i) {
+            CSP_CUDA(cudaMalloc(&hp.dX[i], (size_t)chunk * n * 8));
+            CSP_CUDA(cudaMalloc(&hp.dleaf[i], (size_t)chunk * 4));
+            CSP_CUDA(cudaMalloc(&hp.dval[i], (size_t)chunk * 8));
+            CSP_CUDA(cudaMalloc(&hp.dstat[i], (size_t)chunk));
+        }
+        hp.cap_q = chunk; hp.cap_xbytes = (size_t)chunk * n * 8;
+    }
+    const bool binned = !eval_only && mo && use_binned(mo, chunk);
+    if (binned && (hp.bin_cap < chunk || hp.bin_nl != (int)mo->n_models)) {
+        for (int i = 0; i < HostPipe::NS; ++i) csp_bin_free_sync(&hp.bin[i]);
+        hp.bin_cap = 0;
+        for (int i = 0; i < HostPipe::NS; ++i) CSP_CHECK(csp_bin_alloc_sync((int)mo->n_models, chunk, &hp.bin[i]));
+        hp.bin_cap = chunk; hp.bin_nl = (int)mo->n_models;
     }
     int ci = 0;
     for (long long off = 0; off < m; off += chunk, ++ci) {
@@ -779,7 +808,8 @@ static int run_host(const csp_tree* t, const csp_models* mo, bool eval_only, con
             CSP_CUDA(cudaMemcpyAsync(hp.dleaf[s], leaf_in + off, (size_t)cnt * 4, cudaMemcpyHostToDevice, st));
             CSP_CHECK(csp_eval_dev(mo, hp.dX[s], hp.dleaf[s], cnt, hp.dval[s], st));
         } else {
-            CSP_CHECK(launch_locate(t, mo, hp.dX[s], cnt, hp.dleaf[s], mo ? hp.dval[s] : nullptr, hp.dstat[s], st));
+            CSP_CHECK(launch_locate(t, mo, hp.dX[s], cnt, hp.dleaf[s], mo ? hp.dval[s] : nullptr, hp.dstat[s], st,
+                                    binned ? &hp.bin[s] : nullptr, hp.bin_cap));
         }
         if (leaf) CSP_CUDA(cudaMemcpyAsync(leaf + off, hp.dleaf[s], (size_t)cnt * 4, cudaMemcpyDeviceToHost, st));
         if (val) CSP_CUDA(cudaMemcpyAsync(val + off, hp.dval[s], (size_t)cnt * 8, cudaMemcpyDeviceToHost, st));
