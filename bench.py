@@ -91,6 +91,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def host_threads():
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def grow_config(cb, name):
     root, obj = cb.synthetic.config_tree(name)
     return root, obj
@@ -118,7 +126,7 @@ def cpu_reference_leg(cb, name, nq, nfit, seed=7):
     """Times the reference algorithm (oracle port) on the host: locate+eval of nq queries and nfit leaf fits."""
     from oracle import oracle as O
     oroot, _ = grow_oracle_tree(cb, O, name)
-    threads = O.max_threads()
+    threads = host_threads()
     lv = O.leaves(oroot)
     rng = np.random.default_rng(seed)
     sel = rng.choice(len(lv), size=min(nfit, len(lv)), replace=False)
@@ -145,7 +153,7 @@ def run_reference(args):
     from oracle import oracle as O
     name = args.config
     oroot, _ = grow_oracle_tree(cb, O, name)
-    threads = O.max_threads()
+    threads = host_threads()
     n = oroot.n
     lv = O.leaves(oroot)
     nl = len(lv)
@@ -231,6 +239,7 @@ def main():
         blob = cb.pack_blob(root.tree.flat())
     bcast_ms = 0.0
     if world > 1:
+        dist.all_reduce(torch.zeros(1, device=dev))  # communicator set-up is not part of the broadcast time
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
