@@ -328,6 +328,11 @@ void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
         if (p) cudaFreeAsync(p, st);
 }
 
+// dense_eval.cu
+bool csp_dense_supported(const csp_models* mo);
+int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2* perm, const int* total, long long m, double* dval,
+                   cudaStream_t st);
+
 // After k_locate<P,-1> filled leaf[] and cnt[]: scan, scatter, evaluate.
 int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
                     cudaStream_t st) {
@@ -345,6 +350,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
     }
     CSP_LAUNCHED();
+    if (csp_dense_supported(mo)) return csp_dense_eval(mo, n_sm, dX, w->perm, w->off + nl, m, dval, st);  // K3b: FP64 tensor cores
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);

@@ -581,6 +581,8 @@ void csp_bin_free_sync(BinWorkspace* w);
 void csp_bin_free(BinWorkspace* w, cudaStream_t st);
 int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
                     cudaStream_t st);
+bool csp_dense_supported(const csp_models* mo);  // dense_eval.cu
+int csp_hist_launch(const int* dleaf, long long m, long long n_models, int* cnt, int n_sm, cudaStream_t st);
 
 // Evaluation strategy: with many queries per leaf, bin the located queries by leaf and evaluate model-stationary
 // (binned_eval.cu); otherwise evaluate inside the locate kernel, fetching each query's model record.
@@ -726,6 +728,18 @@ int csp_eval_dev(const csp_models* mo, const double* dX, const int32_t* dleaf, i
     if (m < 0 || (m > 0 && (!dX || !dleaf || !dval))) return csp_set_error(CSP_ERR_INVALID, "bad buffer");
     if (m == 0) return CSP_OK;
     DeviceGuard g(mo->device);
+    if (csp_dense_supported(mo) && m < (1LL << 31) && !(getenv("CSP_EVAL_MODE") && !strcmp(getenv("CSP_EVAL_MODE"), "direct"))) {
+        // large n: group the queries by leaf (histogram, scan, scatter) and evaluate on the FP64 tensor cores (K3b)
+        cudaStream_t st = (cudaStream_t)stream;
+        int nsm = 148;
+        cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, mo->device);
+        BinWorkspace w;
+        int rc = csp_bin_alloc((int)mo->n_models, m, false, st, &w);
+        if (rc == CSP_OK) rc = csp_hist_launch(dleaf, m, mo->n_models, w.cnt, nsm, st);
+        if (rc == CSP_OK) rc = csp_binned_eval(mo, nsm, dX, m, dleaf, dval, &w, st);
+        csp_bin_free(&w, st);
+        return rc;
+    }
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, mo->device);

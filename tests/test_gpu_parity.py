@@ -469,3 +469,34 @@ def test_full_size_properties_c3():
     truth = f["val"][f["leaf_nodes"]]
     ok = fin & (st == 0)
     assert np.median(np.abs(out["direct"][ok] - truth[ok])) < 0.1
+
+
+@pytest.mark.parametrize("n,nl", [(40, 7), (64, 300), (100, 5), (103, 40), (130, 12)])
+def test_k3b_dense_dmma_eval(n, nl):
+    """K3b: grouped evaluation on the FP64 tensor cores (mma.sync DMMA) for n > 32, models supplied per leaf (C4 shape).
+    Long runs (few leaves) and short runs (segments inside a tile), evaluate-only and through the binned pipeline."""
+    import torch
+    rng = np.random.default_rng(n + nl)
+    m = 20000
+    c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))
+    Q = np.triu(rng.standard_normal((nl, n, n)) / n)
+    models = LeafModels.upload(c, g, Q, b)
+    X = rng.standard_normal((m, n))
+    leaf = rng.integers(0, nl, m).astype(np.int32)
+    leaf[::97] = -1  # evaluate-only: negative leaf ids give NaN
+    oval, _ = O.eval_batch(c, g, Q, b, X, np.maximum(leaf, 0), nthreads=O.max_threads())
+    oval[leaf < 0] = np.nan
+    Qs = np.triu(Q) + np.triu(Q, 1).transpose(0, 2, 1)
+    scale = np.abs(c[leaf]) + (np.abs(g[leaf]) * np.abs(X - b[leaf])).sum(1) + np.einsum("qi,qij,qj->q", np.abs(X - b[leaf]), np.abs(Qs[leaf]), np.abs(X - b[leaf])) / 2
+    for mode in ("binned", "direct"):
+        os.environ["CSP_EVAL_MODE"] = mode
+        try:
+            val = models.evaluate(X, leaf)                       # host path
+            vd = models.evaluate(torch.from_numpy(X).cuda(), torch.from_numpy(leaf).cuda())  # resident path
+            torch.cuda.synchronize()
+        finally:
+            os.environ.pop("CSP_EVAL_MODE")
+        for v in (val, vd.cpu().numpy()):
+            assert same(np.isnan(v), np.isnan(oval))
+            ok = ~np.isnan(oval)
+            assert (np.abs(v[ok] - oval[ok]) <= 1e-12 * scale[ok]).all(), mode
