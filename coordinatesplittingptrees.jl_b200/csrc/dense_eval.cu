@@ -26,6 +26,7 @@ struct DenseParams {
     const int* total;
     double* val;
     int NP, LD;  // padded dimension (multiple of 8, >= n + 1) and leading dimension of the shared tiles
+    int bulk;    // rows are 16-byte aligned multiples of 16 bytes: gather them with TMA bulk copies
 };
 
 template <int TR, int NT>  // TR rows per tile (TR/16 warps); NT >= NP/8 column tiles (compile-time bound for the accumulators)
@@ -37,7 +38,9 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
     double* sb = Z + (size_t)TR * LD;      // [n]
     int* s_q = (int*)(sb + ((n + 1) & ~1));  // [TR]
     int* s_leaf = s_q + TR;                // [TR]
-    int* s_seg = s_leaf + TR;              // [1]
+    int* s_seg = s_leaf + TR;              // [1] (+1 pad)
+    uint64_t* bar = (uint64_t*)(s_seg + 2);
+    uint32_t phase = 0;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long tot = *prm.total;
     const long long ntiles = (tot + TR - 1) / TR;
@@ -45,6 +48,11 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
     const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
     const long long t0 = (long long)blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
     int cur_leaf = -1;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     for (long long t = t0; t < t1; ++t) {
         const long long s0 = t * TR;
         const int rows = (int)(tot - s0 < TR ? tot - s0 : TR);
@@ -81,13 +89,31 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
                 }
                 cur_leaf = lf;
             }
-            // Z rows of the segment: z = (x - b, 1, 0 ...)
-            for (int idx = tid; idx < (seg_end - seg_start) * LD; idx += blockDim.x) {
-                const int r = seg_start + idx / LD, k = idx - (idx / LD) * LD;
-                double z = 0.0;
-                if (k < n) z = __ldg(prm.X + (size_t)(unsigned)s_q[r] * n + k) - sb[k];
-                else if (k == n) z = 1.0;
-                Z[(size_t)r * LD + k] = z;
+            // Z rows of the segment: z = (x - b, 1, 0 ...).  The rows are gathered by one TMA bulk copy each (all in
+            // flight at once, completion on an mbarrier), then fixed up in place.
+            const int nseg = seg_end - seg_start;
+            if (prm.bulk) {
+                fence_proxy_async();
+                if (tid == 0) mbar_expect_tx(bar, (uint32_t)((size_t)nseg * n * 8));
+                __syncthreads();
+                for (int r = seg_start + tid; r < seg_end; r += blockDim.x)
+                    bulk_g2s(Z + (size_t)r * LD, prm.X + (size_t)(unsigned)s_q[r] * n, (uint32_t)(n * 8), bar);
+                mbar_wait(bar, phase);
+                phase ^= 1;
+                for (int idx = tid; idx < nseg * LD; idx += blockDim.x) {
+                    const int rr = idx / LD, k = idx - rr * LD;
+                    double* zp = Z + (size_t)(seg_start + rr) * LD + k;
+                    *zp = k < n ? *zp - sb[k] : (k == n ? 1.0 : 0.0);
+                }
+            } else {
+                for (int idx = tid; idx < nseg * LD; idx += blockDim.x) {
+                    const int rr = idx / LD, k = idx - rr * LD;
+                    const int r = seg_start + rr;
+                    double z = 0.0;
+                    if (k < n) z = __ldg(prm.X + (size_t)(unsigned)s_q[r] * n + k) - sb[k];
+                    else if (k == n) z = 1.0;
+                    Z[(size_t)r * LD + k] = z;
+                }
             }
             __syncthreads();
             // this warp's 16 rows: skip if they do not intersect the segment (warp-uniform)
@@ -142,7 +168,7 @@ __global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long
 bool csp_dense_supported(const csp_models* mo) {
     if (mo->degree != 2 || mo->n <= 32) return false;
     const int NP = (mo->n + 1 + 7) / 8 * 8;
-    return NP <= 136;
+    return NP <= 128;  // U (NP x (NP+4)) plus a 64-row Z tile must fit in 220 KB of shared memory
 }
 
 int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2* perm, const int* total, long long m, double* dval,
@@ -153,7 +179,8 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
     prm.X = dX; prm.perm = perm; prm.total = total; prm.val = dval;
     prm.NP = (n + 1 + 7) / 8 * 8;
     prm.LD = prm.NP + 4;  // NP % 8 == 0  =>  LD % 16 in {4, 12}
-    auto smem_for = [&](int TR) { return ((size_t)prm.NP * prm.LD + (size_t)TR * prm.LD + ((n + 1) & ~1)) * 8 + (size_t)(2 * TR + 4) * 4; };
+    prm.bulk = ((n & 1) == 0 && (uintptr_t)dX % 16 == 0) ? 1 : 0;
+    auto smem_for = [&](int TR) { return ((size_t)prm.NP * prm.LD + (size_t)TR * prm.LD + ((n + 1) & ~1)) * 8 + (size_t)(2 * TR + 4) * 4 + 16; };
     const long long max_tiles = (m + 63) / 64;
     const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(max_tiles, std::max(n_sm, 1)));
     auto launch = [&](auto kern, int TR) -> int {

@@ -471,7 +471,7 @@ def test_full_size_properties_c3():
     assert np.median(np.abs(out["direct"][ok] - truth[ok])) < 0.1
 
 
-@pytest.mark.parametrize("n,nl", [(40, 7), (64, 300), (100, 5), (103, 40), (130, 12)])
+@pytest.mark.parametrize("n,nl", [(40, 7), (64, 300), (100, 5), (103, 40), (127, 9), (130, 12)])
 def test_k3b_dense_dmma_eval(n, nl):
     """K3b: grouped evaluation on the FP64 tensor cores (mma.sync DMMA) for n > 32, models supplied per leaf (C4 shape).
     Long runs (few leaves) and short runs (segments inside a tile), evaluate-only and through the binned pipeline."""
