@@ -97,6 +97,8 @@ struct csp_tree {
     mutable std::vector<std::pair<const void*, Geo>> geo;
     // internal streams of the chunked binned pipeline: consecutive chunks alternate between them so that the
     // L1-bound descent of one chunk overlaps the DRAM-bound evaluation of the previous one
+    mutable void* fit_ws = nullptr;  // grow-only scratch of the fit pre-pass (chain results), one fit call at a time per handle
+    mutable size_t fit_ws_bytes = 0;
     mutable cudaStream_t pipe_st[2] = {nullptr, nullptr};
     mutable cudaEvent_t pipe_fork = nullptr, pipe_join[2] = {nullptr, nullptr};
 };

@@ -37,6 +37,8 @@ struct FitParams {
     double* gnat; double* y; uint8_t* prec;       // optional native-form extras (dense, box-major)
     uint8_t* status;
     long long* visited;
+    // results of the chain pre-pass (k_fit_chain), box-major
+    int* ch_status; int* ch_itop; double* ch_c; double* ch_y; double* ch_g; int* ch_step;
     int* scratch;            // global pair tables when they do not fit in shared memory
     int pairs_in_smem;
     int warp_smem_bytes;
@@ -63,9 +65,9 @@ __device__ __forceinline__ double qcoef_lineq(bool same, double dxi, double xk, 
 
 struct QIndex {
     int n, packed;
-    __device__ __forceinline__ long long operator()(int i, int j) const {  // 0-based; order-insensitive (SymmetricArray)
-        if (i > j) { int tmp = i; i = j; j = tmp; }
-        return packed ? csp_a_index(n, i, j) : ((long long)j * n + i);
+    __device__ __forceinline__ int operator()(int i, int j) const {  // 0-based; order-insensitive (SymmetricArray)
+        const int lo = min(i, j), hi = max(i, j);  // n <= 4096: every offset fits 32 bits
+        return packed ? lo * (n + 1) - lo * (lo - 1) / 2 + (hi - lo) : hi * n + lo;
     }
 };
 
@@ -122,21 +124,76 @@ __device__ int chaintop_dev(const TreeView& t, int box, int* covered, int* top_o
     return CSP_FIT_OK;
 }
 
-// Drives `fn(lo, hi)` over the id ranges of splits(box) in iteration order until fn returns true (done).
+// The ids splits(box) yields for one ancestor (or for the box's own subtree): up to three ascending ranges, visited in
+// this order.  Scanning them as ONE virtual sequence keeps the lanes of a chunk busy (the ranges are mostly tiny).
+struct RangeGroup {
+    int lo1, n1, lo2, n2, lo3, n3;
+    __device__ __forceinline__ int total() const { return n1 + n2 + n3; }
+    __device__ __forceinline__ int id(int v) const { return v < n1 ? lo1 + v : (v < n1 + n2 ? lo2 + (v - n1) : lo3 + (v - n1 - n2)); }
+};
+// Drives `fn(group)` over splits(box) in iteration order until fn returns true (done).
 template <class F>
-__device__ __forceinline__ void for_split_ranges(const TreeView& t, int box, F&& fn) {
+__device__ __forceinline__ void for_split_groups(const TreeView& t, int box, F&& fn) {
     int cnode = box;
     int4 ci = t.ninfo[box];
     if (!(ci.w & CSP_NF_LEAF))
-        if (fn(ci.y, ci.y + ci.z)) return;
+        if (fn(RangeGroup{ci.y, ci.z, 0, 0, 0, 0})) return;  // own split, then its subtree in preorder
     while (ci.x != cnode) {
         const int a = ci.x;
         const int4 ai = t.ninfo[a];
-        if (fn(ai.y + 1, ci.y)) return;
-        if (fn(ci.y + ci.z, ai.y + ai.z)) return;
-        if (fn(ai.y, ai.y + 1)) return;
+        // subtrees of a's children before c, those after c, then a's own split
+        if (fn(RangeGroup{ai.y + 1, ci.y - (ai.y + 1), ci.y + ci.z, ai.y + ai.z - (ci.y + ci.z), ai.y, 1})) return;
         cnode = a;
         ci = ai;
+    }
+}
+
+// Chain pre-pass, one THREAD per box: getleaf + chaintop (src/polynomials.jl:22-98) + the chain walk of fit_poly1
+// (src/cs2.jl:183-203).  Both are short sequential integer walks; running them on one lane of a warp-per-box kernel left
+// 31 lanes idle for a fifth of that kernel's instructions.
+__global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* __restrict__ node_ids, long long nb, int* __restrict__ ch_status,
+                                                   int* __restrict__ ch_itop, double* __restrict__ ch_c, double* __restrict__ ch_y,
+                                                   double* __restrict__ ch_g, int* __restrict__ ch_step) {
+    const int n = t.n;
+    for (long long bi = blockIdx.x * (long long)blockDim.x + threadIdx.x; bi < nb; bi += (long long)gridDim.x * blockDim.x) {
+        const int box = node_ids ? node_ids[bi] : t.lnode[bi];
+        int* step = ch_step + bi * n;
+        double* y = ch_y + bi * n;
+        double* g = ch_g + bi * n;
+        int leaf = box;
+        while (!(t.ninfo[leaf].w & CSP_NF_LEAF)) leaf = leaf + 1;  // split.self is the next node in preorder
+        int top = -1;
+        int status = chaintop_dev(t, leaf, step, &top);  // the step row doubles as chaintop's `covered`
+        for (int i = 0; i < n; ++i) step[i] = 0;
+        double cval = dnan();
+        int Itop = -1;
+        if (status == CSP_FIT_OK) {
+            Itop = t.ninfo[top].y;
+            const double* __restrict__ b = t.ipos + (size_t)Itop * n;
+            cval = t.icval[4 * Itop];  // value(top) == value(top.split.self)
+            int cur = top;
+            const int nch = (n + 1) / 2;
+            for (int k = 1; k <= nch; ++k) {
+                const int4 cinfo = t.ninfo[cur];
+                if (cinfo.w & CSP_NF_LEAF) { status = CSP_FIT_CHAIN_UNDEF; break; }
+                const int I = cinfo.y;
+                const int d1 = t.idims[2 * I], d2 = t.idims[2 * I + 1];
+                if (d1 == d2 || d1 > n || step[d1 - 1] != 0 || (d2 <= n && step[d2 - 1] != 0)) {
+                    status = CSP_FIT_CHAIN_ASSERT;
+                    break;
+                }
+                const double x1 = t.ixs[2 * I], x2 = t.ixs[2 * I + 1];
+                const double f0 = t.icval[4 * I], f1 = t.icval[4 * I + 1], f2 = t.icval[4 * I + 2];
+                y[d1 - 1] = x1; step[d1 - 1] = k;
+                if (d2 <= n) { y[d2 - 1] = x2; step[d2 - 1] = k; }
+                g[d1 - 1] = (f1 - f0) / (x1 - b[d1 - 1]);
+                if (d2 <= n) g[d2 - 1] = (f2 - f0) / (x2 - b[d2 - 1]);
+                cur = t.ichild[4 * I + 3];
+            }
+        }
+        ch_status[bi] = status;
+        ch_itop[bi] = Itop;
+        ch_c[bi] = cval;
     }
 }
 
@@ -191,47 +248,21 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
         for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
         __syncwarp();
 
-        int status = CSP_FIT_OK, top = -1;
+        int status = CSP_FIT_OK;
         double cval = dnan();
         if (prm.mode == FIT_MODE_FULL) {
-            // ---- fit_poly1: getleaf, chaintop, walk the chain (src/cs2.jl:162-205)
-            if (lane == 0) {
-                int leaf = box;
-                while (!(t.ninfo[leaf].w & CSP_NF_LEAF)) leaf = leaf + 1;  // split.self is the next node in preorder
-                status = chaintop_dev(t, leaf, w.did, &top);
-            }
-            status = __shfl_sync(FULL, status, 0);
-            top = __shfl_sync(FULL, top, 0);
+            // ---- fit_poly1 (src/cs2.jl:162-205): chain results come from the pre-pass k_fit_chain
+            status = prm.ch_status[bi];
             if (status == CSP_FIT_OK) {
-                const int Itop = t.ninfo[top].y;
-                for (int e = lane; e < n; e += 32) w.sb[e] = t.ipos[(size_t)Itop * n + e];
-                __syncwarp();
-                if (lane == 0) {
-                    cval = t.icval[4 * Itop];  // value(top) == value(top.split.self)
-                    int cur = top;
-                    const int nch = (n + 1) / 2;
-                    for (int k = 1; k <= nch; ++k) {
-                        const int4 cinfo = t.ninfo[cur];
-                        if (cinfo.w & CSP_NF_LEAF) { status = CSP_FIT_CHAIN_UNDEF; break; }
-                        const int I = cinfo.y;
-                        const int d1 = t.idims[2 * I], d2 = t.idims[2 * I + 1];
-                        if (d1 == d2 || d1 > n || w.sstep[d1 - 1] != 0 || (d2 <= n && w.sstep[d2 - 1] != 0)) {
-                            status = CSP_FIT_CHAIN_ASSERT;
-                            break;
-                        }
-                        const double x1 = t.ixs[2 * I], x2 = t.ixs[2 * I + 1];
-                        const double f0 = t.icval[4 * I], f1 = t.icval[4 * I + 1], f2 = t.icval[4 * I + 2];
-                        w.sy[d1 - 1] = x1; w.sstep[d1 - 1] = k;
-                        if (d2 <= n) { w.sy[d2 - 1] = x2; w.sstep[d2 - 1] = k; }
-                        w.sg[d1 - 1] = (f1 - f0) / (x1 - w.sb[d1 - 1]);
-                        if (d2 <= n) w.sg[d2 - 1] = (f2 - f0) / (x2 - w.sb[d2 - 1]);
-                        cur = t.ichild[4 * I + 3];
-                    }
+                const int Itop = prm.ch_itop[bi];
+                cval = prm.ch_c[bi];
+                for (int e = lane; e < n; e += 32) {
+                    w.sb[e] = t.ipos[(size_t)Itop * n + e];
+                    w.sy[e] = prm.ch_y[bi * n + e];
+                    w.sg[e] = prm.ch_g[bi * n + e];
+                    w.sstep[e] = prm.ch_step[bi * n + e];
                 }
-                status = __shfl_sync(FULL, status, 0);
-                cval = __shfl_sync(FULL, cval, 0);
             }
-            for (int e = lane; e < n; e += 32) w.dkey[e] = INT_MAX;  // w.did was chaintop's scratch; keys stay clean
             __syncwarp();
         }
 
@@ -241,11 +272,13 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
             int tpos = 0, foundp = 0, foundd = 0;
             bool need_pairs = npairs > 0, need_diag = prm.mode == FIT_MODE_FULL;
             const int skip = prm.skip;
-            for_split_ranges(t, box, [&](int lo, int hi) -> bool {
-                for (int base = lo; base < hi; base += 32) {
-                    const int id = base + lane;
+            for_split_groups(t, box, [&](const RangeGroup& grp) -> bool {
+                const int total = grp.total();
+                for (int base = 0; base < total; base += 32) {
+                    const int v = base + lane;
+                    const int id = grp.id(v);
                     const int pos = tpos + lane;
-                    const bool act = id < hi && pos >= skip;
+                    const bool act = v < total && pos >= skip;
                     int pidx = -1, dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
                     bool newp = false, newd0 = false, newd1 = false;
                     if (act) {
@@ -285,7 +318,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     if (dk1 >= 0 && w.dkey[dd1 - 1] == dk1) w.did[dd1 - 1] = 2 * id + 1;
                     foundp += __popc(__ballot_sync(FULL, newp));
                     foundd += __popc(__ballot_sync(FULL, newd0)) + __popc(__ballot_sync(FULL, newd1));
-                    tpos += min(32, hi - base);
+                    tpos += min(32, total - base);
                     need_pairs = foundp < npairs;
                     need_diag = prm.mode == FIT_MODE_FULL && foundd < n;
                     if (!need_pairs && !need_diag) return true;
@@ -330,8 +363,10 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                 if (lane == 0) {
                     for (long long e = 0; e < qlen; ++e) Qo[e] = dnan();
                     long long nrem = npairs, tp = 0, examined = 0;
-                    for_split_ranges(t, box, [&](int lo, int hi) -> bool {
-                        for (int id = lo; id < hi; ++id, ++tp) {
+                    for_split_groups(t, box, [&](const RangeGroup& grp) -> bool {
+                        const int total = grp.total();
+                        for (int v = 0; v < total; ++v, ++tp) {
+                            const int id = grp.id(v);
                             if (tp < prm.skip) continue;
                             ++examined;
                             long long slot;
@@ -488,6 +523,30 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
     prm.warp_smem_bytes = (int)per_warp;
     size_t smem = per_warp * W;
+    if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
+        const size_t nb = (size_t)prm.nb;
+        const size_t need = nb * ((size_t)n * 20 + 16) + 64;
+        if (need > t->fit_ws_bytes) {
+            if (t->fit_ws) { CSP_CUDA(cudaDeviceSynchronize()); cudaFree(t->fit_ws); t->fit_ws = nullptr; t->fit_ws_bytes = 0; }
+            CSP_CUDA(cudaMalloc(&t->fit_ws, need));
+            t->fit_ws_bytes = need;
+        }
+        char* base_p = (char*)t->fit_ws;
+        prm.ch_y = (double*)base_p; base_p += nb * n * 8;
+        prm.ch_g = (double*)base_p; base_p += nb * n * 8;
+        prm.ch_c = (double*)base_p; base_p += nb * 8;
+        prm.ch_step = (int*)base_p; base_p += nb * n * 4;
+        prm.ch_status = (int*)base_p; base_p += nb * 4;
+        prm.ch_itop = (int*)base_p;
+        const long long blocks = std::min<long long>((prm.nb + 127) / 128, (long long)std::max(t->n_sm, 1) * 16);
+        {
+            CspTimed tm(CSP_K_FIT, st);
+            k_fit_chain<<<(unsigned)blocks, 128, 0, st>>>(prm.t, prm.node_ids, prm.nb, prm.ch_status, prm.ch_itop, prm.ch_c, prm.ch_y,
+                                                         prm.ch_g, prm.ch_step);
+        }
+        CSP_LAUNCHED();
+        CSP_CUDA(cudaGetLastError());
+    }
     auto launch = [&](auto kern) -> int {
         CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int occ = 0;

@@ -266,6 +266,7 @@ int csp_tree_free(csp_tree* tree) {
     {
         DeviceGuard g(tree->device);
         for (void* p : tree->allocs) cudaFree(p);
+        if (tree->fit_ws) cudaFree(tree->fit_ws);
         for (int i = 0; i < 2; ++i) {
             if (tree->pipe_st[i]) cudaStreamDestroy(tree->pipe_st[i]);
             if (tree->pipe_join[i]) cudaEventDestroy(tree->pipe_join[i]);
