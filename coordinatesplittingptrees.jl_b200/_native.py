@@ -107,6 +107,7 @@ def dev():
         vp, vpp = C.c_void_p, C.POINTER(C.c_void_p)
         L.csp_last_error.restype = C.c_char_p
         L.csp_kernel_launches.restype = C.c_int64
+        L.csp_modelvalue_native.argtypes = [C.c_int32, C.c_double, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
         L.csp_timing_enable.argtypes = [C.c_int]
         L.csp_timing_read.argtypes = [c_f64p, c_i64p]
         L.csp_device_count.argtypes = [C.POINTER(C.c_int)]
@@ -144,4 +145,4 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_tree_pack", "csp_tree_upload_blob", "csp_tree_info", "csp_tree_free", "csp_find_leaf", "csp_find_leaf_dev",
            "csp_fit_boxes", "csp_coefficients_p", "csp_models_fit", "csp_models_refit", "csp_models_upload", "csp_models_download", "csp_models_info",
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
-           "csp_timing_read"]
+           "csp_timing_read", "csp_modelvalue_native"]

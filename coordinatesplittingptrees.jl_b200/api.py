@@ -149,6 +149,23 @@ def modelvalue(c, g, Q, b, x):
         mo.close()
 
 
+def modelvalue_native(c, g, Q, b, y, prec, x):
+    """modelvalue(c, g, Q, b, y, prec, x) for the CS2-native model (reference src/cs2.jl:142-153), evaluated on the GPU in the
+    reference's loop order.  x: one point (n,) -> float, or (m, n) -> array."""
+    import ctypes as C
+    X = np.ascontiguousarray(np.asarray(x, np.float64))
+    single = X.ndim == 1
+    X = np.ascontiguousarray(X.reshape(1, -1) if single else X)
+    m, n = X.shape
+    Qd = np.ascontiguousarray(np.asarray(Q.data if isinstance(Q, SymmetricArray) else Q, np.float64).T)  # column-major .data
+    P = np.ascontiguousarray(np.asarray(prec, bool).T.astype(np.uint8))
+    g, b, y = (np.ascontiguousarray(v, np.float64) for v in (g, b, y))
+    out = np.empty(m)
+    N.dchk(N.dev().csp_modelvalue_native(n, float(c), g.ctypes.data, Qd.ctypes.data, b.ctypes.data, y.ctypes.data, P.ctypes.data,
+                                         X.ctypes.data, m, out.ctypes.data))
+    return float(out[0]) if single else out
+
+
 def fit_leaves(root, skip=0):
     """Batched fit of every leaf, models kept on the device (LeafModels)."""
     return device_tree(root).fit_models(skip=skip)

@@ -506,6 +506,39 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     }
 }
 
+// ---- native-form model evaluation (reference src/cs2.jl:142-153 with Qcoef_value :302-312) --------------------------------
+// One thread per query point, the reference's loop order (j outer, i = j..n inner), no FMA contraction (this TU).
+__global__ void __launch_bounds__(256) k_modelvalue_native(int n, double c, const double* __restrict__ g, const double* __restrict__ Q,
+                                                          const double* __restrict__ b, const double* __restrict__ y,
+                                                          const uint8_t* __restrict__ prec, const double* __restrict__ X, long long m,
+                                                          double* __restrict__ val) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
+        const double* __restrict__ x = X + (size_t)q * n;
+        double dot = 0.0;
+        for (int i = 0; i < n; ++i) dot = dot + g[i] * (x[i] - b[i]);
+        double v = c + dot;
+        for (int j = 0; j < n; ++j)
+            for (int i = j; i < n; ++i) {
+                double coef;
+                if (i == j) {
+                    coef = (x[i] - b[i]) * (x[i] - y[i]) / 2;
+                } else {
+                    const double bi = b[i], bj = b[j], yi = y[i], yj = y[j], xi = x[i], xj = x[j];
+                    const bool pij = prec[(size_t)j * n + i] != 0, pji = prec[(size_t)i * n + j] != 0;  // column-major prec[i,j]
+                    if (((pij & !pji) & (xi == yi)) | ((pji & !pij) & (xj == yj))) {
+                        coef = 0.0 * (xi * xj / 2);  // zero(xi*xj/2)
+                    } else {
+                        const double chiij = pji ? bi : 2 * yi - bi;
+                        const double chiji = pij ? bj : 2 * yj - bj;
+                        coef = ((xi - bi) * (xj - chiji) + (xj - bj) * (xi - chiij)) / 4;
+                    }
+                }
+                if (coef != 0) v = v + Q[(size_t)i * n + j] * coef * (double)(1 + (i != j));  // Q[i,j] reads .data[min,max] = data[j,i]
+            }
+        val[q] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
@@ -720,6 +753,30 @@ int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
     if (scratch) cudaFree(scratch);
     if (rc != CSP_OK) return fail(rc);
     *out = mo;
+    return CSP_OK;
+}
+
+int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q, const double* b, const double* y, const uint8_t* prec,
+                          const double* X, int64_t m, double* val) {
+    if (n < 1 || m < 0 || !g || !Q || !b || !y || !prec || (m > 0 && (!X || !val))) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    if (m == 0) return CSP_OK;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(csp_current_device());
+    DevBuf dgv, dQ, db, dy, dp, dX, dv;
+    CSP_CHECK(dgv.alloc((size_t)n * 8)); CSP_CHECK(dQ.alloc((size_t)n * n * 8)); CSP_CHECK(db.alloc((size_t)n * 8));
+    CSP_CHECK(dy.alloc((size_t)n * 8)); CSP_CHECK(dp.alloc((size_t)n * n)); CSP_CHECK(dX.alloc((size_t)m * n * 8)); CSP_CHECK(dv.alloc((size_t)m * 8));
+    CSP_CUDA(cudaMemcpy(dgv.p, g, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CSP_CUDA(cudaMemcpy(dQ.p, Q, (size_t)n * n * 8, cudaMemcpyHostToDevice));
+    CSP_CUDA(cudaMemcpy(db.p, b, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CSP_CUDA(cudaMemcpy(dy.p, y, (size_t)n * 8, cudaMemcpyHostToDevice));
+    CSP_CUDA(cudaMemcpy(dp.p, prec, (size_t)n * n, cudaMemcpyHostToDevice));
+    CSP_CUDA(cudaMemcpy(dX.p, X, (size_t)m * n * 8, cudaMemcpyHostToDevice));
+    const long long blocks = std::min<long long>((m + 255) / 256, 148 * 8);
+    k_modelvalue_native<<<(unsigned)blocks, 256>>>(n, c, (const double*)dgv.p, (const double*)dQ.p, (const double*)db.p, (const double*)dy.p,
+                                                   (const uint8_t*)dp.p, (const double*)dX.p, m, (double*)dv.p);
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
+    CSP_CUDA(cudaMemcpy(val, dv.p, (size_t)m * 8, cudaMemcpyDeviceToHost));
     return CSP_OK;
 }
 

@@ -137,6 +137,12 @@ int csp_locate_eval(const csp_tree* tree, const csp_models* models, const double
 int csp_locate_eval_dev(const csp_tree* tree, const csp_models* models, const double* dX, int64_t m, int32_t* dleaf,
                         double* dval, uint8_t* dstatus, void* stream);
 
+/* Native-form evaluation of ONE CS2-native model (c, g, Q, b, y, prec) as returned by fit_quadratic_native, at m points:
+ * modelvalue(c, g, Q, b, y, prec, x) (src/cs2.jl:142-153 with Qcoef_value :302-312), in the reference's loop order.
+ * Q: n*n in the .data layout, prec: n*n column-major bytes.  Host buffers. */
+int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q, const double* b, const double* y,
+                          const uint8_t* prec, const double* X, int64_t m, double* val);
+
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process since load (bench.py reports it as gpu_launches). */
 int64_t csp_kernel_launches(void);

@@ -500,3 +500,26 @@ def test_k3b_dense_dmma_eval(n, nl):
             assert same(np.isnan(v), np.isnan(oval))
             ok = ~np.isnan(oval)
             assert (np.abs(v[ok] - oval[ok]) <= 1e-12 * scale[ok]).all(), mode
+
+
+@pytest.mark.parametrize("n", [2, 3, 7, 8])
+def test_native_model_reproduces_every_leaf(n):
+    """runtests.jl:839-844: the CS2-native model (fit_quadratic_native) evaluated with modelvalue(c,g,Q,b,y,prec,x) reproduces
+    f at every leaf position (rtol 1e-7); the GPU evaluation equals the oracle's restatement bit for bit."""
+    rng = np.random.default_rng(70 + n)
+    B = rng.standard_normal((n, n))
+    f = cb.quadnoise_objective((B + B.T) / 2, sigma=0.0)
+    x0 = rng.standard_normal(n)
+    world = cb.World(np.full(n, -np.inf), np.full(n, np.inf), x0, f)
+    root = cb.Box(world, 2)
+    cycle = cb.synthetic.round_robin_dimlists(n)
+    for i in range(2 * len(cycle) + 2):
+        box = cb.addpoint(root, rng.standard_normal(n), cycle[i % len(cycle)], f)
+    c, g, Q, b, y, prec, firstmatch = cb.fit_quadratic_native(box)
+    P = np.array([cb.position(l) for l in cb.leaves(root)])
+    vals = cb.modelvalue_native(c, g, Q, b, y, prec, P)
+    truth = np.array([f(p) for p in P])
+    assert np.allclose(vals, truth, rtol=1e-7, atol=1e-9)
+    ovals = np.array([O.modelvalue_native(c, g, Q.data, b, y, prec, p) for p in P])
+    assert same(vals, ovals)
+    assert cb.modelvalue_native(c, g, Q, b, y, prec, P[0]) == ovals[0]
