@@ -377,11 +377,21 @@ def main():
         kernels[k] = {"ms_per_step": ms, "launches_per_step": cnt, "share": ms / max(pipe_ms, 1e-9),
                       "algorithmic_GBps": b / (ms * 1e-3) / 1e9 if ms > 0 else None, "frac": b / (ms * 1e-3) / 1e9 / peak if ms > 0 else None}
     dom = max((k for k in kernels), key=lambda k: kernels[k]["ms_per_step"])
+    traffic, traffic_src = None, None
+    try:  # DRAM traffic of the dominant kernel from the committed ncu --set full capture, scaled to this run's launch size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        key = {"locate": "k_locate_only", "eval_binned": "k_eval_binned", "scatter": "k_scatter"}.get(dom)
+        if key and n == 10:
+            traffic = tj[key]["dram_bytes_per_query"] * m / max(kernels[dom]["launches_per_step"], 1)
+            traffic_src = "profiles/r1_%s.ncu-rep: %.1f DRAM bytes/query x queries per launch" % (key, tj[key]["dram_bytes_per_query"])
+    except Exception:
+        pass
     names = {"locate": "k_locate<2,-1> (find_leaf_at descent + per-leaf histogram)", "eval_binned": "k_eval_binned_exact<10> (model-stationary modelvalue)",
              "locate_eval_fused": "k_locate<2,8,10> (fused find_leaf_at + modelvalue)", "scatter": "k_scatter", "scan": "k_scan", "eval": "k_eval"}
     alg_bytes = m * BYTES_PER_QUERY(n) + touched * model_bytes(n) + tree.kib * 1024
     roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": kernels[dom]["frac"], "peak_source": peak_src, "traffic": None,
+                "frac": kernels[dom]["frac"], "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,
+                "algorithmic_bytes_per_launch": m * alg_q.get(dom, 0) / max(kernels[dom]["launches_per_step"], 1),
                 "ms_per_launch": kernels[dom]["ms_per_step"] / max(kernels[dom]["launches_per_step"], 1),
                 "launches_per_step": kernels[dom]["launches_per_step"], "share_of_pipeline": kernels[dom]["share"],
                 "bytes_per_query": alg_q.get(dom), "kernels": kernels,

@@ -62,6 +62,16 @@ def pack_blob(flat):
     return blob
 
 
+def save_blob(flat, path):
+    """Write the flattened tree to `path` in the wire format (csp_tree_pack): the persistent on-disk form of a tree."""
+    pack_blob(flat).tofile(path)
+
+
+def load_blob(path):
+    """Read a blob written by save_blob (numpy uint8); pass it to DeviceTree(blob=...)."""
+    return np.fromfile(path, dtype=np.uint8)
+
+
 class DeviceTree:
     """Flattened CSp-tree resident on one GPU (csp_tree)."""
 

@@ -142,3 +142,15 @@ def test_blob_roundtrip_host():
     bad["parent"][3] = 0 if flat["parent"][3] != 0 else 1
     with pytest.raises(cb.CspError):
         cb.pack_blob(bad)
+
+
+def test_blob_file_roundtrip(tmp_path):
+    """The blob is the persistent on-disk format: save, load, bit-identical; header fields decode."""
+    root, _, _ = grow_both(4, 2, 30, seed=3)
+    flat = root.tree.flat()
+    path = tmp_path / "tree.cspb"
+    cb.save_blob(flat, str(path))
+    blob = cb.load_blob(str(path))
+    assert np.array_equal(blob, cb.pack_blob(flat))
+    hdr = np.frombuffer(blob[:32].tobytes(), dtype=np.int32)
+    assert [int(v) for v in hdr[3:8]] == [flat["n"], flat["p"], flat["n_nodes"], flat["n_internal"], flat["n_leaves"]]

@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""Regenerates profiles/README.md from the committed measurement files (run from the repo root)."""
+import csv
+import json
+from collections import defaultdict
+
+rows = list(csv.reader(open('profiles/r1_launches_ncu.csv')))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
+H = rows[hdr]; ki = H.index('Kernel Name'); vi = H.index('Metric Value')
+agg = defaultdict(list)
+for r in rows[hdr + 1:]:
+    if len(r) > vi:
+        agg[r[ki][:70]].append(float(r[vi].replace(',', '')))
+mine = {k: v for k, v in agg.items() if not ('at::' in k or 'at_cuda' in k)}
+tot = sum(sum(v) for v in mine.values())
+lines = [f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {100*sum(v)/tot:.1f} % |" for k, v in mine.items()]
+b = json.load(open('profiles/r1_bench_n1.json'))
+b2 = json.load(open('profiles/r1_bench_n2.json'))
+ref = json.load(open('profiles/r1_bench_reference_arm.json'))
+d = json.load(open('profiles/r1_dense_c4.json'))
+tr = json.load(open('profiles/r1_traffic.json'))
+K = b['roofline']['kernels']
+txt = f"""# profiles/ — round 1 evidence (B200, sm_100a, CUDA 12.9, driver 580)
+
+How these were produced: `tools_gpu_profile.sh` / `tools/prof_dense.sh` under `gpurun` (plain run first, then `ncu` on the
+identical command line, `--clock-control none`); bench lines are plain runs (never under a profiler).
+Workload: BASELINE config C2 — CS2 tree, n = 10, 100 006 leaves, 1e8 resident queries per step (8 GB, larger than L2),
+step = re-fit every leaf model + locate/evaluate every query.  Peak = measured copy bandwidth {b['roofline']['peak']} GB/s
+(`MEASURED_PEAKS.json`).  Regenerate this file with `python tools/make_profiles_readme.py`.
+
+## Files
+| file | what |
+|---|---|
+| `r1_bench_n1.json`, `r1_bench_n2.json` | `bench.py` lines at N = 1 and N = 2 (torchrun, NCCL) |
+| `r1_bench_reference_arm.json` | `bench.py --impl reference` (oracle port on the box's 16 host cores) |
+| `r1_launches_ncu.csv` | every launch of `bench.py --queries 20000000 --steps 3` with `gpu__time_duration.sum` |
+| `r1_<kernel>.ncu-rep` / `.summary.txt` | `ncu --set full --import-source on` capture of one launch + key metrics and per-source-line stall summary (`tools/ncu_metrics.py`, `tools/ncu_lines.py`) |
+| `r1_traffic.json` | DRAM bytes (read + write) per launch of each capture, per query / per leaf |
+| `r1_dense_c4.json` | `tools/bench_dense.py`: config C4 (n = 100, 1e4 leaves) on the DMMA kernel, with a cuBLAS DGEMM peak measured in the same run |
+
+## Headline (N = 1)
+| quantity | value |
+|---|---|
+| locate + evaluate, inputs resident (`value`) | **{b['value']:.3e} queries/s** ({b['ms_per_step']:.2f} ms per 1e8-query step incl. the all-leaf re-fit) |
+| same through the host-buffer C-ABI call, pinned memory, copies timed (`e2e`) | {b['e2e']['value']:.3e} queries/s — PCIe-bound: 9.3 GB per step |
+| all-leaf fits | {b['fits']['value']:.3e} fits/s ({b['fits']['kernel_ms']:.3f} ms for 100 006 leaves, two kernels) |
+| CPU baseline (oracle port, {b['cpu_baseline']['cores']} cores, same box) | {b['cpu_baseline']['value']:.3e} queries/s, {b['cpu_baseline']['fits_per_s']:.3e} fits/s |
+| reference arm (`--impl reference`) | {ref['value']:.3e} queries/s, {ref['fits']['value']:.3e} fits/s |
+| N = 2 (weak scaling, one NCCL broadcast of the tree blob) | {b2['value']:.3e} queries/s |
+| clocks during the timed region | {b['clocks']['sm_mhz']} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'} |
+
+## Where a step's time goes (CUDA events around every launch, `csp_timing_*`; 24 chunks of 4 194 304 queries)
+| kernel | ms / step | launches / step | share | algorithmic B/query | algorithmic GB/s | frac of peak | DRAM B/query (ncu) |
+|---|---|---|---|---|---|---|---|
+| `k_locate_only<2>` (K1: find_leaf_at + histogram) | {K['locate']['ms_per_step']:.2f} | {K['locate']['launches_per_step']:.0f} | {100*K['locate']['share']:.0f} % | 85 | {K['locate']['algorithmic_GBps']:.0f} | {K['locate']['frac']:.2f} | {tr['k_locate_only']['dram_bytes_per_query']:.0f} |
+| `k_scan` | {K['scan']['ms_per_step']:.2f} | {K['scan']['launches_per_step']:.0f} | {100*K['scan']['share']:.0f} % | – | – | – | – |
+| `k_scatter` | {K['scatter']['ms_per_step']:.2f} | {K['scatter']['launches_per_step']:.0f} | {100*K['scatter']['share']:.0f} % | 12 | {K['scatter']['algorithmic_GBps']:.0f} | {K['scatter']['frac']:.2f} | {tr['k_scatter']['dram_bytes_per_query']:.0f} (+ L2 atomics) |
+| `k_eval_binned_exact<10>` (K3a: modelvalue) | {K['eval_binned']['ms_per_step']:.2f} | {K['eval_binned']['launches_per_step']:.0f} | {100*K['eval_binned']['share']:.0f} % | 96 | {K['eval_binned']['algorithmic_GBps']:.0f} | {K['eval_binned']['frac']:.2f} | {tr['k_eval_binned']['dram_bytes_per_query']:.0f} |
+| whole pipeline | {b['roofline']['pipeline']['kernel_ms_per_step']:.2f} | | | 93 | {b['roofline']['pipeline']['achieved']:.0f} | {b['roofline']['pipeline']['frac']:.2f} | |
+| `k_fit_chain` + `k_fit<2>` (K2) | {b['fits']['kernel_ms']:.3f} | 2 | | 5 616 B/leaf | | {b['fits']['frac']:.2f} | {tr['k_fit']['dram_bytes_per_leaf']+tr['k_fit_chain']['dram_bytes_per_leaf']:.0f} B/leaf |
+
+ncu launch list (`r1_launches_ncu.csv`, 2e7 queries per step, cold-cache, serialised — compare shares):
+
+| kernel | launches | mean µs | share |
+|---|---|---|---|
+""" + "\n".join(lines) + f"""
+
+The shares agree with the event timings (at 2e7 queries per step the fit is a larger part of the step; at 1e8 it is 4 %).
+
+## What bounds each kernel (from the `--set full` captures)
+* **K1 `k_locate_only`** — L1/shared-memory wavefront bound: `l1tex__data_pipe_lsu_wavefronts` 81 % of peak (58 % shared: the
+  transposed coordinate reads + the tree-top records; 42 % global: one `LDG.E.256` record per level below the top), DRAM
+  23 %, issue 49 %.  DRAM traffic equals the algorithmic bytes (86 vs 85 B/query): nothing is re-read; the cost is ≈ 9
+  dependent random 32-byte record fetches per query.
+* **K3a `k_eval_binned_exact<10>`** — DRAM bound on *extra* traffic: 228 B/query against 96 algorithmic.  The x rows are
+  gathered a second time at 64-byte DRAM granularity (≈ 128 B for an 80-byte row) and the scattered 8-byte value writes
+  cost a sector read-modify-write (≈ 64 + 32 B).  4.4 TB/s of mostly random 64-128-byte accesses is about what HBM3e
+  delivers; `long_scoreboard` dominates the stalls.
+* **`k_scatter`** — L2 atomic throughput (1e8 returning atomics per step).
+* **K2 `k_fit<2>`** — instruction-issue bound (68 % issue-active, ≈ 3.4 k warp-instructions per leaf, DRAM < 1 %); the work per
+  leaf is small and irregular (≈ 140 splits scanned, 45 + 10 coefficients, all sequential per output entry for bit-exactness).
+* **K3b `k_eval_dmma`** (config C4, `r1_dense_c4.json`) — {d['dmma_kernel_useful_tflops']:.1f} useful TFLOP/s = {100*d['frac_of_dgemm_peak_kernel']:.0f} % of the cuBLAS
+  DGEMM peak measured in the same run ({d['cublas_dgemm_tflops']:.1f} TFLOP/s); SASS `DMMA.8x8x4` (the only FP64 tensor op on sm_100a),
+  `UBLKCP` row gathers; {d['queries_per_s']:.2e} queries/s at n = 100.
+
+## Round-1 progression of the headline (C2, one B200, resident)
+| version | ms / 1e8 queries | queries/s |
+|---|---|---|
+| v1: thread-per-query descent (48-byte records) + per-thread model reads | 52.8 | 1.9e9 |
+| BFS 32-byte records (`LDG.E.256`), warp-cooperative coalesced evaluation | 22.1 | 4.4e9 |
+| uniform packed-A records, 8 lanes per query | 17.9 | 5.4e9 |
+| binned (model-stationary) pipeline, unchunked | 17.0 | 5.7e9 |
+| + L2-friendly 4 M-query chunks, single-launch scan | 12.6 | 7.6e9 |
+| + transposed conflict-free tile, constant-bank bounds, single TMA stage in K1 | 11.6 | 8.2e9 |
+| + record staged per warp in shared memory, perm prefetch in the evaluation | 11.1 | 8.6e9 |
+"""
+open('profiles/README.md', 'w').write(txt)
