@@ -592,7 +592,10 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         // HBM; chunks must stay large enough to amortise the four launches and to keep many queries per leaf.
         // Measured on B200 (C2, 1e8 queries): 0.5M 17.8 ms, 1M 14.5, 2M 12.8, 4M 12.6, 8M 13.2, unchunked 17.0.
         const char* cenv = getenv("CSP_BIN_CHUNK");
-        long long chunk = cenv ? atoll(cenv) : std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24));
+        // With many leaves the runs per leaf must stay long enough to amortise a record fetch per warp (C3, 1e6 leaves, 5e7
+        // queries: 2M chunks 19.4 ms, 8M 11.8, 16M 10.7, unchunked 10.4), hence at least 40 queries per leaf per chunk.
+        long long chunk = cenv ? atoll(cenv)
+                               : std::max<long long>(std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24)), 40LL * mo->n_models);
         chunk = std::min(std::max<long long>(chunk, 1024), m);
         if (preset) chunk = std::min(chunk, preset_cap);
         const long long nchunks = (m + chunk - 1) / chunk;
