@@ -184,7 +184,7 @@ def run_reference(args):
                             "sample": f"{nq} uniform queries per step located + evaluated, {len(boxes)} leaf fits per step; C++ "
                                       "restatement of the Julia reference (oracle/), not Julia"},
            "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(name, m, nl, n):
@@ -194,7 +194,26 @@ def workload_config(name, m, nl, n):
             "step": "refit all leaf models + locate/evaluate all queries", "l2": "inputs larger than L2 (no flush needed)"}
 
 
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    """Route everything written to fd 1 (NCCL / library banners included) to stderr; the JSON line goes to the real stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -420,7 +439,7 @@ def main():
                                              f"{leg['fit_s']:.2f}s on the same tree; C++ restatement of the Julia reference, not Julia"}
         except Exception as ex:
             out["cpu_baseline"] = {"value": None, "error": str(ex)[:200]}
-    print(json.dumps(out), flush=True)
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
