@@ -119,6 +119,16 @@ def coefficients_p(box, skip=0):
     return SymmetricArray(Cp[0])
 
 
+def coefficients_p_sparse(box, pattern, skip=0):
+    """coefficients_p!(Cp, box) with a sparse symmetric Cp (reference src/polynomials.jl:161-230, :244-271): `pattern` is either
+    the string "tridiagonal" (SymTridiagonal: returns its off-diagonal vector ev) or a list of above-diagonal positions (i, j),
+    1-based, i < j (returns {(i, j): value}).  Only those coefficients are determined and the traversal stops once they are."""
+    tri = isinstance(pattern, str) and pattern == "tridiagonal"
+    pat = [(i, i + 1) for i in range(1, box.n)] if tri else [tuple(sorted(p)) for p in pattern]
+    vals, _ = device_tree(box).coefficients_p_sparse(pat, [T.node_id(box)], skip=skip)
+    return vals[0] if tri else {p: float(v) for p, v in zip(pat, vals[0])}
+
+
 def polynomial_full(box, skip=0):
     """Full-degree model at `box`.  p=2: fit_quadratic.  p=1: the degree-1 model (c, g, b) with c = value(box),
     g = coefficients_p(box), b = position(box) (the reference has no CS1 quadratic fit)."""

@@ -39,6 +39,9 @@ struct FitParams {
     long long* visited;
     // results of the chain pre-pass (k_fit_chain), box-major
     int* ch_status; int* ch_itop; double* ch_c; double* ch_y; double* ch_g; int* ch_step;
+    // sparse-pattern coefficients_p (FIT_MODE_COEF, p == 2): slotmap[i*n+j] (i<j, 0-based) = output slot or -1; npat slots; the
+    // output row of a box is then Q[bi*Q_stride + slot]
+    const int* slotmap; int npat; const int* pat_ij;
     int* scratch;            // global pair tables when they do not fit in shared memory
     int pairs_in_smem;
     int warp_smem_bytes;
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     const TreeView& t = prm.t;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
     const int n = t.n;
-    const int npairs = P == 2 ? n * (n - 1) / 2 : n;
+    const int npairs = prm.slotmap ? prm.npat : (P == 2 ? n * (n - 1) / 2 : n);
     const unsigned FULL = 0xffffffffu;
 
     unsigned char* wbase = smem_raw + (size_t)wib * prm.warp_smem_bytes;
@@ -242,7 +245,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
         const int box = prm.node_ids ? prm.node_ids[bi] : t.lnode[bi];
         double* Qo = prm.Q + bi * prm.Q_stride;
         const QIndex qi{n, prm.q_packed};
-        const long long qlen = P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n);
+        const long long qlen = prm.slotmap ? prm.npat : (P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n));
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
         for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
         for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
@@ -287,8 +290,8 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                             dd0 = dd.x; dd1 = dd.y;
                             if (need_pairs && dd0 <= n && dd1 <= n && dd0 != dd1) {
                                 const int i = min(dd0, dd1) - 1, j = max(dd0, dd1) - 1;
-                                pidx = i * n - i * (i + 1) / 2 + (j - i - 1);
-                                newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                                pidx = prm.slotmap ? __ldg(prm.slotmap + i * n + j) : i * n - i * (i + 1) / 2 + (j - i - 1);
+                                if (pidx >= 0) newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
                             }
                             if (need_diag) {
                                 const double2 xs = __ldg((const double2*)t.ixs + id);
@@ -336,7 +339,14 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
 
             // ---- coefficients_p values (src/polynomials.jl:211-226), one lane per slot
             bool sawnan = false;
-            if (P == 2) {
+            if (P == 2 && prm.slotmap) {
+                for (int e = lane; e < npairs; e += 32) {
+                    if (w.pkey[e] == INT_MAX) continue;
+                    const double v = coef_value<2>(t, w.pid[e]);
+                    sawnan |= (v != v);
+                    Qo[e] = v;
+                }
+            } else if (P == 2) {
                 for (int e = lane; e < n * n; e += 32) {
                     const int i = e / n, j = e - i * n;
                     if (i >= j) continue;
@@ -373,7 +383,12 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                             if (P == 2) {
                                 const int d0 = t.idims[2 * id], d1 = t.idims[2 * id + 1];
                                 if (d0 > n || d1 > n) continue;
-                                slot = qi(d0 - 1, d1 - 1);
+                                if (prm.slotmap) {
+                                    slot = d0 == d1 ? -1 : prm.slotmap[(min(d0, d1) - 1) * n + max(d0, d1) - 1];
+                                    if (slot < 0) continue;  // a structural zero reads 0.0, not NaN
+                                } else {
+                                    slot = qi(d0 - 1, d1 - 1);
+                                }
                             } else {
                                 const int d0 = t.idims[id];
                                 if (d0 > n) continue;
@@ -546,7 +561,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     *scratch_out = nullptr;
     if (prm.nb == 0) return CSP_OK;
     const int n = t->v.n, P = t->v.p;
-    const long long npairs = P == 2 ? (long long)n * (n - 1) / 2 : n;
+    const long long npairs = prm.slotmap ? prm.npat : (P == 2 ? (long long)n * (n - 1) / 2 : n);
     size_t base = (size_t)n * 8 * 3 + (size_t)n * 4 * 3;
     size_t withpairs = base + (size_t)npairs * 8;
     prm.pairs_in_smem = withpairs <= 200 * 1024;
@@ -709,6 +724,54 @@ int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, i
         if (scratch) cudaFree(scratch);
         CSP_CHECK(rc);
         CSP_CUDA(cudaMemcpy(Cp + off * (per / 8), dQ.p, cnt * per, cudaMemcpyDeviceToHost));
+        if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
+    }
+    return CSP_OK;
+}
+
+int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, int32_t npat, const int32_t* pat_i,
+                              const int32_t* pat_j, double* vals, int64_t* visited) {
+    CSP_CHECK(check_nodes(t, node_ids, nb));
+    if (t->v.p != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "sparse coefficients_p output is defined for p == 2 (symmetric matrices)");
+    if (skip < 0 || npat < 0 || (npat > 0 && (!pat_i || !pat_j || !vals))) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    const int n = t->v.n;
+    std::vector<int> slot((size_t)n * n, -1);
+    for (int k = 0; k < npat; ++k) {
+        if (!(1 <= pat_i[k] && pat_i[k] < pat_j[k] && pat_j[k] <= n))
+            return csp_set_error(CSP_ERR_INVALID, "pattern entry %d = (%d, %d) must satisfy 1 <= i < j <= n", k, pat_i[k], pat_j[k]);
+        slot[(size_t)(pat_i[k] - 1) * n + (pat_j[k] - 1)] = k;
+    }
+    if (nb == 0) return CSP_OK;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    const long long per = std::max(npat, 1);
+    const long long chunk = std::max<long long>(1, std::min<long long>(nb, (1LL << 30) / (per * 8)));
+    DevBuf dids, dQ, dvis, dslot;
+    if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
+    CSP_CHECK(dQ.alloc(chunk * per * 8));
+    CSP_CHECK(dvis.alloc(chunk * 8));
+    CSP_CHECK(dslot.alloc((size_t)n * n * 4));
+    CSP_CUDA(cudaMemcpy(dslot.p, slot.data(), (size_t)n * n * 4, cudaMemcpyHostToDevice));
+    for (long long off = 0; off < nb; off += chunk) {
+        const long long cnt = std::min(chunk, nb - off);
+        FitParams prm{};
+        prm.t = t->v;
+        prm.nb = cnt; prm.skip = skip; prm.mode = FIT_MODE_COEF;
+        if (node_ids) {
+            CSP_CUDA(cudaMemcpy(dids.p, node_ids + off, cnt * 4, cudaMemcpyHostToDevice));
+            prm.node_ids = (const int*)dids.p;
+        } else {
+            prm.node_ids = t->v.lnode + off;
+        }
+        prm.Q = (double*)dQ.p; prm.Q_stride = per; prm.q_packed = 0;
+        prm.slotmap = (const int*)dslot.p; prm.npat = npat;
+        prm.visited = (long long*)dvis.p;
+        void* scratch = nullptr;
+        int rc = launch_fit(t, prm, 0, &scratch);
+        if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (scratch) cudaFree(scratch);
+        CSP_CHECK(rc);
+        if (npat > 0) CSP_CUDA(cudaMemcpy(vals + off * npat, dQ.p, cnt * (long long)npat * 8, cudaMemcpyDeviceToHost));
         if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
     }
     return CSP_OK;

@@ -169,6 +169,21 @@ class DeviceTree:
             Cp = Cp.reshape(nb, n, n).transpose(0, 2, 1)
         return Cp, vis
 
+    def coefficients_p_sparse(self, pattern, node_ids=None, skip=0):
+        """coefficients_p! into a sparse symmetric output: pattern = [(i, j), ...] above-diagonal positions (1-based, i < j).
+        Returns (values (nb, npat) in pattern order, visited (nb,))."""
+        if node_ids is None:
+            nb, ids = self.n_leaves, None
+        else:
+            ids = np.ascontiguousarray(node_ids, np.int32)
+            nb = len(ids)
+        pi = np.ascontiguousarray([p[0] for p in pattern], np.int32)
+        pj = np.ascontiguousarray([p[1] for p in pattern], np.int32)
+        vals = np.empty((nb, len(pattern)))
+        vis = np.empty(nb, np.int64)
+        N.dchk(N.dev().csp_coefficients_p_sparse(self.h, _ptr(ids), nb, skip, len(pattern), _ptr(pi), _ptr(pj), _ptr(vals), _ptr(vis)))
+        return vals, vis
+
     def fit_models(self, skip=0):
         """Fit every leaf and keep the canonical models on the device (csp_models_fit)."""
         h = C.c_void_p()

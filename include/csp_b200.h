@@ -112,6 +112,13 @@ int csp_fit_boxes(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int
  * visited[nb] (may be NULL) = number of splits the traversal examined. */
 int csp_coefficients_p(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited);
 
+/* coefficients_p!(value, Cp, box; skip) into a SPARSE symmetric output (src/polynomials.jl:161-230 with nnz_offdiag_sym :244-259,
+ * fillnz! :261-271): only the listed above-diagonal positions (pat_i[k] < pat_j[k], 1-based) are filled and the traversal stops as soon
+ * as all of them are; a SymTridiagonal output is the pattern (i, i+1).  vals[nb*npat] in pattern order (NaN where no split supplies
+ * the pair).  Requires p == 2. */
+int csp_coefficients_p_sparse(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, int32_t npat,
+                              const int32_t* pat_i, const int32_t* pat_j, double* vals, int64_t* visited);
+
 /* ---- per-leaf models resident on the device ---------------------------------------------------------------------- */
 /* Fit every leaf and keep the canonical models (c, g, Q, b) on the device for evaluation.  p == 2: fit_quadratic;
  * p == 1: the degree-1 model c = value(leaf), g = coefficients_p(leaf), b = position(leaf). */

@@ -375,6 +375,31 @@ int cspo_coefficients_p_batch(void** boxes, long nb, int skip, double* out, long
     CSPO_CATCH
 }
 
+int cspo_coefficients_p_pattern_batch(void** boxes, long nb, int skip, int npat, const int* pat_i, const int* pat_j, double* out,
+                                      long* visited, long* used, int nthreads, double* seconds) {
+    CSPO_TRY
+    std::vector<std::pair<int, int>> pattern;
+    for (int k = 0; k < npat; ++k) pattern.emplace_back(pat_i[k], pat_j[k]);
+    auto t0 = std::chrono::steady_clock::now();
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (long l = 0; l < nb; ++l) {
+        try {
+            CoefStats st;
+            auto v = coefficients_p_pattern(kValue, (Box*)boxes[l], skip, pattern, &st);
+            std::copy(v.begin(), v.end(), out + (size_t)l * npat);
+            if (visited) visited[l] = st.visited;
+            if (used) used[l] = st.used;
+        } catch (const std::exception& e) {
+#pragma omp critical
+            err = e.what();
+        }
+    }
+    if (!err.empty()) throw JlError(ERR_ERROR, err);
+    if (seconds) *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    CSPO_CATCH
+}
+
 // find_leaf_at + canonical modelvalue with per-leaf models indexed by leaf rank (layouts as in cspo_fit_boxes_batch).
 int cspo_locate_eval_batch(void* root, const double* X, long m, int n, const double* c, const double* g, const double* Q,
                            const double* b, int* leaf_out, double* val_out, unsigned char* status, int nthreads, double* seconds) {

@@ -637,6 +637,48 @@ inline SymArray coefficients_p(const std::function<double(const Box*)>& f, Box* 
     return Cp;
 }
 
+// ---- coefficients_p! into a sparse / tridiagonal symmetric output (p = 2), src/polynomials.jl:182-230 with
+// nnz_offdiag_sym :244-259 (stored entries above the diagonal; SymTridiagonal: its n-1 off-diagonals), fillnz! :261-271 and
+// SymmetricArray getindex :440-443 (a structural zero reads 0.0, which is not NaN, so such pairs are skipped).
+// `pattern` lists the stored above-diagonal positions (i < j, 1-based); out[k] is the coefficient of pattern[k] (NaN if never set).
+inline std::vector<double> coefficients_p_pattern(const std::function<double(const Box*)>& f, Box* box, int skip,
+                                                  const std::vector<std::pair<int, int>>& pattern, CoefStats* stats = nullptr) {
+    if (box->p != 2) throw JlError(ERR_DIMMISMATCH, "DimensionMismatch: output should be 2-dimensional");
+    const double NaN = std::numeric_limits<double>::quiet_NaN();
+    int n = ndims(box);
+    std::vector<int> slot((size_t)n * n, -1);
+    for (size_t k = 0; k < pattern.size(); ++k) {
+        int i = pattern[k].first, j = pattern[k].second;
+        if (!(1 <= i && i < j && j <= n)) throw JlError(ERR_ARGUMENT, "pattern entries must satisfy 1 <= i < j <= n");
+        slot[(size_t)(i - 1) * n + (j - 1)] = (int)k;
+    }
+    std::vector<double> out(pattern.size(), NaN);
+    long nremaining = (long)pattern.size();
+    SplitCursor cur = skipsplits(box, skip);
+    auto result = cur.next();
+    while (result.ok) {
+        Split* split = result.split;
+        result = cur.next();
+        if (stats) stats->visited++;
+        int d1 = split->dims[0], d2 = split->dims[1];
+        if (std::max(d1, d2) > n) continue;
+        int lo = std::min(d1, d2), hi = std::max(d1, d2);
+        int k = lo == hi ? -1 : slot[(size_t)(lo - 1) * n + (hi - 1)];
+        if (k >= 0 && std::isnan(out[k])) {  // isnan(Cp[dims...])
+            double denom = 1.0;
+            for (size_t q = 0; q < 2; ++q) denom *= split->xs[q] - position(split->self, split->dims[q]);
+            double num = 0.0;
+            const int sgn[4] = {1, -1, -1, 1};
+            for (int ichild = 0; ichild < 4; ++ichild) num += (double)sgn[ichild] * f(getchild(split, ichild));
+            out[k] = num / denom;
+            nremaining -= 1;
+            if (stats) stats->used++;
+        }
+        if (nremaining <= 0) break;
+    }
+    return out;
+}
+
 // ---- chi / Qcoef helpers, src/cs2.jl:277-285, 302-325.  prec is n x n column-major bools: prec[i,j] -> prec[(j-1)*n+(i-1)]
 struct Prec {
     int n = 0;

@@ -455,6 +455,25 @@ def coefficients_p_batch(boxes, skip=0, nthreads=1):
     return out, vis, sec.value
 
 
+def coefficients_p_pattern_batch(boxes, pattern, skip=0, nthreads=1):
+    """coefficients_p! into a sparse symmetric output with the given above-diagonal pattern [(i, j), ...] (1-based, i < j).
+    Returns (values (nb, npat), visited, used, seconds)."""
+    nb, npat = len(boxes), len(pattern)
+    pi = np.ascontiguousarray([p[0] for p in pattern], np.int32)
+    pj = np.ascontiguousarray([p[1] for p in pattern], np.int32)
+    out = np.zeros((nb, max(npat, 1)))[:, :npat].copy()
+    vis, used = np.zeros(nb, np.int64), np.zeros(nb, np.int64)
+    sec = C.c_double()
+    _chk(lib().cspo_coefficients_p_pattern_batch(_boxarr(boxes), C.c_long(nb), skip, npat, _ip(pi), _ip(pj), _dp(out),
+                                                 vis.ctypes.data_as(C.POINTER(C.c_long)), used.ctypes.data_as(C.POINTER(C.c_long)),
+                                                 nthreads, C.byref(sec)))
+    return out, vis, used, sec.value
+
+
+def tridiagonal_pattern(n):
+    return [(i, i + 1) for i in range(1, n)]
+
+
 def locate_eval_batch(root, X, c, g, Qdata, b, nthreads=1):
     """Qdata: (nl, n, n) with Qdata[l][i][j] = SymmetricArray .data[i,j] (as returned by fit_boxes_batch)."""
     X = np.ascontiguousarray(X, np.float64)

@@ -523,3 +523,46 @@ def test_native_model_reproduces_every_leaf(n):
     ovals = np.array([O.modelvalue_native(c, g, Q.data, b, y, prec, p) for p in P])
     assert same(vals, ovals)
     assert cb.modelvalue_native(c, g, Q, b, y, prec, P[0]) == ovals[0]
+
+
+@pytest.mark.parametrize("n,npoints", [(4, 12), (10, 300), (21, 60), (300, 4)])
+def test_sparse_pattern_coefficients_bit_exact(n, npoints):
+    """coefficients_p! into SymTridiagonal / sparse symmetric outputs (src/polynomials.jl:244-271,
+    runtests.jl:652-700): values and the number of splits examined bit-exact vs the oracle, for leaves and internal boxes."""
+    root, oroot, _ = grow_both(n, 2, npoints, seed=500 + n, sigma=0.0)
+    dt = cb.device_tree(root)
+    oall = [b for b in O.collect(oroot) if not O.isfake(b)]
+    rng = np.random.default_rng(n)
+    pick = rng.choice(len(oall), size=min(300, len(oall)), replace=False)
+    boxes = [oall[i] for i in pick]
+    ids = np.array([O.preorder_id(b) for b in boxes], np.int32)
+    pats = [O.tridiagonal_pattern(n)]
+    allp = [(i, j) for i in range(1, n + 1) for j in range(i + 1, n + 1)]
+    sel = rng.choice(len(allp), size=min(len(allp), 3 * n), replace=False)
+    pats.append([allp[k] for k in sel])
+    pats.append([])  # an empty pattern determines nothing and examines at most one split
+    for pat in pats:
+        for skip in (0, 2):
+            vals, vis = dt.coefficients_p_sparse(pat, node_ids=ids, skip=skip)
+            ovals, ovis, _, _ = O.coefficients_p_pattern_batch(boxes, pat, skip=skip, nthreads=O.max_threads())
+            assert same(vals, ovals), (len(pat), skip)
+            assert same(vis, ovis), (len(pat), skip)
+
+
+def test_sparse_hessian_reference_case():  # runtests.jl:652-700 through the public API
+    fsparse = lambda x: float(np.sum(np.diff(x) ** 2) / 2)
+    x0 = np.array([0.1, 0.2, 0.3, 0.4])
+    root = cb.Box(cb.World(x0, fsparse), 2)
+    cb.addpoint(root, 2 * x0, [(1, 3), (2, 4)], fsparse)
+    cb.addpoint(root, 3 * x0, [(2, 3), (1, 4)], fsparse)
+    cb.addpoint(root, 4 * x0, [(1, 4), (2, 3)], fsparse)
+    box = cb.addpoint(root, 5 * x0, [(1, 2), (3, 4)], fsparse)
+    ev = cb.coefficients_p_sparse(box, "tridiagonal")
+    assert np.allclose(ev, -1)
+    sp = cb.coefficients_p_sparse(box, [(1, 2), (2, 3), (3, 4), (1, 4)])
+    assert all(abs(sp[(i, i + 1)] + 1) < 1e-12 for i in (1, 2, 3)) and abs(sp[(1, 4)]) < 1e-8
+    Q = cb.coefficients_p(box)
+    assert all(Q[i, i + 1] == sp[(i, i + 1)] for i in (1, 2, 3)) and np.isnan(Q[1, 1])
+    vals, vis = cb.device_tree(root).coefficients_p_sparse([(1, 2), (2, 3), (3, 4)], [cb.node_id(box)])
+    dense_vis = cb.device_tree(root).coefficients_p([cb.node_id(box)])[1]
+    assert vis[0] <= dense_vis[0]

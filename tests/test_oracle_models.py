@@ -298,3 +298,23 @@ def test_cs2_full_models(n):  # runtests.jl:824-859 (dimlists chosen at random i
         assert np.allclose(Q2s, B, rtol=1e-6, atol=1e-8)
         assert np.allclose(g2, Q2s @ b2, rtol=1e-6, atol=1e-8)
     assert nfit >= 5
+
+
+def test_sparse_hessian_patterns():  # runtests.jl:679-699: SymTridiagonal (hesscount 12) and sparse SymmetricArray (16) outputs
+    fsparse = lambda x: float(np.sum(np.diff(x) ** 2) / 2)
+    x0 = np.array([0.1, 0.2, 0.3, 0.4])
+    world = O.World.unbounded(x0, fsparse)
+    root = O.Box(world, 2)
+    O.addpoint(root, 2 * x0, [(1, 3), (2, 4)], fsparse)
+    O.addpoint(root, 3 * x0, [(2, 3), (1, 4)], fsparse)
+    O.addpoint(root, 4 * x0, [(1, 4), (2, 3)], fsparse)
+    box = O.addpoint(root, 5 * x0, [(1, 2), (3, 4)], fsparse)
+    vals, vis, used, _ = O.coefficients_p_pattern_batch([box], O.tridiagonal_pattern(4))
+    assert np.allclose(vals[0], -1) and used[0] * 4 == 12
+    # sparse([1,1,2,2,3,3,4,1], [1,2,2,3,3,4,4,4], ...): above-diagonal stored entries (1,2),(2,3),(3,4),(1,4); nnz_offdiag_sym == 4
+    pat = [(1, 2), (2, 3), (3, 4), (1, 4)]
+    vals, vis, used, _ = O.coefficients_p_pattern_batch([box], pat)
+    assert np.allclose(vals[0][:3], -1) and abs(vals[0][3]) < 1e-8 and used[0] * 4 == 16
+    # the pattern output agrees with the dense output on the stored entries and stops earlier
+    Q, dvis, dused = O.coefficients_p(box, stats=True)
+    assert all(vals[0][k] == O.sym_get(Q, *pat[k]) for k in range(4)) and vis[0] <= dvis
