@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                 for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
                 for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
                 nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - skip : max(0, tpos - skip);
+                if (npairs == 0) nvisited = t.n_internal > skip ? 1 : 0;  // nothing to determine: the reference looks at one split and stops
             }
 
             // ---- coefficients_p values (src/polynomials.jl:211-226), one lane per slot
