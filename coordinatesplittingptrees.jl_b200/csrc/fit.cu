@@ -335,7 +335,6 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                 for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
                 for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
                 nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - skip : max(0, tpos - skip);
-                if (npairs == 0) nvisited = t.n_internal > skip ? 1 : 0;  // nothing to determine: the reference looks at one split and stops
             }
 
             // ---- coefficients_p values (src/polynomials.jl:211-226), one lane per slot
@@ -365,7 +364,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     Qo[e] = v;
                 }
             }
-            sawnan = __any_sync(FULL, sawnan);
+            sawnan = __any_sync(FULL, sawnan) || npairs == 0;  // nothing to determine: replay the reference's loop literally
             __syncwarp();
             if (sawnan) {
                 // A computed coefficient was NaN (non-finite samples or a vanishing denominator).  The reference then keeps
@@ -384,9 +383,8 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                             if (P == 2) {
                                 const int d0 = t.idims[2 * id], d1 = t.idims[2 * id + 1];
                                 if (d0 > n || d1 > n) continue;
-                                if (prm.slotmap) {
+                                if (prm.slotmap) {  // a structural zero reads 0.0, not NaN: nothing is set, but the exit test below runs
                                     slot = d0 == d1 ? -1 : prm.slotmap[(min(d0, d1) - 1) * n + max(d0, d1) - 1];
-                                    if (slot < 0) continue;  // a structural zero reads 0.0, not NaN
                                 } else {
                                     slot = qi(d0 - 1, d1 - 1);
                                 }
@@ -395,10 +393,12 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                                 if (d0 > n) continue;
                                 slot = d0 - 1;
                             }
-                            const double cur = Qo[slot];
-                            if (cur != cur) {
-                                Qo[slot] = P == 2 ? coef_value<2>(t, id) : coef_value<1>(t, id);
-                                nrem -= 1;
+                            if (slot >= 0) {
+                                const double cur = Qo[slot];
+                                if (cur != cur) {
+                                    Qo[slot] = P == 2 ? coef_value<2>(t, id) : coef_value<1>(t, id);
+                                    nrem -= 1;
+                                }
                             }
                             if (nrem <= 0) return true;
                         }
