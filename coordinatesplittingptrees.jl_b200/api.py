@@ -176,6 +176,28 @@ def modelvalue_native(c, g, Q, b, y, prec, x):
     return float(out[0]) if single else out
 
 
+def possemidef(Q):
+    """possemidef(Q) (reference src/posdef.jl:41-68): the full symmetric matrix with the off-diagonals of Q and diagonals raised as
+    needed to make it positive semi-definite; NaN entries count as 0.  Q: SymmetricArray or an n x n array whose sorted-index
+    (upper) triangle holds the values.  Runs on the GPU."""
+    Qd = np.asarray(Q.data if isinstance(Q, SymmetricArray) else Q, np.float64)
+    n = Qd.shape[0]
+    mo = LeafModels.upload(np.zeros(1), np.zeros((1, n)), Qd[None], np.zeros((1, n)))
+    try:
+        out = mo.possemidef().download()["Q"][0]
+    finally:
+        mo.close()
+    U = np.triu(out)
+    return U + np.triu(out, 1).T
+
+
+def minimum(root):
+    """minimum(root): the leaf with the smallest value (reference src/CoordinateSplittingPTrees.jl:64-66)."""
+    f = root.tree.flat()
+    v = f["val"][f["leaf_nodes"]]
+    return root._mk(f["box_of_pre"][f["leaf_nodes"][int(np.argmin(v))]])
+
+
 def fit_leaves(root, skip=0):
     """Batched fit of every leaf, models kept on the device (LeafModels)."""
     return device_tree(root).fit_models(skip=skip)

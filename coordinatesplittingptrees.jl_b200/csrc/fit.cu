@@ -522,6 +522,49 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     }
 }
 
+// ---- possemidef (reference src/posdef.jl:41-68), in place on the resident model records ------------------------------
+// One warp per model, one lane per diagonal entry k: its additions happen in the reference's order (as row index i = k for
+// the columns j < k, then as column index j = k for the rows i > k).  Off-diagonals are untouched.  The record stores the
+// diagonal halved (common.cuh), so Q_kk = 2 * A_kk on the way in and A_kk = Q_kk / 2 on the way out (both exact).
+__device__ __forceinline__ double jl_sign(double q) { return q > 0 ? 1.0 : (q < 0 ? -1.0 : q); }
+__global__ void __launch_bounds__(256) k_possemidef(double* __restrict__ data, int n, int stride, long long n_models) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5, nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long m = warp; m < n_models; m += nwarps) {
+        double* A = data + m * stride + n;
+        auto off = [&](int i, int j) { const int lo = min(i, j), hi = max(i, j); return lo * (n + 1) - lo * (lo - 1) / 2 + (hi - lo); };
+        double newd[32];  // this lane's diagonal entries k = lane, lane + 32, ... (n <= 1024 handled in passes of 32 per lane)
+        for (int base = 0; base < n; base += 32 * 32) {
+            int cnt = 0;
+            for (int k = base + lane; k < n && cnt < 32; k += 32, ++cnt) {
+                const double qkk = fabs(2.0 * A[off(k, k)]);
+                double acc = 0.0;
+                for (int j = 0; j < k; ++j) {  // k plays i: Qp[i,i] += q / r with r from (qjj, qii)
+                    const double q = A[off(k, j)];
+                    if ((q == 0) | (q != q)) continue;
+                    const double qjj = fabs(2.0 * A[off(j, j)]);
+                    double r = jl_sign(q) * sqrt(qjj / qkk);
+                    if (r == 0 || !isfinite(r)) r = jl_sign(q);
+                    acc = acc + q / r;
+                }
+                for (int i = k + 1; i < n; ++i) {  // k plays j: Qp[j,j] += q * r
+                    const double q = A[off(i, k)];
+                    if ((q == 0) | (q != q)) continue;
+                    const double qii = fabs(2.0 * A[off(i, i)]);
+                    double r = jl_sign(q) * sqrt(qkk / qii);
+                    if (r == 0 || !isfinite(r)) r = jl_sign(q);
+                    acc = acc + q * r;
+                }
+                newd[cnt] = (acc != acc || qkk != qkk) ? acc + qkk : (acc > qkk ? acc : qkk);  // Julia max(): NaN-propagating
+            }
+            __syncwarp();  // every lane has read the old diagonal before anyone overwrites it
+            cnt = 0;
+            for (int k = base + lane; k < n && cnt < 32; k += 32, ++cnt) A[off(k, k)] = newd[cnt] * 0.5;
+            __syncwarp();
+        }
+    }
+}
+
 // ---- native-form model evaluation (reference src/cs2.jl:142-153 with Qcoef_value :302-312) --------------------------------
 // One thread per query point, the reference's loop order (j outer, i = j..n inner), no FMA contraction (this TU).
 __global__ void __launch_bounds__(256) k_modelvalue_native(int n, double c, const double* __restrict__ g, const double* __restrict__ Q,
@@ -817,6 +860,18 @@ int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
     if (scratch) cudaFree(scratch);
     if (rc != CSP_OK) return fail(rc);
     *out = mo;
+    return CSP_OK;
+}
+
+int csp_models_possemidef(csp_models* mo, void* stream) {
+    if (!mo) return csp_set_error(CSP_ERR_INVALID, "models is NULL");
+    if (mo->degree != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "possemidef needs quadratic (degree-2) models");
+    if (mo->n > 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "possemidef kernel supports n <= 1024");
+    DeviceGuard dg(mo->device);
+    const long long blocks = std::min<long long>((mo->n_models + 7) / 8, 148 * 8);
+    k_possemidef<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, (cudaStream_t)stream>>>(mo->data, mo->n, mo->stride, mo->n_models);
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
     return CSP_OK;
 }
 

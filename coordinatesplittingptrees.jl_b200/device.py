@@ -249,6 +249,11 @@ class LeafModels:
             out["Q"] = Q.reshape(nl, n, n).transpose(0, 2, 1)
         return out
 
+    def possemidef(self, stream=None):
+        """possemidef (reference src/posdef.jl:41-68) of every model's Q, in place on the device."""
+        N.dchk(N.dev().csp_models_possemidef(self.h, _stream_ptr(stream)))
+        return self
+
     def evaluate(self, X, leaf, val=None, stream=None):
         """modelvalue of model leaf[i] at X[i] (K3, leaf ids supplied)."""
         shape = tuple(X.shape)

@@ -129,6 +129,9 @@ int csp_models_refit(const csp_tree* tree, int32_t skip, csp_models* models, voi
 /* Models supplied by the caller (host arrays, layouts as in csp_fit_boxes; Q may be NULL for degree-1 models). */
 int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double* g, const double* Q, const double* b,
                       csp_models** out);
+/* possemidef(Q) (src/posdef.jl:41-68) applied in place to the Q of every resident model: off-diagonals kept, diagonals raised as
+ * needed to make Q positive semi-definite (NaN off-diagonals count as 0).  Asynchronous on `stream`. */
+int csp_models_possemidef(csp_models* models, void* stream);
 int csp_models_download(const csp_models* models, double* c, double* g, double* Q, double* b, uint8_t* status);
 /* info[0..3] = n, n_models, degree (1|2), device */
 int csp_models_info(const csp_models* models, int64_t info[4]);

@@ -400,6 +400,17 @@ int cspo_coefficients_p_pattern_batch(void** boxes, long nb, int skip, int npat,
     CSPO_CATCH
 }
 
+// possemidef for a batch of matrices in the SymmetricArray .data layout (nb x n*n, column-major each); out: full matrices
+int cspo_possemidef_batch(int n, long nb, const double* Q, double* out) {
+    CSPO_TRY
+    for (long l = 0; l < nb; ++l) {
+        SymArray S = mksym(n, Q + (size_t)l * n * n);
+        auto r = possemidef(S);
+        std::copy(r.begin(), r.end(), out + (size_t)l * n * n);
+    }
+    CSPO_CATCH
+}
+
 // find_leaf_at + canonical modelvalue with per-leaf models indexed by leaf rank (layouts as in cspo_fit_boxes_batch).
 int cspo_locate_eval_batch(void* root, const double* X, long m, int n, const double* c, const double* g, const double* Q,
                            const double* b, int* leaf_out, double* val_out, unsigned char* status, int nthreads, double* seconds) {

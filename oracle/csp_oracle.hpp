@@ -955,6 +955,35 @@ inline void fit_quadratic_gdiag(const std::function<double(const Box*)>& f, SymA
     }
 }
 
+// ---- possemidef, src/posdef.jl:41-68.  Q is read through SymmetricArray getindex; the result is the full
+// symmetric matrix `copy(Q)` with adjusted diagonal (column-major n x n).
+inline std::vector<double> possemidef(const SymArray& Q) {
+    const int n = Q.n;
+    auto sgn = [](double q) { return q > 0 ? 1.0 : (q < 0 ? -1.0 : q); };                    // Julia sign()
+    auto jlmax = [](double a, double b) { return (a != a || b != b) ? a + b : (a > b ? a : b); };  // Julia max(): NaN-propagating
+    std::vector<double> Qp((size_t)n * n);
+    for (int j = 1; j <= n; ++j)
+        for (int i = 1; i <= n; ++i) Qp[(size_t)(j - 1) * n + (i - 1)] = Q.get2(i, j);
+    for (int i = 1; i <= n; ++i) Qp[(size_t)(i - 1) * n + (i - 1)] = 0;
+    for (int j = 1; j <= n; ++j) {
+        double qjj = std::fabs(Q.get2(j, j));
+        for (int i = j + 1; i <= n; ++i) {
+            double q = Q.get2(i, j);
+            if ((q == 0) | (q != q)) continue;
+            double qii = std::fabs(Q.get2(i, i));
+            double r = sgn(q) * std::sqrt(qjj / qii);
+            if (r == 0 || !std::isfinite(r)) r = sgn(q);
+            Qp[(size_t)(j - 1) * n + (j - 1)] += q * r;
+            Qp[(size_t)(i - 1) * n + (i - 1)] += q / r;
+        }
+    }
+    for (int i = 1; i <= n; ++i) {
+        double& d = Qp[(size_t)(i - 1) * n + (i - 1)];
+        d = jlmax(d, std::fabs(Q.get2(i, i)));
+    }
+    return Qp;
+}
+
 // ---- addpoint! (4-argument form), src/CoordinateSplittingPTrees.jl:94-142
 inline Box* addpoint(Box* box, const double* x, int lenx, const std::vector<std::vector<int>>& dimlists, const Objective& metagen) {
     int n = ndims(box);

@@ -470,6 +470,20 @@ def coefficients_p_pattern_batch(boxes, pattern, skip=0, nthreads=1):
     return out, vis, used, sec.value
 
 
+def possemidef(Qdata):
+    """possemidef (posdef.jl:41-68) of matrices given in the SymmetricArray .data layout: Qdata (nb, n, n) with Qdata[l][i][j] =
+    data[i,j] (values at i <= j).  Returns the full adjusted matrices (nb, n, n)."""
+    Q = np.asarray(Qdata, np.float64)
+    single = Q.ndim == 2
+    Q = Q[None] if single else Q
+    nb, n, _ = Q.shape
+    Qf = np.ascontiguousarray(Q.transpose(0, 2, 1))
+    out = np.zeros_like(Qf)
+    _chk(lib().cspo_possemidef_batch(n, C.c_long(nb), _dp(Qf), _dp(out)))
+    out = out.transpose(0, 2, 1)
+    return out[0] if single else out
+
+
 def tridiagonal_pattern(n):
     return [(i, i + 1) for i in range(1, n)]
 

@@ -566,3 +566,32 @@ def test_sparse_hessian_reference_case():  # runtests.jl:652-700 through the pub
     vals, vis = cb.device_tree(root).coefficients_p_sparse([(1, 2), (2, 3), (3, 4)], [cb.node_id(box)])
     dense_vis = cb.device_tree(root).coefficients_p([cb.node_id(box)])[1]
     assert vis[0] <= dense_vis[0]
+
+
+def test_possemidef_goldens_and_batch():
+    """possemidef (src/posdef.jl:41-68) on the GPU: the reference's exact cases (runtests.jl:933-948) and a batch of
+    fitted leaf models, bit-exact vs the oracle."""
+    assert np.array_equal(cb.possemidef(np.array([[4.0, 1], [1, 4]])), [[4, 1], [1, 4]])
+    assert np.array_equal(cb.possemidef(np.array([[1.0, 4], [4, 1]])), [[4, 4], [4, 4]])
+    assert np.array_equal(cb.possemidef(np.array([[4.5, 3], [3, 0.5]])), [[9, 3], [3, 1]])
+    Qp = cb.possemidef(np.array([[0.0, 2], [2, 1]]))
+    assert np.isfinite(Qp).all() and Qp[0, 1] == 2
+    np.linalg.cholesky(Qp)
+    for n, npts in ((7, 60), (10, 200), (40, 6)):
+        root, oroot, _ = grow_both(n, 2, npts, seed=600 + n)
+        models = cb.device_tree(root).fit_models()
+        before = models.download()
+        after = models.possemidef().download()
+        ok = before["status"] == 0
+        oQp = O.possemidef(before["Q"][ok])
+        got = after["Q"][ok]
+        got_full = np.triu(got) + np.triu(got, 1).transpose(0, 2, 1)
+        assert same(got_full, oQp)
+        for k in ("c", "g", "b"):
+            assert same(after[k], before[k])
+        fin = np.isfinite(oQp).all(axis=(1, 2))
+        if fin.any():
+            ev = np.linalg.eigvalsh(oQp[fin])
+            assert ev.min() > -1e-8 * np.abs(oQp[fin]).max()
+    leaf = cb.minimum(root)
+    assert cb.value(leaf) == min(cb.value(l) for l in cb.leaves(root))

@@ -318,3 +318,21 @@ def test_sparse_hessian_patterns():  # runtests.jl:679-699: SymTridiagonal (hess
     # the pattern output agrees with the dense output on the stored entries and stops earlier
     Q, dvis, dused = O.coefficients_p(box, stats=True)
     assert all(vals[0][k] == O.sym_get(Q, *pat[k]) for k in range(4)) and vis[0] <= dvis
+
+
+def test_possemidef_goldens():  # runtests.jl:933-948 ("posdef"), exact equality as in the reference
+    assert np.array_equal(O.possemidef(np.array([[4.0, 1], [1, 4]])), [[4, 1], [1, 4]])
+    assert np.array_equal(O.possemidef(np.array([[1.0, 4], [4, 1]])), [[4, 4], [4, 4]])
+    assert np.array_equal(O.possemidef(np.array([[4.5, 3], [3, 0.5]])), [[9, 3], [3, 1]])
+    Qp = O.possemidef(np.array([[0.0, 2], [2, 1]]))
+    assert np.isfinite(Qp).all() and Qp[0, 1] == 2
+    np.linalg.cholesky(Qp)
+    # only the SymmetricArray (sorted-index) triangle is read
+    assert np.array_equal(O.possemidef(np.array([[1.0, 4], [np.nan, 1]])), [[4, 4], [4, 4]])
+    # NaN off-diagonals are treated as 0 (and stay NaN in the copy); random matrices become positive semi-definite
+    rng = np.random.default_rng(0)
+    for n in (3, 6, 11):
+        A = rng.standard_normal((n, n)); A = (A + A.T) / 2
+        Qp = O.possemidef(np.triu(A))
+        assert np.allclose(Qp - np.diag(np.diag(Qp)), A - np.diag(np.diag(A)))
+        assert np.linalg.eigvalsh(Qp).min() > -1e-9 * np.abs(Qp).max()
