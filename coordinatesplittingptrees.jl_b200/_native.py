@@ -122,6 +122,7 @@ def dev():
         L.csp_find_leaf_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
         L.csp_fit_boxes.argtypes = [vp, vp, C.c_int64, C.c_int32] + [vp] * 8
         L.csp_coefficients_p.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
+        L.csp_fit_gdiag.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
         L.csp_coefficients_p_sparse.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp]
         L.csp_models_fit.argtypes = [vp, C.c_int32, vpp]
         L.csp_models_refit.argtypes = [vp, C.c_int32, vp, vp]
@@ -148,4 +149,4 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_fit_boxes", "csp_coefficients_p", "csp_models_fit", "csp_models_refit", "csp_models_upload", "csp_models_download", "csp_models_info",
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
            "csp_timing_read", "csp_modelvalue_native", "csp_coefficients_p_sparse",
-           "csp_models_possemidef"]
+           "csp_models_possemidef", "csp_fit_gdiag"]

@@ -119,6 +119,14 @@ def coefficients_p(box, skip=0):
     return SymmetricArray(Cp[0])
 
 
+def fit_quadratic_gdiag(box, skip=0):
+    """(c, g, Q, b) from Q = coefficients_p(box) followed by fit_quadratic_gdiag!(Q, box) (reference src/cs2.jl:332-384): the
+    chain-free alternative to fit_quadratic (no "no chain found" failures; b = position(box))."""
+    _require_cs2(box)
+    r = device_tree(box).fit_gdiag([T.node_id(box)], skip=skip)
+    return float(r["c"][0]), r["g"][0], SymmetricArray(r["Q"][0]), r["b"][0]
+
+
 def coefficients_p_sparse(box, pattern, skip=0):
     """coefficients_p!(Cp, box) with a sparse symmetric Cp (reference src/polynomials.jl:161-230, :244-271): `pattern` is either
     the string "tridiagonal" (SymTridiagonal: returns its off-diagonal vector ev) or a list of above-diagonal positions (i, j),

@@ -522,6 +522,124 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     }
 }
 
+// ---- fit_quadratic_gdiag! (reference src/cs2.jl:332-384): chain-free gradient + diagonal from two 1-d equations per dim ----
+// One warp per box; Q (dense .data layout) arrives holding coefficients_p's off-diagonals.  For every dimension d the reference
+// keeps the first two splits (in splits(box) order, after `skip`) that involve d, have finite data and -- for the second --
+// a different xcoef than the first.  Lanes evaluate the candidates of a 32-split chunk in parallel (each an O(n) sequential
+// sum in the reference's order); one lane per dimension then replays the chunk's candidates in order.
+struct GdiagParams {
+    TreeView t;
+    const int* node_ids;
+    long long nb;
+    int skip;
+    double* c; double* g; double* Q; double* b;  // box-major: c[nb], g[nb*n], Q[nb*n*n] (in/out), b[nb*n]
+    int warp_smem_bytes;
+};
+
+__global__ void __launch_bounds__(256) k_gdiag(const GdiagParams prm) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const TreeView& t = prm.t;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
+    const int n = t.n;
+    const unsigned FULL = 0xffffffffu;
+    double* sb = (double*)(smem_raw + (size_t)wib * prm.warp_smem_bytes);
+    double *q1 = sb + n, *q2 = q1 + n, *r1 = q2 + n, *r2 = r1 + n;
+    double* cx = r2 + n;      // [64] candidate xcoef
+    double* cf = cx + 64;     // [64] candidate fd
+    int* cd = (int*)(cf + 64);  // [64] candidate dimension (1-based) or 0
+    for (long long bi = (long long)blockIdx.x * W + wib; bi < prm.nb; bi += (long long)gridDim.x * W) {
+        const int box = prm.node_ids ? prm.node_ids[bi] : t.lnode[bi];
+        double* Qo = prm.Q + bi * (long long)n * n;
+        // b = position(box), c = value(box)
+        const int4 binfo = t.ninfo[box];
+        const bool isroot = binfo.x == box, internal = !(binfo.w & CSP_NF_LEAF);
+        const int Ip = t.ninfo[binfo.x].y, ci = CSP_NF_CHILDINDEX(binfo.w);
+        for (int i = lane; i < n; i += 32) {
+            double bb;
+            if (internal) bb = t.ipos[(size_t)binfo.y * n + i];
+            else if (isroot) bb = dnan();
+            else {
+                bb = t.ipos[(size_t)Ip * n + i];
+                if ((ci & 1) && t.idims[2 * Ip] - 1 == i) bb = t.ixs[2 * Ip];
+                if ((ci & 2) && t.idims[2 * Ip + 1] - 1 == i) bb = t.ixs[2 * Ip + 1];
+            }
+            sb[i] = bb;
+            q1[i] = q2[i] = r1[i] = r2[i] = dnan();
+        }
+        __syncwarp();
+        int tpos = 0;
+        for_split_groups(t, box, [&](const RangeGroup& grp) -> bool {
+            const int total = grp.total();
+            for (int base = 0; base < total; base += 32) {
+                const int v = base + lane;
+                const int pos = tpos + lane;
+                const bool act = v < total && pos >= prm.skip;
+                cd[2 * lane] = cd[2 * lane + 1] = 0;
+                if (act) {
+                    const int id = grp.id(v);
+                    const double* __restrict__ x = t.ipos + (size_t)id * n;
+                    const double f0 = t.icval[4 * id];
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int d = t.idims[2 * id + i];
+                        if (d > n || !(q2[d - 1] != q2[d - 1])) continue;  // fictive, or both equations already known
+                        const double xs = t.ixs[2 * id + i];
+                        const double xd = x[d - 1];
+                        const double xcoef = (xd + xs) / 2 - sb[d - 1];
+                        const double dx = xs - xd;
+                        double fd = (t.icval[4 * id + 1 + i] - f0) / dx;
+                        for (int j = 0; j < n; ++j) {
+                            if (j == d - 1) continue;
+                            const int lo = min(d - 1, j), hi = max(d - 1, j);
+                            fd = fd - Qo[(size_t)hi * n + lo] * (x[j] - sb[j]);
+                        }
+                        cd[2 * lane + i] = d; cx[2 * lane + i] = xcoef; cf[2 * lane + i] = fd;
+                    }
+                }
+                __syncwarp();
+                for (int dd = lane; dd < n; dd += 32) {
+                    if (!(q2[dd] != q2[dd])) continue;
+                    for (int sidx = 0; sidx < 64; ++sidx) {
+                        if (cd[sidx] != dd + 1) continue;
+                        const double xcoef = cx[sidx], fd = cf[sidx];
+                        if (xcoef == q1[dd]) continue;  // not independent of the first equation
+                        if (isfinite(xcoef) && isfinite(fd)) {
+                            if (q1[dd] != q1[dd]) { q1[dd] = xcoef; r1[dd] = fd; }
+                            else { q2[dd] = xcoef; r2[dd] = fd; break; }
+                        }
+                    }
+                }
+                __syncwarp();
+                bool pending = false;
+                for (int dd = lane; dd < n; dd += 32) pending |= (q2[dd] != q2[dd]);
+                tpos += min(32, total - base);
+                if (!__any_sync(FULL, pending)) return true;
+            }
+            return false;
+        });
+        __syncwarp();
+        for (int d = lane; d < n; d += 32) {
+            double gd = dnan();
+            if (!(q2[d] != q2[d])) {  // manual inverse of the 2x2 system (a11 = a21 = 1)
+                const double a12 = q1[d], a22 = q2[d], rr1 = r1[d], rr2 = r2[d];
+                const double det = a22 - a12;
+                gd = (a22 * rr1 - a12 * rr2) / det;
+                Qo[(size_t)d * n + d] = (-rr1 + rr2) / det;
+            }
+            prm.g[bi * n + d] = gd;
+            prm.b[bi * n + d] = sb[d];
+        }
+        if (lane == 0) {
+            double cv;
+            if (internal) cv = t.icval[4 * (size_t)binfo.y];
+            else if (isroot) cv = dnan();
+            else cv = t.icval[4 * (size_t)Ip + ci];
+            prm.c[bi] = cv;
+        }
+        __syncwarp();
+    }
+}
+
 // ---- possemidef (reference src/posdef.jl:41-68), in place on the resident model records ------------------------------
 // One warp per model, one lane per diagonal entry k: its additions happen in the reference's order (as row index i = k for
 // the columns j < k, then as column index j = k for the rows i > k).  Off-diagonals are untouched.  The record stores the
@@ -860,6 +978,58 @@ int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
     if (scratch) cudaFree(scratch);
     if (rc != CSP_OK) return fail(rc);
     *out = mo;
+    return CSP_OK;
+}
+
+int csp_fit_gdiag(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q, double* b) {
+    CSP_CHECK(check_nodes(t, node_ids, nb));
+    if (t->v.p != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "fit_quadratic_gdiag! is defined for Box{2} only (reference src/cs2.jl:332)");
+    if (skip < 0 || !c || !g || !Q || !b) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    if (nb == 0) return CSP_OK;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    const int n = t->v.n;
+    const long long per = (long long)n * n * 8;
+    const long long chunk = std::max<long long>(1, std::min<long long>(nb, (2LL << 30) / per));
+    DevBuf dids, dc, dgv, dQ, db;
+    if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
+    CSP_CHECK(dc.alloc(chunk * 8)); CSP_CHECK(dgv.alloc(chunk * n * 8)); CSP_CHECK(dQ.alloc(chunk * per)); CSP_CHECK(db.alloc(chunk * n * 8));
+    const size_t per_warp = (((size_t)n * 5 + 128) * 8 + 64 * 4 + 15) & ~size_t(15);
+    const int W = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / per_warp));
+    if (per_warp * W > 200 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the gdiag kernel", n);
+    CSP_CUDA(cudaFuncSetAttribute(k_gdiag, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * W)));
+    for (long long off = 0; off < nb; off += chunk) {
+        const long long cnt = std::min(chunk, nb - off);
+        const int* ids = t->v.lnode + off;
+        if (node_ids) {
+            CSP_CUDA(cudaMemcpy(dids.p, node_ids + off, cnt * 4, cudaMemcpyHostToDevice));
+            ids = (const int*)dids.p;
+        }
+        // Q = coefficients_p(box; skip)
+        FitParams fp{};
+        fp.t = t->v; fp.node_ids = ids; fp.nb = cnt; fp.skip = skip; fp.mode = FIT_MODE_COEF;
+        fp.Q = (double*)dQ.p; fp.Q_stride = (long long)n * n; fp.q_packed = 0;
+        void* scratch = nullptr;
+        int rc = launch_fit(t, fp, 0, &scratch);
+        // fit_quadratic_gdiag!(Q, box; skip)
+        if (rc == CSP_OK) {
+            GdiagParams gp{};
+            gp.t = t->v; gp.node_ids = ids; gp.nb = cnt; gp.skip = skip;
+            gp.c = (double*)dc.p; gp.g = (double*)dgv.p; gp.Q = (double*)dQ.p; gp.b = (double*)db.p;
+            gp.warp_smem_bytes = (int)per_warp;
+            const long long grid = std::min<long long>((cnt + W - 1) / W, (long long)std::max(t->n_sm, 1) * 4);
+            k_gdiag<<<(unsigned)grid, W * 32, per_warp * W>>>(gp);
+            CSP_LAUNCHED();
+            if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+                rc = csp_set_error(CSP_ERR_CUDA, "gdiag kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (scratch) cudaFree(scratch);
+        CSP_CHECK(rc);
+        CSP_CUDA(cudaMemcpy(c + off, dc.p, cnt * 8, cudaMemcpyDeviceToHost));
+        CSP_CUDA(cudaMemcpy(g + off * n, dgv.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+        CSP_CUDA(cudaMemcpy(Q + off * (long long)n * n, dQ.p, cnt * per, cudaMemcpyDeviceToHost));
+        CSP_CUDA(cudaMemcpy(b + off * n, db.p, cnt * n * 8, cudaMemcpyDeviceToHost));
+    }
     return CSP_OK;
 }
 

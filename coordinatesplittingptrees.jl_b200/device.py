@@ -152,6 +152,18 @@ class DeviceTree:
             out.update(gnat=gn, y=y, prec=prec.reshape(nb, n, n).transpose(0, 2, 1).astype(bool))
         return out
 
+    def fit_gdiag(self, node_ids=None, skip=0):
+        """coefficients_p + fit_quadratic_gdiag! (chain-free fit) for the listed node ids (None: every leaf): dict c, g, Q, b."""
+        n = self.n
+        if node_ids is None:
+            nb, ids = self.n_leaves, None
+        else:
+            ids = np.ascontiguousarray(node_ids, np.int32)
+            nb = len(ids)
+        c, g, Q, b = np.empty(nb), np.empty((nb, n)), np.empty((nb, n * n)), np.empty((nb, n))
+        N.dchk(N.dev().csp_fit_gdiag(self.h, _ptr(ids), nb, skip, _ptr(c), _ptr(g), _ptr(Q), _ptr(b)))
+        return dict(c=c, g=g, Q=Q.reshape(nb, n, n).transpose(0, 2, 1), b=b)
+
     def coefficients_p(self, node_ids=None, skip=0):
         """coefficients_p for the listed node ids (None: every leaf): (Cp, visited); Cp is (nb,n) for p=1 and (nb,n,n)
         (.data layout, Cp[l,i,j] = data[i,j]) for p=2."""

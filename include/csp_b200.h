@@ -112,6 +112,10 @@ int csp_fit_boxes(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int
  * visited[nb] (may be NULL) = number of splits the traversal examined. */
 int csp_coefficients_p(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited);
 
+/* Q = coefficients_p(value, box; skip) followed by fit_quadratic_gdiag!(value, Q, box; skip) (src/cs2.jl:332-384): the chain-free
+ * fit -- gradient and diagonal from two 1-d difference equations per dimension, b = position(box), c = value(box).  It never
+ * fails with "no chain found"; undetermined entries are NaN.  Outputs as in csp_fit_boxes (g is already canonical).  Requires p == 2. */
+int csp_fit_gdiag(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q, double* b);
 /* coefficients_p!(value, Cp, box; skip) into a SPARSE symmetric output (src/polynomials.jl:161-230 with nnz_offdiag_sym :244-259,
  * fillnz! :261-271): only the listed above-diagonal positions (pat_i[k] < pat_j[k], 1-based) are filled and the traversal stops as soon
  * as all of them are; a SymTridiagonal output is the pattern (i, i+1).  vals[nb*npat] in pattern order (NaN where no split supplies

@@ -400,6 +400,32 @@ int cspo_coefficients_p_pattern_batch(void** boxes, long nb, int skip, int npat,
     CSPO_CATCH
 }
 
+// Q = coefficients_p(box; skip); fit_quadratic_gdiag!(Q, box; skip) for a batch of boxes (layouts as in cspo_fit_boxes_batch)
+int cspo_fit_gdiag_batch(void** boxes, long nb, int skip, double* c, double* g, double* Q, double* b, int nthreads) {
+    CSPO_TRY
+    std::string err;
+#pragma omp parallel for schedule(dynamic, 16) num_threads(nthreads)
+    for (long l = 0; l < nb; ++l) {
+        try {
+            Box* bx = (Box*)boxes[l];
+            int n = ndims(bx);
+            SymArray S = coefficients_p(kValue, bx, skip);
+            std::vector<double> bb = position(bx), gg;
+            double cc;
+            fit_quadratic_gdiag(kValue, S, bx, bb, skip, cc, gg);
+            c[l] = cc;
+            std::copy(gg.begin(), gg.end(), g + (size_t)l * n);
+            std::copy(S.data.begin(), S.data.end(), Q + (size_t)l * n * n);
+            std::copy(bb.begin(), bb.end(), b + (size_t)l * n);
+        } catch (const std::exception& e) {
+#pragma omp critical
+            err = e.what();
+        }
+    }
+    if (!err.empty()) throw JlError(ERR_ERROR, err);
+    CSPO_CATCH
+}
+
 // possemidef for a batch of matrices in the SymmetricArray .data layout (nb x n*n, column-major each); out: full matrices
 int cspo_possemidef_batch(int n, long nb, const double* Q, double* out) {
     CSPO_TRY

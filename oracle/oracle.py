@@ -470,6 +470,13 @@ def coefficients_p_pattern_batch(boxes, pattern, skip=0, nthreads=1):
     return out, vis, used, sec.value
 
 
+def fit_gdiag_batch(boxes, skip=0, nthreads=1):
+    nb, n = len(boxes), boxes[0].n
+    c, g, Q, b = np.zeros(nb), np.zeros((nb, n)), np.zeros((nb, n * n)), np.zeros((nb, n))
+    _chk(lib().cspo_fit_gdiag_batch(_boxarr(boxes), C.c_long(nb), skip, _dp(c), _dp(g), _dp(Q), _dp(b), nthreads))
+    return dict(c=c, g=g, Q=Q.reshape(nb, n, n).transpose(0, 2, 1), b=b)
+
+
 def possemidef(Qdata):
     """possemidef (posdef.jl:41-68) of matrices given in the SymmetricArray .data layout: Qdata (nb, n, n) with Qdata[l][i][j] =
     data[i,j] (values at i <= j).  Returns the full adjusted matrices (nb, n, n)."""

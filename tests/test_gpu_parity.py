@@ -595,3 +595,52 @@ def test_possemidef_goldens_and_batch():
             assert ev.min() > -1e-8 * np.abs(oQp[fin]).max()
     leaf = cb.minimum(root)
     assert cb.value(leaf) == min(cb.value(l) for l in cb.leaves(root))
+
+
+@pytest.mark.parametrize("n,npoints,skip", [(2, 40, 0), (3, 60, 0), (7, 150, 0), (8, 150, 2), (10, 300, 0), (20, 100, 0)])
+def test_fit_gdiag_bit_exact(n, npoints, skip):
+    """coefficients_p + fit_quadratic_gdiag! (src/cs2.jl:332-384), the chain-free fit, bit-exact vs the oracle for
+    every leaf and some internal boxes."""
+    root, oroot, _ = grow_both(n, 2, npoints, seed=700 + n)
+    dt = cb.device_tree(root)
+    oall = [b for b in O.collect(oroot) if not O.isfake(b)]
+    rng = np.random.default_rng(n)
+    pick = rng.choice(len(oall), size=min(400, len(oall)), replace=False)
+    boxes = [oall[i] for i in pick]
+    ids = np.array([O.preorder_id(b) for b in boxes], np.int32)
+    fit = dt.fit_gdiag(node_ids=ids, skip=skip)
+    ofit = O.fit_gdiag_batch(boxes, skip=skip, nthreads=O.max_threads())
+    for k in ("c", "g", "Q", "b"):
+        assert same(fit[k], ofit[k]), k
+    assert np.isfinite(fit["g"]).mean() > 0.5
+
+
+def test_fit_gdiag_like_reference_and_no_chain_fallback():
+    """runtests.jl:851-856: for a quadratic objective the gdiag fit recovers Q ~ B and g ~ Q*b; and it succeeds on leaves where
+    fit_quadratic raises 'no chain found' (SURVEY M7)."""
+    rng = np.random.default_rng(8)
+    n = 6
+    B = rng.standard_normal((n, n)); B = (B + B.T) / 2
+    f = cb.quadnoise_objective(B, sigma=0.0)
+    cycle = []
+    for _ in range(40):
+        perm = rng.permutation(n) + 1
+        cycle.append([(int(perm[i]), int(perm[i + 1])) for i in range(0, n, 2)])
+    lo, up = -np.ones(n), np.ones(n)
+    root = cb.Box(cb.World(lo, up, np.zeros(n), f), 2)
+    cb.addpoints(root, lo + (up - lo) * rng.random((200, n)), cycle, f)
+    dt = cb.device_tree(root)
+    st = dt.fit_boxes()["status"]
+    assert (st == 1).any()
+    g = dt.fit_gdiag()
+    det = np.isfinite(g["Q"][:, np.triu_indices(n)[0], np.triu_indices(n)[1]]).all(1) & np.isfinite(g["g"]).all(1)
+    assert det[st == 1].any()
+    for l in np.flatnonzero(det)[:200]:
+        Qf = np.triu(g["Q"][l]) + np.triu(g["Q"][l], 1).T
+        assert np.allclose(Qf, f.B, rtol=1e-5, atol=1e-7)
+        assert np.allclose(g["g"][l], Qf @ g["b"][l], rtol=1e-5, atol=1e-6)
+    leaf = cb.leaves(root)[int(np.flatnonzero(det & (st == 1))[0])]
+    with pytest.raises(cb.ErrorException):
+        cb.fit_quadratic(leaf)
+    c, gg, Q, b = cb.fit_quadratic_gdiag(leaf)
+    assert np.allclose(Q.full(), f.B, rtol=1e-5, atol=1e-7) and c == cb.value(leaf) and same(b, cb.position(leaf))
