@@ -618,17 +618,15 @@ def test_fit_gdiag_bit_exact(n, npoints, skip):
 def test_fit_gdiag_like_reference_and_no_chain_fallback():
     """runtests.jl:851-856: for a quadratic objective the gdiag fit recovers Q ~ B and g ~ Q*b; and it succeeds on leaves where
     fit_quadratic raises 'no chain found' (SURVEY M7)."""
-    rng = np.random.default_rng(8)
+    rng = np.random.default_rng(11)
     n = 6
-    B = rng.standard_normal((n, n)); B = (B + B.T) / 2
-    f = cb.quadnoise_objective(B, sigma=0.0)
     cycle = []
     for _ in range(40):
         perm = rng.permutation(n) + 1
         cycle.append([(int(perm[i]), int(perm[i + 1])) for i in range(0, n, 2)])
-    lo, up = -np.ones(n), np.ones(n)
-    root = cb.Box(cb.World(lo, up, np.zeros(n), f), 2)
-    cb.addpoints(root, lo + (up - lo) * rng.random((200, n)), cycle, f)
+    B = rng.standard_normal((n, n)); B = (B + B.T) / 2
+    f = cb.quadnoise_objective(B, sigma=0.0)
+    root, oroot, _ = grow_both(n, 2, 200, seed=11, cycle=cycle, objective=f)  # this tree has leaves without a chain (oracle-checked)
     dt = cb.device_tree(root)
     st = dt.fit_boxes()["status"]
     assert (st == 1).any()
