@@ -344,7 +344,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
     }
     CSP_LAUNCHED();
-    const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
+    const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * (8 / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_SCATTER, st);
         k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);

@@ -134,6 +134,7 @@ int csp_require_device();  // CSP_OK or CSP_ERR_NO_DEVICE
 // Optional per-kernel timing with CUDA events on the launching stream (csp_timing_enable / csp_timing_read).
 enum { CSP_K_LOCATE = 0, CSP_K_LOCATE_EVAL, CSP_K_SCAN, CSP_K_SCATTER, CSP_K_EVAL_BINNED, CSP_K_EVAL, CSP_K_FIT, CSP_K_CLASSES };
 extern bool g_csp_timing;
+extern int g_csp_grid_div;  // >1 while two chunks are in flight on two streams: persistent grids shrink so that both fit on the SMs
 void csp_timing_begin(int cls, cudaStream_t st);
 void csp_timing_end(cudaStream_t st);
 struct CspTimed {

@@ -520,7 +520,7 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
     if (prm.bounds_in_params)
         for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
     long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
-    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * g->occ);
+    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * std::max(1, g->occ / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_LOCATE, st);
         kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
@@ -620,6 +620,7 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         }
         BinWorkspace w[2];
         int rc = CSP_OK;
+        g_csp_grid_div = ns;
         if (preset) w[0] = *preset;
         for (int i = 0; i < ns && rc == CSP_OK && !preset; ++i) rc = csp_bin_alloc((int)mo->n_models, chunk, dleaf == nullptr, ss[i], &w[i]);
         long long ci = 0;
@@ -635,6 +636,7 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
             if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
         }
+        g_csp_grid_div = 1;
         if (preset) preset->epoch = w[0].epoch;
         for (int i = 0; i < ns; ++i) {
             if (!preset) csp_bin_free(&w[i], ss[i]);

@@ -30,6 +30,7 @@ int csp_require_device() {
 }
 
 bool g_csp_timing = false;
+int g_csp_grid_div = 1;
 namespace {
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 std::vector<TimedLaunch> g_timed;
