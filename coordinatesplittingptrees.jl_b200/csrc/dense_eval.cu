@@ -66,11 +66,10 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
         int seg_start = 0;
         while (seg_start < rows) {
             const int lf = s_leaf[seg_start];
-            if (tid == 0) {
-                int e = seg_start + 1;
-                while (e < rows && s_leaf[e] == lf) ++e;
-                *s_seg = e;
-            }
+            if (tid == 0) *s_seg = rows;
+            __syncthreads();
+            for (int r = seg_start + 1 + tid; r < rows; r += blockDim.x)  // end of the run of `lf`: first row with another leaf
+                if (s_leaf[r] != lf) atomicMin(s_seg, r);
             __syncthreads();
             const int seg_end = *s_seg;
             const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
@@ -79,13 +78,11 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
                 for (int i = tid; i < n; i += blockDim.x) sb[i] = __ldg(M + i);
                 __syncthreads();
                 const double* __restrict__ A = M + n;
-                const int ncoef = (n + 1) * (n + 2) / 2;
-                int i = 0, e = tid;  // packed row-major upper triangle: walk (row, offset) forward by blockDim entries
-                while (i <= n && e >= n + 1 - i) { e -= n + 1 - i; ++i; }
-                for (int k = tid; k < ncoef; k += blockDim.x) {
-                    U[(size_t)i * LD + i + e] = __ldg(A + k);
-                    e += blockDim.x;
-                    while (i <= n && e >= n + 1 - i) { e -= n + 1 - i; ++i; }
+                const int nwarps = blockDim.x >> 5;
+                for (int i = warp; i <= n; i += nwarps) {  // row i of the packed triangle: n + 1 - i coefficients, coalesced
+                    const double* __restrict__ Ar = A + (i * (n + 1) - i * (i - 1) / 2);
+                    double* Ur = U + (size_t)i * LD + i;
+                    for (int e = lane; e < n + 1 - i; e += 32) Ur[e] = __ldg(Ar + e);
                 }
                 cur_leaf = lf;
             }
@@ -100,10 +97,9 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
                     bulk_g2s(Z + (size_t)r * LD, prm.X + (size_t)(unsigned)s_q[r] * n, (uint32_t)(n * 8), bar);
                 mbar_wait(bar, phase);
                 phase ^= 1;
-                for (int idx = tid; idx < nseg * LD; idx += blockDim.x) {
-                    const int rr = idx / LD, k = idx - rr * LD;
-                    double* zp = Z + (size_t)(seg_start + rr) * LD + k;
-                    *zp = k < n ? *zp - sb[k] : (k == n ? 1.0 : 0.0);
+                for (int rr = warp; rr < nseg; rr += (int)(blockDim.x >> 5)) {  // one warp per row, lanes over columns
+                    double* zr = Z + (size_t)(seg_start + rr) * LD;
+                    for (int k = lane; k < LD; k += 32) zr[k] = k < n ? zr[k] - sb[k] : (k == n ? 1.0 : 0.0);
                 }
             } else {
                 for (int idx = tid; idx < nseg * LD; idx += blockDim.x) {

@@ -15,12 +15,18 @@ rows = list(csv.reader(io.StringIO(txt)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "Line No"]
 if not hi:
     sys.exit("no source rows (was the report captured with --import-source on and built with -lineinfo?)")
-for h in hi[:1]:
+per_all = {}
+for h in hi:
     H = rows[h]
+    fname = ""
+    for r in rows[max(0, h - 3):h]:
+        if r and r[0] == "File Path":
+            fname = r[1].split("/")[-1]
     c = {name: H.index(name) for name in ("Line No", "# Samples", "Instructions Executed") if name in H}
     stalls = [(i, n) for i, n in enumerate(H) if n.startswith("stall_") and "Not Issued" not in n]
     src_col = 1
     per = defaultdict(lambda: [0, 0, defaultdict(int), ""])
+    per_all[fname] = per
     cur_line, cur_src = None, ""
     for r in rows[h + 1:]:
         if not r or r[0] in ("File Path", "Function Name", "Line No"):
@@ -43,9 +49,10 @@ for h in hi[:1]:
                 e[2][n] += int(r[i] or 0)
             except ValueError:
                 pass
-    tot = sum(e[0] for e in per.values()) or 1
-    toti = sum(e[1] for e in per.values()) or 1
-    print(f"total samples {tot}, total warp instructions {toti}")
-    for line, e in sorted(per.items(), key=lambda kv: -kv[1][0])[:top]:
-        st = ", ".join(f"{n[6:]}={v * 100 // max(e[0], 1)}%" for n, v in sorted(e[2].items(), key=lambda kv: -kv[1])[:3] if v)
-        print(f"L{line:>4s} {100 * e[0] / tot:5.1f}% smp {100 * e[1] / toti:5.1f}% inst | {e[3].strip()[:90]} | {st}")
+flat = [(f, l, e) for f, per in per_all.items() for l, e in per.items()]
+tot = sum(e[0] for _, _, e in flat) or 1
+toti = sum(e[1] for _, _, e in flat) or 1
+print(f"total samples {tot}, total warp instructions {toti}")
+for f, line, e in sorted(flat, key=lambda t: -t[2][0])[:top]:
+    st = ", ".join(f"{n[6:]}={v * 100 // max(e[0], 1)}%" for n, v in sorted(e[2].items(), key=lambda kv: -kv[1])[:3] if v)
+    print(f"{f[:16]:16s} L{line:>4s} {100 * e[0] / tot:5.1f}% smp {100 * e[1] / toti:5.1f}% inst | {e[3].strip()[:80]} | {st}")
