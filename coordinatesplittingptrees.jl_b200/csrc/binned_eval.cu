@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
 
 // ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
-                                                 int2* __restrict__ perm, double* __restrict__ val) {
+                                                 int2* __restrict__ perm, int* __restrict__ slot_of) {
     // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
@@ -97,8 +97,18 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, l
         for (int u = 0; u < 4; ++u) {
             const long long q = q0 + u * stride;
             if (lf[u] >= 0) perm[slot[u]] = make_int2((int)q, lf[u]);
-            else if (lf[u] == -1) val[q] = dnan_b();  // outside the world: the reference throws (src/tree.jl:359)
+            if (lf[u] != -2) slot_of[q] = slot[u];  // -1: outside the world (the reference throws, src/tree.jl:359)
         }
+    }
+}
+
+// values come back from leaf-sorted order to query order: a gather (reads hit L2: the chunk's sorted values were just
+// written) followed by coalesced writes -- instead of scattered 8-byte writes, which cost a sector read-modify-write each
+__global__ void __launch_bounds__(256) k_unpermute(const int* __restrict__ slot_of, const double* __restrict__ vsorted, long long m,
+                                                   double* __restrict__ val) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
+        const int s = slot_of[q];
+        val[q] = s >= 0 ? vsorted[s] : dnan_b();
     }
 }
 
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const 
                 if (i < n) acc = fma(__ldg(A + i), z[i], acc);
             acc += __ldg(A + n);
         }
-        val[(unsigned)ql.x] = acc;
+        val[s] = acc;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
     }
 }
 
@@ -245,7 +255,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
             }
             __syncwarp();  // the slot is re-staged for the next distinct leaf / next iteration
         }
-        if (valid) val[(unsigned)ql.x] = result;
+        if (valid) val[s] = result;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
         ql = qn;
     }
 }
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_generic(const ModelsView mv
             for (int i = 0; i < n; ++i) acc = fma(__ldg(A + i), __ldg(x + i) - __ldg(M + i), acc);
             acc += __ldg(A + n);
         }
-        val[(unsigned)ql.x] = acc;
+        val[s] = acc;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
     }
 }
 
@@ -287,6 +297,8 @@ struct BinWorkspace {
     int* cursor = nullptr;   // [nl]
     int* partial = nullptr;  // [2*nblocks]: block sums, then epoch flags
     int2* perm = nullptr;    // [m]
+    int* slot = nullptr;     // [m] sorted position of each query (-1: outside the world)
+    double* vsorted = nullptr;  // [m] values in leaf-sorted order
     int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
     int epoch = 0;
 };
@@ -299,6 +311,8 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMemsetAsync(w->partial, 0, (size_t)std::max(nblocks, 1) * 8, st));
     CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
+    CSP_CUDA(cudaMallocAsync(&w->slot, (size_t)m * 4, st));
+    CSP_CUDA(cudaMallocAsync(&w->vsorted, (size_t)m * 8, st));
     if (need_leaf) CSP_CUDA(cudaMallocAsync(&w->leaf, (size_t)m * 4, st));
     CSP_CUDA(cudaMemsetAsync(w->cnt, 0, (size_t)nl * 4, st));
     return CSP_OK;
@@ -311,19 +325,21 @@ int csp_bin_alloc_sync(int nl, long long m, BinWorkspace* w) {
     CSP_CUDA(cudaMalloc(&w->cursor, (size_t)nl * 4));
     CSP_CUDA(cudaMalloc(&w->partial, (size_t)std::max(nblocks, 1) * 8));
     CSP_CUDA(cudaMalloc(&w->perm, (size_t)m * sizeof(int2)));
+    CSP_CUDA(cudaMalloc(&w->slot, (size_t)m * 4));
+    CSP_CUDA(cudaMalloc(&w->vsorted, (size_t)m * 8));
     CSP_CUDA(cudaMemset(w->cnt, 0, (size_t)nl * 4));
     CSP_CUDA(cudaMemset(w->partial, 0, (size_t)std::max(nblocks, 1) * 8));
     w->epoch = 0;
     return CSP_OK;
 }
 void csp_bin_free_sync(BinWorkspace* w) {
-    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
+    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->slot, w->vsorted, w->leaf};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     *w = BinWorkspace();
 }
 void csp_bin_free(BinWorkspace* w, cudaStream_t st) {
-    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->leaf};
+    void* ptrs[] = {w->cnt, w->off, w->cursor, w->partial, w->perm, w->slot, w->vsorted, w->leaf};
     for (void* p : ptrs)
         if (p) cudaFreeAsync(p, st);
 }
@@ -347,17 +363,27 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * (8 / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_SCATTER, st);
-        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, dval);
+        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, w->slot);
     }
     CSP_LAUNCHED();
-    if (csp_dense_supported(mo)) return csp_dense_eval(mo, n_sm, dX, w->perm, w->off + nl, m, dval, st);  // K3b: FP64 tensor cores
+    auto unpermute = [&]() -> int {
+        CspTimed tm(CSP_K_SCATTER, st);
+        k_unpermute<<<(unsigned)blocks, 256, 0, st>>>(w->slot, w->vsorted, m, dval);
+        CSP_LAUNCHED();
+        CSP_CUDA(cudaGetLastError());
+        return CSP_OK;
+    };
+    if (csp_dense_supported(mo)) {  // K3b: FP64 tensor cores
+        CSP_CHECK(csp_dense_eval(mo, n_sm, dX, w->perm, w->off + nl, m, w->vsorted, st));
+        return unpermute();
+    }
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)
     auto launch = [&](auto kern) {
         CspTimed tm(CSP_K_EVAL_BINNED, st);
-        kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, dval);
+        kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
         CSP_LAUNCHED();
     };
     const bool vec_ok = aligned || (n & 1);
@@ -390,5 +416,5 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     else if (n <= 32 && vec_ok) launch(k_eval_binned<32>);
     else launch(k_eval_binned_generic);
     CSP_CUDA(cudaGetLastError());
-    return CSP_OK;
+    return unpermute();
 }

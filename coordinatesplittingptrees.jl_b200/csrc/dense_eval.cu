@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
                         if (J < nt) s = fma(acc[h][J][0], zr[8 * J], fma(acc[h][J][1], zr[8 * J + 1], s));
                     s += __shfl_xor_sync(0xffffffffu, s, 1);
                     s += __shfl_xor_sync(0xffffffffu, s, 2);
-                    if ((lane & 3) == 0 && row >= seg_start && row < seg_end) prm.val[(unsigned)s_q[row]] = s;
+                    if ((lane & 3) == 0 && row >= seg_start && row < seg_end) prm.val[s0 + row] = s;  // leaf-sorted position
                 }
             }
             seg_start = seg_end;

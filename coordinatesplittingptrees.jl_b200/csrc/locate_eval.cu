@@ -547,6 +547,8 @@ struct BinWorkspace {
     int* cursor = nullptr;
     int* partial = nullptr;
     int2* perm = nullptr;
+    int* slot = nullptr;
+    double* vsorted = nullptr;
     int* leaf = nullptr;
     int epoch = 0;
 };
