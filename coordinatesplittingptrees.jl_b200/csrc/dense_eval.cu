@@ -11,6 +11,10 @@
 // that both fragment loads are conflict-free (rows 4 apart in 8-byte banks).  A warp owns 16 rows x all NP columns
 // (accumulators in registers), so every U fragment it loads feeds two MMAs; k-steps below a column tile's diagonal are
 // skipped (half the MMAs).
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "common.cuh"
 
 __device__ __forceinline__ double dnan_d() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -27,6 +31,7 @@ struct DenseParams {
     double* val;
     int NP, LD;  // padded dimension (multiple of 8, >= n + 1) and leading dimension of the shared tiles
     int bulk;    // rows are 16-byte aligned multiples of 16 bytes: gather them with TMA bulk copies
+    long long* prof;  // optional [grid][8] per-phase clock counters (CSP_DMMA_PROF=1), else nullptr
 };
 
 template <int TR, int NT>  // TR rows per tile (TR/16 warps); NT >= NP/8 column tiles (compile-time bound for the accumulators)
@@ -152,6 +157,185 @@ __global__ void __launch_bounds__(TR * 2) k_eval_dmma(const DenseParams prm) {
     }
 }
 
+// Software-pipelined variant (the default whenever the rows can be gathered by TMA):
+//   * two Z buffers: while the MMAs of tile t run, the TMA row gathers of tile t+1 are in flight (perm entries of tile
+//     t+2 are already in registers);
+//   * no fix-up pass: Z holds the raw query rows, z = x - b is formed in registers when the A fragments are loaded (the
+//     padding columns [n] = 1, (n, LD) = 0 are written once per buffer; TMA never touches them; b is padded with 0);
+//   * U is stored packed by 8-row blocks (block kb keeps columns >= 8 kb only): half the shared memory of the square
+//     layout, same conflict-free fragment loads (row stride = 4 mod 8 doubles);
+//   * JS warps share each 16-row slab, the warp of column group jg taking the column tiles J = jg (mod JS): TR/16*JS warps keep the DMMA pipe
+//     fed; the JS partial row sums are combined in a fixed order through shared memory.
+__host__ __device__ __forceinline__ int dmma_ubase(int kb, int LD) { return 8 * (kb * LD - 4 * kb * (kb - 1)); }
+
+// One warp's share of a 16-row slab: W = z U over its NL column tiles J = jj*JS + jg, then the partial row dots W . z.
+// Column tile J is needed for k < 8 (J + 1) only (U is upper triangular): stage s runs the k range in which exactly the
+// tiles jj >= s are live, so the tile loops are unrolled and free of predicates.
+template <int NL, int JS>
+__device__ __forceinline__ void dmma_slab(const double* __restrict__ Z, const double* __restrict__ U, const double* __restrict__ sb,
+                                          double* __restrict__ part, int r0, int jg, int NP, int LD, int lane) {
+    double acc[2][NL][2];
+#pragma unroll
+    for (int jj = 0; jj < NL; ++jj) { acc[0][jj][0] = acc[0][jj][1] = acc[1][jj][0] = acc[1][jj][1] = 0.0; }
+    const double* za = Z + (size_t)(r0 + (lane >> 2)) * LD + (lane & 3);
+    const double* sbk = sb + (lane & 3);
+#pragma unroll
+    for (int s2 = 0; s2 < NL; ++s2) {
+        const int k_lo = s2 == 0 ? 0 : 8 * ((s2 - 1) * JS + jg + 1);
+        int k_hi = 8 * (s2 * JS + jg + 1);
+        if (k_hi > NP) k_hi = NP;
+#pragma unroll 2
+        for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
+            const int kb = k0 >> 3;
+            const double bk = sbk[k0];
+            const double a0 = za[k0] - bk, a1 = za[(size_t)8 * LD + k0] - bk;  // z = x - b, formed in registers
+            const double* ub = U + dmma_ubase(kb, LD) + ((k0 & 4) + (lane & 3)) * (LD - 8 * kb) + (lane >> 2) + 8 * (jg - kb);
+            double bf[NL];
+#pragma unroll
+            for (int jj = s2; jj < NL; ++jj) bf[jj] = ub[8 * JS * jj];
+#pragma unroll
+            for (int jj = s2; jj < NL; ++jj) {
+                dmma884(acc[0][jj][0], acc[0][jj][1], a0, bf[jj]);
+                dmma884(acc[1][jj][0], acc[1][jj][1], a1, bf[jj]);
+            }
+        }
+    }
+    // thread holds W[row][8J + 2*(lane&3) + {0,1}] for row = r0 + 8h + lane/4
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int row = r0 + 8 * h + (lane >> 2);
+        const double* zr = Z + (size_t)row * LD + 2 * (lane & 3) + 8 * jg;
+        const double* br = sb + 2 * (lane & 3) + 8 * jg;
+        double sacc = 0.0;
+#pragma unroll
+        for (int jj = 0; jj < NL; ++jj)
+            sacc = fma(acc[h][jj][0], zr[8 * JS * jj] - br[8 * JS * jj], fma(acc[h][jj][1], zr[8 * JS * jj + 1] - br[8 * JS * jj + 1], sacc));
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+        if ((lane & 3) == 0) part[row] = sacc;
+    }
+}
+
+template <int TR, int NTJ, int JS>  // NTJ = ceil(nt / JS): every warp owns NTJ or NTJ - 1 column tiles
+__global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma2(const DenseParams prm) {
+    extern __shared__ __align__(16) double sm[];
+    const int n = prm.mv.n, NP = prm.NP, LD = prm.LD, nt = NP / 8;
+    const int usz = dmma_ubase(nt, LD);
+    double* U = sm;                                  // packed upper block-triangle
+    double* Zb = U + usz;                            // [2][TR][LD]
+    double* sb = Zb + (size_t)2 * TR * LD;           // [NP]  (b, zero padded)
+    double* s_part = sb + NP;                        // [JS][TR]
+    int* s_q = (int*)(s_part + JS * TR);             // [2][TR]
+    int* s_leaf = s_q + 2 * TR;                      // [2][TR]
+    uint64_t* bar = (uint64_t*)(s_leaf + 2 * TR);    // [2]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int rg = warp / JS, jg = (warp + rg) % JS;  // rotated so that every SM sub-partition (warp % 4) sees all column groups
+    const long long tot = *prm.total;
+    const long long ntiles = (tot + TR - 1) / TR;
+    const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * TR * (LD - n); i += blockDim.x) {  // padding columns of both Z buffers
+        const int r = i / (LD - n), k = n + (i - r * (LD - n));
+        Zb[(size_t)r * LD + k] = k == n ? 1.0 : 0.0;
+    }
+    auto perm_at = [&](long long t) -> int2 {  // this thread's perm entry of tile t (rows past the end: leaf -1)
+        const long long s = t * TR + tid;
+        return (tid < TR && t < t1 && s < tot) ? prm.perm[s] : make_int2(0, -1);
+    };
+    auto tile_rows = [&](long long t) { const long long r = tot - t * TR; return (int)(r < TR ? r : TR); };
+    // publish tile t's perm entries, arm the barrier and start the row gathers into buffer `buf` (which must be free)
+    auto start_tile = [&](long long t, int buf, int2 ql) {
+        if (tid < TR) { s_q[buf * TR + tid] = ql.x; s_leaf[buf * TR + tid] = ql.y; }
+        const int rows = tile_rows(t);
+        fence_proxy_async();
+        if (tid == 0) mbar_expect_tx(&bar[buf], (uint32_t)((size_t)rows * n * 8));
+        __syncthreads();
+        // a few copies per warp (TMA issue is serial within a warp)
+        constexpr int RPW = TR / (TR / 16 * JS);
+        const int r = warp * RPW + lane;
+        if (lane < RPW && r < rows)
+            bulk_g2s(Zb + ((size_t)buf * TR + r) * LD, prm.X + (size_t)(unsigned)s_q[buf * TR + r] * n, (uint32_t)(n * 8), &bar[buf]);
+    };
+    uint32_t phase[2] = {0, 0};
+    int cur_leaf = -1;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();
+#define CSP_TICK(k) do { if (prm.prof && tid == 0) { const long long now_ = clock64(); pc[k] += now_ - tk; tk = now_; } } while (0)
+    int2 nxt = make_int2(0, -1);
+    __syncthreads();
+    if (t0 < t1) {
+        start_tile(t0, 0, perm_at(t0));
+        nxt = perm_at(t0 + 1);
+    }
+    for (long long t = t0; t < t1; ++t) {
+        const int buf = (int)((t - t0) & 1);
+        const int rows = tile_rows(t);
+        if (t + 1 < t1) {  // the other buffer was released by the barrier that ended the previous iteration
+            start_tile(t + 1, buf ^ 1, nxt);
+            nxt = perm_at(t + 2);
+        }
+        CSP_TICK(0);
+        if (buf == 0) { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; }
+        else { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
+        CSP_TICK(1);
+        const double* Z = Zb + (size_t)buf * TR * LD;
+        const int* leaf_of = s_leaf + buf * TR;
+        int seg_start = 0;
+        while (seg_start < rows) {
+            const int lf = leaf_of[seg_start];
+            int seg_end = rows;
+            if (leaf_of[rows - 1] != lf) {  // sorted by leaf: first row of another leaf, by bisection (every thread, same result)
+                int lo = seg_start, hi = rows - 1;  // leaf_of[lo] == lf, leaf_of[hi] != lf
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (leaf_of[mid] == lf) lo = mid; else hi = mid;
+                }
+                seg_end = hi;
+            }
+            CSP_TICK(2);
+            if (lf != cur_leaf) {  // expand the record: b (zero padded) and the packed U
+                const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
+                for (int i = tid; i < usz; i += blockDim.x) U[i] = 0.0;
+                for (int i = tid; i < NP; i += blockDim.x) sb[i] = i < n ? __ldg(M + i) : 0.0;
+                __syncthreads();
+                const double* __restrict__ A = M + n;
+                for (int i = warp; i <= n; i += nwarps) {  // row i of the packed triangle: n + 1 - i coefficients, coalesced
+                    const double* __restrict__ Ar = A + (i * (n + 1) - i * (i - 1) / 2);
+                    const int kb = i >> 3;
+                    double* Ur = U + dmma_ubase(kb, LD) + (i & 7) * (LD - 8 * kb) + (i - 8 * kb);
+                    for (int e = lane; e < n + 1 - i; e += 32) Ur[e] = __ldg(Ar + e);
+                }
+                cur_leaf = lf;
+                __syncthreads();
+                CSP_TICK(3);
+            }
+            const int r0 = rg * 16;
+            const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
+            if (active) {
+                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS>(Z, U, sb, s_part + jg * TR, r0, jg, NP, LD, lane);
+                else dmma_slab<NTJ - 1, JS>(Z, U, sb, s_part + jg * TR, r0, jg, NP, LD, lane);
+            }
+            __syncthreads();
+            if (tid >= seg_start && tid < seg_end) {
+                double v = s_part[tid];
+#pragma unroll
+                for (int g2 = 1; g2 < JS; ++g2) v += s_part[g2 * TR + tid];
+                prm.val[t * TR + tid] = v;
+            }
+            seg_start = seg_end;
+            __syncthreads();
+            CSP_TICK(4);
+        }
+    }
+    if (prm.prof && tid == 0)
+        for (int k = 0; k < 8; ++k) prm.prof[blockIdx.x * 8 + k] = pc[k];
+#undef CSP_TICK
+}
+
 // per-leaf histogram for the evaluate-only entry point (leaf ids supplied by the caller)
 __global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long long m, long long n_models, int* __restrict__ cnt) {
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
@@ -191,6 +375,39 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
         return CSP_OK;
     };
     const int nt = prm.NP / 8;
+    if (prm.bulk && !(getenv("CSP_DMMA_PIPELINE") && atoi(getenv("CSP_DMMA_PIPELINE")) == 0)) {  // pipelined variant
+        constexpr int TR = 64, JS = 4;
+        const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + JS * TR) * 8 + (size_t)(4 * TR) * 4 + 16;
+        const unsigned grid2 = (unsigned)std::max<long long>(1, std::min<long long>((m + TR - 1) / TR, std::max(n_sm, 1)));
+        auto launch2 = [&](auto kern) -> int {
+            const bool prof = getenv("CSP_DMMA_PROF") && atoi(getenv("CSP_DMMA_PROF"));
+            if (prof) CSP_CUDA(cudaMalloc(&prm.prof, (size_t)grid2 * 8 * sizeof(long long)));
+            CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            {
+                CspTimed tm(CSP_K_EVAL_BINNED, st);
+                kern<<<grid2, TR * 2 * JS, smem, st>>>(prm);
+            }
+            CSP_LAUNCHED();
+            CSP_CUDA(cudaGetLastError());
+            if (prof) {  // developer aid: per-phase clock totals, averaged over the CTAs
+                std::vector<long long> h((size_t)grid2 * 8);
+                CSP_CUDA(cudaMemcpy(h.data(), prm.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+                cudaFree(prm.prof);
+                static const char* names[5] = {"prefetch", "gather_wait", "segment", "expand_U", "mma+epilogue"};
+                for (int k = 0; k < 5; ++k) {
+                    double sum = 0;
+                    for (unsigned b = 0; b < grid2; ++b) sum += (double)h[(size_t)b * 8 + k];
+                    fprintf(stderr, "[csp dmma prof] %-13s %12.0f clk/CTA\n", names[k], sum / grid2);
+                }
+            }
+            return CSP_OK;
+        };
+        if (smem <= 227 * 1024) {
+            if (nt <= 8) return launch2(k_eval_dmma2<TR, 2, JS>);  // nt >= 5 (n > 32)
+            if (nt <= 12) return launch2(k_eval_dmma2<TR, 3, JS>);
+            return launch2(k_eval_dmma2<TR, 4, JS>);
+        }
+    }
     if (nt <= 9) return smem_for(128) <= 220 * 1024 ? launch(k_eval_dmma<128, 9>, 128) : launch(k_eval_dmma<64, 9>, 64);
     if (nt <= 13) return smem_for(128) <= 220 * 1024 ? launch(k_eval_dmma<128, 13>, 128) : launch(k_eval_dmma<64, 13>, 64);
     if (smem_for(64) > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the DMMA evaluation kernel", n);
