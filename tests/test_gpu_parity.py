@@ -471,13 +471,14 @@ def test_full_size_properties_c3():
     assert np.median(np.abs(out["direct"][ok] - truth[ok])) < 0.1
 
 
-@pytest.mark.parametrize("n,nl", [(40, 7), (64, 300), (100, 5), (103, 40), (127, 9), (130, 12)])
-def test_k3b_dense_dmma_eval(n, nl):
+@pytest.mark.parametrize("n,nl,m", [(33, 11, 20000), (40, 7, 20000), (64, 300, 20000), (64, 3, 150000), (71, 3, 20000), (72, 50, 20000),
+                                    (95, 6, 20000), (96, 2, 20000), (100, 5, 20000), (103, 40, 20000), (127, 9, 20000), (130, 12, 20000)])
+def test_k3b_dense_dmma_eval(n, nl, m):
     """K3b: grouped evaluation on the FP64 tensor cores (mma.sync DMMA) for n > 32, models supplied per leaf (C4 shape).
-    Long runs (few leaves) and short runs (segments inside a tile), evaluate-only and through the binned pipeline."""
+    Long runs (few leaves, several tiles per CTA: the double-buffered pipeline) and short runs (segments inside a tile), every
+    column-tile count 5..16, even n (TMA row gathers) and odd n (cp.async gathers), evaluate-only and through the binned pipeline."""
     import torch
     rng = np.random.default_rng(n + nl)
-    m = 20000
     c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))
     Q = np.triu(rng.standard_normal((nl, n, n)) / n)
     models = LeafModels.upload(c, g, Q, b)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Config C4: CS1 tree, n=100, 1e4 leaves, models (c,g,Q,b) supplied per leaf, many queries per leaf, grouped
 by leaf -> K3b (FP64 tensor-core DMMA) evaluation.  Reports queries/s, useful TFLOP/s (2n^2+5n+2 flop/query) and the
-fraction of a cuBLAS DGEMM peak measured in the same run (8192^3, torch.matmul float64).
+fraction of a cuBLAS DGEMM peak measured in the same run (8192^3, torch.matmul float64), plus the issued DMMA flop
+against the DMMA pipe peak measured by tools/ubench/fp64_peaks.cu.
     python tools/bench_dense.py [--n 100] [--leaves 10000] [--queries 20000000] [--steps 5]"""
 import argparse
 import json
@@ -57,9 +58,13 @@ gemm_ms = timed(lambda: torch.matmul(A, B), 3)
 dgemm_tf = 2 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12
 flop_q = 2 * n * n + 5 * n + 2
 kms = kt["eval_binned"][0] / max(kt["eval_binned"][1], 1)
+nt = (n + 1 + 7) // 8
+issued_q = sum(2 * (J + 1) for J in range(nt)) * 2 * 512 / 16  # DMMA.8x8x4 flop issued per query row (triangular skipping)
+DMMA_PEAK_TF = 37.1  # tools/ubench/fp64_peaks.cu on this pool's B200 (DMMA.8x8x4, shared FP64 pipe)
 out = {"config": "C4: n=%d, %d leaves, %d queries grouped by leaf, models supplied" % (n, nl, m), "queries_per_s": m / (ms * 1e-3),
        "ms_per_step": ms, "useful_tflops": m * flop_q / (ms * 1e-3) / 1e12, "dmma_kernel_ms": kms,
        "dmma_kernel_useful_tflops": m * flop_q / (kms * 1e-3) / 1e12, "cublas_dgemm_tflops": dgemm_tf,
        "frac_of_dgemm_peak_kernel": m * flop_q / (kms * 1e-3) / 1e12 / dgemm_tf, "kernels": {k: v for k, v in kt.items() if v[1]},
-       "hbm_bytes_per_query": 8 * n + 12, "sample_val": float(val[12345].item())}
+       "dmma_issued_tflops": m * issued_q / (kms * 1e-3) / 1e12, "dmma_pipe_peak_tflops": DMMA_PEAK_TF,
+       "dmma_pipe_frac": m * issued_q / (kms * 1e-3) / 1e12 / DMMA_PEAK_TF, "hbm_bytes_per_query": 8 * n + 12, "sample_val": float(val[12345].item())}
 print(json.dumps(out))
