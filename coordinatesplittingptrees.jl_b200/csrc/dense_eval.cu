@@ -232,6 +232,164 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
 #undef CSP_TICK
 }
 
+// ---- n > 127: U no longer fits in shared memory -------------------------------------------------------------------
+// The Z tile stays resident (TR rows x LD, single buffer) and U is streamed through shared memory one 8-column panel at a
+// time (double-buffered 8-byte cp.async straight from the packed record: rows k < 8 (J + 1) of columns [8J, 8J + 8); the
+// panels of a leaf come from L2 for every tile after the first).  The 16 warps are TR/16 row groups x KG k-groups: a warp
+// multiplies its 16 rows by its share of the panel's k range (two interleaved accumulator sets for ILP) and folds the
+// result straight into its running row dot  sum_c W[r][c] z[c], which is linear in W -- so the k-groups' partial dots
+// simply add up, once per tile, in a fixed order through shared memory.
+constexpr int PANEL_LD = 12;  // 8 columns + 4 padding doubles: row stride 4 mod 8 (conflict-free B fragments)
+
+template <int TR>
+__global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) {
+    constexpr int RG = TR / 16, KG = 16 / RG;
+    extern __shared__ __align__(16) double sm[];
+    const int n = prm.mv.n, NP = prm.NP, LD = prm.LD, nt = NP / 8;
+    double* Z = sm;                                   // [TR][LD]
+    double* Up = Z + (size_t)TR * LD;                 // [2][NP][PANEL_LD]
+    double* sb = Up + (size_t)2 * NP * PANEL_LD;      // [NP]  (b, zero padded)
+    double* s_part = sb + NP;                         // [KG][TR]
+    int* s_q = (int*)(s_part + KG * TR);              // [TR]
+    int* s_leaf = s_q + TR;                           // [TR]
+    uint64_t* bar = (uint64_t*)(s_leaf + TR);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int rg = warp / KG, kg = warp - rg * KG;
+    const long long tot = *prm.total;
+    const long long ntiles = (tot + TR - 1) / TR;
+    const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long t0 = (long long)blockIdx.x * per, t1 = t0 + per < ntiles ? t0 + per : ntiles;
+    if (tid == 0) {
+        mbar_init(bar, prm.bulk ? 1 : blockDim.x);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TR * (LD - n); i += blockDim.x) {  // padding columns of Z
+        const int r = i / (LD - n), k = n + (i - r * (LD - n));
+        Z[(size_t)r * LD + k] = k == n ? 1.0 : 0.0;
+    }
+    uint32_t phase = 0;
+    int cur_leaf = -1;
+    for (long long t = t0; t < t1; ++t) {
+        const long long r_left = tot - t * TR;
+        const int rows = (int)(r_left < TR ? r_left : TR);
+        __syncthreads();  // previous tile fully consumed (Z, s_q, s_leaf, s_part)
+        if (tid < TR) {
+            const int2 ql = tid < rows ? prm.perm[t * TR + tid] : make_int2(0, -1);
+            s_q[tid] = ql.x;
+            s_leaf[tid] = ql.y;
+        }
+        if (prm.bulk) {
+            fence_proxy_async();
+            if (tid == 0) mbar_expect_tx(bar, (uint32_t)((size_t)rows * n * 8));
+            __syncthreads();
+            for (int r = tid; r < rows; r += blockDim.x)
+                bulk_g2s(Z + (size_t)r * LD, prm.X + (size_t)(unsigned)s_q[r] * n, (uint32_t)(n * 8), bar);
+        } else {
+            __syncthreads();
+            for (int r = warp; r < rows; r += 16) {
+                const double* __restrict__ src = prm.X + (size_t)(unsigned)s_q[r] * n;
+                double* dst = Z + (size_t)r * LD;
+                for (int k = lane; k < n; k += 32) cp_async8(dst + k, src + k);
+            }
+            cp_async_arrive(bar);
+        }
+        mbar_wait(bar, phase);
+        phase ^= 1;
+        int seg_start = 0;
+        while (seg_start < rows) {
+            const int lf = s_leaf[seg_start];
+            int seg_end = rows;
+            if (s_leaf[rows - 1] != lf) {  // sorted by leaf: bisection for the first row of another leaf
+                int lo = seg_start, hi = rows - 1;
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_leaf[mid] == lf) lo = mid; else hi = mid;
+                }
+                seg_end = hi;
+            }
+            const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
+            const double* __restrict__ A = M + n;
+            if (lf != cur_leaf) {
+                for (int i = tid; i < NP; i += blockDim.x) sb[i] = i < n ? __ldg(M + i) : 0.0;
+                cur_leaf = lf;  // made visible by the first panel barrier below
+            }
+            // panel J -> buffer J & 1: rows k < 8 (J + 1), columns 8J .. 8J + 7 of U (zero below the diagonal and past n)
+            auto issue_panel = [&](int J) {
+                double* dst = Up + (size_t)(J & 1) * NP * PANEL_LD;
+                const int cnt = (8 * J + 8) * 8;
+                for (int e = tid; e < cnt; e += blockDim.x) {
+                    const int k = e >> 3, c = 8 * J + (e & 7);
+                    if (c >= k && c <= n) cp_async8(dst + k * PANEL_LD + (e & 7), A + ((size_t)k * (n + 1) - (size_t)k * (k - 1) / 2 + (c - k)));
+                    else dst[k * PANEL_LD + (e & 7)] = 0.0;
+                }
+            };
+            const int r0 = rg * 16;
+            const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
+            const double* za = Z + (size_t)(r0 + (lane >> 2)) * LD + (lane & 3);
+            const double* sbk = sb + (lane & 3);
+            double sacc[2] = {0.0, 0.0};
+            issue_panel(0);
+            for (int J = 0; J < nt; ++J) {
+                asm volatile("cp.async.wait_all;" ::: "memory");
+                __syncthreads();  // panel J (and sb) visible; everybody is done with panel J - 1
+                if (J + 1 < nt) issue_panel(J + 1);
+                if (active) {
+                    const double* ub = Up + (size_t)(J & 1) * NP * PANEL_LD + (lane & 3) * PANEL_LD + (lane >> 2);
+                    const int ksteps = 2 * (J + 1);
+                    const int ks0 = kg * ksteps / KG, ks1 = (kg + 1) * ksteps / KG;
+                    double acc[2][2][2] = {{{0.0, 0.0}, {0.0, 0.0}}, {{0.0, 0.0}, {0.0, 0.0}}};  // [set][row half][2]
+                    int ks = ks0;
+                    for (; ks + 1 < ks1; ks += 2) {
+                        const int k0 = 4 * ks;
+                        const double bk0 = sbk[k0], bk1 = sbk[k0 + 4];
+                        const double a00 = za[k0] - bk0, a01 = za[(size_t)8 * LD + k0] - bk0;
+                        const double a10 = za[k0 + 4] - bk1, a11 = za[(size_t)8 * LD + k0 + 4] - bk1;
+                        const double b0 = ub[k0 * PANEL_LD], b1 = ub[(k0 + 4) * PANEL_LD];
+                        dmma884(acc[0][0][0], acc[0][0][1], a00, b0);
+                        dmma884(acc[0][1][0], acc[0][1][1], a01, b0);
+                        dmma884(acc[1][0][0], acc[1][0][1], a10, b1);
+                        dmma884(acc[1][1][0], acc[1][1][1], a11, b1);
+                    }
+                    if (ks < ks1) {
+                        const int k0 = 4 * ks;
+                        const double bk0 = sbk[k0];
+                        const double a00 = za[k0] - bk0, a01 = za[(size_t)8 * LD + k0] - bk0;
+                        const double b0 = ub[k0 * PANEL_LD];
+                        dmma884(acc[0][0][0], acc[0][0][1], a00, b0);
+                        dmma884(acc[0][1][0], acc[0][1][1], a01, b0);
+                    }
+                    // fold into the running row dots: thread holds W[row][8J + 2*(lane&3) + {0,1}]
+                    const int c = 8 * J + 2 * (lane & 3);
+                    const double bc0 = sb[c], bc1 = sb[c + 1];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double* zr = Z + (size_t)(r0 + 8 * h + (lane >> 2)) * LD + c;
+                        sacc[h] = fma(acc[0][h][0] + acc[1][h][0], zr[0] - bc0, fma(acc[0][h][1] + acc[1][h][1], zr[1] - bc1, sacc[h]));
+                    }
+                }
+            }
+            if (active) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    double v = sacc[h];
+                    v += __shfl_xor_sync(0xffffffffu, v, 1);
+                    v += __shfl_xor_sync(0xffffffffu, v, 2);
+                    if ((lane & 3) == 0) s_part[kg * TR + r0 + 8 * h + (lane >> 2)] = v;
+                }
+            }
+            __syncthreads();
+            if (tid >= seg_start && tid < seg_end) {
+                double v = s_part[tid];
+#pragma unroll
+                for (int g2 = 1; g2 < KG; ++g2) v += s_part[g2 * TR + tid];
+                prm.val[t * TR + tid] = v;
+            }
+            seg_start = seg_end;
+            __syncthreads();
+        }
+    }
+}
+
 // per-leaf histogram for the evaluate-only entry point (leaf ids supplied by the caller)
 __global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long long m, long long n_models, int* __restrict__ cnt) {
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
@@ -241,10 +399,17 @@ __global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long
 }
 
 // ---- host side -----------------------------------------------------------------------------------------------------
+static size_t panel_smem(int NP, int TR) {
+    const int KG = 16 / (TR / 16);
+    return ((size_t)TR * (NP + 4) + (size_t)2 * NP * PANEL_LD + NP + (size_t)KG * TR) * 8 + (size_t)(2 * TR) * 4 + 16;
+}
+
 bool csp_dense_supported(const csp_models* mo) {
     if (mo->degree != 2 || mo->n <= 32) return false;
     const int NP = (mo->n + 1 + 7) / 8 * 8;
-    return NP <= 128;  // packed U (<= 72 KB) plus two 64-row Z tiles (<= 132 KB) fit in the 227 KB of shared memory
+    // NP <= 128: packed U (<= 72 KB) plus two 64-row Z tiles (<= 132 KB) fit in the 227 KB of shared memory;
+    // beyond that the panel kernel needs a 16-row Z tile and two U panels (n up to ~700)
+    return NP <= 128 || panel_smem(NP, 16) <= 227 * 1024;
 }
 
 int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2* perm, const int* total, long long m, double* dval,
@@ -257,6 +422,24 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
     prm.LD = prm.NP + 4;  // NP % 8 == 0  =>  LD % 16 in {4, 12}
     prm.bulk = ((n & 1) == 0 && (uintptr_t)dX % 16 == 0) ? 1 : 0;
     const int nt = prm.NP / 8;
+    if (prm.NP > 128) {  // U streamed in panels
+        auto launchp = [&](auto kern, int TR) -> int {
+            const size_t smem = panel_smem(prm.NP, TR);
+            const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((m + TR - 1) / TR, std::max(n_sm, 1)));
+            CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            {
+                CspTimed tm(CSP_K_EVAL_BINNED, st);
+                kern<<<grid, 512, smem, st>>>(prm);
+            }
+            CSP_LAUNCHED();
+            CSP_CUDA(cudaGetLastError());
+            return CSP_OK;
+        };
+        if (panel_smem(prm.NP, 64) <= 227 * 1024) return launchp(k_eval_dmma_panel<64>, 64);
+        if (panel_smem(prm.NP, 32) <= 227 * 1024) return launchp(k_eval_dmma_panel<32>, 32);
+        if (panel_smem(prm.NP, 16) <= 227 * 1024) return launchp(k_eval_dmma_panel<16>, 16);
+        return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the DMMA evaluation kernels", n);
+    }
     {
         constexpr int TR = 64, JS = 4;  // 16 warps per CTA, one CTA per SM
         const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + JS * TR) * 8 + (size_t)(4 * TR) * 4 + 16;

@@ -472,11 +472,13 @@ def test_full_size_properties_c3():
 
 
 @pytest.mark.parametrize("n,nl,m", [(33, 11, 20000), (40, 7, 20000), (64, 300, 20000), (64, 3, 150000), (71, 3, 20000), (72, 50, 20000),
-                                    (95, 6, 20000), (96, 2, 20000), (100, 5, 20000), (103, 40, 20000), (127, 9, 20000), (130, 12, 20000)])
+                                    (95, 6, 20000), (96, 2, 20000), (100, 5, 20000), (103, 40, 20000), (127, 9, 20000), (128, 4, 20000), (130, 12, 20000),
+                                    (200, 150, 20000), (300, 3, 30000), (301, 7, 8000), (400, 2, 8000), (600, 3, 4000), (720, 2, 2000)])
 def test_k3b_dense_dmma_eval(n, nl, m):
     """K3b: grouped evaluation on the FP64 tensor cores (mma.sync DMMA) for n > 32, models supplied per leaf (C4 shape).
     Long runs (few leaves, several tiles per CTA: the double-buffered pipeline) and short runs (segments inside a tile), every
-    column-tile count 5..16, even n (TMA row gathers) and odd n (cp.async gathers), evaluate-only and through the binned pipeline."""
+    column-tile count 5..16, even n (TMA row gathers) and odd n (cp.async gathers), evaluate-only and through the binned pipeline.
+    n > 127 runs the panel-streaming kernel (64-, 32- and 16-row tiles as shared memory allows); n = 720 is past it (generic kernel)."""
     import torch
     rng = np.random.default_rng(n + nl)
     c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))

@@ -57,7 +57,7 @@ B = torch.randn((8192, 8192), dtype=torch.float64, device=dev)
 gemm_ms = timed(lambda: torch.matmul(A, B), 3)
 dgemm_tf = 2 * 8192 ** 3 / (gemm_ms * 1e-3) / 1e12
 flop_q = 2 * n * n + 5 * n + 2
-kms = kt["eval_binned"][0] / max(kt["eval_binned"][1], 1)
+kms = (kt["eval_binned"][0] + kt["eval"][0]) / a.steps  # evaluation kernel time per step (DMMA kernel when n is in 33..127)
 nt = (n + 1 + 7) // 8
 issued_q = sum(2 * (J + 1) for J in range(nt)) * 2 * 512 / 16  # DMMA.8x8x4 flop issued per query row (triangular skipping)
 DMMA_PEAK_TF = 37.1  # tools/ubench/fp64_peaks.cu on this pool's B200 (DMMA.8x8x4, shared FP64 pipe)
