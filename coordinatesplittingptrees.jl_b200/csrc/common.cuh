@@ -60,6 +60,8 @@ struct TreeView {
     const int* ichild;     // [n_internal*2^p] node ids of the children
     const double* ipos;    // [n_internal*n]   position(box)
     const int* lnode;      // [n_leaves] node id of each leaf
+    const long long* lpoff;  // [n_leaves+1] offsets into lpath (depth prefix sums)
+    const int2* lpath;     // per leaf, bottom-up: (first internal id, internal count) of every ancestor's subtree
 };
 
 // Per-leaf canonical models, one record of `stride` doubles per leaf.  With z = (x - b, 1) the canonical model
@@ -97,6 +99,8 @@ struct csp_tree {
     mutable std::vector<std::pair<const void*, Geo>> geo;
     // internal streams of the chunked binned pipeline: consecutive chunks alternate between them so that the
     // L1-bound descent of one chunk overlaps the DRAM-bound evaluation of the previous one
+    const int4* fit_units = nullptr;  // [n_fit_units] leaf ids (-1 padded) of the real leaves under each split that has any (fit.cu)
+    long long n_fit_units = 0;
     mutable void* fit_ws = nullptr;  // grow-only scratch of the fit pre-pass (chain results), one fit call at a time per handle
     mutable size_t fit_ws_bytes = 0;
     mutable cudaStream_t pipe_st[2] = {nullptr, nullptr};

@@ -17,6 +17,8 @@
 // reference's early exit becomes "stop when every slot is filled".  The O(n) / O(n^2) floating-point work is then done
 // one lane per output entry, sequentially in the reference's order.
 #include <climits>
+#include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -42,8 +44,11 @@ struct FitParams {
     // sparse-pattern coefficients_p (FIT_MODE_COEF, p == 2): slotmap[i*n+j] (i<j, 0-based) = output slot or -1; npat slots; the
     // output row of a box is then Q[bi*Q_stride + slot]
     const int* slotmap; int npat; const int* pat_ij;
+    unsigned long long* prof;  // optional [8] per-phase clock totals (CSP_FIT_PROF=1)
     int* scratch;            // global pair tables when they do not fit in shared memory
     int pairs_in_smem;
+    int q_in_smem;           // the box's Q / record is assembled in shared memory and written out once, coalesced
+    const int4* units; long long n_units;  // all-leaf fits: the real leaves (output rows, -1 padded) under each split that has any
     int warp_smem_bytes;
 };
 
@@ -79,7 +84,9 @@ struct WarpCtx {
     int lane, n, npairs;
     double *sb, *sy, *sg;
     int *sstep, *dkey, *did, *pkey, *pid;
+    int *g_lo1, *g_n1, *g_lo2, *g_lo3, *g_pre;  // one window of up to 32 range groups (g_pre has 33 entries)
 };
+#define FIT_WINDOW_INTS (4 * 32 + 33 + 3)  // keeps the following doubles 8-byte aligned
 
 // chaintop (src/polynomials.jl:22-98) on the flat arrays; executed by one lane.  Returns CSP_FIT_* and the top NODE id.
 __device__ int chaintop_dev(const TreeView& t, int box, int* covered, int* top_out) {
@@ -203,16 +210,16 @@ __global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* 
 template <int P>
 __device__ __forceinline__ double coef_value(const TreeView& t, int id) {
     if (P == 2) {  // src/polynomials.jl:212-224 with p = 2: s = +1, signs (+,-,-,+)
-        const double x0 = t.ixs[2 * id], x1 = t.ixs[2 * id + 1];
-        const double s0 = t.ixself[2 * id], s1 = t.ixself[2 * id + 1];
+        const double2 xs = __ldg((const double2*)t.ixs + id), xf = __ldg((const double2*)t.ixself + id);
+        const double2 f01 = __ldg((const double2*)t.icval + 2 * id), f23 = __ldg((const double2*)t.icval + 2 * id + 1);
         double denom = 1.0;
-        denom = denom * (x0 - s0);
-        denom = denom * (x1 - s1);
+        denom = denom * (xs.x - xf.x);
+        denom = denom * (xs.y - xf.y);
         double num = 0.0;
-        num = num + 1.0 * t.icval[4 * id + 0];
-        num = num + -1.0 * t.icval[4 * id + 1];
-        num = num + -1.0 * t.icval[4 * id + 2];
-        num = num + 1.0 * t.icval[4 * id + 3];
+        num = num + 1.0 * f01.x;
+        num = num + -1.0 * f01.y;
+        num = num + -1.0 * f23.x;
+        num = num + 1.0 * f23.y;
         return num / denom;
     } else {  // p = 1: s = -1, signs (-,+)
         double denom = 1.0;
@@ -224,6 +231,143 @@ __device__ __forceinline__ double coef_value(const TreeView& t, int id) {
     }
 }
 
+// The splits(box) traversal, flattened: for a window of up to 32 consecutive range groups (one lane per ancestor) the
+// group sizes are prefix-summed, and each 32-split chunk of the window's virtual sequence maps its lanes back to
+// (group, offset) by bisection -- the many one-split groups next to a leaf share a chunk instead of taking one each.
+// DIAG == false: first occurrence per off-diagonal pair slot (coefficients_p).  DIAG == true: first qualifying split per
+// diagonal entry (fit_poly2_diag!).  Returns through tpos the number of positions walked and through found the slots filled.
+template <int P, bool DIAG>
+__device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w, int box, int nslots, int& tpos, int& found) {
+    const TreeView& t = prm.t;
+    const int lane = w.lane, n = w.n, skip = prm.skip;
+    const unsigned FULL = 0xffffffffu;
+    tpos = 0; found = 0;
+    if (nslots <= 0) return;
+    const int4 binfo0 = t.ninfo[box];
+    int cI = binfo0.y, cS = binfo0.z;                  // (first internal id, internal count) of the child we climb from
+    const int lf = t.nleaf[box];
+    const bool use_path = t.lpath != nullptr && lf >= 0;   // leaves: ancestor (I, S) pairs precomputed at upload
+    const long long pbase = use_path ? t.lpoff[lf] : 0;
+    const int pdepth = use_path ? (int)(t.lpoff[lf + 1] - pbase) : 0;
+    int pk = 0;
+    int wnode = box;  // lane 0's position in the fallback walk
+    int4 winfo = binfo0;
+    bool pseudo = !(binfo0.w & CSP_NF_LEAF);  // an internal box yields its own split and subtree first
+    bool more = true, done = false;
+    while (more && !done) {
+        int cnt, Ia = 0, Sa = 0;
+        if (pseudo) {
+            cnt = 1;
+        } else if (use_path) {
+            cnt = min(32, pdepth - pk);
+            if (lane < cnt) { const int2 a = __ldg(t.lpath + pbase + pk + lane); Ia = a.x; Sa = a.y; }
+            pk += cnt;
+            more = pk < pdepth;
+        } else {
+            if (lane == 0) {
+                int c = 0;
+                while (c < 32 && winfo.x != wnode) {
+                    wnode = winfo.x;
+                    winfo = t.ninfo[wnode];
+                    w.g_lo1[c] = winfo.y; w.g_n1[c] = winfo.z;
+                    ++c;
+                }
+                w.g_pre[0] = c; w.g_pre[1] = winfo.x != wnode;
+            }
+            __syncwarp();
+            cnt = w.g_pre[0]; more = w.g_pre[1] != 0;
+            if (lane < cnt) { Ia = w.g_lo1[lane]; Sa = w.g_n1[lane]; }
+            __syncwarp();
+        }
+        if (cnt == 0) break;
+        int lo1, n1, lo2, tot;
+        if (pseudo) {
+            lo1 = cI; n1 = cS; lo2 = 0; tot = lane == 0 ? cS : 0;
+        } else {
+            int Ic = __shfl_up_sync(FULL, Ia, 1), Sc = __shfl_up_sync(FULL, Sa, 1);
+            if (lane == 0) { Ic = cI; Sc = cS; }
+            lo1 = Ia + 1; n1 = Ic - lo1; lo2 = Ic + Sc;
+            tot = lane < cnt ? n1 + (Ia + Sa - lo2) + 1 : 0;
+            cI = __shfl_sync(FULL, Ia, cnt - 1); cS = __shfl_sync(FULL, Sa, cnt - 1);
+        }
+        int pre = tot;  // inclusive scan
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += u; }
+        const int total = __shfl_sync(FULL, pre, 31);
+        if (lane < cnt) { w.g_lo1[lane] = lo1; w.g_n1[lane] = n1; w.g_lo2[lane] = lo2; w.g_lo3[lane] = Ia; w.g_pre[lane] = pre - tot; }
+        if (lane == cnt - 1) w.g_pre[cnt] = total;
+        __syncwarp();
+        for (int base = 0; base < total; base += 32) {
+            const int v = base + lane;
+            int id = 0;
+            if (v < total) {
+                int gsel = 0;
+#pragma unroll
+                for (int sft = 16; sft; sft >>= 1) { const int c = gsel + sft; if (c < cnt && w.g_pre[c] <= v) gsel = c; }
+                const int off = v - w.g_pre[gsel], gtot = w.g_pre[gsel + 1] - w.g_pre[gsel], gn1 = w.g_n1[gsel];
+                id = off < gn1 ? w.g_lo1[gsel] + off : ((pseudo || off < gtot - 1) ? w.g_lo2[gsel] + (off - gn1) : w.g_lo3[gsel]);
+            }
+            const int pos = tpos + lane;
+            const bool act = v < total && pos >= skip;
+            if (!DIAG) {
+                int pidx = -1;
+                bool newp = false;
+                if (act) {
+                    if (P == 2) {
+                        const int2 dd = __ldg((const int2*)t.idims + id);
+                        if (dd.x <= n && dd.y <= n && dd.x != dd.y) {
+                            const int i = min(dd.x, dd.y) - 1, j = max(dd.x, dd.y) - 1;
+                            pidx = prm.slotmap ? __ldg(prm.slotmap + i * n + j) : i * n - i * (i + 1) / 2 + (j - i - 1);
+                            if (pidx >= 0) newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                        }
+                    } else {
+                        const int dd0 = __ldg(t.idims + id);
+                        if (dd0 <= n) {
+                            pidx = dd0 - 1;
+                            newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                        }
+                    }
+                }
+                __syncwarp();
+                if (pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
+                found += __popc(__ballot_sync(FULL, newp));
+            } else {
+                int dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
+                bool newd0 = false, newd1 = false;
+                if (act) {
+                    const int2 dd = __ldg((const int2*)t.idims + id);
+                    dd0 = dd.x; dd1 = dd.y;
+                    const double2 xs = __ldg((const double2*)t.ixs + id);
+                    const double2 xf = __ldg((const double2*)t.ixself + id);
+                    if (dd0 <= n && w.dkey[dd0 - 1] > 2 * pos &&
+                        (newinfo(xs.x, w.sb[dd0 - 1], w.sy[dd0 - 1]) || newinfo(xf.x, w.sb[dd0 - 1], w.sy[dd0 - 1]))) {
+                        dk0 = 2 * pos;
+                        newd0 = atomicMin(&w.dkey[dd0 - 1], dk0) == INT_MAX;
+                    }
+                    if (dd1 <= n && w.dkey[dd1 - 1] > 2 * pos + 1 &&
+                        (newinfo(xs.y, w.sb[dd1 - 1], w.sy[dd1 - 1]) || newinfo(xf.y, w.sb[dd1 - 1], w.sy[dd1 - 1]))) {
+                        dk1 = 2 * pos + 1;
+                        newd1 = atomicMin(&w.dkey[dd1 - 1], dk1) == INT_MAX;
+                    }
+                }
+                __syncwarp();
+                if (dk0 >= 0 && w.dkey[dd0 - 1] == dk0) w.did[dd0 - 1] = 2 * id;
+                if (dk1 >= 0 && w.dkey[dd1 - 1] == dk1) w.did[dd1 - 1] = 2 * id + 1;
+                found += __popc(__ballot_sync(FULL, newd0)) + __popc(__ballot_sync(FULL, newd1));
+            }
+            tpos += min(32, total - base);
+            if (found >= nslots) { done = true; break; }
+        }
+        __syncwarp();
+        if (pseudo) { pseudo = false; more = true; }  // now climb from the box itself
+    }
+    __syncwarp();
+}
+
+// One warp per work unit.  A unit is one box, or -- for the all-leaf model fits (prm.units) -- the real leaves that are
+// children of one split: their splits() traversals are identical (each leaf child has an empty subtree, so the two sibling
+// ranges of the parent's group always join to the parent's whole subtree), hence so are their off-diagonal coefficients;
+// the pair scan and the coefficient values are computed once and only fit_poly1 / fit_poly2_diag! / canonicalize run per leaf.
 template <int P>
 __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -237,107 +381,41 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
     WarpCtx w;
     w.lane = lane; w.n = n; w.npairs = npairs;
     w.sb = (double*)wbase; w.sy = w.sb + n; w.sg = w.sy + n;
-    w.sstep = (int*)(w.sg + n); w.dkey = w.sstep + n; w.did = w.dkey + n;
+    const long long qlen = prm.slotmap ? prm.npat : (P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n));
+    double* sQ = (double*)(w.sg + n);  // [qlen] when q_in_smem
+    w.g_lo1 = (int*)(sQ + (prm.q_in_smem ? qlen : 0)); w.g_n1 = w.g_lo1 + 32; w.g_lo2 = w.g_n1 + 32; w.g_lo3 = w.g_lo2 + 32; w.g_pre = w.g_lo3 + 32;
+    w.sstep = w.g_lo1 + FIT_WINDOW_INTS; w.dkey = w.sstep + n; w.did = w.dkey + n;
     if (prm.pairs_in_smem) { w.pkey = w.did + n; w.pid = w.pkey + npairs; }
     else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 2 * (size_t)npairs; w.pid = w.pkey + npairs; }
+    const QIndex qi{n, prm.q_packed};
+    const long long nunits = prm.units ? prm.n_units : prm.nb;
 
-    for (long long bi = (long long)blockIdx.x * W + wib; bi < prm.nb; bi += (long long)gridDim.x * W) {
-        const int box = prm.node_ids ? prm.node_ids[bi] : t.lnode[bi];
-        double* Qo = prm.Q + bi * prm.Q_stride;
-        const QIndex qi{n, prm.q_packed};
-        const long long qlen = prm.slotmap ? prm.npat : (P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n));
+    long long tk = clock64();
+#define FIT_TICK(k) do { if (prm.prof) { __syncwarp(); if (lane == 0) { const long long now_ = clock64(); atomicAdd(prm.prof + (k), (unsigned long long)(now_ - tk)); tk = now_; } } } while (0)
+    for (long long ui = (long long)blockIdx.x * W + wib; ui < nunits; ui += (long long)gridDim.x * W) {
+        int4 members = make_int4(-1, -1, -1, -1);  // box indices (output rows) of the unit
+        if (prm.units) members = prm.units[ui];
+        const long long bi0 = prm.units ? members.x : ui;
+        const int box = prm.node_ids ? prm.node_ids[bi0] : t.lnode[bi0];
+        double* Qo = prm.q_in_smem ? sQ : prm.Q + bi0 * prm.Q_stride;
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
         for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
-        for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
         __syncwarp();
+        FIT_TICK(0);
 
-        int status = CSP_FIT_OK;
-        double cval = dnan();
-        if (prm.mode == FIT_MODE_FULL) {
-            // ---- fit_poly1 (src/cs2.jl:162-205): chain results come from the pre-pass k_fit_chain
-            status = prm.ch_status[bi];
-            if (status == CSP_FIT_OK) {
-                const int Itop = prm.ch_itop[bi];
-                cval = prm.ch_c[bi];
-                for (int e = lane; e < n; e += 32) {
-                    w.sb[e] = t.ipos[(size_t)Itop * n + e];
-                    w.sy[e] = prm.ch_y[bi * n + e];
-                    w.sg[e] = prm.ch_g[bi * n + e];
-                    w.sstep[e] = prm.ch_step[bi * n + e];
-                }
-            }
-            __syncwarp();
+        // ---- coefficients_p (src/polynomials.jl:182-230): first split per off-diagonal slot, then its value
+        int tpos, foundp;
+        fit_scan<P, false>(prm, w, box, npairs, tpos, foundp);
+        FIT_TICK(1);
+        long long nvisited;
+        {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
+            int mx = -1;
+            for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
+            for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+            nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - prm.skip : max(0, tpos - prm.skip);
         }
-
-        long long nvisited = 0;
-        if (status == CSP_FIT_OK) {
-            // ---- the splits(box) scan: first occurrence per coefficient slot
-            int tpos = 0, foundp = 0, foundd = 0;
-            bool need_pairs = npairs > 0, need_diag = prm.mode == FIT_MODE_FULL;
-            const int skip = prm.skip;
-            for_split_groups(t, box, [&](const RangeGroup& grp) -> bool {
-                const int total = grp.total();
-                for (int base = 0; base < total; base += 32) {
-                    const int v = base + lane;
-                    const int id = grp.id(v);
-                    const int pos = tpos + lane;
-                    const bool act = v < total && pos >= skip;
-                    int pidx = -1, dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
-                    bool newp = false, newd0 = false, newd1 = false;
-                    if (act) {
-                        if (P == 2) {
-                            const int2 dd = __ldg((const int2*)t.idims + id);
-                            dd0 = dd.x; dd1 = dd.y;
-                            if (need_pairs && dd0 <= n && dd1 <= n && dd0 != dd1) {
-                                const int i = min(dd0, dd1) - 1, j = max(dd0, dd1) - 1;
-                                pidx = prm.slotmap ? __ldg(prm.slotmap + i * n + j) : i * n - i * (i + 1) / 2 + (j - i - 1);
-                                if (pidx >= 0) newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
-                            }
-                            if (need_diag) {
-                                const double2 xs = __ldg((const double2*)t.ixs + id);
-                                const double2 xf = __ldg((const double2*)t.ixself + id);
-                                if (dd0 <= n && w.dkey[dd0 - 1] > 2 * pos &&
-                                    (newinfo(xs.x, w.sb[dd0 - 1], w.sy[dd0 - 1]) || newinfo(xf.x, w.sb[dd0 - 1], w.sy[dd0 - 1]))) {
-                                    dk0 = 2 * pos;
-                                    newd0 = atomicMin(&w.dkey[dd0 - 1], dk0) == INT_MAX;
-                                }
-                                if (dd1 <= n && w.dkey[dd1 - 1] > 2 * pos + 1 &&
-                                    (newinfo(xs.y, w.sb[dd1 - 1], w.sy[dd1 - 1]) || newinfo(xf.y, w.sb[dd1 - 1], w.sy[dd1 - 1]))) {
-                                    dk1 = 2 * pos + 1;
-                                    newd1 = atomicMin(&w.dkey[dd1 - 1], dk1) == INT_MAX;
-                                }
-                            }
-                        } else {
-                            dd0 = __ldg(t.idims + id);
-                            if (need_pairs && dd0 <= n) {
-                                pidx = dd0 - 1;
-                                newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
-                            }
-                        }
-                    }
-                    __syncwarp();
-                    if (pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
-                    if (dk0 >= 0 && w.dkey[dd0 - 1] == dk0) w.did[dd0 - 1] = 2 * id;
-                    if (dk1 >= 0 && w.dkey[dd1 - 1] == dk1) w.did[dd1 - 1] = 2 * id + 1;
-                    foundp += __popc(__ballot_sync(FULL, newp));
-                    foundd += __popc(__ballot_sync(FULL, newd0)) + __popc(__ballot_sync(FULL, newd1));
-                    tpos += min(32, total - base);
-                    need_pairs = foundp < npairs;
-                    need_diag = prm.mode == FIT_MODE_FULL && foundd < n;
-                    if (!need_pairs && !need_diag) return true;
-                }
-                return false;
-            });
-            __syncwarp();
-            // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
-            {
-                int mx = -1;
-                for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
-                for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-                nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - skip : max(0, tpos - skip);
-            }
-
-            // ---- coefficients_p values (src/polynomials.jl:211-226), one lane per slot
+        {
+            // values (src/polynomials.jl:211-226), one lane per slot
             bool sawnan = false;
             if (P == 2 && prm.slotmap) {
                 for (int e = lane; e < npairs; e += 32) {
@@ -347,14 +425,13 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     Qo[e] = v;
                 }
             } else if (P == 2) {
-                for (int e = lane; e < n * n; e += 32) {
-                    const int i = e / n, j = e - i * n;
-                    if (i >= j) continue;
-                    const int pidx = i * n - i * (i + 1) / 2 + (j - i - 1);
-                    if (w.pkey[pidx] == INT_MAX) continue;
-                    const double v = coef_value<2>(t, w.pid[pidx]);
+                for (int e = lane; e < npairs; e += 32) {  // one lane per pair slot; (i, j) are the winning split's dimensions
+                    if (w.pkey[e] == INT_MAX) continue;
+                    const int id = w.pid[e];
+                    const int2 dd = __ldg((const int2*)t.idims + id);
+                    const double v = coef_value<2>(t, id);
                     sawnan |= (v != v);
-                    Qo[qi(i, j)] = v;
+                    Qo[qi(dd.x - 1, dd.y - 1)] = v;
                 }
             } else {
                 for (int e = lane; e < n; e += 32) {
@@ -366,6 +443,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
             }
             sawnan = __any_sync(FULL, sawnan) || npairs == 0;  // nothing to determine: replay the reference's loop literally
             __syncwarp();
+            FIT_TICK(2);
             if (sawnan) {
                 // A computed coefficient was NaN (non-finite samples or a vanishing denominator).  The reference then keeps
                 // overwriting that slot from later splits while still counting it towards `nremaining`; reproduce that
@@ -410,116 +488,154 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                 __syncwarp();
             }
 
-            if (prm.mode == FIT_MODE_FULL) {
-                // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per diagonal entry, sequential over k
-                for (int d = lane; d < n; d += 32) {
-                    if (w.dkey[d] == INT_MAX) continue;
-                    const int code = w.did[d];
-                    const int id = code >> 1, dimidx = code & 1;  // 0-based dimidx
-                    const double* xpos = t.ipos + (size_t)id * n;
-                    const double bd = w.sb[d], yd = w.sy[d];
-                    const double xsd = t.ixs[2 * id + dimidx];
-                    const int d2 = t.idims[2 * id + (1 - dimidx)] - 1;  // the split's other dimension (0-based; may be fictive)
-                    const double xs2 = t.ixs[2 * id + (1 - dimidx)];
-                    double xnew, xd, fchild, fref;
-                    bool swapped;
-                    if (newinfo(xsd, bd, yd)) {
-                        swapped = false;
-                        xnew = xsd; xd = xpos[d];
-                        fchild = t.icval[4 * id + (1 + dimidx)];  // split.others.children[dimidx]
-                        fref = t.icval[4 * id];                   // split.self
-                    } else {
-                        swapped = true;  // evaluate from children[3]'s position instead
-                        xnew = xpos[d]; xd = xsd;
-                        fchild = t.icval[4 * id + (2 - dimidx)];  // split.others.children[3-dimidx]
-                        fref = t.icval[4 * id + 3];
-                    }
-                    const double dxi = xnew - xd;
-                    const double coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
-                    double consts = -w.sg[d];
-                    const int sd = w.sstep[d];
-                    for (int k = 0; k < n; ++k) {
-                        if (k == d) continue;
-                        double xk = xpos[k];
-                        if (swapped && k == d2) xk = xs2;
-                        const bool precdk = sd <= w.sstep[k];  // prec[d,k]: d split before-or-with k
-                        const double xc = qcoef_lineq(false, dxi, xk, w.sb[k], w.sy[k], precdk);
-                        consts = consts - Qo[qi(d, k)] * xc;
-                    }
-                    Qo[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
-                }
-                __syncwarp();
-            }
         }
 
-        // ---- outputs
-        if (prm.mode == FIT_MODE_FULL) {
-            const bool ok = status == CSP_FIT_OK;
-            if (!ok) for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
-            for (int i = lane; i < n; i += 32) {
-                double gc = dnan(), bb = dnan();
-                if (ok) {  // canonicalize (src/cs2.jl:132-140): sequential over j
-                    gc = w.sg[i];
-                    const int si = w.sstep[i];
-                    for (int j = 0; j < n; ++j) {
-                        const double chi = (i == j) ? w.sy[j] : (si <= w.sstep[j] ? w.sb[j] : 2 * w.sy[j] - w.sb[j]);
-                        gc = gc + (w.sb[j] - chi) * Qo[qi(i, j)] / 2;
+        // ---- per member box: fit_poly1 results, fit_poly2_diag!, canonicalize, outputs
+#pragma unroll 1
+        for (int mi = 0; mi < 4; ++mi) {
+            const long long bi = prm.units ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : (mi == 0 ? ui : -1);
+            if (bi < 0) break;
+            double* Qg = prm.Q + bi * prm.Q_stride;
+            int status = CSP_FIT_OK;
+            double cval = dnan();
+            if (prm.mode == FIT_MODE_FULL) {
+                if (mi > 0)  // entries the previous member set: diagonal, g column, c
+                    for (int e = lane; e < n + (prm.q_packed ? 1 : 0); e += 32) { Qo[qi(e, e)] = dnan(); if (prm.q_packed && e < n) Qo[qi(e, n)] = dnan(); }
+                for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
+                // fit_poly1 (src/cs2.jl:162-205): chain results come from the pre-pass k_fit_chain
+                status = prm.ch_status[bi];
+                if (status == CSP_FIT_OK) {
+                    const int Itop = prm.ch_itop[bi];
+                    cval = prm.ch_c[bi];
+                    for (int e = lane; e < n; e += 32) {
+                        w.sb[e] = t.ipos[(size_t)Itop * n + e];
+                        w.sy[e] = prm.ch_y[bi * n + e];
+                        w.sg[e] = prm.ch_g[bi * n + e];
+                        w.sstep[e] = prm.ch_step[bi * n + e];
                     }
-                    bb = w.sb[i];
                 }
-                if (prm.q_packed) {  // model record: g is A's last column, the diagonal is stored halved (exact scaling)
-                    Qo[qi(i, n)] = gc;
-                    if (ok) Qo[qi(i, i)] = Qo[qi(i, i)] * 0.5;
-                } else if (prm.g) {
-                    prm.g[bi * prm.g_stride + i] = gc;
+                __syncwarp();
+                if (status == CSP_FIT_OK) {
+                    int dpos, foundd;
+                    fit_scan<P, true>(prm, w, box, n, dpos, foundd);
+                    FIT_TICK(2);
+                    // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per diagonal entry, sequential over k
+                    for (int d = lane; d < n; d += 32) {
+                        if (w.dkey[d] == INT_MAX) continue;
+                        const int code = w.did[d];
+                        const int id = code >> 1, dimidx = code & 1;  // 0-based dimidx
+                        const double* xpos = t.ipos + (size_t)id * n;
+                        const double bd = w.sb[d], yd = w.sy[d];
+                        const double xsd = t.ixs[2 * id + dimidx];
+                        const int d2 = t.idims[2 * id + (1 - dimidx)] - 1;  // the split's other dimension (0-based; may be fictive)
+                        const double xs2 = t.ixs[2 * id + (1 - dimidx)];
+                        double xnew, xd, fchild, fref;
+                        bool swapped;
+                        if (newinfo(xsd, bd, yd)) {
+                            swapped = false;
+                            xnew = xsd; xd = xpos[d];
+                            fchild = t.icval[4 * id + (1 + dimidx)];  // split.others.children[dimidx]
+                            fref = t.icval[4 * id];                   // split.self
+                        } else {
+                            swapped = true;  // evaluate from children[3]'s position instead
+                            xnew = xpos[d]; xd = xsd;
+                            fchild = t.icval[4 * id + (2 - dimidx)];  // split.others.children[3-dimidx]
+                            fref = t.icval[4 * id + 3];
+                        }
+                        const double dxi = xnew - xd;
+                        const double coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
+                        double consts = -w.sg[d];
+                        const int sd = w.sstep[d];
+                        for (int k = 0; k < n; ++k) {
+                            if (k == d) continue;
+                            double xk = xpos[k];
+                            if (swapped && k == d2) xk = xs2;
+                            const bool precdk = sd <= w.sstep[k];  // prec[d,k]: d split before-or-with k
+                            const double xc = qcoef_lineq(false, dxi, xk, w.sb[k], w.sy[k], precdk);
+                            consts = consts - Qo[qi(d, k)] * xc;
+                        }
+                        Qo[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
+                    }
+                    __syncwarp();
+                    FIT_TICK(3);
                 }
-                if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
-                if (prm.gnat) prm.gnat[bi * n + i] = ok ? w.sg[i] : dnan();
-                if (prm.y) prm.y[bi * n + i] = ok ? w.sy[i] : dnan();
             }
-            if (prm.prec)
-                for (int e = lane; e < n * n; e += 32) {
-                    const int j = e / n, i = e - j * n;  // column-major: prec[i,j]
-                    prm.prec[bi * (long long)n * n + e] = ok && (w.sstep[i] <= w.sstep[j]) ? 1 : 0;
+
+            // ---- outputs
+            if (prm.mode == FIT_MODE_FULL) {
+                const bool ok = status == CSP_FIT_OK;
+                if (!ok) for (long long e = lane; e < qlen; e += 32) Qg[e] = dnan();
+                for (int i = lane; i < n; i += 32) {
+                    double gc = dnan(), bb = dnan();
+                    if (ok) {  // canonicalize (src/cs2.jl:132-140): sequential over j
+                        gc = w.sg[i];
+                        const int si = w.sstep[i];
+                        for (int j = 0; j < n; ++j) {
+                            const double chi = (i == j) ? w.sy[j] : (si <= w.sstep[j] ? w.sb[j] : 2 * w.sy[j] - w.sb[j]);
+                            gc = gc + (w.sb[j] - chi) * Qo[qi(i, j)] / 2;
+                        }
+                        bb = w.sb[i];
+                    }
+                    if (prm.q_packed) {  // model record: g is A's last column, the diagonal is stored halved (exact scaling)
+                        Qo[qi(i, n)] = gc;
+                        if (ok) Qo[qi(i, i)] = Qo[qi(i, i)] * 0.5;
+                    } else if (prm.g) {
+                        prm.g[bi * prm.g_stride + i] = gc;
+                    }
+                    if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
+                    if (prm.gnat) prm.gnat[bi * n + i] = ok ? w.sg[i] : dnan();
+                    if (prm.y) prm.y[bi * n + i] = ok ? w.sy[i] : dnan();
                 }
-            if (lane == 0) {
-                if (prm.q_packed) Qo[qi(n, n)] = ok ? cval : dnan();
-                else if (prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
-            }
-        } else if (prm.mode == FIT_MODE_LIN) {
-            // degree-1 model of a CS1 box: c = value(box), b = position(box), g = Cp (already in Qo == g slot)
-            const int4 binfo = t.ninfo[box];
-            const bool isroot = binfo.x == box;
-            const int Ip = t.ninfo[binfo.x].y, ci = CSP_NF_CHILDINDEX(binfo.w);
-            const bool internal = !(binfo.w & CSP_NF_LEAF);
-            for (int i = lane; i < n; i += 32) {
-                double bb;
-                if (internal) bb = t.ipos[(size_t)binfo.y * n + i];
-                else if (isroot) bb = dnan();  // a tree without splits carries no positions on the device
-                else {
-                    bb = t.ipos[(size_t)Ip * n + i];
-                    if (P == 1) { if (ci == 1 && t.idims[Ip] - 1 == i) bb = t.ixs[Ip]; }
+                if (prm.prec)
+                    for (int e = lane; e < n * n; e += 32) {
+                        const int j = e / n, i = e - j * n;  // column-major: prec[i,j]
+                        prm.prec[bi * (long long)n * n + e] = ok && (w.sstep[i] <= w.sstep[j]) ? 1 : 0;
+                    }
+                if (lane == 0) {
+                    if (prm.q_packed) Qo[qi(n, n)] = ok ? cval : dnan();
+                    else if (prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
+                }
+            } else if (prm.mode == FIT_MODE_LIN) {
+                // degree-1 model of a CS1 box: c = value(box), b = position(box), g = Cp (already in Qo == g slot)
+                const int4 binfo = t.ninfo[box];
+                const bool isroot = binfo.x == box;
+                const int Ip = t.ninfo[binfo.x].y, ci = CSP_NF_CHILDINDEX(binfo.w);
+                const bool internal = !(binfo.w & CSP_NF_LEAF);
+                for (int i = lane; i < n; i += 32) {
+                    double bb;
+                    if (internal) bb = t.ipos[(size_t)binfo.y * n + i];
+                    else if (isroot) bb = dnan();  // a tree without splits carries no positions on the device
                     else {
-                        if ((ci & 1) && t.idims[2 * Ip] - 1 == i) bb = t.ixs[2 * Ip];
-                        if ((ci & 2) && t.idims[2 * Ip + 1] - 1 == i) bb = t.ixs[2 * Ip + 1];
+                        bb = t.ipos[(size_t)Ip * n + i];
+                        if (P == 1) { if (ci == 1 && t.idims[Ip] - 1 == i) bb = t.ixs[Ip]; }
+                        else {
+                            if ((ci & 1) && t.idims[2 * Ip] - 1 == i) bb = t.ixs[2 * Ip];
+                            if ((ci & 2) && t.idims[2 * Ip + 1] - 1 == i) bb = t.ixs[2 * Ip + 1];
+                        }
                     }
+                    if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
                 }
-                if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
+                if (lane == 0 && prm.c) {
+                    double cv;
+                    if (internal) cv = t.icval[(size_t)binfo.y << P];
+                    else if (isroot) cv = dnan();
+                    else cv = t.icval[((size_t)Ip << P) + ci];
+                    prm.c[bi * prm.c_stride] = cv;
+                }
             }
-            if (lane == 0 && prm.c) {
-                double cv;
-                if (internal) cv = t.icval[(size_t)binfo.y << P];
-                else if (isroot) cv = dnan();
-                else cv = t.icval[((size_t)Ip << P) + ci];
-                prm.c[bi * prm.c_stride] = cv;
+            if (prm.q_in_smem && !(prm.mode == FIT_MODE_FULL && status != CSP_FIT_OK)) {
+                __syncwarp();
+                for (long long e = lane; e < qlen; e += 32) Qg[e] = Qo[e];
             }
+            if (lane == 0) {
+                if (prm.status) prm.status[bi] = (uint8_t)status;
+                if (prm.visited) prm.visited[bi] = nvisited;
+            }
+            __syncwarp();
+            FIT_TICK(4);
         }
-        if (lane == 0) {
-            if (prm.status) prm.status[bi] = (uint8_t)status;
-            if (prm.visited) prm.visited[bi] = nvisited;
-        }
-        __syncwarp();
     }
+#undef FIT_TICK
 }
 
 // ---- fit_quadratic_gdiag! (reference src/cs2.jl:332-384): chain-free gradient + diagonal from two 1-d equations per dim ----
@@ -724,7 +840,9 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     if (prm.nb == 0) return CSP_OK;
     const int n = t->v.n, P = t->v.p;
     const long long npairs = prm.slotmap ? prm.npat : (P == 2 ? (long long)n * (n - 1) / 2 : n);
-    size_t base = (size_t)n * 8 * 3 + (size_t)n * 4 * 3;
+    const long long qlen = prm.slotmap ? prm.npat : (P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n));
+    prm.q_in_smem = qlen <= 1024 ? 1 : 0;  // up to 8 KB per warp
+    size_t base = (size_t)n * 8 * 3 + (prm.q_in_smem ? (size_t)qlen * 8 : 0) + FIT_WINDOW_INTS * 4 + (size_t)n * 4 * 3;
     size_t withpairs = base + (size_t)npairs * 8;
     prm.pairs_in_smem = withpairs <= 200 * 1024;
     size_t per_warp = prm.pairs_in_smem ? withpairs : base;
@@ -733,6 +851,11 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
     prm.warp_smem_bytes = (int)per_warp;
     size_t smem = per_warp * W;
+    if (prm.mode == FIT_MODE_FULL && P == 2 && !prm.node_ids && prm.nb == t->v.n_leaves && prm.q_in_smem && t->fit_units &&
+        !(getenv("CSP_FIT_SHARED") && atoi(getenv("CSP_FIT_SHARED")) == 0)) {
+        prm.units = t->fit_units;  // all leaves: sibling leaves share the off-diagonal work
+        prm.n_units = t->n_fit_units;
+    }
     if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
         const size_t nb = (size_t)prm.nb;
         const size_t need = nb * ((size_t)n * 20 + 16) + 64;
@@ -762,10 +885,16 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         int occ = 0;
         CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
         if (occ < 1) return csp_set_error(CSP_ERR_CUDA, "fit kernel does not fit on an SM (smem %zu)", smem);
-        long long grid = std::min<long long>((prm.nb + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
+        const long long nunits = prm.units ? prm.n_units : prm.nb;
+        long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {
             CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 2 * npairs * sizeof(int)));
             prm.scratch = (int*)*scratch_out;
+        }
+        const bool prof = getenv("CSP_FIT_PROF") && atoi(getenv("CSP_FIT_PROF"));
+        if (prof) {
+            CSP_CUDA(cudaMalloc(&prm.prof, 8 * sizeof(unsigned long long)));
+            CSP_CUDA(cudaMemset(prm.prof, 0, 8 * sizeof(unsigned long long)));
         }
         {
             CspTimed tm(CSP_K_FIT, st);
@@ -773,6 +902,13 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         }
         CSP_LAUNCHED();
         CSP_CUDA(cudaGetLastError());
+        if (prof) {  // developer aid: warp-clock totals per phase
+            unsigned long long h[8];
+            CSP_CUDA(cudaMemcpy(h, prm.prof, sizeof(h), cudaMemcpyDeviceToHost));
+            cudaFree(prm.prof);
+            static const char* names[5] = {"init+chain", "scan", "coefficients", "diagonal", "canon+output"};
+            for (int k = 0; k < 5; ++k) fprintf(stderr, "[csp fit prof] %-13s %10.0f clk/box\n", names[k], (double)h[k] / (double)prm.nb);
+        }
         return CSP_OK;
     };
     return P == 2 ? launch(k_fit<2>) : launch(k_fit<1>);

@@ -167,6 +167,21 @@ static int to_device(csp_tree* t, const std::vector<T>& h, const T** out) {
     return CSP_OK;
 }
 
+// ancestor table for the leaf fits (fit.cu): one thread per leaf climbs to the root once per tree version
+__global__ void __launch_bounds__(256) k_build_paths(const int4* __restrict__ ninfo, const int* __restrict__ lnode, const long long* __restrict__ lpoff,
+                                                     int2* __restrict__ lpath, int n_leaves) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < n_leaves; l += gridDim.x * blockDim.x) {
+        int v = lnode[l];
+        int4 ci = ninfo[v];
+        long long o = lpoff[l];
+        while (ci.x != v) {
+            v = ci.x;
+            ci = ninfo[v];
+            lpath[o++] = make_int2(ci.y, ci.z);
+        }
+    }
+}
+
 static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     const int n = d->n, p = d->p, C = 1 << p, nn = d->n_nodes, ni = d->n_internal, nl = d->n_leaves;
     // derived per-node arrays
@@ -256,6 +271,36 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     CSP_CHECK(to_device(t, std::vector<int>(d->child, d->child + (size_t)ni * C), &v.ichild));
     CSP_CHECK(to_device(t, std::vector<double>(d->pos, d->pos + (size_t)ni * n), &v.ipos));
     CSP_CHECK(to_device(t, lnode, &v.lnode));
+    {
+        std::vector<long long> lpoff((size_t)nl + 1, 0);
+        for (int l = 0; l < nl; ++l) lpoff[l + 1] = lpoff[l] + depth[lnode[l]];
+        CSP_CHECK(to_device(t, lpoff, &v.lpoff));
+        void* lp = nullptr;
+        const size_t bytes = std::max<size_t>((size_t)lpoff[nl] * sizeof(int2), 16);
+        CSP_CUDA(cudaMalloc(&lp, bytes));
+        t->allocs.push_back(lp);
+        t->bytes += bytes;
+        v.lpath = (const int2*)lp;
+        if (nl > 0) {
+            k_build_paths<<<std::min(4096, (nl + 255) / 256), 256>>>(v.ninfo, v.lnode, v.lpoff, (int2*)lp, nl);
+            CSP_CUDA(cudaGetLastError());
+        }
+    }
+    {   // fit work units: the real leaves that are children of the same split share their splits() traversal
+        std::vector<int4> units;
+        units.reserve((size_t)ni);
+        for (int I = 0; I < ni; ++I) {
+            int m[4] = {-1, -1, -1, -1}, cnt = 0;
+            for (int k = 0; k < C && cnt < 4; ++k) {
+                const int c = d->child[(size_t)I * C + k];
+                if (d->internal_id[c] < 0 && d->leaf_id[c] >= 0) m[cnt++] = d->leaf_id[c];
+            }
+            if (cnt) units.push_back(make_int4(m[0], m[1], m[2], m[3]));
+        }
+        if (ni == 0 && nl == 1) units.push_back(make_int4(0, -1, -1, -1));  // the root is the only leaf
+        CSP_CHECK(to_device(t, units, &t->fit_units));
+        t->n_fit_units = (long long)units.size();
+    }
     t->max_depth = maxdepth;
     return CSP_OK;
 }
