@@ -79,6 +79,16 @@ struct QIndex {
     }
 };
 
+// Offset of Q[i][j] (symmetric) for j = 0, 1, 2, ... without recomputing QIndex each time: start() then step(j) moves j -> j + 1.
+struct QWalk {
+    int idx, i, n, packed;
+    __device__ __forceinline__ QWalk(int i_, int n_, int packed_) : idx(packed_ ? i_ : i_ * n_), i(i_), n(n_), packed(packed_) {}
+    __device__ __forceinline__ void step(int j) {
+        if (packed) idx += j < i ? n - j : 1;  // column i of rows j < i, then row i
+        else idx += j < i ? 1 : n;             // hi * n + lo
+    }
+};
+
 // per-warp state shared by the helpers
 struct WarpCtx {
     int lane, n, npairs;
@@ -237,7 +247,7 @@ __device__ __forceinline__ double coef_value(const TreeView& t, int id) {
 // DIAG == false: first occurrence per off-diagonal pair slot (coefficients_p).  DIAG == true: first qualifying split per
 // diagonal entry (fit_poly2_diag!).  Returns through tpos the number of positions walked and through found the slots filled.
 template <int P, bool DIAG>
-__device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w, int box, int nslots, int& tpos, int& found) {
+__device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w, int box, int nslots, int& tpos, int& found, int& sw_cnt, int& sw_total) {
     const TreeView& t = prm.t;
     const int lane = w.lane, n = w.n, skip = prm.skip;
     const unsigned FULL = 0xffffffffu;
@@ -254,9 +264,14 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
     int4 winfo = binfo0;
     bool pseudo = !(binfo0.w & CSP_NF_LEAF);  // an internal box yields its own split and subtree first
     bool more = true, done = false;
+    // sw_cnt > 0: an earlier scan of the same box found that its whole traversal is ONE window, still in shared memory
+    const bool reuse = sw_cnt > 0;
     while (more && !done) {
         int cnt, Ia = 0, Sa = 0;
-        if (pseudo) {
+        if (reuse) {
+            cnt = sw_cnt;
+            more = false;
+        } else if (pseudo) {
             cnt = 1;
         } else if (use_path) {
             cnt = min(32, pdepth - pk);
@@ -280,6 +295,10 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
             __syncwarp();
         }
         if (cnt == 0) break;
+        int total;
+        if (reuse) {
+            total = sw_total;
+        } else {
         int lo1, n1, lo2, tot;
         if (pseudo) {
             lo1 = cI; n1 = cS; lo2 = 0; tot = lane == 0 ? cS : 0;
@@ -293,10 +312,12 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
         int pre = tot;  // inclusive scan
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(FULL, pre, o); if (lane >= o) pre += u; }
-        const int total = __shfl_sync(FULL, pre, 31);
+        total = __shfl_sync(FULL, pre, 31);
         if (lane < cnt) { w.g_lo1[lane] = lo1; w.g_n1[lane] = n1; w.g_lo2[lane] = lo2; w.g_lo3[lane] = Ia; w.g_pre[lane] = pre - tot; }
         if (lane == cnt - 1) w.g_pre[cnt] = total;
         __syncwarp();
+        if (!pseudo && !more && tpos == 0) { sw_cnt = cnt; sw_total = total; }  // first and only window
+        }
         for (int base = 0; base < total; base += 32) {
             const int v = base + lane;
             int id = 0;
@@ -369,7 +390,7 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
 // ranges of the parent's group always join to the parent's whole subtree), hence so are their off-diagonal coefficients;
 // the pair scan and the coefficient values are computed once and only fit_poly1 / fit_poly2_diag! / canonicalize run per leaf.
 template <int P>
-__global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
+__global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TreeView& t = prm.t;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -404,8 +425,8 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
         FIT_TICK(0);
 
         // ---- coefficients_p (src/polynomials.jl:182-230): first split per off-diagonal slot, then its value
-        int tpos, foundp;
-        fit_scan<P, false>(prm, w, box, npairs, tpos, foundp);
+        int tpos, foundp, sw_cnt = 0, sw_total = 0;
+        fit_scan<P, false>(prm, w, box, npairs, tpos, foundp, sw_cnt, sw_total);
         FIT_TICK(1);
         long long nvisited;
         {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
@@ -517,7 +538,7 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                 __syncwarp();
                 if (status == CSP_FIT_OK) {
                     int dpos, foundd;
-                    fit_scan<P, true>(prm, w, box, n, dpos, foundd);
+                    fit_scan<P, true>(prm, w, box, n, dpos, foundd, sw_cnt, sw_total);
                     FIT_TICK(2);
                     // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per diagonal entry, sequential over k
                     for (int d = lane; d < n; d += 32) {
@@ -546,13 +567,16 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                         const double coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
                         double consts = -w.sg[d];
                         const int sd = w.sstep[d];
-                        for (int k = 0; k < n; ++k) {
-                            if (k == d) continue;
-                            double xk = xpos[k];
+                        QWalk qw(d, n, prm.q_packed);
+#pragma unroll 4
+                        for (int k = 0; k < n; ++k) {  // the loads do not depend on the running sum: unrolled, they overlap
+                            double xk = __ldg(xpos + k);
                             if (swapped && k == d2) xk = xs2;
                             const bool precdk = sd <= w.sstep[k];  // prec[d,k]: d split before-or-with k
                             const double xc = qcoef_lineq(false, dxi, xk, w.sb[k], w.sy[k], precdk);
-                            consts = consts - Qo[qi(d, k)] * xc;
+                            const double term = Qo[qw.idx] * xc;
+                            qw.step(k);
+                            if (k != d) consts = consts - term;
                         }
                         Qo[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
                     }
@@ -570,9 +594,11 @@ __global__ void __launch_bounds__(256) k_fit(const FitParams prm) {
                     if (ok) {  // canonicalize (src/cs2.jl:132-140): sequential over j
                         gc = w.sg[i];
                         const int si = w.sstep[i];
+                        QWalk qw(i, n, prm.q_packed);
                         for (int j = 0; j < n; ++j) {
                             const double chi = (i == j) ? w.sy[j] : (si <= w.sstep[j] ? w.sb[j] : 2 * w.sy[j] - w.sb[j]);
-                            gc = gc + (w.sb[j] - chi) * Qo[qi(i, j)] / 2;
+                            gc = gc + (w.sb[j] - chi) * Qo[qw.idx] / 2;
+                            qw.step(j);
                         }
                         bb = w.sb[i];
                     }
