@@ -32,9 +32,6 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
 // arrive on `bar` once all of this thread's earlier cp.async have landed (the barrier's count already includes it)
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -48,6 +48,7 @@ struct FitParams {
     int* scratch;            // global pair tables when they do not fit in shared memory
     int pairs_in_smem;
     int q_in_smem;           // the box's Q / record is assembled in shared memory and written out once, coalesced
+    int tiles;               // large n (Q stays in global memory): per-warp staging tiles for the O(n^2) loops
     const int4* units; long long n_units;  // all-leaf fits: the real leaves (output rows, -1 padded) under each split that has any
     int warp_smem_bytes;
 };
@@ -94,9 +95,12 @@ struct WarpCtx {
     int lane, n, npairs;
     double *sb, *sy, *sg;
     int *sstep, *dkey, *did, *pkey, *pid;
+    int* plist;  // global-scratch mode only: the slots filled so far, so that nothing has to sweep all n(n-1)/2 of them
     int *g_lo1, *g_n1, *g_lo2, *g_lo3, *g_pre;  // one window of up to 32 range groups (g_pre has 33 entries)
 };
 #define FIT_WINDOW_INTS (4 * 32 + 33 + 3)  // keeps the following doubles 8-byte aligned
+#define FIT_TKB 16                        // k-block width of the staging tiles (rows padded to FIT_TKB + 1 doubles)
+#define FIT_TILE_BYTES (2 * 32 * (FIT_TKB + 1) * 8 + 32 * 4)
 
 // chaintop (src/polynomials.jl:22-98) on the flat arrays; executed by one lane.  Returns CSP_FIT_* and the top NODE id.
 __device__ int chaintop_dev(const TreeView& t, int box, int* covered, int* top_out) {
@@ -246,7 +250,7 @@ __device__ __forceinline__ double coef_value(const TreeView& t, int id) {
 // (group, offset) by bisection -- the many one-split groups next to a leaf share a chunk instead of taking one each.
 // DIAG == false: first occurrence per off-diagonal pair slot (coefficients_p).  DIAG == true: first qualifying split per
 // diagonal entry (fit_poly2_diag!).  Returns through tpos the number of positions walked and through found the slots filled.
-template <int P, bool DIAG>
+template <int P, bool DIAG, bool BIG>
 __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w, int box, int nslots, int& tpos, int& found, int& sw_cnt, int& sw_total) {
     const TreeView& t = prm.t;
     const int lane = w.lane, n = w.n, skip = prm.skip;
@@ -351,7 +355,9 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
                 }
                 __syncwarp();
                 if (pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
-                found += __popc(__ballot_sync(FULL, newp));
+                const unsigned nb = __ballot_sync(FULL, newp);
+                if (BIG && w.plist && newp) w.plist[found + __popc(nb & ((1u << lane) - 1))] = pidx;
+                found += __popc(nb);
             } else {
                 int dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
                 bool newd0 = false, newd1 = false;
@@ -389,8 +395,8 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
 // children of one split: their splits() traversals are identical (each leaf child has an empty subtree, so the two sibling
 // ranges of the parent's group always join to the parent's whole subtree), hence so are their off-diagonal coefficients;
 // the pair scan and the coefficient values are computed once and only fit_poly1 / fit_poly2_diag! / canonicalize run per leaf.
-template <int P>
-__global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
+template <int P, bool BIG>  // BIG: pair tables in global scratch and/or Q in global memory (large n)
+__global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TreeView& t = prm.t;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -407,7 +413,16 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
     w.g_lo1 = (int*)(sQ + (prm.q_in_smem ? qlen : 0)); w.g_n1 = w.g_lo1 + 32; w.g_lo2 = w.g_n1 + 32; w.g_lo3 = w.g_lo2 + 32; w.g_pre = w.g_lo3 + 32;
     w.sstep = w.g_lo1 + FIT_WINDOW_INTS; w.dkey = w.sstep + n; w.did = w.dkey + n;
     if (prm.pairs_in_smem) { w.pkey = w.did + n; w.pid = w.pkey + npairs; }
-    else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 2 * (size_t)npairs; w.pid = w.pkey + npairs; }
+    else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 3 * (size_t)npairs; w.pid = w.pkey + npairs; }
+    w.plist = (!BIG || prm.pairs_in_smem) ? nullptr : w.pid + npairs;
+    if (w.plist) {  // the table is cleared once; afterwards every unit resets just the slots it filled
+        for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
+        __syncwarp();
+    }
+    // staging tiles sit at the end of the warp's slice (only allocated when prm.tiles)
+    double* tq = (double*)(wbase + prm.warp_smem_bytes - FIT_TILE_BYTES);
+    double* tx = tq + 32 * (FIT_TKB + 1);
+    int* s_id = (int*)(tx + 32 * (FIT_TKB + 1));
     const QIndex qi{n, prm.q_packed};
     const long long nunits = prm.units ? prm.n_units : prm.nb;
 
@@ -420,33 +435,37 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
         const int box = prm.node_ids ? prm.node_ids[bi0] : t.lnode[bi0];
         double* Qo = prm.q_in_smem ? sQ : prm.Q + bi0 * prm.Q_stride;
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
-        for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
+        if (!w.plist) for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
         __syncwarp();
         FIT_TICK(0);
 
         // ---- coefficients_p (src/polynomials.jl:182-230): first split per off-diagonal slot, then its value
         int tpos, foundp, sw_cnt = 0, sw_total = 0;
-        fit_scan<P, false>(prm, w, box, npairs, tpos, foundp, sw_cnt, sw_total);
+        fit_scan<P, false, BIG>(prm, w, box, npairs, tpos, foundp, sw_cnt, sw_total);
         FIT_TICK(1);
         long long nvisited;
         {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
             int mx = -1;
-            for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
+            if (w.plist) { for (int e = lane; e < foundp; e += 32) mx = max(mx, w.pkey[w.plist[e]]); }
+            else for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
             for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
             nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - prm.skip : max(0, tpos - prm.skip);
         }
         {
             // values (src/polynomials.jl:211-226), one lane per slot
             bool sawnan = false;
+            const int nslot = w.plist ? foundp : npairs;
             if (P == 2 && prm.slotmap) {
-                for (int e = lane; e < npairs; e += 32) {
+                for (int e0 = lane; e0 < nslot; e0 += 32) {
+                    const int e = w.plist ? w.plist[e0] : e0;
                     if (w.pkey[e] == INT_MAX) continue;
                     const double v = coef_value<2>(t, w.pid[e]);
                     sawnan |= (v != v);
                     Qo[e] = v;
                 }
             } else if (P == 2) {
-                for (int e = lane; e < npairs; e += 32) {  // one lane per pair slot; (i, j) are the winning split's dimensions
+                for (int e0 = lane; e0 < nslot; e0 += 32) {  // one lane per pair slot; (i, j) are the winning split's dimensions
+                    const int e = w.plist ? w.plist[e0] : e0;
                     if (w.pkey[e] == INT_MAX) continue;
                     const int id = w.pid[e];
                     const int2 dd = __ldg((const int2*)t.idims + id);
@@ -464,6 +483,10 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
             }
             sawnan = __any_sync(FULL, sawnan) || npairs == 0;  // nothing to determine: replay the reference's loop literally
             __syncwarp();
+            if (w.plist) {
+                for (int e0 = lane; e0 < foundp; e0 += 32) w.pkey[w.plist[e0]] = INT_MAX;
+                __syncwarp();
+            }
             FIT_TICK(2);
             if (sawnan) {
                 // A computed coefficient was NaN (non-finite samples or a vanishing denominator).  The reference then keeps
@@ -538,9 +561,81 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
                 __syncwarp();
                 if (status == CSP_FIT_OK) {
                     int dpos, foundd;
-                    fit_scan<P, true>(prm, w, box, n, dpos, foundd, sw_cnt, sw_total);
+                    fit_scan<P, true, BIG>(prm, w, box, n, dpos, foundd, sw_cnt, sw_total);
                     FIT_TICK(2);
                     // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per diagonal entry, sequential over k
+                    if (BIG && prm.tiles) {
+                        // Large n, Q in global memory.  Lanes own d = r0 + lane; k advances in blocks of FIT_TKB.  Left of the diagonal
+                        // block Q[d][k] lives at row k, column d: adjacent lanes read adjacent doubles.  From the diagonal block on it
+                        // lives in row d (a stride of ~n doubles between lanes), and the split positions x[k] are a different row
+                        // per lane: both are staged through shared memory, two 128-byte row segments per load instruction.
+                        for (int r0 = 0; r0 < n; r0 += 32) {
+                            const int d = r0 + lane;
+                            const bool have = d < n && w.dkey[d] != INT_MAX;
+                            int id = -1, d2 = -1, sd = 0;
+                            double xs2 = 0.0, xnew = 0.0, xd = 0.0, fchild = 0.0, fref = 0.0, dxi = 0.0, coef = 0.0, consts = 0.0;
+                            bool swapped = false;
+                            if (have) {
+                                const int code = w.did[d];
+                                id = code >> 1;
+                                const int dimidx = code & 1;
+                                const double bd = w.sb[d], yd = w.sy[d];
+                                const double xsd = t.ixs[2 * id + dimidx], xposd = t.ipos[(size_t)id * n + d];
+                                d2 = t.idims[2 * id + (1 - dimidx)] - 1;
+                                xs2 = t.ixs[2 * id + (1 - dimidx)];
+                                if (newinfo(xsd, bd, yd)) {
+                                    xnew = xsd; xd = xposd;
+                                    fchild = t.icval[4 * id + (1 + dimidx)];
+                                    fref = t.icval[4 * id];
+                                } else {
+                                    swapped = true;
+                                    xnew = xposd; xd = xsd;
+                                    fchild = t.icval[4 * id + (2 - dimidx)];
+                                    fref = t.icval[4 * id + 3];
+                                }
+                                dxi = xnew - xd;
+                                coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
+                                consts = -w.sg[d];
+                                sd = w.sstep[d];
+                            }
+                            __syncwarp();
+                            s_id[lane] = id;
+                            __syncwarp();
+                            for (int k0 = 0; k0 < n; k0 += FIT_TKB) {
+                                const bool stageQ = k0 + FIT_TKB > r0;  // the diagonal block and everything right of it
+                                {
+                                    const int kk = lane & (FIT_TKB - 1), k = k0 + kk;
+                                    for (int rr = lane / FIT_TKB; rr < 32; rr += 32 / FIT_TKB) {
+                                        const int rid = s_id[rr];
+                                        if (rid >= 0 && k < n) {  // asynchronous copies: all of a block's loads are in flight together
+                                            cp_async8(tx + rr * (FIT_TKB + 1) + kk, t.ipos + (size_t)rid * n + k);
+                                            if (stageQ) cp_async8(tq + rr * (FIT_TKB + 1) + kk, Qo + qi(r0 + rr, k));
+                                        }
+                                    }
+                                }
+                                if (!stageQ && d < n) {  // left of the diagonal: row k0 + kk, column d -- coalesced as is
+                                    for (int kk = 0; kk < FIT_TKB; ++kk) cp_async8(tq + lane * (FIT_TKB + 1) + kk, Qo + qi(k0 + kk, d));
+                                }
+                                cp_async_wait_all();
+                                __syncwarp();
+                                if (have) {
+                                    const int kend = min(FIT_TKB, n - k0);
+                                    for (int kk = 0; kk < kend; ++kk) {
+                                        const int k = k0 + kk;
+                                        double xk = tx[lane * (FIT_TKB + 1) + kk];
+                                        if (swapped && k == d2) xk = xs2;
+                                        const bool precdk = sd <= w.sstep[k];
+                                        const double xc = qcoef_lineq(false, dxi, xk, w.sb[k], w.sy[k], precdk);
+                                        const double q = tq[lane * (FIT_TKB + 1) + kk];
+                                        const double term = q * xc;
+                                        if (k != d) consts = consts - term;
+                                    }
+                                }
+                                __syncwarp();
+                            }
+                            if (have) Qo[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
+                        }
+                    } else
                     for (int d = lane; d < n; d += 32) {
                         if (w.dkey[d] == INT_MAX) continue;
                         const int code = w.did[d];
@@ -589,9 +684,37 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
             if (prm.mode == FIT_MODE_FULL) {
                 const bool ok = status == CSP_FIT_OK;
                 if (!ok) for (long long e = lane; e < qlen; e += 32) Qg[e] = dnan();
-                for (int i = lane; i < n; i += 32) {
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
                     double gc = dnan(), bb = dnan();
-                    if (ok) {  // canonicalize (src/cs2.jl:132-140): sequential over j
+                    if (BIG && ok && prm.tiles) {  // canonicalize with Q staged as in the diagonal solve above (whole warp takes part)
+                        const bool have = i < n;
+                        const int si = have ? w.sstep[i] : 0;
+                        if (have) gc = w.sg[i];
+                        for (int j0 = 0; j0 < n; j0 += FIT_TKB) {
+                            const bool stageQ = j0 + FIT_TKB > i0;
+                            if (stageQ) {
+                                const int jj = lane & (FIT_TKB - 1), j = j0 + jj;
+                                for (int rr = lane / FIT_TKB; rr < 32; rr += 32 / FIT_TKB)
+                                    if (i0 + rr < n && j < n) cp_async8(tq + rr * (FIT_TKB + 1) + jj, Qo + qi(i0 + rr, j));
+                            } else if (have) {
+                                for (int jj = 0; jj < FIT_TKB; ++jj) cp_async8(tq + lane * (FIT_TKB + 1) + jj, Qo + qi(j0 + jj, i));
+                            }
+                            cp_async_wait_all();
+                            __syncwarp();
+                            if (have) {
+                                const int jend = min(FIT_TKB, n - j0);
+                                for (int jj = 0; jj < jend; ++jj) {
+                                    const int j = j0 + jj;
+                                    const double chi = (i == j) ? w.sy[j] : (si <= w.sstep[j] ? w.sb[j] : 2 * w.sy[j] - w.sb[j]);
+                                    const double q = tq[lane * (FIT_TKB + 1) + jj];
+                                    gc = gc + (w.sb[j] - chi) * q / 2;
+                                }
+                            }
+                            __syncwarp();
+                        }
+                        if (have) bb = w.sb[i];
+                    } else if (ok && i < n) {  // canonicalize (src/cs2.jl:132-140): sequential over j
                         gc = w.sg[i];
                         const int si = w.sstep[i];
                         QWalk qw(i, n, prm.q_packed);
@@ -602,6 +725,7 @@ __global__ void __launch_bounds__(256, 4) k_fit(const FitParams prm) {
                         }
                         bb = w.sb[i];
                     }
+                    if (i >= n) continue;
                     if (prm.q_packed) {  // model record: g is A's last column, the diagonal is stored halved (exact scaling)
                         Qo[qi(i, n)] = gc;
                         if (ok) Qo[qi(i, i)] = Qo[qi(i, i)] * 0.5;
@@ -870,10 +994,12 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     prm.q_in_smem = qlen <= 1024 ? 1 : 0;  // up to 8 KB per warp
     size_t base = (size_t)n * 8 * 3 + (prm.q_in_smem ? (size_t)qlen * 8 : 0) + FIT_WINDOW_INTS * 4 + (size_t)n * 4 * 3;
     size_t withpairs = base + (size_t)npairs * 8;
-    prm.pairs_in_smem = withpairs <= 200 * 1024;
+    prm.pairs_in_smem = withpairs <= 24 * 1024;  // larger tables live in (L2-resident) global scratch, see WarpCtx::plist
     size_t per_warp = prm.pairs_in_smem ? withpairs : base;
     per_warp = (per_warp + 15) & ~size_t(15);
-    int W = (int)std::min<size_t>(8, std::max<size_t>(1, (64 * 1024) / per_warp));
+    prm.tiles = (!prm.q_in_smem && prm.mode == FIT_MODE_FULL) ? 1 : 0;
+    if (prm.tiles) per_warp += FIT_TILE_BYTES;  // multiple of 16
+    int W = (int)std::min<size_t>(8, std::max<size_t>(1, ((prm.tiles ? 110 : 64) * 1024) / per_warp));
     if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
     prm.warp_smem_bytes = (int)per_warp;
     size_t smem = per_warp * W;
@@ -914,7 +1040,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         const long long nunits = prm.units ? prm.n_units : prm.nb;
         long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {
-            CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 2 * npairs * sizeof(int)));
+            CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 3 * npairs * sizeof(int)));
             prm.scratch = (int*)*scratch_out;
         }
         const bool prof = getenv("CSP_FIT_PROF") && atoi(getenv("CSP_FIT_PROF"));
@@ -937,7 +1063,9 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         }
         return CSP_OK;
     };
-    return P == 2 ? launch(k_fit<2>) : launch(k_fit<1>);
+    const bool big = !prm.pairs_in_smem || prm.tiles;
+    if (P == 2) return big ? launch(k_fit<2, true>) : launch(k_fit<2, false>);
+    return big ? launch(k_fit<1, true>) : launch(k_fit<1, false>);
 }
 
 // dense NaN-filled status helper for node id validation
