@@ -121,6 +121,11 @@ int csp_set_error(int code, const char* fmt, ...);
 extern std::atomic<long long> g_csp_launches;
 int csp_current_device();
 int csp_require_device();  // CSP_OK or CSP_ERR_NO_DEVICE
+// Device memory for handles and temporaries: stream-ordered allocations (legacy default stream) from the device's default
+// pool, whose release threshold is raised once so that freed blocks are reused -- re-uploading a tree or re-fitting models
+// every optimiser iteration then costs no cudaMalloc / cudaFree.  Callers synchronise before freeing memory other streams used.
+int csp_dev_alloc(void** p, size_t bytes);
+void csp_dev_free(void* p);
 
 #define CSP_CUDA(call)                                                                                         \
     do {                                                                                                       \

@@ -1012,8 +1012,8 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         const size_t nb = (size_t)prm.nb;
         const size_t need = nb * ((size_t)n * 20 + 16) + 64;
         if (need > t->fit_ws_bytes) {
-            if (t->fit_ws) { CSP_CUDA(cudaDeviceSynchronize()); cudaFree(t->fit_ws); t->fit_ws = nullptr; t->fit_ws_bytes = 0; }
-            CSP_CUDA(cudaMalloc(&t->fit_ws, need));
+            if (t->fit_ws) { CSP_CUDA(cudaDeviceSynchronize()); csp_dev_free(t->fit_ws); t->fit_ws = nullptr; t->fit_ws_bytes = 0; }
+            CSP_CHECK(csp_dev_alloc(&t->fit_ws, need));
             t->fit_ws_bytes = need;
         }
         char* base_p = (char*)t->fit_ws;
@@ -1040,7 +1040,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         const long long nunits = prm.units ? prm.n_units : prm.nb;
         long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {
-            CSP_CUDA(cudaMalloc(scratch_out, (size_t)grid * W * 3 * npairs * sizeof(int)));
+            CSP_CHECK(csp_dev_alloc(scratch_out, (size_t)grid * W * 3 * npairs * sizeof(int)));
             prm.scratch = (int*)*scratch_out;
         }
         const bool prof = getenv("CSP_FIT_PROF") && atoi(getenv("CSP_FIT_PROF"));
@@ -1083,11 +1083,8 @@ static int check_nodes(const csp_tree* t, const int32_t* node_ids, int64_t nb) {
 
 struct DevBuf {
     void* p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    int alloc(size_t bytes) {
-        CSP_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 16)));
-        return CSP_OK;
-    }
+    ~DevBuf() { csp_dev_free(p); }  // every user synchronises before its buffers go out of scope
+    int alloc(size_t bytes) { return csp_dev_alloc(&p, bytes); }
 };
 
 extern "C" {
@@ -1130,7 +1127,7 @@ int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "fit kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (scratch) cudaFree(scratch);
+        csp_dev_free(scratch);
         CSP_CHECK(rc);
         if (c) CSP_CUDA(cudaMemcpy(c + off, dc.p, cnt * 8, cudaMemcpyDeviceToHost));
         if (g) CSP_CUDA(cudaMemcpy(g + off * n, dg_.p, cnt * n * 8, cudaMemcpyDeviceToHost));
@@ -1173,7 +1170,7 @@ int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, i
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (scratch) cudaFree(scratch);
+        csp_dev_free(scratch);
         CSP_CHECK(rc);
         CSP_CUDA(cudaMemcpy(Cp + off * (per / 8), dQ.p, cnt * per, cudaMemcpyDeviceToHost));
         if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
@@ -1221,7 +1218,7 @@ int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (scratch) cudaFree(scratch);
+        csp_dev_free(scratch);
         CSP_CHECK(rc);
         if (npat > 0) CSP_CUDA(cudaMemcpy(vals + off * npat, dQ.p, cnt * (long long)npat * 8, cudaMemcpyDeviceToHost));
         if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
@@ -1259,13 +1256,13 @@ int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
     mo->stride = csp_model_stride(n, mo->degree);
     mo->n_models = t->v.n_leaves;
     auto fail = [&](int rc) { csp_models_free(mo); return rc; };
-    if (cudaMalloc(&mo->data, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess || cudaMalloc(&mo->status, (size_t)mo->n_models) != cudaSuccess)
+    if (csp_dev_alloc((void**)&mo->data, (size_t)mo->n_models * mo->stride * 8) != CSP_OK || csp_dev_alloc((void**)&mo->status, (size_t)mo->n_models) != CSP_OK)
         return fail(csp_set_error(CSP_ERR_NOMEM, "cannot allocate %lld model records of %d doubles", mo->n_models, mo->stride));
     if (cudaMemset(mo->data, 0, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess) return fail(csp_set_error(CSP_ERR_CUDA, "memset failed"));
     void* scratch = nullptr;
     int rc = models_fit_launch(t, skip, mo, 0, &scratch);
     if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "fit kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (scratch) cudaFree(scratch);
+    csp_dev_free(scratch);
     if (rc != CSP_OK) return fail(rc);
     *out = mo;
     return CSP_OK;
@@ -1313,7 +1310,7 @@ int csp_fit_gdiag(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
             if (cudaGetLastError() != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
                 rc = csp_set_error(CSP_ERR_CUDA, "gdiag kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
-        if (scratch) cudaFree(scratch);
+        csp_dev_free(scratch);
         CSP_CHECK(rc);
         CSP_CUDA(cudaMemcpy(c + off, dc.p, cnt * 8, cudaMemcpyDeviceToHost));
         CSP_CUDA(cudaMemcpy(g + off * n, dgv.p, cnt * n * 8, cudaMemcpyDeviceToHost));
@@ -1369,7 +1366,7 @@ int csp_models_refit(const csp_tree* t, int32_t skip, csp_models* mo, void* stre
     int rc = models_fit_launch(t, skip, mo, (cudaStream_t)stream, &scratch);
     if (scratch) {  // large-n path uses a global scratch table: wait before releasing it
         cudaStreamSynchronize((cudaStream_t)stream);
-        cudaFree(scratch);
+        csp_dev_free(scratch);
     }
     return rc;
 }

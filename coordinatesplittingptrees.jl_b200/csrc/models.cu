@@ -9,8 +9,9 @@ int csp_models_free(csp_models* mo) {
     if (!mo) return CSP_OK;
     {
         DeviceGuard g(mo->device);
-        if (mo->data) cudaFree(mo->data);
-        if (mo->status) cudaFree(mo->status);
+        cudaDeviceSynchronize();
+        csp_dev_free(mo->data);
+        csp_dev_free(mo->status);
     }
     delete mo;
     return CSP_OK;
@@ -38,7 +39,7 @@ int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double
     const long long slab = std::max<long long>(1, (256LL << 20) / (long long)(S * 8));
     std::vector<double> stage((size_t)std::min<long long>(slab, n_models) * S);
     auto fail = [&](int rc) { csp_models_free(mo); return rc; };
-    if (cudaMalloc(&mo->data, (size_t)n_models * S * 8) != cudaSuccess || cudaMalloc(&mo->status, (size_t)n_models) != cudaSuccess)
+    if (csp_dev_alloc((void**)&mo->data, (size_t)n_models * S * 8) != CSP_OK || csp_dev_alloc((void**)&mo->status, (size_t)n_models) != CSP_OK)
         return fail(csp_set_error(CSP_ERR_NOMEM, "cannot allocate %lld model records", (long long)n_models));
     if (cudaMemset(mo->status, 0, (size_t)n_models) != cudaSuccess) return fail(csp_set_error(CSP_ERR_CUDA, "memset failed"));
     for (long long off = 0; off < n_models; off += slab) {

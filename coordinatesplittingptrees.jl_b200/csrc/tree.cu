@@ -2,6 +2,10 @@
 // Replaces the Box/Split/World object graph (reference src/types.jl:7-23,155-192) by SoA arrays in HBM.
 #include <cstring>
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "common.cuh"
 
 std::atomic<long long> g_csp_launches{0};
@@ -18,6 +22,38 @@ int csp_set_error(int code, const char* fmt, ...) {
     return code;
 }
 int csp_current_device() { return g_device; }
+int csp_dev_alloc(void** p, size_t bytes) {
+    static bool ready[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+        ready[dev] = true;
+    }
+    *p = nullptr;
+    cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), (cudaStream_t)0);
+    if (e != cudaSuccess) {  // give cached blocks back and retry once before reporting
+        cudaGetLastError();
+        cudaMemPool_t pool;
+        cudaDeviceSynchronize();
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+        e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), (cudaStream_t)0);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return csp_set_error(CSP_ERR_NOMEM, "cannot allocate %zu bytes of device memory: %s", bytes, cudaGetErrorString(e));
+    }
+    cudaStreamSynchronize((cudaStream_t)0);  // the block may be used from any stream right away
+    return CSP_OK;
+}
+void csp_dev_free(void* p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}
 int csp_require_device() {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
@@ -159,7 +195,7 @@ template <class T>
 static int to_device(csp_tree* t, const std::vector<T>& h, const T** out) {
     void* p = nullptr;
     size_t bytes = std::max<size_t>(h.size() * sizeof(T), 16);
-    CSP_CUDA(cudaMalloc(&p, bytes));
+    CSP_CHECK(csp_dev_alloc(&p, bytes));
     t->allocs.push_back(p);
     t->bytes += bytes;
     if (!h.empty()) CSP_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -183,6 +219,10 @@ __global__ void __launch_bounds__(256) k_build_paths(const int4* __restrict__ ni
 }
 
 static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
+    const bool uprof = getenv("CSP_UPLOAD_PROF") && atoi(getenv("CSP_UPLOAD_PROF"));
+    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double tp0 = tnow();
+    auto lap = [&](const char* what) { if (uprof) { const double t1 = tnow(); fprintf(stderr, "[csp upload prof] %-22s %8.3f ms\n", what, t1 - tp0); tp0 = t1; } };
     const int n = d->n, p = d->p, C = 1 << p, nn = d->n_nodes, ni = d->n_internal, nl = d->n_leaves;
     // derived per-node arrays
     std::vector<int4> ninfo(nn);
@@ -200,6 +240,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
         if (v > 0) depth[v] = depth[d->parent[v]] + 1;
         if (d->leaf_id[v] >= 0) { lnode[d->leaf_id[v]] = v; maxdepth = std::max(maxdepth, depth[v]); }
     }
+    lap("node info");
     // derived per-internal arrays (preorder ids)
     std::vector<double> ixself((size_t)ni * p), icval((size_t)ni * C);
     for (int I = 0; I < ni; ++I) {
@@ -209,6 +250,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
         }
         for (int k = 0; k < C; ++k) icval[(size_t)I * C + k] = d->val[d->child[(size_t)I * C + k]];
     }
+    lap("xself / child values");
     // descent records in BFS order (see common.cuh)
     std::vector<DRec1> r1(p == 1 ? ni : 0);
     std::vector<DRec2> r2(p == 2 ? ni : 0);
@@ -252,6 +294,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             }
         }
     }
+    lap("descent records");
     t->h_lower.assign(d->lower, d->lower + n);
     t->h_upper.assign(d->upper, d->upper + n);
     TreeView& v = t->v;
@@ -271,13 +314,14 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     CSP_CHECK(to_device(t, std::vector<int>(d->child, d->child + (size_t)ni * C), &v.ichild));
     CSP_CHECK(to_device(t, std::vector<double>(d->pos, d->pos + (size_t)ni * n), &v.ipos));
     CSP_CHECK(to_device(t, lnode, &v.lnode));
+    lap("uploads");
     {
         std::vector<long long> lpoff((size_t)nl + 1, 0);
         for (int l = 0; l < nl; ++l) lpoff[l + 1] = lpoff[l] + depth[lnode[l]];
         CSP_CHECK(to_device(t, lpoff, &v.lpoff));
         void* lp = nullptr;
         const size_t bytes = std::max<size_t>((size_t)lpoff[nl] * sizeof(int2), 16);
-        CSP_CUDA(cudaMalloc(&lp, bytes));
+        CSP_CHECK(csp_dev_alloc(&lp, bytes));
         t->allocs.push_back(lp);
         t->bytes += bytes;
         v.lpath = (const int2*)lp;
@@ -286,6 +330,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             CSP_CUDA(cudaGetLastError());
         }
     }
+    lap("ancestor paths");
     {   // fit work units: the real leaves that are children of the same split share their splits() traversal
         std::vector<int4> units;
         units.reserve((size_t)ni);
@@ -301,6 +346,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
         CSP_CHECK(to_device(t, units, &t->fit_units));
         t->n_fit_units = (long long)units.size();
     }
+    lap("fit units");
     t->max_depth = maxdepth;
     return CSP_OK;
 }
@@ -311,8 +357,9 @@ int csp_tree_free(csp_tree* tree) {
     if (!tree) return CSP_OK;
     {
         DeviceGuard g(tree->device);
-        for (void* p : tree->allocs) cudaFree(p);
-        if (tree->fit_ws) cudaFree(tree->fit_ws);
+        cudaDeviceSynchronize();  // work on any stream may still read the tree
+        for (void* p : tree->allocs) csp_dev_free(p);
+        csp_dev_free(tree->fit_ws);
         for (int i = 0; i < 2; ++i) {
             if (tree->pipe_st[i]) cudaStreamDestroy(tree->pipe_st[i]);
             if (tree->pipe_join[i]) cudaEventDestroy(tree->pipe_join[i]);
