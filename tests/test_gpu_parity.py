@@ -10,7 +10,7 @@ import pytest
 import csp_b200 as cb
 from csp_b200.device import DeviceTree, LeafModels
 from oracle import oracle as O
-from helpers import grow_both
+from helpers import oracle_objective, grow_both
 
 pytestmark = pytest.mark.gpu
 
@@ -132,6 +132,65 @@ def test_fit_leaves_bit_exact(n, npoints, skip):
     oCp, ovis, _ = O.coefficients_p_batch(olv, skip=skip, nthreads=O.max_threads())
     assert same(Cp, oCp.reshape(len(olv), n, n).transpose(0, 2, 1))
     assert same(vis, ovis)
+
+
+def _deep_tree(n, depth_points, seed):
+    """A tree whose leaves near x* sit under more than 32 ancestors: every point lands in the box the previous one created."""
+    obj = cb.synthetic.quad_objective(n, seed, sigma=1e-3)
+    rng = np.random.default_rng(seed)
+    xstar = rng.random(n) * 0.5 + 0.1
+    delta = rng.random(n) * 0.3 + 0.1
+    X = np.array([xstar + delta * 0.8 ** k for k in range(depth_points)])
+    lo, up, pos = np.full(n, -1.0), np.full(n, 1.0), np.zeros(n)
+    cycle = cb.synthetic.round_robin_dimlists(n)
+    root = cb.Box(cb.World(lo, up, pos, obj), 2)
+    cb.addpoints(root, X, cycle, obj)
+    oroot = O.Box(O.World(lo, up, pos, obj(pos)), 2)
+    fp, ctx = oracle_objective(obj)
+    O.addpoints_cycle(oroot, X, cycle, fp, ctx)
+    O.index_tree(oroot)
+    return root, oroot
+
+
+@pytest.mark.parametrize("case", ["n2", "n6_failures", "n10", "n20", "n40_smem_limit", "n50_global_q", "deep_n2", "deep_n4"])
+def test_all_leaf_model_fit_bit_exact(case, monkeypatch):
+    """csp_models_fit (the resident all-leaf fit: sibling leaves share the split scan and the off-diagonal coefficients, the
+    record is assembled in shared memory) equals the per-box path and the oracle bit for bit -- including trees where
+    chaintop fails for some siblings only, records too large for shared memory, and leaves under more than 32 ancestors
+    (several ancestor windows per traversal)."""
+    if case.startswith("deep"):
+        n = int(case[-1])
+        root, oroot = _deep_tree(n, 70 if n == 2 else 45, seed=77 + n)
+    elif case == "n6_failures":
+        rng = np.random.default_rng(5)
+        cycle = []
+        for _ in range(40):
+            perm = rng.permutation(6) + 1
+            cycle.append([(int(perm[i]), int(perm[i + 1])) for i in range(0, 6, 2)])
+        root, oroot, _ = grow_both(6, 2, 160, seed=9, cycle=cycle)
+    else:
+        n = int(case.split("_")[0][1:])
+        root, oroot, _ = grow_both(n, 2, {2: 300, 10: 400, 20: 150, 40: 30, 50: 30}[n], seed=600 + n)
+    n = root.n
+    dt = cb.device_tree(root)
+    olv = O.leaves(oroot)
+    if case.startswith("deep"):
+        assert dt.max_depth > 32, dt.max_depth
+    ofit = O.fit_boxes_batch(olv, nthreads=O.max_threads())
+    if case == "n6_failures":
+        assert set(np.unique(ofit["status"])) >= {0, 1}
+    iu = np.triu_indices(n)
+    for shared in ("1", "0"):
+        monkeypatch.setenv("CSP_FIT_SHARED", shared)
+        mo = dt.fit_models().download()
+        assert same(mo["status"], ofit["status"])
+        assert same(mo["c"], ofit["c"]) and same(mo["g"], ofit["g"]) and same(mo["b"], ofit["b"])
+        # download returns Q in the SymmetricArray .data layout (values at [i, j], i <= j)
+        assert same(mo["Q"][:, iu[0], iu[1]], ofit["Q"][:, iu[0], iu[1]])
+    box = dt.fit_boxes()
+    for k in ("c", "g", "b", "status"):
+        assert same(box[k], ofit[k]), k
+    assert same(box["Q"][:, iu[0], iu[1]], ofit["Q"][:, iu[0], iu[1]])
 
 
 def test_fit_internal_boxes_and_failures():
