@@ -35,6 +35,13 @@ int csp_dev_alloc(void** p, size_t bytes) {
         ready[dev] = true;
     }
     *p = nullptr;
+    // size classes (x1.125 steps, 64 KB aligned): a tree that grows a little every optimiser iteration keeps landing in the
+    // blocks its previous version released instead of making the pool map new memory
+    if (bytes > 65536) {
+        size_t cls = 65536;
+        while (cls < bytes) cls = (cls + cls / 8 + 65535) & ~size_t(65535);
+        bytes = cls;
+    }
     cudaError_t e = cudaMallocAsync(p, std::max<size_t>(bytes, 16), (cudaStream_t)0);
     if (e != cudaSuccess) {  // give cached blocks back and retry once before reporting
         cudaGetLastError();
@@ -378,8 +385,8 @@ int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out) {
     csp_tree* t = new csp_tree();
     t->device = csp_current_device();
     DeviceGuard g(t->device);
-    cudaDeviceProp prop{};
-    if (cudaGetDeviceProperties(&prop, t->device) == cudaSuccess) t->n_sm = prop.multiProcessorCount;
+    int sms = 0;  // (cudaGetDeviceProperties costs milliseconds per call)
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device) == cudaSuccess) t->n_sm = sms;
     int rc = upload_impl(desc, t);
     if (rc != CSP_OK) { csp_tree_free(t); return rc; }
     *out = t;

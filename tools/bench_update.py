@@ -12,12 +12,15 @@ X = cb.synthetic.uniform_queries(root, 10000, seed=1)
 cb.find_leaf_at(root, X)
 t = {"addpoint": 0.0, "flatten": 0.0, "upload": 0.0, "locate_1e4": 0.0, "fit_all": 0.0}
 iters = 10
-for it in range(iters):
+WARM = 3  # untimed iterations: the allocation pool and the CUDA context reach their steady state
+for it in range(-WARM, iters):
     t0 = time.perf_counter(); cb.addpoint(root, rng.random(10) * 2 - 1, cycle[it % 9], obj); t1 = time.perf_counter()
     flat = root.tree.flat(); t2 = time.perf_counter()
     dt = cb.device_tree(root); t3 = time.perf_counter()
     dt.find_leaf(X); t4 = time.perf_counter()
     m = dt.fit_models(); m.close(); t5 = time.perf_counter()
+    if it < 0:
+        continue
     for k, v in zip(t, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
         t[k] += v / iters
 print(json.dumps({k: round(v * 1e3, 3) for k, v in t.items()} | {"unit": "ms per iteration", "leaves": root.tree.counts()["n_leaves"]}))
