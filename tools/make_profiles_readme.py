@@ -20,6 +20,7 @@ ref = json.load(open('profiles/r1_bench_reference_arm.json'))
 d = json.load(open('profiles/r1_dense_c4.json'))
 d64 = json.load(open('profiles/r1_dense_n64.json'))
 d300 = json.load(open('profiles/r1_dense_n300.json'))
+c4 = json.load(open('profiles/r1_c4_end_to_end.json'))
 c3 = json.load(open('profiles/r1_bench_c3.json'))
 fits = [json.loads(l) for l in open('profiles/r1_fits.jsonl') if l.strip()]
 upd = json.load(open('profiles/r1_update_loop.json'))
@@ -43,6 +44,7 @@ step = re-fit every leaf model + locate/evaluate every query.  Peak = measured c
 | `r1_<kernel>.ncu-rep` / `.summary.txt` | `ncu --set full --import-source on` capture of one launch + key metrics and per-source-line stall summary (`tools/ncu_metrics.py`, `tools/ncu_lines.py`); `k_fit` is the C2 launch, `k_fit_C3` the C3 launch, `k_eval_dmma` config C4 |
 | `r1_traffic.json` | DRAM bytes (read + write) per launch of each capture, per query / per leaf (`tools/make_traffic_json.py`) |
 | `r1_dense_c4.json`, `r1_dense_n64.json`, `r1_dense_n300.json` | `tools/bench_dense.py`: grouped dense evaluation on the DMMA kernels (C4: n = 100; n = 64; n = 300 = the panel-streaming kernel), with a cuBLAS DGEMM rate measured in the same run and the issued-DMMA fraction of the measured pipe peak |
+| `r1_c4_end_to_end.json` | `tools/bench_c4.py`: the whole C4 path (CS1 tree n = 100 grown by 100 addpoint!s, K1 locate + binning + DMMA evaluation, 2e7 resident uniform queries) |
 | `r1_fp64_peaks.txt` | `tools/ubench/fp64_peaks.cu`: raw DMMA.8x8x4 / DFMA throughput of the box (the K3b roofline denominator) |
 | `r1_fits.jsonl` | `tools/bench_fits.py C2 C3 C5`: all-leaf fit time, fits/s and fraction of the HBM roofline with SURVEY 8(d)'s algorithmic bytes |
 | `r1_update_loop.json` | `tools/bench_update.py`: one optimiser-loop iteration on a C2-sized tree (addpoint, re-flatten, re-upload, 1e4 queries, all-leaf fit) |
@@ -57,6 +59,7 @@ step = re-fit every leaf model + locate/evaluate every query.  Peak = measured c
 | reference arm (`--impl reference`) | {ref['value']:.3e} queries/s, {ref['fits']['value']:.3e} fits/s |
 | N = 2 (weak scaling, one NCCL broadcast of the tree blob) | {b2['value']:.3e} queries/s |
 | config C3 (n = 20, 1e6 leaves), N = 1 | {c3['value']:.3e} queries/s ({c3['ms_per_step']:.1f} ms per 1e8-query step, of which {c3['fits']['kernel_ms']:.2f} ms re-fit all 1 000 021 leaves: {c3['fits']['value']:.3e} fits/s, {c3['fits']['frac']:.2f} of the HBM roofline) |
+| config C4 end to end (CS1 n = 100, 1e4 leaves, locate + DMMA evaluation), N = 1 | {c4['queries_per_s']:.3e} queries/s ({c4['ms_per_step']:.1f} ms per 2e7 queries: locate {c4['kernel_ms_per_step']['locate']:.1f}, evaluation {c4['kernel_ms_per_step']['eval_binned']:.1f}) |
 | clocks during the timed region | {b['clocks']['sm_mhz']} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'} |
 
 ## Where a step's time goes (CUDA events around every launch, `csp_timing_*`; 24 chunks of 4 194 304 queries)
