@@ -162,29 +162,43 @@ __global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const 
     }
 }
 
-// Compile-time n.  A warp takes 32 consecutive binned positions.  The x rows are gathered straight into registers
-// (128-bit loads); the leaf's record is brought into the warp's shared-memory slot by ONE coalesced cooperative read
-// (so all of it is in flight at once, instead of a chain of register-limited batches) and then read back as broadcast
-// 128-bit shared loads.  A warp whose positions straddle several leaves repeats the staging once per distinct leaf.
+// Compile-time n.  A warp owns a CONTIGUOUS range of binned positions and walks it 32 at a time.  The x rows are gathered
+// straight into registers (128-bit loads).  Leaf records go through two per-warp shared-memory slots filled by 16-byte
+// cp.async copies: the record of the leaf in use stays put while the run continues over the following iterations, and the
+// next distinct leaf's record (known from the sorted perm entries already in registers) is fetched while the current one
+// is being evaluated, so the record latency is off the critical path.  Records are read back as broadcast 128-bit loads.
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, const double* __restrict__ X,
                                                           const int2* __restrict__ perm, const int* __restrict__ total,
                                                           double* __restrict__ val) {
     constexpr int NC = (N + 1) * (N + 2) / 2;  // coefficients of the packed (N+1)x(N+1) triangle
-    constexpr bool VEC = (N & 1) == 0;         // record, A block and x rows are 16-byte aligned
-    extern __shared__ __align__(16) double s_rec[];  // [warps][stride]
+    constexpr bool VEC = (N & 1) == 0;         // A block and x rows are 16-byte aligned
+    extern __shared__ __align__(16) double s_rec[];  // [warps][2][stride]
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, stride = mv.stride;
-    double* rec = s_rec + (size_t)(threadIdx.x >> 5) * stride;
+    double* slot = s_rec + (size_t)(threadIdx.x >> 5) * 2 * stride;
     const long long tot = *total;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int2 ql = s < tot ? perm[s] : make_int2(0, -1);
-    for (; s - lane < tot; s += step) {  // warp-uniform trip count
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long per = ((tot + 31) / 32 + nwarps - 1) / nwarps * 32;  // positions per warp, a multiple of 32
+    const long long start = wid * per, end = start + per < tot ? start + per : tot;
+    if (start >= end) return;
+    auto fetch = [&](int lf, int b) {  // whole record (stride % 4 == 0 doubles, 32-byte aligned) into slot b
+        const double* __restrict__ M = mv.data + (size_t)lf * stride;
+        double* dst = slot + (size_t)b * stride;
+        for (int k = lane * 2; k < stride; k += 64) cp_async16(dst + k, M + k);
+    };
+    int cur = 0, staged = -1, pre = -1;  // slot in use, leaf it holds, leaf in flight into the other slot (warp-uniform)
+    long long s = start + lane;
+    int2 ql = s < end ? perm[s] : make_int2(0, -1);
+    for (; s - lane < end; s += 32) {
         const bool valid = ql.y >= 0;
-        const long long sn = s + step;
-        const int2 qn = sn < tot ? perm[sn] : make_int2(0, -1);  // next iteration's position, in flight during this one
-        double x[N];
+        const long long sn = s + 32;
+        const int2 qn = sn < end ? perm[sn] : make_int2(0, -1);  // the next 32 positions, in flight during this iteration
+        double x[N + 1];
         if (valid) {
             const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
             if constexpr (VEC) {
@@ -205,25 +219,53 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
             const int lf = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
             const bool mine = valid && ql.y == lf;
             todo &= ~__ballot_sync(FULL, mine);
-            const double* __restrict__ M = mv.data + (size_t)lf * stride;
-            for (int k = lane * 2; k < stride; k += 64) *(double2*)(rec + k) = __ldg((const double2*)(M + k));  // stride % 4 == 0
-            __syncwarp();
+            // bring lf into the current slot
+            if (lf != staged) {
+                if (lf == pre) {
+                    cur ^= 1;
+                } else {  // nothing useful was prefetched (first leaf of the range)
+                    cp_async_wait_all();
+                    __syncwarp();
+                    fetch(lf, cur);
+                }
+                staged = lf;
+                pre = -1;
+                cp_async_wait_all();
+                __syncwarp();
+            }
+            // start fetching the next distinct leaf: among the remaining lanes of this iteration, else in the next 32 positions
+            if (pre < 0) {
+                int nl = -1;
+                if (todo) {
+                    nl = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
+                } else {
+                    const unsigned other = __ballot_sync(FULL, qn.y >= 0 && qn.y != lf);
+                    if (other) nl = __shfl_sync(FULL, qn.y, __ffs(other) - 1);
+                }
+                if (nl >= 0) {
+                    fetch(nl, cur ^ 1);
+                    pre = nl;
+                }
+            }
             if (mine) {
-                double z[N + 1];
+                const double* rec = slot + (size_t)cur * stride;
+                // z = x - b in place (a thread is `mine` exactly once per iteration)
                 if constexpr (VEC) {
 #pragma unroll
                     for (int i = 0; i < N; i += 2) {
                         const double2 b = *(const double2*)(rec + i);
-                        z[i] = x[i] - b.x;
-                        z[i + 1] = x[i + 1] - b.y;
+                        x[i] -= b.x;
+                        x[i + 1] -= b.y;
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < N; ++i) z[i] = x[i] - rec[i];
+                    for (int i = 0; i < N; ++i) x[i] -= rec[i];
                 }
-                z[N] = 1.0;
+                x[N] = 1.0;
                 const double* A = rec + N;
-                double acc0 = 0.0, acc1 = 0.0, row = 0.0;
+                // Row i of the triangle: sum_j A_ij z_j, then times z_i.  Each row's sum runs as four interleaved partial chains
+                // (and the rows alternate between two outer accumulators), so the dependent-FMA latency overlaps.
+                double acc0 = 0.0, acc1 = 0.0, rp[4] = {0.0, 0.0, 0.0, 0.0};
                 int i = 0, j = 0;  // all static after unrolling
 #pragma unroll
                 for (int k = 0; k < NC; k += (VEC ? 2 : 1)) {
@@ -239,10 +281,15 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
                     for (int u = 0; u < (VEC ? 2 : 1); ++u) {
                         if (k + u < NC) {
                             const double a = u ? a1 : a0;
-                            row = (j == i) ? a * z[j] : fma(a, z[j], row);
+                            const int part = (j - i) & 3;
+                            rp[part] = (j - i < 4) ? a * x[j] : fma(a, x[j], rp[part]);
                             if (j == N) {
-                                if (i & 1) acc1 = fma(row, z[i], acc1);
-                                else acc0 = fma(row, z[i], acc0);
+                                const int len = N + 1 - i;
+                                double row = rp[0];
+                                if (len > 1) row += rp[1];
+                                if (len > 2) row += (len > 3) ? rp[2] + rp[3] : rp[2];
+                                if (i & 1) acc1 = fma(row, x[i], acc1);
+                                else acc0 = fma(row, x[i], acc0);
                                 ++i;
                                 j = i;
                             } else {
@@ -253,11 +300,12 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
                 }
                 result = acc0 + acc1;
             }
-            __syncwarp();  // the slot is re-staged for the next distinct leaf / next iteration
+            __syncwarp();
         }
         if (valid) val[s] = result;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
         ql = qn;
     }
+    cp_async_wait_all();  // a prefetch may still be in flight
 }
 
 // any n: z recomputed on the fly (two extra loads per term)
@@ -390,7 +438,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     bool done = false;
     if (mo->degree == 2 && vec_ok) {
         done = true;
-        dyn_smem = (size_t)8 * mo->stride * sizeof(double);
+        dyn_smem = (size_t)8 * 2 * mo->stride * sizeof(double);  // 8 warps x two record slots
         switch (n) {
             case 2: launch(k_eval_binned_exact<2>); break;
             case 3: launch(k_eval_binned_exact<3>); break;
