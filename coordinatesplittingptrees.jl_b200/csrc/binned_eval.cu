@@ -10,6 +10,8 @@
 //   k_scatter                    slot = offsets[leaf]++ ; perm[slot] = (query, leaf)
 //   k_eval_binned<NPAD>          thread s: (q, leaf) = perm[s]; gather x[q]; value = sum A_ij z_i z_j; val[q] = value
 // Evaluation arithmetic: reference src/cs2.jl:155-159 (summation order not pinned by the reference).
+#include <cstdlib>
+
 #include "common.cuh"
 
 __device__ __forceinline__ double dnan_b() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -162,15 +164,161 @@ __global__ void __launch_bounds__(256) k_eval_binned(const ModelsView mv, const 
     }
 }
 
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+// Tensor-core variant for even n in [8, 30] (degree 2).  Delivering every coefficient to every thread through shared memory
+// caps the FMA kernel below at a quarter of the FP64 rate (a broadcast 128-bit shared load still costs four register-file
+// wavefronts); an MMA takes each coefficient once per 8 rows instead.  A warp walks its contiguous range 32 positions at a
+// time as four 8-row groups: Z (A operand, rows = queries) is loaded straight from global memory in fragment layout -- the
+// four lanes of a row read 32 contiguous bytes per k-step, i.e. whole sectors of the x row -- with b subtracted in
+// registers; U (B operand) fragments and the b entries a lane needs live in registers for as long as the leaf's run lasts
+// and are re-read from the staged record (same double-buffered cp.async slots as below) only when the leaf changes.
+// W = Z U, then the row dot with z (re-read from L1) and a quad reduction.  A group that straddles two leaves is computed
+// once per leaf with the other rows masked at the store.
+template <int N>
+__global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, const double* __restrict__ X,
+                                                        const int2* __restrict__ perm, const int* __restrict__ total,
+                                                        double* __restrict__ val) {
+    static_assert((N & 1) == 0 && N >= 2 && N <= 30, "even n only");
+    constexpr int NP = (N + 1 + 7) / 8 * 8, KS = NP / 4, NT = NP / 8;
+    extern __shared__ __align__(16) double s_rec[];  // [warps][2][stride]
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, stride = mv.stride;
+    const int r = lane >> 2, t = lane & 3;
+    double* slot = s_rec + (size_t)(threadIdx.x >> 5) * 2 * stride;
+    const long long tot = *total;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long per = ((tot + 31) / 32 + nwarps - 1) / nwarps * 32;
+    const long long start = wid * per, end = start + per < tot ? start + per : tot;
+    if (start >= end) return;
+    auto fetch = [&](int lf, int b) {
+        const double* __restrict__ M = mv.data + (size_t)lf * stride;
+        double* dst = slot + (size_t)b * stride;
+        for (int k = lane * 2; k < stride; k += 64) cp_async16(dst + k, M + k);
+    };
+    int cur = 0, staged = -1, pre = -1;
+    double uf[KS][NT], bA[KS], bE[NT][2];  // per-leaf fragments (registers)
+    long long s0 = start;
+    int2 ql = s0 + lane < end ? perm[s0 + lane] : make_int2(0, -1);
+    for (; s0 < end; s0 += 32) {
+        const bool valid = ql.y >= 0;
+        const int2 qn = s0 + 32 + lane < end ? perm[s0 + 32 + lane] : make_int2(0, -1);
+        unsigned todo = __ballot_sync(FULL, valid);
+        while (todo) {
+            const int lf = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
+            const unsigned minemask = __ballot_sync(FULL, valid && ql.y == lf);
+            todo &= ~minemask;
+            if (lf != staged) {
+                if (lf == pre) {
+                    cur ^= 1;
+                } else {
+                    cp_async_wait_all();
+                    __syncwarp();
+                    fetch(lf, cur);
+                }
+                staged = lf;
+                pre = -1;
+                cp_async_wait_all();
+                __syncwarp();
+                // fragments of the new leaf
+                const double* rec = slot + (size_t)cur * stride;
+                const double* A = rec + N;
+#pragma unroll
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int k = 4 * ks + t;
+                    bA[ks] = k < N ? rec[k] : 0.0;
+#pragma unroll
+                    for (int J = 0; J < NT; ++J) {
+                        const int col = 8 * J + r;
+                        uf[ks][J] = (J >= ks / 2 && k <= col && col <= N) ? A[k * (N + 1) - k * (k - 1) / 2 + (col - k)] : 0.0;
+                    }
+                }
+#pragma unroll
+                for (int J = 0; J < NT; ++J) {
+                    const int col = 8 * J + 2 * t;
+                    bE[J][0] = col < N ? rec[col] : 0.0;
+                    bE[J][1] = col + 1 < N ? rec[col + 1] : 0.0;
+                }
+            }
+            if (pre < 0) {  // start fetching the next distinct leaf
+                int nl = -1;
+                if (todo) {
+                    nl = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
+                } else {
+                    const unsigned other = __ballot_sync(FULL, qn.y >= 0 && qn.y != lf);
+                    if (other) nl = __shfl_sync(FULL, qn.y, __ffs(other) - 1);
+                }
+                if (nl >= 0) {
+                    fetch(nl, cur ^ 1);
+                    pre = nl;
+                }
+            }
+            // groups in batches: all the global loads of a batch are issued before its first MMA
+            constexpr int GB = KS <= 4 ? 4 : 2;
+#pragma unroll
+            for (int g0 = 0; g0 < 4; g0 += GB) {
+                double a[GB][KS];
+                const double* xps[GB];
+                bool rm[GB];
+#pragma unroll
+                for (int gg = 0; gg < GB; ++gg) {
+                    const int g = g0 + gg;
+                    const int rq = __shfl_sync(FULL, ql.x, 8 * g + r);
+                    rm[gg] = (minemask >> (8 * g + r)) & 1u;
+                    xps[gg] = X + (size_t)(unsigned)rq * N;
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks) {
+                        const int k = 4 * ks + t;
+                        double v = 0.0;
+                        if (k < N) { if (rm[gg]) v = __ldg(xps[gg] + k); }
+                        else if (k == N) v = 1.0;
+                        a[gg][ks] = v;
+                    }
+                }
+#pragma unroll
+                for (int gg = 0; gg < GB; ++gg) {
+                    const int g = g0 + gg;
+                    if (!((minemask >> (8 * g)) & 0xffu)) continue;  // warp-uniform: no row of this group belongs to lf
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+                        if (4 * ks + t < N && rm[gg]) a[gg][ks] -= bA[ks];
+                    double w[NT][2];
+#pragma unroll
+                    for (int J = 0; J < NT; ++J) { w[J][0] = 0.0; w[J][1] = 0.0; }
+#pragma unroll
+                    for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+                        for (int J = ks / 2; J < NT; ++J) dmma884(w[J][0], w[J][1], a[gg][ks], uf[ks][J]);
+                    double dot = 0.0;
+#pragma unroll
+                    for (int J = 0; J < NT; ++J) {
+                        const int col = 8 * J + 2 * t;
+                        double z0 = 0.0, z1 = 0.0;
+                        if (col + 1 < N) {
+                            if (rm[gg]) { const double2 xv = __ldg((const double2*)(xps[gg] + col)); z0 = xv.x - bE[J][0]; z1 = xv.y - bE[J][1]; }
+                        } else if (col == N) {
+                            z0 = 1.0;
+                        }
+                        dot = fma(w[J][0], z0, fma(w[J][1], z1, dot));
+                    }
+                    dot += __shfl_xor_sync(FULL, dot, 1);
+                    dot += __shfl_xor_sync(FULL, dot, 2);
+                    if (t == 0 && rm[gg]) val[s0 + 8 * g + r] = dot;
+                }
+            }
+        }
+        ql = qn;
+    }
+    cp_async_wait_all();
+}
+
 // Compile-time n.  A warp owns a CONTIGUOUS range of binned positions and walks it 32 at a time.  The x rows are gathered
 // straight into registers (128-bit loads).  Leaf records go through two per-warp shared-memory slots filled by 16-byte
 // cp.async copies: the record of the leaf in use stays put while the run continues over the following iterations, and the
 // next distinct leaf's record (known from the sorted perm entries already in registers) is fetched while the current one
 // is being evaluated, so the record latency is off the critical path.  Records are read back as broadcast 128-bit loads.
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
-}
-
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, const double* __restrict__ X,
                                                           const int2* __restrict__ perm, const int* __restrict__ total,
@@ -430,6 +578,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)
     auto launch = [&](auto kern) {
+        if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
         CspTimed tm(CSP_K_EVAL_BINNED, st);
         kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
         CSP_LAUNCHED();
@@ -439,6 +588,16 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     if (mo->degree == 2 && vec_ok) {
         done = true;
         dyn_smem = (size_t)8 * 2 * mo->stride * sizeof(double);  // 8 warps x two record slots
+        const bool mma = !(getenv("CSP_EVAL_MMA") && atoi(getenv("CSP_EVAL_MMA")) == 0);
+        // FP64 tensor cores from n = 16 up (measured, 1e8 queries: n = 20 10.4 -> 7.5 ms; n = 10 4.0 -> 7.7 ms: too little MMA work
+        // per 8-row group to pay for the fragment bookkeeping, so small n keeps the FMA kernel)
+        switch (mma ? n : -1) {
+            case 16: launch(k_eval_binned_mma<16>); return unpermute();
+            case 20: launch(k_eval_binned_mma<20>); return unpermute();
+            case 24: launch(k_eval_binned_mma<24>); return unpermute();
+            case 30: launch(k_eval_binned_mma<30>); return unpermute();
+            default: break;
+        }
         switch (n) {
             case 2: launch(k_eval_binned_exact<2>); break;
             case 3: launch(k_eval_binned_exact<3>); break;

@@ -189,6 +189,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "memory");
     } while (!ok);
 }
+// FP64 tensor-core MMA (SASS DMMA.8x8x4): D[8x8] += A[8x4] (row) * B[4x8] (col); lane = 4*row + k holds A[row][k], lane = 4*col + k
+// holds B[k][col], lane = 4*row + t holds D[row][2t], D[row][2t+1]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
 __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }

@@ -28,9 +28,6 @@
 
 __device__ __forceinline__ double dnan_d() { return __longlong_as_double(0x7ff8000000000000LL); }
 
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 // arrive on `bar` once all of this thread's earlier cp.async have landed (the barrier's count already includes it)
 __device__ __forceinline__ void cp_async_arrive(uint64_t* bar) {

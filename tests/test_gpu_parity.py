@@ -281,8 +281,8 @@ def test_cs1_gradient_bit_exact(n, npoints):
 
 
 @pytest.mark.parametrize("mode", ["direct", "binned"])
-@pytest.mark.parametrize("n,p,npoints", [(2, 2, 200), (3, 2, 150), (10, 2, 400), (13, 2, 60), (20, 2, 120), (25, 2, 40), (2, 1, 300),
-                                         (40, 1, 30)])
+@pytest.mark.parametrize("n,p,npoints", [(2, 2, 200), (3, 2, 150), (10, 2, 400), (13, 2, 60), (16, 2, 100), (20, 2, 120), (24, 2, 50),
+                                         (25, 2, 40), (30, 2, 40), (2, 1, 300), (40, 1, 30)])
 def test_locate_eval_parity(n, p, npoints, mode, monkeypatch):
     """Both evaluation strategies (model fetched per query inside the locate kernel / queries binned by leaf and evaluated
     model-stationary) against the oracle."""
