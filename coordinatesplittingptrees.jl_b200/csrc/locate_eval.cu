@@ -400,6 +400,70 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
     }
 }
 
+// K1 without staging: a warp takes 32 consecutive queries.  Their rows are one contiguous block of 32 n doubles, which the
+// warp streams once, fully coalesced, for the root bounds check (src/tree.jl:357-360; one 32-bit "bad row" mask per lane,
+// OR-reduced with redux.sync); each lane then descends for its own query reading the few coordinates it needs from the
+// same addresses, which the first pass has just pulled into L1/L2.  No shared-memory tile, so occupancy is not tied to n.
+template <int P>
+__global__ void __launch_bounds__(256) k_locate_wide(const __grid_constant__ LocateOnlyParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = prm.t.n;
+    const size_t rec_bytes = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    unsigned char* s_top = smem_raw;
+    double* s_lower = (double*)(smem_raw + (((size_t)prm.top * rec_bytes + 127) & ~(size_t)127));
+    double* s_upper = s_lower + n;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n; i += blockDim.x) { s_lower[i] = prm.t.lower[i]; s_upper[i] = prm.t.upper[i]; }
+    {
+        const int4* src = (const int4*)prm.t.drec;
+        int4* dst = (int4*)s_top;
+        const int n16 = (int)((size_t)prm.top * rec_bytes / 16);
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + tid) >> 5;
+    const long long nbatch = (prm.m + 31) / 32;
+    const bool vec = prm.bulk && (n & 1) == 0;  // 16-byte aligned base and even n: whole rows in double2 steps
+    for (long long bt = wid; bt < nbatch; bt += nwarps) {
+        const long long q0 = bt * 32;
+        const int rows = (int)(prm.m - q0 < 32 ? prm.m - q0 : 32);
+        const double* __restrict__ base = prm.X + (size_t)q0 * n;
+        unsigned bad = 0;
+        if (vec) {
+            const int total = rows * n / 2;  // double2 elements; a pair never straddles two rows (n even)
+            int row = 0, col = 2 * lane;
+            while (col >= n) { col -= n; ++row; }
+            for (int e = lane; e < total; e += 32) {
+                const double2 v = __ldg((const double2*)base + e);
+                const bool ok = (v.x >= s_lower[col]) & (v.x <= s_upper[col]) & (v.y >= s_lower[col + 1]) & (v.y <= s_upper[col + 1]);
+                if (!ok) bad |= 1u << row;
+                col += 64;
+                while (col >= n) { col -= n; ++row; }
+            }
+        } else {
+            const int total = rows * n;
+            int row = 0, col = lane;
+            while (col >= n) { col -= n; ++row; }
+            for (int e = lane; e < total; e += 32) {
+                const double v = __ldg(base + e);
+                if (!((v >= s_lower[col]) & (v <= s_upper[col]))) bad |= 1u << row;
+                col += 32;
+                while (col >= n) { col -= n; ++row; }
+            }
+        }
+        bad = __reduce_or_sync(0xffffffffu, bad);
+        if (lane < rows) {
+            const bool ok = !((bad >> lane) & 1u);
+            int lf = -1;
+            if (ok) lf = descend<P>(prm.t, base + (size_t)lane * n, 1, s_top, prm.top);
+            const long long q = q0 + lane;
+            if (prm.leaf) prm.leaf[q] = lf;
+            if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+        }
+    }
+}
+
 // eval-only kernel: leaf ids supplied (scattered models); one thread per query
 __global__ void __launch_bounds__(256) k_eval(const ModelsView mv, const double* __restrict__ X, const int* __restrict__ leaf,
                                              long long m, double* __restrict__ val) {
@@ -487,7 +551,50 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
 }
 
 template <int P>
+static int launch_locate_wide(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
+    auto kern = k_locate_wide<P>;
+    const int n = t->v.n;
+    const size_t rec = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    const char* env = getenv("CSP_TOP_RECORDS");
+    int top = env ? atoi(env) : 341;
+    top = std::max(0, std::min(top, t->v.n_internal));
+    const size_t smem = (((size_t)top * rec + 127) & ~(size_t)127) + (size_t)2 * n * 8 + 16;
+    const csp_tree::Geo* g = nullptr;
+    for (auto& e : t->geo)
+        if (e.first == (const void*)kern) g = &e.second;
+    if (!g) {
+        csp_tree::Geo ng{};
+        ng.tile = 256; ng.stages = 1; ng.top = top; ng.smem = smem;
+        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 1024)));
+        CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ng.occ, kern, 256, smem));
+        if (ng.occ < 1) return csp_set_error(CSP_ERR_CUDA, "descent kernel does not fit on an SM (smem %zu)", smem);
+        t->geo.emplace_back((const void*)kern, ng);
+        g = &t->geo.back().second;
+    }
+    LocateOnlyParams prm{};
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.tile = 256; prm.bulk = lp.bulk; prm.top = g->top;
+    const long long nbatch = (prm.m + 31) / 32;
+    const long long grid = std::min<long long>((nbatch + 7) / 8, (long long)std::max(t->n_sm, 1) * std::max(1, g->occ / g_csp_grid_div));
+    {
+        CspTimed tm(CSP_K_LOCATE, st);
+        kern<<<(unsigned)grid, 256, g->smem, st>>>(prm);
+    }
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
+    return CSP_OK;
+}
+
+template <int P>
 static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
+    {
+        // Measured (B200): n = 10: tiled 4.5 ms vs wide 6.0 ms per 1e8 queries; n = 20: 7.0 vs 9.5; n = 100: 6.9 vs 3.0 ms per 2e7
+        // (5.3 TB/s).  The staged tile wins while whole tiles of >= 128 queries fit four CTAs to an SM; beyond n = 32 the tile
+        // shrinks to a warp or two per CTA and streaming straight from global memory wins.
+        const char* wenv = getenv("CSP_LOCATE_WIDE");  // 1: always, 0: never, unset: by n
+        const int wide_from = 33;
+        if (wenv ? atoi(wenv) != 0 : t->v.n >= wide_from) return launch_locate_wide<P>(t, lp, st);
+    }
     auto kern = k_locate_only<P>;
     const int n = t->v.n;
     const csp_tree::Geo* g = nullptr;
