@@ -405,8 +405,13 @@ def main():
             traffic_src = "profiles/r1_%s.ncu-rep: %.1f DRAM bytes/query x queries per launch" % (key, tj[key]["dram_bytes_per_query"])
     except Exception:
         pass
-    names = {"locate": "k_locate<2,-1> (find_leaf_at descent + per-leaf histogram)", "eval_binned": "k_eval_binned_exact<10> (model-stationary modelvalue)",
-             "locate_eval_fused": "k_locate<2,8,10> (fused find_leaf_at + modelvalue)", "scatter": "k_scatter", "scan": "k_scan", "eval": "k_eval"}
+    p_ = tree.p
+    eval_name = ("k_eval_dmma (FP64 tensor cores, grouped dense modelvalue)" if n > 32 else
+                 "k_eval_binned_mma<%d> (model-stationary modelvalue on the FP64 tensor cores)" % n if (n >= 16 and n % 2 == 0) else
+                 "k_eval_binned_exact<%d> (model-stationary modelvalue)" % n)
+    names = {"locate": ("k_locate_wide<%d>" if n > 32 else "k_locate_only<%d>") % p_ + " (find_leaf_at descent + per-leaf histogram)",
+             "eval_binned": eval_name, "locate_eval_fused": "k_locate<%d,...> (fused find_leaf_at + modelvalue)" % p_,
+             "scatter": "k_scatter + k_unpermute", "scan": "k_scan", "eval": "k_eval"}
     alg_bytes = m * BYTES_PER_QUERY(n) + touched * model_bytes(n) + tree.kib * 1024
     roofline = {"bound": "hbm", "kernel": names.get(dom, dom), "achieved": kernels[dom]["algorithmic_GBps"], "peak": peak, "unit": "GB/s",
                 "frac": kernels[dom]["frac"], "peak_source": peak_src, "traffic": traffic, "traffic_source": traffic_src,

@@ -52,11 +52,16 @@ def edge_queries(root, oroot, rng, m):
 
 TREES = [  # (n, p, npoints)
     (1, 1, 50), (2, 1, 500), (5, 1, 200), (1, 2, 30), (2, 2, 200), (3, 2, 150), (7, 2, 200), (10, 2, 400), (20, 2, 120),
+    (33, 2, 40), (40, 1, 60), (64, 2, 20), (101, 1, 15),  # n > 32: the streaming kernel (k_locate_wide)
 ]
 
 
+@pytest.mark.parametrize("kernel", ["default", "tiled", "wide"])
 @pytest.mark.parametrize("n,p,npoints", TREES)
-def test_find_leaf_bit_exact(n, p, npoints):
+def test_find_leaf_bit_exact(n, p, npoints, kernel, monkeypatch):
+    """Both descent kernels (TMA-staged transposed tile / streaming) on every tree, whatever the default choice for its n."""
+    if kernel != "default":
+        monkeypatch.setenv("CSP_LOCATE_WIDE", "1" if kernel == "wide" else "0")
     root, oroot, _ = grow_both(n, p, npoints, seed=100 + n + p)
     rng = np.random.default_rng(n * 7 + p)
     X = edge_queries(root, oroot, rng, 20000)
