@@ -11,6 +11,7 @@ python tools/bench_dense.py > $O/ev_dense_c4.json 2>> $O/ev_dense.err
 python tools/bench_dense.py --n 64 > $O/ev_dense_n64.json 2>> $O/ev_dense.err
 python tools/bench_dense.py --n 300 --leaves 1000 --queries 2000000 > $O/ev_dense_n300.json 2>> $O/ev_dense.err
 cat $O/ev_dense_c4.json | cut -c1-300
+python tools/bench_c4.py > $O/ev_c4.json 2> $O/ev_c4.err; cut -c1-200 $O/ev_c4.json
 python tools/bench_fits.py C2 C3 C5 > $O/ev_fits.jsonl 2> $O/ev_fits.err; cut -c1-140 $O/ev_fits.jsonl
 python tools/bench_update.py > $O/ev_update.json 2> $O/ev_update.err; cat $O/ev_update.json
 tools/ubench/fp64_peaks > $O/ev_fp64_peaks.txt 2>&1; head -3 $O/ev_fp64_peaks.txt

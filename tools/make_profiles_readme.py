@@ -41,7 +41,7 @@ step = re-fit every leaf model + locate/evaluate every query.  Peak = measured c
 | `r1_bench_c3.json` | `bench.py --config C3 --steps 5` (n = 20, 1 000 021 leaves, 1e8 queries per step) |
 | `r1_bench_reference_arm.json` | `bench.py --impl reference` (oracle port on the box's host cores) |
 | `r1_launches_ncu.csv` | every launch of `bench.py --queries 20000000 --steps 3` with `gpu__time_duration.sum` |
-| `r1_<kernel>.ncu-rep` / `.summary.txt` | `ncu --set full --import-source on` capture of one launch + key metrics and per-source-line stall summary (`tools/ncu_metrics.py`, `tools/ncu_lines.py`); `k_fit` is the C2 launch, `k_fit_C3` the C3 launch, `k_eval_dmma` config C4 |
+| `r1_<kernel>.ncu-rep` / `.summary.txt` | `ncu --set full --import-source on` capture of one launch + key metrics and per-source-line stall summary (`tools/ncu_metrics.py`, `tools/ncu_lines.py`); `k_fit` is the C2 launch, `k_fit_C3` the C3 launch, `k_eval_binned_C3` = `k_eval_binned_mma<20>` on one 4e7-query chunk of C3, `k_eval_dmma` and `k_locate_wide_C4` config C4 |
 | `r1_traffic.json` | DRAM bytes (read + write) per launch of each capture, per query / per leaf (`tools/make_traffic_json.py`) |
 | `r1_dense_c4.json`, `r1_dense_n64.json`, `r1_dense_n300.json` | `tools/bench_dense.py`: grouped dense evaluation on the DMMA kernels (C4: n = 100; n = 64; n = 300 = the panel-streaming kernel), with a cuBLAS DGEMM rate measured in the same run and the issued-DMMA fraction of the measured pipe peak |
 | `r1_c4_end_to_end.json` | `tools/bench_c4.py`: the whole C4 path (CS1 tree n = 100 grown by 100 addpoint!s, K1 locate + binning + DMMA evaluation, 2e7 resident uniform queries) |
@@ -88,6 +88,11 @@ The shares agree with the event timings (at 2e7 queries per step the fit is a la
 * **K3a `k_eval_binned_exact<10>`** — DRAM bound on *extra* traffic: {tr['k_eval_binned']['dram_bytes_per_query']:.0f} B/query against 96 algorithmic (63 % of DRAM
   peak while it runs).  The x rows are gathered a second time at 64-byte DRAM granularity (≈ 128 B for an 80-byte row);
   values are written in sorted order (coalesced) and `k_unpermute` gathers them back from L2.  `long_scoreboard` dominates.
+* **K1 `k_locate_wide<1>`** (n > 32; config C4, n = 100) — HBM bound: {tr['k_locate_wide_C4']['dram_bytes_per_query']:.0f} B/query of DRAM traffic for 805 algorithmic
+  ({tr['k_locate_wide_C4']['dram_bytes_read']/tr['k_locate_wide_C4']['duration_us_under_ncu']/1e3:.0f} GB/s read while it runs): the rows are streamed once for the bounds check and the descent's re-reads mostly hit L1/L2.
+* **K3a `k_eval_binned_mma<20>`** (config C3, n = 20) — latency bound at 16 warps/SM (128 registers): DRAM 48 %, DMMA pipe 31 %,
+  `long_scoreboard` on the x-row gathers; {tr['k_eval_binned_C3']['dram_bytes_per_query']:.0f} B/query of DRAM traffic for 176 algorithmic (sector-granular second read of x + one
+  2 KB record per ~40-query run).  The FMA kernel it replaces was bound by shared-memory read bandwidth (65 % `l1tex`, 18 % issue).
 * **`k_scatter`** — L2 atomic latency/throughput (1e8 returning atomics per step; `lg_throttle` + `long_scoreboard`, issue 6 %).
 * **K2 `k_fit<2>`** — instruction-issue / latency bound (≈ 60 % issue-active, 64 registers, 32 warps/SM; ≈ 2.0 k warp-instructions
   per leaf at n = 10 and 3.5 k at n = 20; DRAM 2–6 %).  Sibling leaves share the split scan and the off-diagonal coefficients;
