@@ -49,6 +49,7 @@ struct FitParams {
     int pairs_in_smem;
     int q_in_smem;           // the box's Q / record is assembled in shared memory and written out once, coalesced
     int tiles;               // large n (Q stays in global memory): per-warp staging tiles for the O(n^2) loops
+    unsigned long long* work_counter;  // optional (zeroed before the launch): warps claim units dynamically instead of striding
     const int4* units; long long n_units;  // all-leaf fits: the real leaves (output rows, -1 padded) under each split that has any
     int warp_smem_bytes;
 };
@@ -428,7 +429,13 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
 
     long long tk = clock64();
 #define FIT_TICK(k) do { if (prm.prof) { __syncwarp(); if (lane == 0) { const long long now_ = clock64(); atomicAdd(prm.prof + (k), (unsigned long long)(now_ - tk)); tk = now_; } } } while (0)
-    for (long long ui = (long long)blockIdx.x * W + wib; ui < nunits; ui += (long long)gridDim.x * W) {
+    for (long long ui = (long long)blockIdx.x * W + wib;; ui += (long long)gridDim.x * W) {
+        if (prm.work_counter) {  // units differ in cost (depth, subtree sizes): claim them one at a time
+            unsigned long long c = 0;
+            if (lane == 0) c = atomicAdd(prm.work_counter, 1ull);
+            ui = (long long)__shfl_sync(FULL, c, 0);
+        }
+        if (ui >= nunits) break;
         int4 members = make_int4(-1, -1, -1, -1);  // box indices (output rows) of the unit
         if (prm.units) members = prm.units[ui];
         const long long bi0 = prm.units ? members.x : ui;
@@ -1010,7 +1017,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     }
     if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
         const size_t nb = (size_t)prm.nb;
-        const size_t need = nb * ((size_t)n * 20 + 16) + 64;
+        const size_t need = nb * ((size_t)n * 20 + 16) + 64 + 64;  // chain rows + alignment slack + the work counter
         if (need > t->fit_ws_bytes) {
             if (t->fit_ws) { CSP_CUDA(cudaDeviceSynchronize()); csp_dev_free(t->fit_ws); t->fit_ws = nullptr; t->fit_ws_bytes = 0; }
             CSP_CHECK(csp_dev_alloc(&t->fit_ws, need));
@@ -1022,7 +1029,10 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         prm.ch_c = (double*)base_p; base_p += nb * 8;
         prm.ch_step = (int*)base_p; base_p += nb * n * 4;
         prm.ch_status = (int*)base_p; base_p += nb * 4;
-        prm.ch_itop = (int*)base_p;
+        prm.ch_itop = (int*)base_p; base_p += nb * 4;
+        prm.work_counter = (unsigned long long*)(((uintptr_t)base_p + 63) & ~(uintptr_t)63);
+        if (getenv("CSP_FIT_DYNAMIC") && atoi(getenv("CSP_FIT_DYNAMIC")) == 0) prm.work_counter = nullptr;
+        else CSP_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned long long), st));
         const long long blocks = std::min<long long>((prm.nb + 127) / 128, (long long)std::max(t->n_sm, 1) * 16);
         {
             CspTimed tm(CSP_K_FIT, st);
