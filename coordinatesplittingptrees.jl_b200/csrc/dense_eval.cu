@@ -63,7 +63,7 @@ __device__ __forceinline__ void dmma_slab(const double* __restrict__ Z, const do
         const int k_lo = s2 == 0 ? 0 : 8 * ((s2 - 1) * JS + jg + 1);
         int k_hi = 8 * (s2 * JS + jg + 1);
         if (k_hi > NP) k_hi = NP;
-#pragma unroll 2
+#pragma unroll 4
         for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
             const int kb = k0 >> 3;
             const double bk = sbk[k0];
@@ -103,8 +103,8 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
     double* U = sm;                                  // packed upper block-triangle
     double* Zb = U + usz;                            // [2][TR][LD]
     double* sb = Zb + (size_t)2 * TR * LD;           // [NP]  (b, zero padded)
-    double* s_part = sb + NP;                        // [JS][TR]
-    int* s_q = (int*)(s_part + JS * TR);             // [2][TR]
+    double* s_part = sb + NP;                        // [2][JS][TR]  (alternating by tile: one barrier per tile)
+    int* s_q = (int*)(s_part + 2 * JS * TR);         // [2][TR]
     int* s_leaf = s_q + 2 * TR;                      // [2][TR]
     uint64_t* bar = (uint64_t*)(s_leaf + 2 * TR);    // [2]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
         else { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
         CSP_TICK(1);
         const double* Z = Zb + (size_t)buf * TR * LD;
+        double* part = s_part + (size_t)buf * JS * TR;
         const int* leaf_of = s_leaf + buf * TR;
         int seg_start = 0;
         while (seg_start < rows) {
@@ -204,20 +205,22 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
             const int r0 = rg * 16;
             const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
             if (active) {
-                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS>(Z, U, sb, s_part + jg * TR, r0, jg, NP, LD, lane);
-                else dmma_slab<NTJ - 1, JS>(Z, U, sb, s_part + jg * TR, r0, jg, NP, LD, lane);
+                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS>(Z, U, sb, part + jg * TR, r0, jg, NP, LD, lane);
+                else dmma_slab<NTJ - 1, JS>(Z, U, sb, part + jg * TR, r0, jg, NP, LD, lane);
             }
             CSP_TICK(5);
             __syncthreads();
             CSP_TICK(6);
             if (tid >= seg_start && tid < seg_end) {
-                double v = s_part[tid];
+                double v = part[tid];
 #pragma unroll
-                for (int g2 = 1; g2 < JS; ++g2) v += s_part[g2 * TR + tid];
+                for (int g2 = 1; g2 < JS; ++g2) v += part[g2 * TR + tid];
                 prm.val[t * TR + tid] = v;
             }
             seg_start = seg_end;
-            __syncthreads();
+            // Another segment of this tile reuses `part`; the next TILE uses the other half, and nobody can reach the tile after
+            // that before passing the barrier above once more, i.e. after everybody has finished this read.
+            if (seg_start < rows) __syncthreads();
             CSP_TICK(4);
         }
     }
@@ -436,7 +439,7 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
     }
     {
         constexpr int TR = 64, JS = 4;  // 16 warps per CTA, one CTA per SM
-        const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + JS * TR) * 8 + (size_t)(4 * TR) * 4 + 16;
+        const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + 2 * JS * TR) * 8 + (size_t)(4 * TR) * 4 + 16;
         const unsigned grid2 = (unsigned)std::max<long long>(1, std::min<long long>((m + TR - 1) / TR, std::max(n_sm, 1)));
         auto launch2 = [&](auto kern) -> int {
             const bool prof = getenv("CSP_DMMA_PROF") && atoi(getenv("CSP_DMMA_PROF"));
