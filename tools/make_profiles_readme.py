@@ -16,6 +16,7 @@ tot = sum(sum(v) for v in mine.values())
 lines = [f"| `{k}` | {len(v)} | {sum(v)/len(v)/1e3:.1f} | {100*sum(v)/tot:.1f} % |" for k, v in mine.items()]
 b = json.load(open('profiles/r1_bench_n1.json'))
 b2 = json.load(open('profiles/r1_bench_n2.json'))
+b8 = json.load(open('profiles/r1_bench_n8.json'))
 ref = json.load(open('profiles/r1_bench_reference_arm.json'))
 d = json.load(open('profiles/r1_dense_c4.json'))
 d64 = json.load(open('profiles/r1_dense_n64.json'))
@@ -37,7 +38,7 @@ step = re-fit every leaf model + locate/evaluate every query.  Peak = measured c
 ## Files
 | file | what |
 |---|---|
-| `r1_bench_n1.json`, `r1_bench_n2.json` | `bench.py` lines at N = 1 and N = 2 (torchrun, NCCL) on config C2 |
+| `r1_bench_n1.json`, `r1_bench_n2.json`, `r1_bench_n8.json` | `bench.py` lines at N = 1, 2 and 8 (torchrun, NCCL) on config C2 |
 | `r1_bench_c3.json` | `bench.py --config C3 --steps 5` (n = 20, 1 000 021 leaves, 1e8 queries per step) |
 | `r1_bench_reference_arm.json` | `bench.py --impl reference` (oracle port on the box's host cores) |
 | `r1_launches_ncu.csv` | every launch of `bench.py --queries 20000000 --steps 3` with `gpu__time_duration.sum` |
@@ -58,6 +59,7 @@ step = re-fit every leaf model + locate/evaluate every query.  Peak = measured c
 | CPU baseline (oracle port, {b['cpu_baseline']['cores']} cores, same box) | {b['cpu_baseline']['value']:.3e} queries/s, {b['cpu_baseline']['fits_per_s']:.3e} fits/s |
 | reference arm (`--impl reference`) | {ref['value']:.3e} queries/s, {ref['fits']['value']:.3e} fits/s |
 | N = 2 (weak scaling, one NCCL broadcast of the tree blob) | {b2['value']:.3e} queries/s |
+| N = 8 (`r1_bench_n8.json`, same box type, 10 steps) | {b8['value']:.3e} queries/s ({b8['value']/8/b['value']:.2f} of 8x the N = 1 value; tree broadcast {b8['tree_broadcast_ms']:.1f} ms once) |
 | config C3 (n = 20, 1e6 leaves), N = 1 | {c3['value']:.3e} queries/s ({c3['ms_per_step']:.1f} ms per 1e8-query step, of which {c3['fits']['kernel_ms']:.2f} ms re-fit all 1 000 021 leaves: {c3['fits']['value']:.3e} fits/s, {c3['fits']['frac']:.2f} of the HBM roofline) |
 | config C4 end to end (CS1 n = 100, 1e4 leaves, locate + DMMA evaluation), N = 1 | {c4['queries_per_s']:.3e} queries/s ({c4['ms_per_step']:.1f} ms per 2e7 queries: locate {c4['kernel_ms_per_step']['locate']:.1f}, evaluation {c4['kernel_ms_per_step']['eval_binned']:.1f}) |
 | clocks during the timed region | {b['clocks']['sm_mhz']} / {b['clocks']['sm_max_mhz']} MHz, throttle reasons: {b['clocks']['reasons'] or 'none'} |
