@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         if (prm.units) members = prm.units[ui];
         const long long bi0 = prm.units ? members.x : ui;
         const int box = prm.node_ids ? prm.node_ids[bi0] : t.lnode[bi0];
-        double* Qo = prm.q_in_smem ? sQ : prm.Q + bi0 * prm.Q_stride;
+        double* Qo = prm.q_in_smem ? sQ : prm.Q + bi0 * prm.Q_stride;  // global-Q mode: assembled in the first member's record
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
         if (!w.plist) for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
         __syncwarp();
@@ -541,16 +541,29 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
 
         }
 
+        if (prm.units && !prm.q_in_smem) {  // large records: hand the shared off-diagonals to the other members' records now
+            __syncwarp();
+#pragma unroll 1
+            for (int mi = 1; mi < 4; ++mi) {
+                const long long bm = mi == 1 ? members.y : mi == 2 ? members.z : members.w;
+                if (bm < 0) break;
+                double* Qm = prm.Q + bm * prm.Q_stride;
+                for (long long e = lane; e < qlen; e += 32) Qm[e] = Qo[e];
+            }
+            __syncwarp();
+        }
+
         // ---- per member box: fit_poly1 results, fit_poly2_diag!, canonicalize, outputs
 #pragma unroll 1
         for (int mi = 0; mi < 4; ++mi) {
             const long long bi = prm.units ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : (mi == 0 ? ui : -1);
             if (bi < 0) break;
             double* Qg = prm.Q + bi * prm.Q_stride;
+            if (!prm.q_in_smem) Qo = Qg;
             int status = CSP_FIT_OK;
             double cval = dnan();
             if (prm.mode == FIT_MODE_FULL) {
-                if (mi > 0)  // entries the previous member set: diagonal, g column, c
+                if (mi > 0 && prm.q_in_smem)  // entries the previous member set: diagonal, g column, c
                     for (int e = lane; e < n + (prm.q_packed ? 1 : 0); e += 32) { Qo[qi(e, e)] = dnan(); if (prm.q_packed && e < n) Qo[qi(e, n)] = dnan(); }
                 for (int e = lane; e < n; e += 32) { w.dkey[e] = INT_MAX; w.sstep[e] = 0; }
                 // fit_poly1 (src/cs2.jl:162-205): chain results come from the pre-pass k_fit_chain
@@ -1010,7 +1023,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
     prm.warp_smem_bytes = (int)per_warp;
     size_t smem = per_warp * W;
-    if (prm.mode == FIT_MODE_FULL && P == 2 && !prm.node_ids && prm.nb == t->v.n_leaves && prm.q_in_smem && t->fit_units &&
+    if (prm.mode == FIT_MODE_FULL && P == 2 && !prm.node_ids && prm.nb == t->v.n_leaves && t->fit_units &&
         !(getenv("CSP_FIT_SHARED") && atoi(getenv("CSP_FIT_SHARED")) == 0)) {
         prm.units = t->fit_units;  // all leaves: sibling leaves share the off-diagonal work
         prm.n_units = t->n_fit_units;
@@ -1047,6 +1060,11 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         int occ = 0;
         CSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, W * 32, smem));
         if (occ < 1) return csp_set_error(CSP_ERR_CUDA, "fit kernel does not fit on an SM (smem %zu)", smem);
+        // Sharing divides the number of work items by ~3: with large records (few warps resident) that only pays while there
+        // are still many items per warp (C5, 3 450 splits with leaves on 1 480 warps: 16 ms per leaf vs 19 ms shared;
+        // C5det, 44 850: 1 593 vs 611 ms).
+        const bool force_shared = getenv("CSP_FIT_SHARED") && atoi(getenv("CSP_FIT_SHARED")) == 2;  // tests
+        if (prm.units && !prm.q_in_smem && !force_shared && prm.n_units < 8LL * std::max(t->n_sm, 1) * occ * W) prm.units = nullptr;
         const long long nunits = prm.units ? prm.n_units : prm.nb;
         long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {

@@ -185,7 +185,7 @@ def test_all_leaf_model_fit_bit_exact(case, monkeypatch):
     if case == "n6_failures":
         assert set(np.unique(ofit["status"])) >= {0, 1}
     iu = np.triu_indices(n)
-    for shared in ("1", "0"):
+    for shared in ("1", "0", "2"):  # default policy, never, always (also for records that stay in global memory)
         monkeypatch.setenv("CSP_FIT_SHARED", shared)
         mo = dt.fit_models().download()
         assert same(mo["status"], ofit["status"])
