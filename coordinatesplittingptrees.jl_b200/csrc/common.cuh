@@ -101,6 +101,7 @@ struct csp_tree {
     // L1-bound descent of one chunk overlaps the DRAM-bound evaluation of the previous one
     const int4* fit_units = nullptr;  // [n_fit_units] leaf ids (-1 padded) of the real leaves under each split that has any (fit.cu)
     long long n_fit_units = 0;
+    mutable double* fit_coef = nullptr;  // [n_internal] highest-order coefficient of every split (built on the first fit)
     mutable void* fit_ws = nullptr;  // grow-only scratch of the fit pre-pass (chain results), one fit call at a time per handle
     mutable size_t fit_ws_bytes = 0;
     mutable cudaStream_t pipe_st[2] = {nullptr, nullptr};

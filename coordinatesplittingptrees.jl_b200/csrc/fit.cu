@@ -49,6 +49,7 @@ struct FitParams {
     int pairs_in_smem;
     int q_in_smem;           // the box's Q / record is assembled in shared memory and written out once, coalesced
     int tiles;               // large n (Q stays in global memory): per-warp staging tiles for the O(n^2) loops
+    const double* coef;      // [n_internal] coef_value of every split, precomputed once per tree (nullptr: compute in place)
     unsigned long long* work_counter;  // optional (zeroed before the launch): warps claim units dynamically instead of striding
     const int4* units; long long n_units;  // all-leaf fits: the real leaves (output rows, -1 padded) under each split that has any
     int warp_smem_bytes;
@@ -97,6 +98,7 @@ struct WarpCtx {
     double *sb, *sy, *sg;
     int *sstep, *dkey, *did, *pkey, *pid;
     int* plist;  // global-scratch mode only: the slots filled so far, so that nothing has to sweep all n(n-1)/2 of them
+    unsigned long long* pk64;  // global-scratch mode: (scan position << 32 | split id) per slot, all ones = empty: one atomic per hit
     int *g_lo1, *g_n1, *g_lo2, *g_lo3, *g_pre;  // one window of up to 32 range groups (g_pre has 33 entries)
 };
 #define FIT_WINDOW_INTS (4 * 32 + 33 + 3)  // keeps the following doubles 8-byte aligned
@@ -246,6 +248,13 @@ __device__ __forceinline__ double coef_value(const TreeView& t, int id) {
     }
 }
 
+// The coefficient a split contributes (src/polynomials.jl:212-224) depends on the split alone: evaluated once per tree, so the
+// per-box work is a gather of 8 bytes instead of 64 bytes and a division per slot (same operations, same bits).
+template <int P>
+__global__ void __launch_bounds__(256) k_coef_table(const TreeView t, double* __restrict__ out) {
+    for (int id = blockIdx.x * blockDim.x + threadIdx.x; id < t.n_internal; id += gridDim.x * blockDim.x) out[id] = coef_value<P>(t, id);
+}
+
 // The splits(box) traversal, flattened: for a window of up to 32 consecutive range groups (one lane per ancestor) the
 // group sizes are prefix-summed, and each 32-split chunk of the window's virtual sequence maps its lanes back to
 // (group, offset) by bisection -- the many one-split groups next to a leaf share a chunk instead of taking one each.
@@ -344,18 +353,22 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
                         if (dd.x <= n && dd.y <= n && dd.x != dd.y) {
                             const int i = min(dd.x, dd.y) - 1, j = max(dd.x, dd.y) - 1;
                             pidx = prm.slotmap ? __ldg(prm.slotmap + i * n + j) : i * n - i * (i + 1) / 2 + (j - i - 1);
-                            if (pidx >= 0) newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                            if (pidx >= 0) {
+                                if (BIG && w.plist) newp = atomicMin(&w.pk64[pidx], ((unsigned long long)(unsigned)pos << 32) | (unsigned)id) == ~0ull;
+                                else newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                            }
                         }
                     } else {
                         const int dd0 = __ldg(t.idims + id);
                         if (dd0 <= n) {
                             pidx = dd0 - 1;
-                            newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
+                            if (BIG && w.plist) newp = atomicMin(&w.pk64[pidx], ((unsigned long long)(unsigned)pos << 32) | (unsigned)id) == ~0ull;
+                            else newp = atomicMin(&w.pkey[pidx], pos) == INT_MAX;
                         }
                     }
                 }
                 __syncwarp();
-                if (pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
+                if (!(BIG && w.plist) && pidx >= 0 && w.pkey[pidx] == pos) w.pid[pidx] = id;  // exactly one lane per slot holds the minimum
                 const unsigned nb = __ballot_sync(FULL, newp);
                 if (BIG && w.plist && newp) w.plist[found + __popc(nb & ((1u << lane) - 1))] = pidx;
                 found += __popc(nb);
@@ -414,10 +427,11 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
     w.g_lo1 = (int*)(sQ + (prm.q_in_smem ? qlen : 0)); w.g_n1 = w.g_lo1 + 32; w.g_lo2 = w.g_n1 + 32; w.g_lo3 = w.g_lo2 + 32; w.g_pre = w.g_lo3 + 32;
     w.sstep = w.g_lo1 + FIT_WINDOW_INTS; w.dkey = w.sstep + n; w.did = w.dkey + n;
     if (prm.pairs_in_smem) { w.pkey = w.did + n; w.pid = w.pkey + npairs; }
-    else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 3 * (size_t)npairs; w.pid = w.pkey + npairs; }
-    w.plist = (!BIG || prm.pairs_in_smem) ? nullptr : w.pid + npairs;
+    else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 3 * (size_t)((npairs + 1) & ~1); w.pid = w.pkey + npairs; }
+    w.plist = (!BIG || prm.pairs_in_smem) ? nullptr : w.pkey + 2 * (size_t)((npairs + 1) & ~1);
+    w.pk64 = (unsigned long long*)w.pkey;  // (8-byte aligned: the per-warp slice is a multiple of 8 bytes)
     if (w.plist) {  // the table is cleared once; afterwards every unit resets just the slots it filled
-        for (int e = lane; e < npairs; e += 32) w.pkey[e] = INT_MAX;
+        for (int e = lane; e < npairs; e += 32) w.pk64[e] = ~0ull;
         __syncwarp();
     }
     // staging tiles sit at the end of the warp's slice (only allocated when prm.tiles)
@@ -453,7 +467,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         long long nvisited;
         {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
             int mx = -1;
-            if (w.plist) { for (int e = lane; e < foundp; e += 32) mx = max(mx, w.pkey[w.plist[e]]); }
+            if (w.plist) { for (int e = lane; e < foundp; e += 32) mx = max(mx, (int)(w.pk64[w.plist[e]] >> 32)); }
             else for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
             for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
             nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - prm.skip : max(0, tpos - prm.skip);
@@ -465,25 +479,28 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             if (P == 2 && prm.slotmap) {
                 for (int e0 = lane; e0 < nslot; e0 += 32) {
                     const int e = w.plist ? w.plist[e0] : e0;
-                    if (w.pkey[e] == INT_MAX) continue;
-                    const double v = coef_value<2>(t, w.pid[e]);
+                    if (!w.plist && w.pkey[e] == INT_MAX) continue;
+                    const int sid = w.plist ? (int)(w.pk64[e] & 0xffffffffu) : w.pid[e];
+                    const double v = prm.coef ? __ldg(prm.coef + sid) : coef_value<2>(t, sid);
                     sawnan |= (v != v);
                     Qo[e] = v;
                 }
             } else if (P == 2) {
                 for (int e0 = lane; e0 < nslot; e0 += 32) {  // one lane per pair slot; (i, j) are the winning split's dimensions
                     const int e = w.plist ? w.plist[e0] : e0;
-                    if (w.pkey[e] == INT_MAX) continue;
-                    const int id = w.pid[e];
+                    if (!w.plist && w.pkey[e] == INT_MAX) continue;
+                    const int id = w.plist ? (int)(w.pk64[e] & 0xffffffffu) : w.pid[e];
                     const int2 dd = __ldg((const int2*)t.idims + id);
-                    const double v = coef_value<2>(t, id);
+                    const double v = prm.coef ? __ldg(prm.coef + id) : coef_value<2>(t, id);
                     sawnan |= (v != v);
                     Qo[qi(dd.x - 1, dd.y - 1)] = v;
                 }
             } else {
-                for (int e = lane; e < n; e += 32) {
-                    if (w.pkey[e] == INT_MAX) continue;
-                    const double v = coef_value<1>(t, w.pid[e]);
+                for (int e0 = lane; e0 < nslot; e0 += 32) {
+                    const int e = w.plist ? w.plist[e0] : e0;
+                    if (!w.plist && w.pkey[e] == INT_MAX) continue;
+                    const int sid = w.plist ? (int)(w.pk64[e] & 0xffffffffu) : w.pid[e];
+                    const double v = prm.coef ? __ldg(prm.coef + sid) : coef_value<1>(t, sid);
                     sawnan |= (v != v);
                     Qo[e] = v;
                 }
@@ -491,7 +508,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             sawnan = __any_sync(FULL, sawnan) || npairs == 0;  // nothing to determine: replay the reference's loop literally
             __syncwarp();
             if (w.plist) {
-                for (int e0 = lane; e0 < foundp; e0 += 32) w.pkey[w.plist[e0]] = INT_MAX;
+                for (int e0 = lane; e0 < foundp; e0 += 32) w.pk64[w.plist[e0]] = ~0ull;
                 __syncwarp();
             }
             FIT_TICK(2);
@@ -1028,6 +1045,19 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         prm.units = t->fit_units;  // all leaves: sibling leaves share the off-diagonal work
         prm.n_units = t->n_fit_units;
     }
+    if (t->v.n_internal > 0 && !(getenv("CSP_FIT_COEF_TABLE") && atoi(getenv("CSP_FIT_COEF_TABLE")) == 0)) {
+        if (!t->fit_coef) {
+            void* pc = nullptr;
+            CSP_CHECK(csp_dev_alloc(&pc, (size_t)t->v.n_internal * sizeof(double)));
+            const int blocks = std::min(4096, (t->v.n_internal + 255) / 256);
+            if (P == 2) k_coef_table<2><<<blocks, 256, 0, st>>>(t->v, (double*)pc);
+            else k_coef_table<1><<<blocks, 256, 0, st>>>(t->v, (double*)pc);
+            CSP_LAUNCHED();
+            CSP_CUDA(cudaGetLastError());
+            t->fit_coef = (double*)pc;
+        }
+        prm.coef = t->fit_coef;
+    }
     if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
         const size_t nb = (size_t)prm.nb;
         const size_t need = nb * ((size_t)n * 20 + 16) + 64 + 64;  // chain rows + alignment slack + the work counter
@@ -1068,7 +1098,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         const long long nunits = prm.units ? prm.n_units : prm.nb;
         long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {
-            CSP_CHECK(csp_dev_alloc(scratch_out, (size_t)grid * W * 3 * npairs * sizeof(int)));
+            CSP_CHECK(csp_dev_alloc(scratch_out, (size_t)grid * W * 3 * ((npairs + 1) & ~1LL) * sizeof(int)));
             prm.scratch = (int*)*scratch_out;
         }
         const bool prof = getenv("CSP_FIT_PROF") && atoi(getenv("CSP_FIT_PROF"));

@@ -367,6 +367,7 @@ int csp_tree_free(csp_tree* tree) {
         cudaDeviceSynchronize();  // work on any stream may still read the tree
         for (void* p : tree->allocs) csp_dev_free(p);
         csp_dev_free(tree->fit_ws);
+        csp_dev_free(tree->fit_coef);
         for (int i = 0; i < 2; ++i) {
             if (tree->pipe_st[i]) cudaStreamDestroy(tree->pipe_st[i]);
             if (tree->pipe_join[i]) cudaEventDestroy(tree->pipe_join[i]);
