@@ -332,7 +332,109 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
         __syncwarp();
         if (!pseudo && !more && tpos == 0) { sw_cnt = cnt; sw_total = total; }  // first and only window
         }
-        for (int base = 0; base < total; base += 32) {
+        bool fast = false;
+        if constexpr (!DIAG && BIG && P == 2) {
+            if (w.plist) {  // global pair table: four chunks per round, their loads and atomics all in flight together
+                fast = true;
+                constexpr int KU = 4;
+                for (int base = 0; base < total; base += 32 * KU) {
+                    int idv[KU], pidx[KU];
+                    bool newp[KU];
+#pragma unroll
+                    for (int u = 0; u < KU; ++u) {
+                        const int v = base + 32 * u + lane;
+                        idv[u] = -1; pidx[u] = -1; newp[u] = false;
+                        if (v < total && tpos + 32 * u + lane >= skip) {
+                            int gsel = 0;
+#pragma unroll
+                            for (int sft = 16; sft; sft >>= 1) { const int c = gsel + sft; if (c < cnt && w.g_pre[c] <= v) gsel = c; }
+                            const int off = v - w.g_pre[gsel], gtot = w.g_pre[gsel + 1] - w.g_pre[gsel], gn1 = w.g_n1[gsel];
+                            idv[u] = off < gn1 ? w.g_lo1[gsel] + off : ((pseudo || off < gtot - 1) ? w.g_lo2[gsel] + (off - gn1) : w.g_lo3[gsel]);
+                        }
+                    }
+                    int2 ddv[KU];
+#pragma unroll
+                    for (int u = 0; u < KU; ++u) ddv[u] = idv[u] >= 0 ? __ldg((const int2*)t.idims + idv[u]) : make_int2(n + 1, n + 1);
+#pragma unroll
+                    for (int u = 0; u < KU; ++u) {
+                        const int2 dd = ddv[u];
+                        if (dd.x <= n && dd.y <= n && dd.x != dd.y) {
+                            const int i = min(dd.x, dd.y) - 1, j = max(dd.x, dd.y) - 1;
+                            pidx[u] = prm.slotmap ? __ldg(prm.slotmap + i * n + j) : i * n - i * (i + 1) / 2 + (j - i - 1);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < KU; ++u)
+                        if (pidx[u] >= 0)
+                            newp[u] = atomicMin(&w.pk64[pidx[u]], ((unsigned long long)(unsigned)(tpos + 32 * u + lane) << 32) | (unsigned)idv[u]) == ~0ull;
+#pragma unroll
+                    for (int u = 0; u < KU; ++u) {
+                        const unsigned nb = __ballot_sync(FULL, newp[u]);
+                        if (newp[u]) w.plist[found + __popc(nb & ((1u << lane) - 1))] = pidx[u];
+                        found += __popc(nb);
+                    }
+                    tpos += min(32 * KU, total - base);
+                    if (found >= nslots) { done = true; break; }
+                }
+            }
+        }
+        if constexpr (DIAG && BIG && P == 2) {  // large n: the diagonal candidates of four chunks per round, loads in flight together
+            fast = true;
+            constexpr int KU = 4;
+            for (int base = 0; base < total; base += 32 * KU) {
+                int idv[KU];
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    const int v = base + 32 * u + lane;
+                    idv[u] = -1;
+                    if (v < total && tpos + 32 * u + lane >= skip) {
+                        int gsel = 0;
+#pragma unroll
+                        for (int sft = 16; sft; sft >>= 1) { const int c = gsel + sft; if (c < cnt && w.g_pre[c] <= v) gsel = c; }
+                        const int off = v - w.g_pre[gsel], gtot = w.g_pre[gsel + 1] - w.g_pre[gsel], gn1 = w.g_n1[gsel];
+                        idv[u] = off < gn1 ? w.g_lo1[gsel] + off : ((pseudo || off < gtot - 1) ? w.g_lo2[gsel] + (off - gn1) : w.g_lo3[gsel]);
+                    }
+                }
+                int2 ddv[KU];
+                double2 xsv[KU], xfv[KU];
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    ddv[u] = make_int2(n + 1, n + 1); xsv[u] = make_double2(0.0, 0.0); xfv[u] = xsv[u];
+                    if (idv[u] >= 0) {
+                        ddv[u] = __ldg((const int2*)t.idims + idv[u]);
+                        xsv[u] = __ldg((const double2*)t.ixs + idv[u]);
+                        xfv[u] = __ldg((const double2*)t.ixself + idv[u]);
+                    }
+                }
+                int dk0[KU], dk1[KU];
+                bool nd0[KU], nd1[KU];
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    const int pos = tpos + 32 * u + lane, dd0 = ddv[u].x, dd1 = ddv[u].y;
+                    dk0[u] = -1; dk1[u] = -1; nd0[u] = false; nd1[u] = false;
+                    if (dd0 <= n && w.dkey[dd0 - 1] > 2 * pos &&
+                        (newinfo(xsv[u].x, w.sb[dd0 - 1], w.sy[dd0 - 1]) || newinfo(xfv[u].x, w.sb[dd0 - 1], w.sy[dd0 - 1]))) {
+                        dk0[u] = 2 * pos;
+                        nd0[u] = atomicMin(&w.dkey[dd0 - 1], dk0[u]) == INT_MAX;
+                    }
+                    if (dd1 <= n && w.dkey[dd1 - 1] > 2 * pos + 1 &&
+                        (newinfo(xsv[u].y, w.sb[dd1 - 1], w.sy[dd1 - 1]) || newinfo(xfv[u].y, w.sb[dd1 - 1], w.sy[dd1 - 1]))) {
+                        dk1[u] = 2 * pos + 1;
+                        nd1[u] = atomicMin(&w.dkey[dd1 - 1], dk1[u]) == INT_MAX;
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    if (dk0[u] >= 0 && w.dkey[ddv[u].x - 1] == dk0[u]) w.did[ddv[u].x - 1] = 2 * idv[u];
+                    if (dk1[u] >= 0 && w.dkey[ddv[u].y - 1] == dk1[u]) w.did[ddv[u].y - 1] = 2 * idv[u] + 1;
+                    found += __popc(__ballot_sync(FULL, nd0[u])) + __popc(__ballot_sync(FULL, nd1[u]));
+                }
+                tpos += min(32 * KU, total - base);
+                if (found >= nslots) { done = true; break; }
+            }
+        }
+        for (int base = 0; !fast && base < total; base += 32) {
             const int v = base + lane;
             int id = 0;
             if (v < total) {
@@ -467,8 +569,15 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         long long nvisited;
         {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
             int mx = -1;
-            if (w.plist) { for (int e = lane; e < foundp; e += 32) mx = max(mx, (int)(w.pk64[w.plist[e]] >> 32)); }
-            else for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
+            if (w.plist) {  // four independent gathers in flight per lane
+                for (int e0 = lane; e0 < foundp; e0 += 128) {
+                    int ev[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ev[u] = e0 + 32 * u < foundp ? w.plist[e0 + 32 * u] : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (ev[u] >= 0) mx = max(mx, (int)(w.pk64[ev[u]] >> 32));
+                }
+            } else for (int e = lane; e < npairs; e += 32) mx = max(mx, w.pkey[e] == INT_MAX ? -1 : w.pkey[e]);
             for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
             nvisited = (foundp >= npairs && npairs > 0) ? (long long)mx + 1 - prm.skip : max(0, tpos - prm.skip);
         }
@@ -476,7 +585,35 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             // values (src/polynomials.jl:211-226), one lane per slot
             bool sawnan = false;
             const int nslot = w.plist ? foundp : npairs;
-            if (P == 2 && prm.slotmap) {
+            if (BIG && w.plist) {
+                // global table: slot -> (winning split) -> value -> output, four slots per lane per round so that the dependent
+                // gathers of a round overlap; the slots are handed back empty in the same pass
+                for (int e0 = lane; e0 < nslot; e0 += 128) {
+                    int ev[4], sid[4];
+                    double vv[4];
+                    int2 ddv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) ev[u] = e0 + 32 * u < nslot ? w.plist[e0 + 32 * u] : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) sid[u] = ev[u] >= 0 ? (int)(w.pk64[ev[u]] & 0xffffffffu) : -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        vv[u] = 0.0; ddv[u] = make_int2(1, 1);
+                        if (sid[u] >= 0) {
+                            vv[u] = prm.coef ? __ldg(prm.coef + sid[u]) : (P == 2 ? coef_value<2>(t, sid[u]) : coef_value<1>(t, sid[u]));
+                            if (P == 2 && !prm.slotmap) ddv[u] = __ldg((const int2*)t.idims + sid[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        if (sid[u] < 0) continue;
+                        sawnan |= (vv[u] != vv[u]);
+                        if (P == 2 && !prm.slotmap) Qo[qi(ddv[u].x - 1, ddv[u].y - 1)] = vv[u];
+                        else Qo[ev[u]] = vv[u];
+                        w.pk64[ev[u]] = ~0ull;
+                    }
+                }
+            } else if (P == 2 && prm.slotmap) {
                 for (int e0 = lane; e0 < nslot; e0 += 32) {
                     const int e = w.plist ? w.plist[e0] : e0;
                     if (!w.plist && w.pkey[e] == INT_MAX) continue;
@@ -507,10 +644,6 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             }
             sawnan = __any_sync(FULL, sawnan) || npairs == 0;  // nothing to determine: replay the reference's loop literally
             __syncwarp();
-            if (w.plist) {
-                for (int e0 = lane; e0 < foundp; e0 += 32) w.pk64[w.plist[e0]] = ~0ull;
-                __syncwarp();
-            }
             FIT_TICK(2);
             if (sawnan) {
                 // A computed coefficient was NaN (non-finite samples or a vanishing denominator).  The reference then keeps
@@ -565,7 +698,13 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
                 const long long bm = mi == 1 ? members.y : mi == 2 ? members.z : members.w;
                 if (bm < 0) break;
                 double* Qm = prm.Q + bm * prm.Q_stride;
-                for (long long e = lane; e < qlen; e += 32) Qm[e] = Qo[e];
+                for (long long e = lane; e < qlen; e += 256) {  // eight loads in flight, then eight stores
+                    double tv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) tv[u] = e + 32 * u < qlen ? Qo[e + 32 * u] : 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) if (e + 32 * u < qlen) Qm[e + 32 * u] = tv[u];
+                }
             }
             __syncwarp();
         }
