@@ -2,13 +2,15 @@
 //
 // The fused kernel of locate_eval.cu fetches a model record (8(n+1)(n+2)/2 + 8n bytes) from L2 for EVERY query; with
 // many queries per leaf that traffic (and the per-query reduction work) dominates.  Here the located queries are
-// counting-sorted by leaf id, so that consecutive evaluation threads share a leaf: the record is read once per warp as
-// uniform (broadcast) loads that hit L1, each thread owns one query with its z = (x - b, 1) vector in registers, and
-// there is no cross-lane reduction at all.  Pipeline (all on the caller's stream):
-//   k_locate<P,-1> + histogram   leaf ids in query order, count per leaf (global reductions)   [locate_eval.cu]
-//   k_scan_*                     exclusive prefix sum over the per-leaf counts -> segment offsets
-//   k_scatter                    slot = offsets[leaf]++ ; perm[slot] = (query, leaf)
-//   k_eval_binned<NPAD>          thread s: (q, leaf) = perm[s]; gather x[q]; value = sum A_ij z_i z_j; val[q] = value
+// counting-sorted by leaf id, so that consecutive evaluation positions share a leaf and a record is fetched once per run.
+// Pipeline (all on the caller's stream, chunk by chunk):
+//   k_locate_only / k_locate_wide   leaf ids in query order + per-leaf histogram (global reductions)   [locate_eval.cu]
+//   k_scan                          exclusive prefix sum over the per-leaf counts -> segment offsets (single launch)
+//   k_scatter                       slot = offsets[leaf]++ ; perm[slot] = (query, leaf) ; slot_of[query] = slot
+//   evaluation in sorted order      k_eval_binned_exact<N> (FMA, small n), k_eval_binned_mma<N> (FP64 tensor cores, even n in
+//                                   16..30), k_eval_dmma / k_eval_dmma_panel (n > 32, dense_eval.cu), generic fallbacks;
+//                                   values written at the sorted position (coalesced)
+//   k_unpermute                     val[q] = sorted_val[slot_of[q]]  (the chunk's values are still in L2)
 // Evaluation arithmetic: reference src/cs2.jl:155-159 (summation order not pinned by the reference).
 #include <cstdlib>
 

@@ -9,13 +9,15 @@
 //   fit_poly2_diag!         src/cs2.jl:208-274  (+ Qcoef_lineq :314-325)
 //   canonicalize / chi      src/cs2.jl:132-140, 277-280
 //
-// Work decomposition: one warp per box.  The reference's `splits(box)` traversal (src/tree.jl:461-540) is replaced by
-// the preorder identity: for each ancestor a of the box, bottom-up, coming from child c, the iterator
-// yields the internal-node id ranges [I_a+1, I_c) and [I_c+S_c, I_a+S_a) in ascending order, then I_a itself.  So the
-// traversal is a list of contiguous, coalesced range scans over the per-split SoA arrays; "first split in iteration
-// order wins" becomes an integer atomicMin on the scan position per coefficient slot (shared memory), and the
-// reference's early exit becomes "stop when every slot is filled".  The O(n) / O(n^2) floating-point work is then done
-// one lane per output entry, sequentially in the reference's order.
+// Work decomposition: one warp per work unit -- a box, or (all-leaf fits) the real leaves under one split, whose traversals
+// coincide (see k_fit).  The reference's `splits(box)` traversal (src/tree.jl:461-540) is replaced by the preorder identity
+// (SURVEY.md 3.3): for each ancestor a of the box, bottom-up, coming from child c, the iterator yields the internal-node id
+// ranges [I_a+1, I_c) and [I_c+S_c, I_a+S_a) in ascending order, then I_a itself.  So the traversal is a list of contiguous
+// range scans over the per-split SoA arrays, flattened into one virtual sequence per window of 32 ancestors (fit_scan);
+// "first split in iteration order wins" becomes an integer atomicMin on the scan position per coefficient slot (shared
+// memory, or an L2-resident global table for large n), and the reference's early exit becomes "stop when every slot is
+// filled".  The O(n) / O(n^2) floating-point work is then done one lane per output entry, sequentially in the reference's
+// order (tiles staged through shared memory for large n).
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
