@@ -604,14 +604,24 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
         csp_tree::Geo ng{};
         const size_t rec = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
         const char* env = getenv("CSP_TOP_RECORDS");
-        int top = env ? atoi(env) : 341;  // levels 0-4 of a CS2 tree
-        top = std::max(0, std::min(top, t->v.n_internal));
-        int tl = 256;
         auto need = [&](int tile, int tp) {
             return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)2 * tile * n * 8 + (size_t)2 * n * 8 + 16;
         };
-        while (need(tl, top) > 56 * 1024 && tl > 32) tl /= 2;  // four CTAs per SM when possible
-        while (need(tl, top) > 200 * 1024 && top > 0) top /= 2;
+        // Staged tree top: levels 0-4 (341 records), 0-3 (85) or 0-2 (21) of a CS2 tree -- whichever keeps the most queries
+        // resident per SM (the descent is bound by L1/LSU throughput and latency, not by where the top records live:
+        // C3, n = 20: 341 records -> 4 CTAs, 7.0 ms per 1e8 queries; 85 -> 5 CTAs, 6.3 ms).
+        int top = 0, tl = 256;
+        long long best = -1;
+        for (int cand : {341, 85, 21}) {
+            int tp = env ? atoi(env) : cand;
+            tp = std::max(0, std::min(tp, t->v.n_internal));
+            int tile = 256;
+            while (need(tile, tp) > 56 * 1024 && tile > 32) tile /= 2;  // four or more CTAs per SM when possible
+            while (need(tile, tp) > 200 * 1024 && tp > 0) tp /= 2;
+            const long long resident = std::min<long long>(2048, (long long)((227 * 1024) / std::max<size_t>(need(tile, tp), 1)) * tile);
+            if (resident > best) { best = resident; top = tp; tl = tile; }
+            if (env) break;
+        }
         if (need(tl, top) > 200 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the tiled descent kernel", n);
         ng.tile = tl; ng.stages = 1; ng.top = top; ng.smem = need(tl, top);
         CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
