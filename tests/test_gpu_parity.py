@@ -709,3 +709,35 @@ def test_fit_gdiag_like_reference_and_no_chain_fallback():
         cb.fit_quadratic(leaf)
     c, gg, Q, b = cb.fit_quadratic_gdiag(leaf)
     assert np.allclose(Q.full(), f.B, rtol=1e-5, atol=1e-7) and c == cb.value(leaf) and same(b, cb.position(leaf))
+
+
+@pytest.mark.parametrize("case", ["cs2_n4", "cs2_n10", "cs1_n3"])
+def test_committed_fixtures_on_gpu(case):
+    """The CUDA path against the committed vectors of tests/golden/ (oracle-generated, see its README): leaf ids, status,
+    coefficients_p, visited counts and the full CS2 fit, bit for bit, without running the oracle."""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_fixtures", os.path.join(here, "golden", "make_fixtures.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    gold = np.load(os.path.join(here, "golden", case + ".npz"))
+    root, _, X = mf.build(case)
+    assert same(X, gold["X"])
+    dt = cb.device_tree(root)
+    leaf, status = dt.find_leaf(X)
+    assert same(leaf, gold["leaf"]) and same(status, gold["status"])
+    Cp, vis = dt.coefficients_p()
+    n = root.n
+    if mf.CASES[case]["p"] == 2:
+        assert same(Cp, gold["Cp"].reshape(-1, n, n).transpose(0, 2, 1))
+        fit = dt.fit_boxes()
+        assert same(fit["status"], gold["fit_status"])
+        for k in ("c", "g", "Q", "b"):
+            assert same(fit[k], gold[k]), k
+        mo = dt.fit_models().download()
+        iu = np.triu_indices(n)
+        assert same(mo["status"], gold["fit_status"]) and same(mo["c"], gold["c"]) and same(mo["g"], gold["g"])
+        assert same(mo["Q"][:, iu[0], iu[1]], gold["Q"][:, iu[0], iu[1]])
+    else:
+        assert same(Cp, gold["Cp"])
+    assert same(vis, gold["visited"])

@@ -336,3 +336,22 @@ def test_possemidef_goldens():  # runtests.jl:933-948 ("posdef"), exact equality
         Qp = O.possemidef(np.triu(A))
         assert np.allclose(Qp - np.diag(np.diag(Qp)), A - np.diag(np.diag(A)))
         assert np.linalg.eigvalsh(Qp).min() > -1e-9 * np.abs(Qp).max()
+
+
+@pytest.mark.parametrize("case", ["cs2_n4", "cs2_n10", "cs1_n3"])
+def test_committed_fixtures_match_oracle(case):
+    """tests/golden/*.npz (oracle outputs on small seeded trees, tests/golden/make_fixtures.py) still equal what the oracle
+    computes today, bit for bit: the vectors the GPU parity tests compare with cannot drift silently."""
+    import importlib.util
+    import os
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_fixtures", os.path.join(here, "golden", "make_fixtures.py"))
+    mf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mf)
+    gold = np.load(os.path.join(here, "golden", case + ".npz"))
+    root, oroot, X = mf.build(case)
+    assert np.array_equal(X, gold["X"])
+    out = mf.oracle_outputs(oroot, X, mf.CASES[case]["p"])
+    assert set(out) == set(gold.files)
+    for k in gold.files:
+        assert np.array_equal(out[k], gold[k], equal_nan=True), k
