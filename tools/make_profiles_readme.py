@@ -127,7 +127,7 @@ re-upload {upd['upload']}, 1e4 queries {upd['locate_1e4']}, all-leaf fit (alloca
 | + sorted-order value writes, L2-resident unpermute gather | 10.8 | 9.2e9 |
 
 Other kernels over the round: all-leaf fits C2 0.48 -> 0.34 ms, C3 11.9 -> 5.35 ms (flattened ancestor windows, sibling-shared scan,
-record assembled in shared memory, dynamic unit scheduling, per-split coefficient table), C5 (n = 300) 26.7 -> 14.1 ms, C5det 1 593 -> 445 ms; K3b at C4 24.9 -> 12.1 ms per 2e7 queries (software-pipelined DMMA
+record assembled in shared memory, dynamic unit scheduling, per-split coefficient table), C5 (n = 300) 26.7 -> 14.1 ms, C5det 1 593 -> 445 ms; K3b at C4 24.9 -> 11.7 ms per 2e7 queries (software-pipelined DMMA
 kernel), n = 300 evaluation 8.0e6 -> 1.4e8 queries/s (panel-streaming DMMA kernel); C3 step 26.8 -> 23.4 ms (tensor-core evaluation at n = 20);
 C4 end to end 6.7e8 -> 1.25e9 queries/s (one chunk for the dense path, streaming descent kernel for n > 32).
 """
