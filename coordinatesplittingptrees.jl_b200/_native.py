@@ -53,7 +53,7 @@ class TreeDesc(C.Structure):
 
 
 _HOST_ERR = {-1: ErrorException, -2: DimensionMismatch, -3: AssertionError, -5: ArgumentError, -6: BoundsError}
-_DEV_ERR = {-1: ArgumentError, -2: CspError, -3: MemoryError, -4: CspError, -5: NoDeviceError}
+_DEV_ERR = {-1: ArgumentError, -2: CspError, -3: MemoryError, -4: CspError, -5: NoDeviceError, -6: CspError}
 
 _host = None
 _dev = None
@@ -135,6 +135,24 @@ def dev():
         L.csp_eval_dev.argtypes = [vp, vp, vp, C.c_int64, vp, vp]
         L.csp_locate_eval.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
         L.csp_locate_eval_dev.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp, vp]
+        L.csp_models_alloc.argtypes = [vp, vpp]
+        L.csp_models_refit_range.argtypes = [vp, C.c_int32, vp, C.c_int64, C.c_int64, vp]
+        L.csp_models_download_rows.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
+        # multi-GPU layer (comm.cu)
+        L.csp_init.argtypes = [C.c_int, c_i32p]
+        L.csp_comm_unique_id.argtypes = [vp]
+        L.csp_init_rank.argtypes = [C.c_int, C.c_int, C.c_int, vp]
+        L.csp_comm_info.argtypes = [c_i64p]
+        L.csp_shard_tree_broadcast.argtypes = [vp, C.c_size_t, C.c_int, vpp]
+        L.csp_shard_tree_get.argtypes = [vp, C.c_int, vpp]
+        L.csp_shard_tree_free.argtypes = [vp]
+        L.csp_shard_fit.argtypes = [vp, C.c_int32, vpp, vpp]
+        L.csp_shard_models_get.argtypes = [vp, C.c_int, vpp]
+        L.csp_shard_models_free.argtypes = [vp]
+        L.csp_shard_locate_eval_dev.argtypes = [vp, vp, vpp, c_i64p, vpp, vpp, vpp, C.c_int, vp, vp, C.c_int64, vpp]
+        L.csp_shard_gather_dev.argtypes = [vpp, vpp, c_i64p, C.c_int, vp, vp, vpp]
+        L.csp_shard_locate_eval.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
+        L.csp_shard_timing.argtypes = [c_f64p]
         _dev = L
     return _dev
 
@@ -149,4 +167,7 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_fit_boxes", "csp_coefficients_p", "csp_models_fit", "csp_models_refit", "csp_models_upload", "csp_models_download", "csp_models_info",
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
            "csp_timing_read", "csp_modelvalue_native", "csp_coefficients_p_sparse",
-           "csp_models_possemidef", "csp_fit_gdiag"]
+           "csp_models_possemidef", "csp_fit_gdiag", "csp_models_alloc", "csp_models_refit_range", "csp_models_download_rows",
+           "csp_init", "csp_comm_unique_id", "csp_init_rank", "csp_shutdown", "csp_comm_info", "csp_shard_tree_broadcast",
+           "csp_shard_tree_get", "csp_shard_tree_free", "csp_shard_fit", "csp_shard_models_get", "csp_shard_models_free",
+           "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]

@@ -19,9 +19,11 @@
 __device__ __forceinline__ double dnan_b() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // ---- exclusive scan of cnt[0..nl) into off[0..nl] (off[nl] = total) -- one launch, chained across blocks ------------
-// Block b publishes its sum with an epoch-stamped flag and adds up the sums of the blocks before it (blocks are
-// dispatched in index order, so a block only ever waits for blocks that are already running).  cnt is zeroed on the way
-// out, ready for the next chunk's histogram.
+// Block b publishes its sum with an epoch-stamped flag and adds up the sums of the blocks before it.  b is a LOGICAL block id
+// taken from an atomic ticket when the block starts running (CUDA does not promise that blockIdx order is dispatch order): a
+// block only ever waits for tickets handed out before its own, i.e. for blocks that are already resident.  The block that
+// draws the last ticket resets the counter for the next launch.  cnt is zeroed on the way out, ready for the next chunk's
+// histogram.
 #define SCAN_T 256
 #define SCAN_PER 8  // elements per thread => 2048 per block
 
@@ -36,10 +38,17 @@ __device__ __forceinline__ int block_sum(int v, int* ws) {  // all threads get t
 }
 
 __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, int* __restrict__ off, int* __restrict__ cursor,
-                                                volatile int* bsum, volatile int* bflag, int epoch) {
+                                                volatile int* bsum, volatile int* bflag, int* ticket, int epoch) {
     __shared__ int ws[SCAN_T / 32];
     __shared__ int carry;
-    const int b = blockIdx.x, base = b * SCAN_T * SCAN_PER;
+    __shared__ int s_ticket;
+    if (threadIdx.x == 0) {
+        const int tk = atomicAdd(ticket, 1);
+        if (tk == (int)gridDim.x - 1) *ticket = 0;  // every ticket of this launch has been drawn
+        s_ticket = tk;
+    }
+    __syncthreads();
+    const int b = s_ticket, base = b * SCAN_T * SCAN_PER;
     int v[SCAN_PER], s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_PER; ++k) {
@@ -84,7 +93,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
 }
 
 // ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int* __restrict__ cursor,
+// Leaf ids outside [0, n_models) (caller-supplied ids of csp_eval*) are treated like "outside the world": slot -1, value NaN.
+__global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int n_models, int* __restrict__ cursor,
                                                  int2* __restrict__ perm, int* __restrict__ slot_of) {
     // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -94,6 +104,7 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, l
         for (int u = 0; u < 4; ++u) {
             const long long q = q0 + u * stride;
             lf[u] = q < m ? leaf[q] : -2;
+            if (lf[u] >= n_models) lf[u] = -1;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) slot[u] = lf[u] >= 0 ? atomicAdd(cursor + lf[u], 1) : -1;
@@ -493,7 +504,7 @@ struct BinWorkspace {
     int* cnt = nullptr;      // [nl]
     int* off = nullptr;      // [nl + 1]; off[nl] = number of located queries
     int* cursor = nullptr;   // [nl]
-    int* partial = nullptr;  // [2*nblocks]: block sums, then epoch flags
+    int* partial = nullptr;  // [2*nblocks + 1]: block sums, epoch flags, ticket counter
     int2* perm = nullptr;    // [m]
     int* slot = nullptr;     // [m] sorted position of each query (-1: outside the world)
     double* vsorted = nullptr;  // [m] values in leaf-sorted order
@@ -506,8 +517,8 @@ int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorks
     CSP_CUDA(cudaMallocAsync(&w->cnt, (size_t)nl * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->off, (size_t)(nl + 1) * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->cursor, (size_t)nl * 4, st));
-    CSP_CUDA(cudaMallocAsync(&w->partial, (size_t)std::max(nblocks, 1) * 8, st));
-    CSP_CUDA(cudaMemsetAsync(w->partial, 0, (size_t)std::max(nblocks, 1) * 8, st));
+    CSP_CUDA(cudaMallocAsync(&w->partial, ((size_t)std::max(nblocks, 1) * 8 + 8), st));
+    CSP_CUDA(cudaMemsetAsync(w->partial, 0, ((size_t)std::max(nblocks, 1) * 8 + 8), st));
     CSP_CUDA(cudaMallocAsync(&w->perm, (size_t)m * sizeof(int2), st));
     CSP_CUDA(cudaMallocAsync(&w->slot, (size_t)m * 4, st));
     CSP_CUDA(cudaMallocAsync(&w->vsorted, (size_t)m * 8, st));
@@ -521,12 +532,12 @@ int csp_bin_alloc_sync(int nl, long long m, BinWorkspace* w) {
     CSP_CUDA(cudaMalloc(&w->cnt, (size_t)nl * 4));
     CSP_CUDA(cudaMalloc(&w->off, (size_t)(nl + 1) * 4));
     CSP_CUDA(cudaMalloc(&w->cursor, (size_t)nl * 4));
-    CSP_CUDA(cudaMalloc(&w->partial, (size_t)std::max(nblocks, 1) * 8));
+    CSP_CUDA(cudaMalloc(&w->partial, ((size_t)std::max(nblocks, 1) * 8 + 8)));
     CSP_CUDA(cudaMalloc(&w->perm, (size_t)m * sizeof(int2)));
     CSP_CUDA(cudaMalloc(&w->slot, (size_t)m * 4));
     CSP_CUDA(cudaMalloc(&w->vsorted, (size_t)m * 8));
     CSP_CUDA(cudaMemset(w->cnt, 0, (size_t)nl * 4));
-    CSP_CUDA(cudaMemset(w->partial, 0, (size_t)std::max(nblocks, 1) * 8));
+    CSP_CUDA(cudaMemset(w->partial, 0, ((size_t)std::max(nblocks, 1) * 8 + 8)));
     w->epoch = 0;
     return CSP_OK;
 }
@@ -555,13 +566,13 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     w->epoch += 1;
     {
         CspTimed tm(CSP_K_SCAN, st);
-        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->epoch);
+        k_scan<<<nblocks, SCAN_T, 0, st>>>(w->cnt, nl, w->off, w->cursor, w->partial, w->partial + nblocks, w->partial + 2 * nblocks, w->epoch);
     }
     CSP_LAUNCHED();
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * (8 / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_SCATTER, st);
-        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, w->cursor, w->perm, w->slot);
+        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->cursor, w->perm, w->slot);
     }
     CSP_LAUNCHED();
     auto unpermute = [&]() -> int {

@@ -1,0 +1,558 @@
+// comm.cu -- multi-GPU layer of libcsp_b200.so: NCCL clique, tree broadcast (C1), leaf-sharded fits with
+// an all-gather of the records, query shards with a pipelined gather of (leaf id, value) to one rank (C2).
+//
+// The path shards with no exchange step, so the collectives are exactly three: one broadcast per tree version, one all-gather per
+// re-fit, one gather per query batch.  NCCL is loaded with dlopen when the clique is formed (libnccl.so.2: the copy already in
+// the process -- e.g. the one torch brought -- else the system library), so a single-GPU user never needs it.
+// One host thread may drive several GPUs (single-process mode): every NCCL call sequence over the local ranks is grouped.
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <chrono>
+#include <cstring>
+#include <thread>
+
+#include "common.cuh"
+
+namespace {
+
+struct NcclApi {
+    void* h = nullptr;
+    ncclResult_t (*GetVersion)(int*) = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi N;
+
+int load_nccl() {
+    if (N.h) return CSP_OK;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);  // the copy this process already uses, if any
+    const char* env = getenv("CSP_NCCL_LIB");
+    if (!h && env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return csp_set_error(CSP_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+    bool ok = true;
+    auto sym = [&](const char* name) { void* p = dlsym(h, name); if (!p) ok = false; return p; };
+    N.GetVersion = (decltype(N.GetVersion))sym("ncclGetVersion");
+    N.GetUniqueId = (decltype(N.GetUniqueId))sym("ncclGetUniqueId");
+    N.CommInitRank = (decltype(N.CommInitRank))sym("ncclCommInitRank");
+    N.CommInitAll = (decltype(N.CommInitAll))sym("ncclCommInitAll");
+    N.CommDestroy = (decltype(N.CommDestroy))sym("ncclCommDestroy");
+    N.GroupStart = (decltype(N.GroupStart))sym("ncclGroupStart");
+    N.GroupEnd = (decltype(N.GroupEnd))sym("ncclGroupEnd");
+    N.Broadcast = (decltype(N.Broadcast))sym("ncclBroadcast");
+    N.Send = (decltype(N.Send))sym("ncclSend");
+    N.Recv = (decltype(N.Recv))sym("ncclRecv");
+    N.GetErrorString = (decltype(N.GetErrorString))sym("ncclGetErrorString");
+    if (!ok) return csp_set_error(CSP_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
+    N.h = h;
+    return CSP_OK;
+}
+
+#define CSP_NCCL(call)                                                                                              \
+    do {                                                                                                            \
+        ncclResult_t _r = (call);                                                                                   \
+        if (_r != ncclSuccess)                                                                                      \
+            return csp_set_error(CSP_ERR_NCCL, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, N.GetErrorString(_r)); \
+    } while (0)
+
+struct Rank {
+    int rank = 0, device = 0;
+    ncclComm_t comm = nullptr;
+    cudaStream_t st = nullptr;   // library stream (used when the caller passes no stream)
+    cudaStream_t cst = nullptr;  // communication stream: gathers run here behind the next chunk's kernels
+    cudaEvent_t fork = nullptr, join = nullptr;
+    cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+struct Ctx {
+    bool init = false;
+    int world = 0, version = 0;
+    std::vector<Rank> local;
+    cudaEvent_t tev[6][2] = {};  // timing events on local rank 0's streams
+    bool tset[6] = {};
+    double wall_ms[6] = {};
+};
+Ctx G;
+
+void shard_range(long long total, int world, int rank, long long* lo, long long* hi) {
+    const long long base = total / world, rem = total % world;
+    *lo = rank * base + std::min<long long>(rank, rem);
+    *hi = *lo + base + (rank < rem ? 1 : 0);
+}
+
+int finish_init() {
+    for (Rank& r : G.local) {
+        DeviceGuard g(r.device);
+        CSP_CUDA(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
+        CSP_CUDA(cudaStreamCreateWithFlags(&r.cst, cudaStreamNonBlocking));
+        CSP_CUDA(cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming));
+        CSP_CUDA(cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming));
+        for (auto& e : r.chunk_ev) CSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    {
+        DeviceGuard g(G.local[0].device);
+        for (auto& pr : G.tev)
+            for (auto& e : pr) CSP_CUDA(cudaEventCreate(&e));
+    }
+    G.init = true;
+    return CSP_OK;
+}
+
+int need_init() {
+    if (!G.init) return csp_set_error(CSP_ERR_INVALID, "call csp_init or csp_init_rank first");
+    return CSP_OK;
+}
+cudaStream_t stream_of(void* const* streams, size_t i) { return streams && streams[i] ? (cudaStream_t)streams[i] : G.local[i].st; }
+void tbegin(int k, cudaStream_t st) { DeviceGuard g(G.local[0].device); cudaEventRecord(G.tev[k][0], st); }
+void tend(int k, cudaStream_t st) { DeviceGuard g(G.local[0].device); cudaEventRecord(G.tev[k][1], st); G.tset[k] = true; }
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+struct csp_shard_tree {
+    std::vector<csp_tree*> trees;
+};
+struct csp_shard_models {
+    std::vector<csp_models*> models;
+};
+
+extern "C" {
+
+int csp_comm_info(int64_t info[4]) {
+    if (!info) return csp_set_error(CSP_ERR_INVALID, "info is NULL");
+    info[0] = G.init ? G.world : 0;
+    info[1] = G.init ? (int64_t)G.local.size() : 0;
+    info[2] = G.init ? G.local[0].rank : 0;
+    info[3] = G.init ? G.version : 0;
+    return CSP_OK;
+}
+
+int csp_init(int ndev, const int* devs) {
+    if (G.init) return csp_set_error(CSP_ERR_INVALID, "already initialised (csp_shutdown first)");
+    CSP_CHECK(csp_require_device());
+    int have = 0;
+    CSP_CUDA(cudaGetDeviceCount(&have));
+    if (ndev < 1 || ndev > have) return csp_set_error(CSP_ERR_INVALID, "ndev=%d, %d CUDA devices present", ndev, have);
+    std::vector<int> d(ndev);
+    for (int i = 0; i < ndev; ++i) {
+        d[i] = devs ? devs[i] : i;
+        if (d[i] < 0 || d[i] >= have) return csp_set_error(CSP_ERR_INVALID, "device %d out of range", d[i]);
+    }
+    G.world = ndev;
+    G.local.assign(ndev, Rank());
+    for (int i = 0; i < ndev; ++i) { G.local[i].rank = i; G.local[i].device = d[i]; }
+    if (ndev > 1) {
+        CSP_CHECK(load_nccl());
+        N.GetVersion(&G.version);
+        std::vector<ncclComm_t> comms(ndev);
+        CSP_NCCL(N.CommInitAll(comms.data(), ndev, d.data()));
+        for (int i = 0; i < ndev; ++i) G.local[i].comm = comms[i];
+    }
+    return finish_init();
+}
+
+int csp_comm_unique_id(void* id128) {
+    if (!id128) return csp_set_error(CSP_ERR_INVALID, "id128 is NULL");
+    CSP_CHECK(load_nccl());
+    ncclUniqueId id;
+    CSP_NCCL(N.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, sizeof id);
+    return CSP_OK;
+}
+
+int csp_init_rank(int world, int rank, int device, const void* id128) {
+    if (G.init) return csp_set_error(CSP_ERR_INVALID, "already initialised (csp_shutdown first)");
+    CSP_CHECK(csp_require_device());
+    if (world < 1 || rank < 0 || rank >= world) return csp_set_error(CSP_ERR_INVALID, "bad rank %d of %d", rank, world);
+    int have = 0;
+    CSP_CUDA(cudaGetDeviceCount(&have));
+    if (device < 0 || device >= have) return csp_set_error(CSP_ERR_INVALID, "device %d out of range", device);
+    G.world = world;
+    G.local.assign(1, Rank());
+    G.local[0].rank = rank; G.local[0].device = device;
+    if (world > 1) {
+        if (!id128) return csp_set_error(CSP_ERR_INVALID, "id128 is NULL");
+        CSP_CHECK(load_nccl());
+        N.GetVersion(&G.version);
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof id);
+        DeviceGuard g(device);
+        CSP_NCCL(N.CommInitRank(&G.local[0].comm, world, id, rank));
+    }
+    return finish_init();
+}
+
+int csp_shutdown(void) {
+    if (!G.init) return CSP_OK;
+    for (Rank& r : G.local) {
+        DeviceGuard g(r.device);
+        cudaDeviceSynchronize();
+        if (r.comm) N.CommDestroy(r.comm);
+        if (r.st) cudaStreamDestroy(r.st);
+        if (r.cst) cudaStreamDestroy(r.cst);
+        if (r.fork) cudaEventDestroy(r.fork);
+        if (r.join) cudaEventDestroy(r.join);
+        for (auto& e : r.chunk_ev) if (e) cudaEventDestroy(e);
+    }
+    {
+        DeviceGuard g(G.local[0].device);
+        for (auto& pr : G.tev)
+            for (auto& e : pr) if (e) cudaEventDestroy(e);
+    }
+    G = Ctx();
+    return CSP_OK;
+}
+
+int csp_shard_synchronize(void) {
+    CSP_CHECK(need_init());
+    for (Rank& r : G.local) {
+        DeviceGuard g(r.device);
+        CSP_CUDA(cudaStreamSynchronize(r.st));
+        CSP_CUDA(cudaStreamSynchronize(r.cst));
+    }
+    return CSP_OK;
+}
+
+int csp_shard_timing(double ms[6]) {
+    if (!ms) return csp_set_error(CSP_ERR_INVALID, "ms is NULL");
+    CSP_CHECK(need_init());
+    for (Rank& r : G.local) { DeviceGuard g(r.device); CSP_CUDA(cudaDeviceSynchronize()); }
+    DeviceGuard g(G.local[0].device);
+    for (int k = 0; k < 6; ++k) {
+        ms[k] = G.wall_ms[k];
+        float e = 0;
+        if (G.tset[k] && cudaEventElapsedTime(&e, G.tev[k][0], G.tev[k][1]) == cudaSuccess) ms[k] = e;
+    }
+    cudaGetLastError();
+    return CSP_OK;
+}
+
+// ---- C1: tree broadcast ------------------------------------------------------------------------------------------------
+int csp_shard_tree_broadcast(const void* blob, size_t bytes, int root, csp_shard_tree** out) {
+    if (!out) return csp_set_error(CSP_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    CSP_CHECK(need_init());
+    if (root < 0 || root >= G.world) return csp_set_error(CSP_ERR_INVALID, "root %d out of range", root);
+    const size_t nl = G.local.size();
+    int root_local = -1;
+    for (size_t i = 0; i < nl; ++i)
+        if (G.local[i].rank == root) root_local = (int)i;
+    if (root_local >= 0 && (!blob || bytes < 64)) return csp_set_error(CSP_ERR_INVALID, "the root rank needs a packed tree blob");
+    // 1. every rank learns the size
+    unsigned long long sz = root_local >= 0 ? (unsigned long long)bytes : 0ull;
+    if (G.world > 1 && nl < (size_t)G.world) {  // other processes exist
+        std::vector<void*> dsz(nl, nullptr);
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            CSP_CHECK(csp_dev_alloc(&dsz[i], 8));
+            if ((int)i == root_local) CSP_CUDA(cudaMemcpyAsync(dsz[i], &sz, 8, cudaMemcpyHostToDevice, G.local[i].st));
+        }
+        CSP_NCCL(N.GroupStart());
+        for (size_t i = 0; i < nl; ++i) CSP_NCCL(N.Broadcast(dsz[i], dsz[i], 8, ncclUint8, root, G.local[i].comm, G.local[i].st));
+        CSP_NCCL(N.GroupEnd());
+        {
+            DeviceGuard g(G.local[0].device);
+            CSP_CUDA(cudaMemcpyAsync(&sz, dsz[0], 8, cudaMemcpyDeviceToHost, G.local[0].st));
+            CSP_CUDA(cudaStreamSynchronize(G.local[0].st));
+        }
+        for (size_t i = 0; i < nl; ++i) { DeviceGuard g(G.local[i].device); cudaStreamSynchronize(G.local[i].st); csp_dev_free(dsz[i]); }
+    }
+    if (sz < 64) return csp_set_error(CSP_ERR_INVALID, "broadcast tree blob is too small (%llu bytes)", sz);
+    // 2. blob to the root's GPU, 3. one broadcast, 4. upload on every GPU from the device buffer
+    std::vector<void*> dbuf(nl, nullptr);
+    auto cleanup = [&]() { for (size_t i = 0; i < nl; ++i) if (dbuf[i]) { DeviceGuard g(G.local[i].device); csp_dev_free(dbuf[i]); } };
+    for (size_t i = 0; i < nl; ++i) {
+        DeviceGuard g(G.local[i].device);
+        int rc = csp_dev_alloc(&dbuf[i], sz);
+        if (rc != CSP_OK) { cleanup(); return rc; }
+    }
+    if (root_local >= 0) {
+        Rank& r = G.local[root_local];
+        DeviceGuard g(r.device);
+        if (root_local == 0) tbegin(0, r.st);
+        cudaError_t e = cudaMemcpyAsync(dbuf[root_local], blob, sz, cudaMemcpyHostToDevice, r.st);
+        if (root_local == 0) tend(0, r.st);
+        if (e != cudaSuccess) { cleanup(); return csp_set_error(CSP_ERR_CUDA, "blob copy failed: %s", cudaGetErrorString(e)); }
+    }
+    if (G.world > 1) {
+        tbegin(1, G.local[0].st);
+        ncclResult_t r1 = N.GroupStart();
+        for (size_t i = 0; i < nl && r1 == ncclSuccess; ++i)
+            r1 = N.Broadcast(dbuf[i], dbuf[i], sz, ncclUint8, root, G.local[i].comm, G.local[i].st);
+        ncclResult_t r2 = N.GroupEnd();
+        tend(1, G.local[0].st);
+        if (r1 != ncclSuccess || r2 != ncclSuccess) {
+            cleanup();
+            return csp_set_error(CSP_ERR_NCCL, "tree broadcast failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+        }
+    }
+    csp_shard_tree* st = new csp_shard_tree();
+    st->trees.assign(nl, nullptr);
+    int rc = CSP_OK;
+    for (size_t i = 0; i < nl; ++i) {
+        DeviceGuard g(G.local[i].device);
+        if (cudaStreamSynchronize(G.local[i].st) != cudaSuccess) { rc = csp_set_error(CSP_ERR_CUDA, "broadcast stream failed: %s", cudaGetErrorString(cudaGetLastError())); break; }
+    }
+    const double t0 = now_ms();
+    for (size_t i = 0; i < nl && rc == CSP_OK; ++i) {
+        rc = csp_set_device(G.local[i].device);
+        if (rc == CSP_OK) rc = csp_tree_upload_blob(dbuf[i], sz, &st->trees[i]);
+    }
+    G.wall_ms[2] = now_ms() - t0;
+    cleanup();
+    if (rc != CSP_OK) { csp_shard_tree_free(st); return rc; }
+    *out = st;
+    return CSP_OK;
+}
+
+int csp_shard_tree_get(const csp_shard_tree* st, int local_index, csp_tree** tree) {
+    if (!st || !tree || local_index < 0 || local_index >= (int)st->trees.size()) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    *tree = st->trees[local_index];
+    return CSP_OK;
+}
+
+int csp_shard_tree_free(csp_shard_tree* st) {
+    if (!st) return CSP_OK;
+    for (csp_tree* t : st->trees) csp_tree_free(t);
+    delete st;
+    return CSP_OK;
+}
+
+// ---- leaf-sharded fit + all-gather of the records -------------------------------------------------------------------------
+int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** models, void* const* streams) {
+    if (!st || !models) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    CSP_CHECK(need_init());
+    const size_t nl = G.local.size();
+    if (st->trees.size() != nl) return csp_set_error(CSP_ERR_INVALID, "sharded tree does not belong to this clique");
+    csp_shard_models* sm = *models;
+    const bool fresh = sm == nullptr;
+    if (fresh) {
+        sm = new csp_shard_models();
+        sm->models.assign(nl, nullptr);
+        for (size_t i = 0; i < nl; ++i) {
+            int rc = csp_models_alloc(st->trees[i], &sm->models[i]);
+            if (rc != CSP_OK) { csp_shard_models_free(sm); return rc; }
+        }
+    } else if (sm->models.size() != nl) {
+        return csp_set_error(CSP_ERR_INVALID, "sharded models do not belong to this clique");
+    }
+    auto fail = [&](int rc) { if (fresh) csp_shard_models_free(sm); return rc; };
+    const long long nleaves = sm->models[0]->n_models;
+    for (size_t i = 0; i < nl; ++i) {
+        long long lo, hi;
+        shard_range(nleaves, G.world, G.local[i].rank, &lo, &hi);
+        cudaStream_t s = stream_of(streams, i);
+        if (i == 0) tbegin(3, s);
+        int rc = csp_models_refit_range(st->trees[i], skip, sm->models[i], lo, hi, s);
+        if (i == 0) tend(3, s);
+        if (rc != CSP_OK) return fail(rc);
+    }
+    if (G.world > 1) {
+        // "all-gather-v": every owner broadcasts its range of records (and status bytes) in place; one group
+        tbegin(4, stream_of(streams, 0));
+        ncclResult_t r1 = N.GroupStart();
+        for (size_t i = 0; i < nl && r1 == ncclSuccess; ++i) {
+            csp_models* mo = sm->models[i];
+            cudaStream_t s = stream_of(streams, i);
+            for (int r = 0; r < G.world && r1 == ncclSuccess; ++r) {
+                long long lo, hi;
+                shard_range(nleaves, G.world, r, &lo, &hi);
+                if (hi <= lo) continue;
+                double* p = mo->data + (size_t)lo * mo->stride;
+                r1 = N.Broadcast(p, p, (size_t)(hi - lo) * mo->stride, ncclDouble, r, G.local[i].comm, s);
+                if (r1 == ncclSuccess) r1 = N.Broadcast(mo->status + lo, mo->status + lo, (size_t)(hi - lo), ncclUint8, r, G.local[i].comm, s);
+            }
+        }
+        ncclResult_t r2 = N.GroupEnd();
+        tend(4, stream_of(streams, 0));
+        if (r1 != ncclSuccess || r2 != ncclSuccess)
+            return fail(csp_set_error(CSP_ERR_NCCL, "record all-gather failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2)));
+    }
+    if (fresh) {
+        for (size_t i = 0; i < nl; ++i) { DeviceGuard g(G.local[i].device); cudaStreamSynchronize(stream_of(streams, i)); }
+        *models = sm;
+    }
+    return CSP_OK;
+}
+
+int csp_shard_models_get(const csp_shard_models* sm, int local_index, csp_models** models) {
+    if (!sm || !models || local_index < 0 || local_index >= (int)sm->models.size()) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    *models = sm->models[local_index];
+    return CSP_OK;
+}
+
+int csp_shard_models_free(csp_shard_models* sm) {
+    if (!sm) return CSP_OK;
+    for (csp_models* m : sm->models) csp_models_free(m);
+    delete sm;
+    return CSP_OK;
+}
+
+// ---- C2: gather of (leaf id, value) to one rank ---------------------------------------------------------------------------
+// One pipeline step: queries [off, off + cnt_r) of every rank r that still has some.  Sends / receives of all local ranks are one
+// NCCL group (a single thread may drive several GPUs); the root copies its own part with a device-to-device copy.
+static int gather_step(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, long long off, long long chunk,
+                       int root, int32_t* dleaf_all, double* dval_all, const std::vector<cudaStream_t>& cs) {
+    const size_t nl = G.local.size();
+    int root_local = -1;
+    for (size_t i = 0; i < nl; ++i)
+        if (G.local[i].rank == root) root_local = (int)i;
+    bool grouped = false;
+    ncclResult_t r1 = ncclSuccess;
+    auto group = [&]() { if (!grouped && G.world > 1) { r1 = N.GroupStart(); grouped = true; } };
+    for (size_t i = 0; i < nl && r1 == ncclSuccess; ++i) {
+        const Rank& rk = G.local[i];
+        const long long cnt = std::min<long long>(chunk, counts[rk.rank] - off);
+        if (cnt <= 0) continue;
+        if ((int)i == root_local) continue;  // handled below
+        group();
+        r1 = N.Send(dleaf[i] + off, (size_t)cnt, ncclInt32, root, rk.comm, cs[i]);
+        if (r1 == ncclSuccess) r1 = N.Send(dval[i] + off, (size_t)cnt, ncclFloat64, root, rk.comm, cs[i]);
+    }
+    if (root_local >= 0 && r1 == ncclSuccess) {
+        const Rank& rk = G.local[root_local];
+        long long base = 0;
+        for (int r = 0; r < G.world && r1 == ncclSuccess; ++r) {
+            const long long cnt = std::min<long long>(chunk, counts[r] - off);
+            if (cnt > 0) {
+                if (r == root) {
+                    DeviceGuard g(rk.device);
+                    if (dleaf_all + base + off != dleaf[root_local] + off)
+                        CSP_CUDA(cudaMemcpyAsync(dleaf_all + base + off, dleaf[root_local] + off, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs[root_local]));
+                    if (dval_all + base + off != dval[root_local] + off)
+                        CSP_CUDA(cudaMemcpyAsync(dval_all + base + off, dval[root_local] + off, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, cs[root_local]));
+                } else {
+                    group();
+                    r1 = N.Recv(dleaf_all + base + off, (size_t)cnt, ncclInt32, r, rk.comm, cs[root_local]);
+                    if (r1 == ncclSuccess) r1 = N.Recv(dval_all + base + off, (size_t)cnt, ncclFloat64, r, rk.comm, cs[root_local]);
+                }
+            }
+            base += counts[r];
+        }
+    }
+    ncclResult_t r2 = grouped ? N.GroupEnd() : ncclSuccess;
+    if (r1 != ncclSuccess || r2 != ncclSuccess)
+        return csp_set_error(CSP_ERR_NCCL, "result gather failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+    return CSP_OK;
+}
+
+static int check_counts(const int64_t* counts, int gather_root, const void* a, const void* b) {
+    if (!counts) return csp_set_error(CSP_ERR_INVALID, "counts is NULL");
+    for (int r = 0; r < G.world; ++r)
+        if (counts[r] < 0) return csp_set_error(CSP_ERR_INVALID, "counts[%d] < 0", r);
+    if (gather_root >= G.world) return csp_set_error(CSP_ERR_INVALID, "gather_root %d out of range", gather_root);
+    if (gather_root >= 0)
+        for (const Rank& rk : G.local)
+            if (rk.rank == gather_root && (!a || !b)) return csp_set_error(CSP_ERR_INVALID, "the gather root needs dleaf_all and dval_all");
+    return CSP_OK;
+}
+
+int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, int gather_root,
+                         int32_t* dleaf_all, double* dval_all, void* const* streams) {
+    CSP_CHECK(need_init());
+    if (!dleaf || !dval || gather_root < 0) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    CSP_CHECK(check_counts(counts, gather_root, dleaf_all, dval_all));
+    const size_t nl = G.local.size();
+    std::vector<cudaStream_t> s(nl);
+    long long mx = 0;
+    for (size_t i = 0; i < nl; ++i) s[i] = stream_of(streams, i);
+    for (int r = 0; r < G.world; ++r) mx = std::max<long long>(mx, counts[r]);
+    tbegin(5, s[0]);
+    int rc = mx > 0 ? gather_step(dleaf, dval, counts, 0, mx, gather_root, dleaf_all, dval_all, s) : CSP_OK;
+    tend(5, s[0]);
+    return rc;
+}
+
+int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* sm, const double* const* dX, const int64_t* counts,
+                              int32_t* const* dleaf, double* const* dval, uint8_t* const* dstatus, int gather_root,
+                              int32_t* dleaf_all, double* dval_all, int64_t chunk, void* const* streams) {
+    CSP_CHECK(need_init());
+    if (!st || !sm || !dX || !dleaf || !dval) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    const size_t nl = G.local.size();
+    if (st->trees.size() != nl || sm->models.size() != nl) return csp_set_error(CSP_ERR_INVALID, "handles do not belong to this clique");
+    CSP_CHECK(check_counts(counts, gather_root, dleaf_all, dval_all));
+    const int n = st->trees[0]->v.n;
+    if (chunk <= 0) chunk = 1LL << 24;
+    long long mx = 0;
+    for (int r = 0; r < G.world; ++r) mx = std::max<long long>(mx, counts[r]);
+    std::vector<cudaStream_t> s(nl), cs(nl);
+    const bool gather = gather_root >= 0 && G.world > 1;
+    for (size_t i = 0; i < nl; ++i) {
+        s[i] = stream_of(streams, i);
+        cs[i] = gather ? G.local[i].cst : s[i];
+        if (gather) {  // the communication stream starts behind everything already queued on the caller's stream
+            DeviceGuard g(G.local[i].device);
+            CSP_CUDA(cudaEventRecord(G.local[i].fork, s[i]));
+            CSP_CUDA(cudaStreamWaitEvent(cs[i], G.local[i].fork, 0));
+        }
+    }
+    int step = 0;
+    for (long long off = 0; off < mx; off += chunk, ++step) {
+        for (size_t i = 0; i < nl; ++i) {
+            const Rank& rk = G.local[i];
+            const long long cnt = std::min<long long>(chunk, counts[rk.rank] - off);
+            if (cnt <= 0) continue;
+            uint8_t* stp = dstatus && dstatus[i] ? dstatus[i] + off : nullptr;
+            CSP_CHECK(csp_locate_eval_dev(st->trees[i], sm->models[i], dX[i] + (size_t)off * n, cnt, dleaf[i] + off, dval[i] + off, stp, s[i]));
+            if (gather) {
+                DeviceGuard g(rk.device);
+                cudaEvent_t ev = G.local[i].chunk_ev[step & 3];
+                CSP_CUDA(cudaEventRecord(ev, s[i]));
+                CSP_CUDA(cudaStreamWaitEvent(cs[i], ev, 0));
+            }
+        }
+        if (gather_root >= 0)
+            CSP_CHECK(gather_step((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, dleaf_all, dval_all, cs));
+    }
+    if (gather)
+        for (size_t i = 0; i < nl; ++i) {  // the caller's stream ends behind the last gather step
+            DeviceGuard g(G.local[i].device);
+            CSP_CUDA(cudaEventRecord(G.local[i].join, cs[i]));
+            CSP_CUDA(cudaStreamWaitEvent(s[i], G.local[i].join, 0));
+        }
+    return CSP_OK;
+}
+
+// ---- host buffers: one pipeline (and one host thread) per local GPU ----------------------------------------------------------
+int csp_shard_locate_eval(const csp_shard_tree* st, const csp_shard_models* sm, const double* X, int64_t m, int32_t* leaf, double* val,
+                          uint8_t* status) {
+    CSP_CHECK(need_init());
+    if (!st || !sm) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    const size_t nl = G.local.size();
+    if (st->trees.size() != nl || sm->models.size() != nl) return csp_set_error(CSP_ERR_INVALID, "handles do not belong to this clique");
+    if (m < 0 || (m > 0 && (!X || !val))) return csp_set_error(CSP_ERR_INVALID, "bad buffer");
+    if (m == 0) return CSP_OK;
+    const int n = st->trees[0]->v.n;
+    std::vector<int> rcs(nl, CSP_OK);
+    std::vector<std::string> msgs(nl);
+    auto work = [&](size_t i) {
+        long long lo, hi;
+        shard_range(m, (int)nl, (int)i, &lo, &hi);
+        if (hi <= lo) return;
+        rcs[i] = csp_locate_eval(st->trees[i], sm->models[i], X + (size_t)lo * n, hi - lo, leaf ? leaf + lo : nullptr, val + lo,
+                                 status ? status + lo : nullptr);
+        if (rcs[i] != CSP_OK) msgs[i] = csp_last_error();  // the message is thread-local
+    };
+    if (nl == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < nl; ++i) th.emplace_back(work, i);
+        for (auto& t : th) t.join();
+    }
+    for (size_t i = 0; i < nl; ++i)
+        if (rcs[i] != CSP_OK) return csp_set_error(rcs[i], "GPU %d: %s", G.local[i].device, msgs[i].c_str());
+    return CSP_OK;
+}
+
+}  // extern "C"

@@ -32,6 +32,7 @@ struct FitParams {
     TreeView t;
     const int* node_ids;  // null: every leaf in leaves(root) order
     long long nb;
+    long long row_lo, row_hi;  // node_ids == null only: fit just the leaves (= output rows) in [row_lo, row_hi) (leaf-sharded fits)
     int skip, mode;
     // strided outputs (doubles); *_stride in doubles per box
     double* c; long long c_stride;
@@ -180,11 +181,11 @@ __device__ __forceinline__ void for_split_groups(const TreeView& t, int box, F&&
 // Chain pre-pass, one THREAD per box: getleaf + chaintop (src/polynomials.jl:22-98) + the chain walk of fit_poly1
 // (src/cs2.jl:183-203).  Both are short sequential integer walks; running them on one lane of a warp-per-box kernel left
 // 31 lanes idle for a fifth of that kernel's instructions.
-__global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* __restrict__ node_ids, long long nb, int* __restrict__ ch_status,
+__global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* __restrict__ node_ids, long long row_lo, long long nb, int* __restrict__ ch_status,
                                                    int* __restrict__ ch_itop, double* __restrict__ ch_c, double* __restrict__ ch_y,
                                                    double* __restrict__ ch_g, int* __restrict__ ch_step) {
     const int n = t.n;
-    for (long long bi = blockIdx.x * (long long)blockDim.x + threadIdx.x; bi < nb; bi += (long long)gridDim.x * blockDim.x) {
+    for (long long bi = row_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; bi < nb; bi += (long long)gridDim.x * blockDim.x) {
         const int box = node_ids ? node_ids[bi] : t.lnode[bi];
         int* step = ch_step + bi * n;
         double* y = ch_y + bi * n;
@@ -543,7 +544,8 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
     double* tx = tq + 32 * (FIT_TKB + 1);
     int* s_id = (int*)(tx + 32 * (FIT_TKB + 1));
     const QIndex qi{n, prm.q_packed};
-    const long long nunits = prm.units ? prm.n_units : prm.nb;
+    const bool ranged = prm.row_lo > 0 || prm.row_hi < prm.nb;  // a leaf-range shard of an all-leaf fit
+    const long long nunits = prm.units ? prm.n_units : prm.row_hi - prm.row_lo;
 
     long long tk = clock64();
 #define FIT_TICK(k) do { if (prm.prof) { __syncwarp(); if (lane == 0) { const long long now_ = clock64(); atomicAdd(prm.prof + (k), (unsigned long long)(now_ - tk)); tk = now_; } } } while (0)
@@ -555,8 +557,19 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         }
         if (ui >= nunits) break;
         int4 members = make_int4(-1, -1, -1, -1);  // box indices (output rows) of the unit
-        if (prm.units) members = prm.units[ui];
-        const long long bi0 = prm.units ? members.x : ui;
+        if (prm.units) {
+            members = prm.units[ui];
+            if (ranged) {  // keep the members this shard owns, in front (any member can lead: their traversals coincide)
+                int mm[4] = {members.x, members.y, members.z, members.w}, k = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (mm[u] >= prm.row_lo && mm[u] < prm.row_hi) mm[k++] = mm[u];
+                for (int u = k; u < 4; ++u) mm[u] = -1;
+                members = make_int4(mm[0], mm[1], mm[2], mm[3]);
+                if (k == 0) continue;  // a unit of another shard
+            }
+        }
+        const long long bi0 = prm.units ? members.x : prm.row_lo + ui;
         const int box = prm.node_ids ? prm.node_ids[bi0] : t.lnode[bi0];
         double* Qo = prm.q_in_smem ? sQ : prm.Q + bi0 * prm.Q_stride;  // global-Q mode: assembled in the first member's record
         for (long long e = lane; e < qlen; e += 32) Qo[e] = dnan();
@@ -714,7 +727,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         // ---- per member box: fit_poly1 results, fit_poly2_diag!, canonicalize, outputs
 #pragma unroll 1
         for (int mi = 0; mi < 4; ++mi) {
-            const long long bi = prm.units ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : (mi == 0 ? ui : -1);
+            const long long bi = prm.units ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : (mi == 0 ? bi0 : -1);
             if (bi < 0) break;
             double* Qg = prm.Q + bi * prm.Q_stride;
             if (!prm.q_in_smem) Qo = Qg;
@@ -1166,6 +1179,8 @@ __global__ void __launch_bounds__(256) k_modelvalue_native(int n, double c, cons
 static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void** scratch_out) {
     *scratch_out = nullptr;
     if (prm.nb == 0) return CSP_OK;
+    if (prm.node_ids || prm.row_hi <= 0) { prm.row_lo = 0; prm.row_hi = prm.nb; }
+    if (prm.row_lo >= prm.row_hi) return CSP_OK;
     const int n = t->v.n, P = t->v.p;
     const long long npairs = prm.slotmap ? prm.npat : (P == 2 ? (long long)n * (n - 1) / 2 : n);
     const long long qlen = prm.slotmap ? prm.npat : (P == 1 ? n : (prm.q_packed ? (long long)(n + 1) * (n + 2) / 2 : (long long)n * n));
@@ -1217,10 +1232,10 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         prm.work_counter = (unsigned long long*)(((uintptr_t)base_p + 63) & ~(uintptr_t)63);
         if (getenv("CSP_FIT_DYNAMIC") && atoi(getenv("CSP_FIT_DYNAMIC")) == 0) prm.work_counter = nullptr;
         else CSP_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned long long), st));
-        const long long blocks = std::min<long long>((prm.nb + 127) / 128, (long long)std::max(t->n_sm, 1) * 16);
+        const long long blocks = std::min<long long>((prm.row_hi - prm.row_lo + 127) / 128, (long long)std::max(t->n_sm, 1) * 16);
         {
             CspTimed tm(CSP_K_FIT, st);
-            k_fit_chain<<<(unsigned)blocks, 128, 0, st>>>(prm.t, prm.node_ids, prm.nb, prm.ch_status, prm.ch_itop, prm.ch_c, prm.ch_y,
+            k_fit_chain<<<(unsigned)blocks, 128, 0, st>>>(prm.t, prm.node_ids, prm.row_lo, prm.row_hi, prm.ch_status, prm.ch_itop, prm.ch_c, prm.ch_y,
                                                          prm.ch_g, prm.ch_step);
         }
         CSP_LAUNCHED();
@@ -1236,7 +1251,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         // C5det, 44 850: 1 593 vs 611 ms).
         const bool force_shared = getenv("CSP_FIT_SHARED") && atoi(getenv("CSP_FIT_SHARED")) == 2;  // tests
         if (prm.units && !prm.q_in_smem && !force_shared && prm.n_units < 8LL * std::max(t->n_sm, 1) * occ * W) prm.units = nullptr;
-        const long long nunits = prm.units ? prm.n_units : prm.nb;
+        const long long nunits = prm.units ? prm.n_units : prm.row_hi - prm.row_lo;
         long long grid = std::min<long long>((nunits + W - 1) / W, (long long)std::max(t->n_sm, 1) * occ);
         if (!prm.pairs_in_smem) {
             CSP_CHECK(csp_dev_alloc(scratch_out, (size_t)grid * W * 3 * ((npairs + 1) & ~1LL) * sizeof(int)));
@@ -1425,11 +1440,13 @@ int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_
     return CSP_OK;
 }
 
-static int models_fit_launch(const csp_tree* t, int32_t skip, csp_models* mo, cudaStream_t st, void** scratch) {
+static int models_fit_launch(const csp_tree* t, int32_t skip, csp_models* mo, cudaStream_t st, void** scratch, long long row_lo = 0,
+                             long long row_hi = -1) {
     const int n = t->v.n;
     FitParams prm{};
     prm.t = t->v;
     prm.node_ids = nullptr; prm.nb = mo->n_models; prm.skip = skip;
+    prm.row_lo = row_lo; prm.row_hi = row_hi < 0 ? mo->n_models : row_hi;
     prm.mode = mo->degree == 2 ? FIT_MODE_FULL : FIT_MODE_LIN;
     prm.b = mo->data; prm.b_stride = mo->stride;
     prm.status = mo->status;
@@ -1555,14 +1572,39 @@ int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q,
     return CSP_OK;
 }
 
+int csp_models_alloc(const csp_tree* t, csp_models** out) {
+    if (!t || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    CSP_CHECK(csp_require_device());
+    DeviceGuard dg(t->device);
+    csp_models* mo = new csp_models();
+    mo->device = t->device; mo->n = t->v.n; mo->degree = t->v.p == 2 ? 2 : 1;
+    mo->stride = csp_model_stride(mo->n, mo->degree);
+    mo->n_models = t->v.n_leaves;
+    if (csp_dev_alloc((void**)&mo->data, (size_t)mo->n_models * mo->stride * 8) != CSP_OK || csp_dev_alloc((void**)&mo->status, (size_t)mo->n_models) != CSP_OK ||
+        cudaMemset(mo->data, 0, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess || cudaMemset(mo->status, 0, (size_t)mo->n_models) != cudaSuccess) {
+        csp_models_free(mo);
+        return csp_set_error(CSP_ERR_NOMEM, "cannot allocate %d model records", t->v.n_leaves);
+    }
+    *out = mo;
+    return CSP_OK;
+}
+
 int csp_models_refit(const csp_tree* t, int32_t skip, csp_models* mo, void* stream) {
+    return csp_models_refit_range(t, skip, mo, 0, t ? t->v.n_leaves : 0, stream);
+}
+
+int csp_models_refit_range(const csp_tree* t, int32_t skip, csp_models* mo, int64_t leaf_lo, int64_t leaf_hi, void* stream) {
     if (!t || !mo) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
     if (mo->device != t->device || mo->n != t->v.n || mo->n_models != t->v.n_leaves || mo->degree != (t->v.p == 2 ? 2 : 1))
         return csp_set_error(CSP_ERR_INVALID, "models handle does not belong to this tree");
+    if (leaf_lo < 0 || leaf_hi > t->v.n_leaves || leaf_lo > leaf_hi)
+        return csp_set_error(CSP_ERR_INVALID, "leaf range [%lld, %lld) outside [0, %d)", (long long)leaf_lo, (long long)leaf_hi, t->v.n_leaves);
+    if (leaf_lo == leaf_hi) return CSP_OK;
     DeviceGuard dg(t->device);
     void* scratch = nullptr;
-    int rc = models_fit_launch(t, skip, mo, (cudaStream_t)stream, &scratch);
+    int rc = models_fit_launch(t, skip, mo, (cudaStream_t)stream, &scratch, leaf_lo, leaf_hi);
     if (scratch) {  // large-n path uses a global scratch table: wait before releasing it
         cudaStreamSynchronize((cudaStream_t)stream);
         csp_dev_free(scratch);

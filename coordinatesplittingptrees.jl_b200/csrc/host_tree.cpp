@@ -134,6 +134,7 @@ int do_split(HostTree& t, int par, int k, const int* dims, const double* xs, int
         if (x[j] == hi && hi != t.upper[d[j] - 1]) return fail(E_ERROR, "cannot split at the upper edge of a box that is not at the world edge");
         if (!(x[j] != t.pos[(size_t)par * n + d[j] - 1])) return fail(E_ERROR, "position is identical to the parent");
     }
+    if (t.isfake(par)) t.n_fake_leaves--;  // a fake leaf that gets split becomes an internal box (counted there from now on)
     const int s = (int)(t.sdims.size() / p);
     t.sdims.insert(t.sdims.end(), d.begin(), d.end());
     t.sxs.insert(t.sxs.end(), x.begin(), x.end());
@@ -181,6 +182,7 @@ int do_addpoint(HostTree& t, int box, const double* x, int lenx, int ndl, const 
     for (int i = 0, o = 0; i < ndl; o += dl_len[i], ++i) {
         const int k = dl_len[i];
         const int* dl = dl_flat + o;
+        if (k < 1 || k > t.p || k > 8) return fail(E_DIMMISMATCH, "number of split dimensions must be between 1 and p");
         metas.clear();
         for (unsigned c = 1; c <= (1u << k) - 1; ++c) {  // corner positions in bit-pattern order
             double save[8];

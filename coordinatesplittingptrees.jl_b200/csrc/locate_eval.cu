@@ -803,7 +803,7 @@ struct HostPipe {
     bool streams = false;
 };
 static HostPipe g_hostpipe[64];
-static std::mutex g_hostpipe_mu;
+static std::mutex g_hostpipe_mu[64];  // one pipeline per device: different GPUs run concurrently (csp_shard_locate_eval)
 
 static int run_host(const csp_tree* t, const csp_models* mo, bool eval_only, const double* X, const int32_t* leaf_in, long long m,
                     int32_t* leaf, double* val, uint8_t* status);
@@ -888,7 +888,7 @@ static int run_host(const csp_tree* t, const csp_models* mo, bool eval_only, con
     long long chunk = std::max<long long>(4096, (256LL << 20) / (8LL * n));
     chunk = std::min(chunk, m);
     if (dev < 0 || dev >= 64) return csp_set_error(CSP_ERR_INVALID, "device index %d not supported by the host path", dev);
-    std::lock_guard<std::mutex> lock(g_hostpipe_mu);
+    std::lock_guard<std::mutex> lock(g_hostpipe_mu[dev]);
     HostPipe& hp = g_hostpipe[dev];
     if (!hp.streams) {
         for (int i = 0; i < HostPipe::NS; ++i) CSP_CUDA(cudaStreamCreateWithFlags(&hp.st[i], cudaStreamNonBlocking));

@@ -3,6 +3,46 @@
 // (src/types.jl:432-454): column-major n x n, values at [i,j] with i <= j.
 #include "common.cuh"
 
+// record -> (c, g, Q in the .data layout, b) for cnt records of a staged slab; output row of record l is L0 + l
+static void unpack_records(const csp_models* mo, const double* stage, long long cnt, long long L0, double* c, double* g, double* Q, double* b) {
+    const int n = mo->n;
+    const size_t S = mo->stride;
+    const double NaN = __builtin_nan("");
+    for (long long l = 0; l < cnt; ++l) {
+        const double* r = stage + (size_t)l * S;
+        const long long L = L0 + l;
+        for (int i = 0; i < n; ++i)
+            if (b) b[L * n + i] = r[i];
+        if (mo->degree == 2) {
+            const double* A = r + n;
+            if (Q) {
+                double* q = Q + (size_t)L * n * n;
+                for (size_t e = 0; e < (size_t)n * n; ++e) q[e] = NaN;  // the SymmetricArray fill value below the diagonal
+                for (int i = 0; i < n; ++i)
+                    for (int j = i; j < n; ++j) q[(size_t)j * n + i] = (i == j ? 2.0 : 1.0) * A[csp_a_index(n, i, j)];
+            }
+            for (int i = 0; i < n; ++i)
+                if (g) g[L * n + i] = A[csp_a_index(n, i, n)];
+            if (c) c[L] = A[csp_a_index(n, n, n)];
+        } else {
+            for (int i = 0; i < n; ++i)
+                if (g) g[L * n + i] = r[n + i];
+            if (c) c[L] = r[2 * n];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_gather_rows(const double* __restrict__ data, const uint8_t* __restrict__ status, int stride,
+                                                     const int* __restrict__ ids, long long nb, double* __restrict__ out,
+                                                     uint8_t* __restrict__ st_out) {
+    for (long long r = blockIdx.x; r < nb; r += gridDim.x) {
+        const double* src = data + (size_t)ids[r] * stride;
+        double* dst = out + (size_t)r * stride;
+        for (int e = threadIdx.x; e < stride; e += blockDim.x) dst[e] = src[e];
+        if (threadIdx.x == 0) st_out[r] = status[ids[r]];
+    }
+}
+
 extern "C" {
 
 int csp_models_free(csp_models* mo) {
@@ -72,39 +112,50 @@ int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double
 int csp_models_download(const csp_models* mo, double* c, double* g, double* Q, double* b, uint8_t* status) {
     if (!mo) return csp_set_error(CSP_ERR_INVALID, "models is NULL");
     DeviceGuard dg(mo->device);
-    const int n = mo->n;
     const size_t S = mo->stride;
     const long long slab = std::max<long long>(1, (256LL << 20) / (long long)(S * 8));
     std::vector<double> stage((size_t)std::min<long long>(slab, mo->n_models) * S);
-    const double NaN = __builtin_nan("");
     for (long long off = 0; off < mo->n_models; off += slab) {
         const long long cnt = std::min<long long>(slab, mo->n_models - off);
         CSP_CUDA(cudaMemcpy(stage.data(), mo->data + (size_t)off * S, (size_t)cnt * S * 8, cudaMemcpyDeviceToHost));
-        for (long long l = 0; l < cnt; ++l) {
-            const double* r = stage.data() + (size_t)l * S;
-            const long long L = off + l;
-            for (int i = 0; i < n; ++i)
-                if (b) b[L * n + i] = r[i];
-            if (mo->degree == 2) {
-                const double* A = r + n;
-                if (Q) {
-                    double* q = Q + (size_t)L * n * n;
-                    for (size_t e = 0; e < (size_t)n * n; ++e) q[e] = NaN;  // the SymmetricArray fill value below the diagonal
-                    for (int i = 0; i < n; ++i)
-                        for (int j = i; j < n; ++j) q[(size_t)j * n + i] = (i == j ? 2.0 : 1.0) * A[csp_a_index(n, i, j)];
-                }
-                for (int i = 0; i < n; ++i)
-                    if (g) g[L * n + i] = A[csp_a_index(n, i, n)];
-                if (c) c[L] = A[csp_a_index(n, n, n)];
-            } else {
-                for (int i = 0; i < n; ++i)
-                    if (g) g[L * n + i] = r[n + i];
-                if (c) c[L] = r[2 * n];
-            }
-        }
+        unpack_records(mo, stage.data(), cnt, off, c, g, Q, b);
     }
     if (status) CSP_CUDA(cudaMemcpy(status, mo->status, (size_t)mo->n_models, cudaMemcpyDeviceToHost));
     return CSP_OK;
+}
+
+int csp_models_download_rows(const csp_models* mo, const int32_t* leaf_ids, int64_t nb, double* c, double* g, double* Q, double* b,
+                             uint8_t* status) {
+    if (!mo || (nb > 0 && !leaf_ids) || nb < 0) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    for (int64_t i = 0; i < nb; ++i)
+        if (leaf_ids[i] < 0 || leaf_ids[i] >= mo->n_models) return csp_set_error(CSP_ERR_INVALID, "leaf id %d out of range at %lld", leaf_ids[i], (long long)i);
+    if (nb == 0) return CSP_OK;
+    DeviceGuard dg(mo->device);
+    const size_t S = mo->stride;
+    const long long slab = std::max<long long>(1, (128LL << 20) / (long long)(S * 8));
+    const long long cap = std::min<long long>(slab, nb);
+    std::vector<double> stage((size_t)cap * S);
+    std::vector<uint8_t> hst((size_t)cap);
+    void *dids = nullptr, *drows = nullptr, *dst = nullptr;
+    CSP_CHECK(csp_dev_alloc(&dids, (size_t)cap * 4));
+    int rc = csp_dev_alloc(&drows, (size_t)cap * S * 8);
+    if (rc == CSP_OK) rc = csp_dev_alloc(&dst, (size_t)cap);
+    for (long long off = 0; off < nb && rc == CSP_OK; off += cap) {
+        const long long cnt = std::min<long long>(cap, nb - off);
+        cudaError_t e = cudaMemcpy(dids, leaf_ids + off, (size_t)cnt * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            k_gather_rows<<<(unsigned)std::min<long long>(cnt, 148 * 16), 128>>>(mo->data, mo->status, (int)S, (const int*)dids, cnt, (double*)drows, (uint8_t*)dst);
+            CSP_LAUNCHED();
+            e = cudaMemcpy(stage.data(), drows, (size_t)cnt * S * 8, cudaMemcpyDeviceToHost);
+        }
+        if (e == cudaSuccess) e = cudaMemcpy(hst.data(), dst, (size_t)cnt, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { rc = csp_set_error(CSP_ERR_CUDA, "row download failed: %s", cudaGetErrorString(e)); break; }
+        unpack_records(mo, stage.data(), cnt, 0, c ? c + off : nullptr, g ? g + off * mo->n : nullptr,
+                       Q ? Q + (size_t)off * mo->n * mo->n : nullptr, b ? b + off * mo->n : nullptr);
+        if (status) std::copy(hst.begin(), hst.begin() + cnt, status + off);
+    }
+    csp_dev_free(dids); csp_dev_free(drows); csp_dev_free(dst);
+    return rc;
 }
 
 }  // extern "C"

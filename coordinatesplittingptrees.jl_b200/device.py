@@ -27,6 +27,30 @@ def _ptr(a):
     return a.ctypes.data
 
 
+_NP_OF = {"int32": np.int32, "float64": np.float64, "uint8": np.uint8}
+
+
+def _check_buf(buf, m, dtype, like, what):
+    """Validate a caller-supplied in/out buffer before its pointer crosses the C ABI: element type, contiguity, length >= m,
+    and residency matching the query array (CUDA tensor on the same device, or numpy)."""
+    if buf is None:
+        return None
+    if _is_cuda_tensor(like):
+        import torch
+        if not _is_cuda_tensor(buf) or buf.device != like.device:
+            raise TypeError(f"{what} must be a CUDA tensor on {like.device} (the queries are resident there)")
+        if buf.dtype != getattr(torch, dtype) or not buf.is_contiguous():
+            raise TypeError(f"{what} must be a contiguous {dtype} tensor")
+        if buf.numel() < m:
+            raise N.DimensionMismatch(f"{what} holds {buf.numel()} elements, {m} needed")
+    else:
+        if not isinstance(buf, np.ndarray) or buf.dtype != _NP_OF[dtype] or not buf.flags.c_contiguous or not buf.flags.writeable:
+            raise TypeError(f"{what} must be a writable C-contiguous numpy {dtype} array")
+        if buf.size < m:
+            raise N.DimensionMismatch(f"{what} holds {buf.size} elements, {m} needed")
+    return buf
+
+
 def _stream_ptr(stream):
     if stream is None:
         try:
@@ -107,6 +131,8 @@ class DeviceTree:
         """Batched find_leaf_at.  X: (m, n) float64 numpy array (host path) or torch CUDA tensor (resident path).
         Returns (leaf ids int32, status uint8)."""
         m = self._check_X(X)
+        _check_buf(leaf, m, "int32", X, "leaf")
+        _check_buf(status, m, "uint8", X, "status")
         if _is_cuda_tensor(X):
             import torch
             leaf = torch.empty(m, dtype=torch.int32, device=X.device) if leaf is None else leaf
@@ -202,6 +228,17 @@ class DeviceTree:
         N.dchk(N.dev().csp_models_fit(self.h, skip, C.byref(h)))
         return LeafModels(h)
 
+    def alloc_models(self):
+        """An unfitted LeafModels for this tree (csp_models_alloc), to be filled by refit_models / refit_models_range."""
+        h = C.c_void_p()
+        N.dchk(N.dev().csp_models_alloc(self.h, C.byref(h)))
+        return LeafModels(h)
+
+    def refit_models_range(self, models, leaf_lo, leaf_hi, skip=0, stream=None):
+        """Re-fit only the leaves [leaf_lo, leaf_hi) into `models` (the per-GPU piece of a leaf-sharded fit)."""
+        N.dchk(N.dev().csp_models_refit_range(self.h, skip, models.h, int(leaf_lo), int(leaf_hi), _stream_ptr(stream)))
+        return models
+
     def refit_models(self, models, skip=0, stream=None):
         """Re-fit every leaf into an existing LeafModels (asynchronous, no allocation)."""
         N.dchk(N.dev().csp_models_refit(self.h, skip, models.h, _stream_ptr(stream)))
@@ -211,6 +248,9 @@ class DeviceTree:
     def locate_eval(self, models, X, leaf=None, val=None, status=None, stream=None):
         """Fused find_leaf_at + modelvalue.  Returns (leaf ids, values, status)."""
         m = self._check_X(X)
+        _check_buf(leaf, m, "int32", X, "leaf")
+        _check_buf(val, m, "float64", X, "val")
+        _check_buf(status, m, "uint8", X, "status")
         if _is_cuda_tensor(X):
             import torch
             leaf = torch.empty(m, dtype=torch.int32, device=X.device) if leaf is None else leaf
@@ -261,6 +301,19 @@ class LeafModels:
             out["Q"] = Q.reshape(nl, n, n).transpose(0, 2, 1)
         return out
 
+    def download_rows(self, leaf_ids):
+        """The records of the listed leaves only (csp_models_download_rows): dict like download()."""
+        ids = np.ascontiguousarray(leaf_ids, np.int32)
+        nb, n = len(ids), self.n
+        c, g, b = np.empty(nb), np.empty((nb, n)), np.empty((nb, n))
+        Q = np.empty((nb, n * n)) if self.degree == 2 else None
+        st = np.empty(nb, np.uint8)
+        N.dchk(N.dev().csp_models_download_rows(self.h, _ptr(ids), nb, _ptr(c), _ptr(g), _ptr(Q), _ptr(b), _ptr(st)))
+        out = dict(c=c, g=g, b=b, status=st)
+        if Q is not None:
+            out["Q"] = Q.reshape(nb, n, n).transpose(0, 2, 1)
+        return out
+
     def possemidef(self, stream=None):
         """possemidef (reference src/posdef.jl:41-68) of every model's Q, in place on the device."""
         N.dchk(N.dev().csp_models_possemidef(self.h, _stream_ptr(stream)))
@@ -272,13 +325,24 @@ class LeafModels:
         if len(shape) != 2 or shape[1] != self.n:
             raise N.DimensionMismatch(f"models have {self.n} dimensions, got a query array of shape {shape}")
         m = shape[0]
+        _check_buf(val, m, "float64", X, "val")
         if _is_cuda_tensor(X):
             import torch
+            if X.dtype != torch.float64 or not X.is_contiguous():
+                raise TypeError("resident queries must be a contiguous float64 CUDA tensor")
+            if not _is_cuda_tensor(leaf):
+                leaf = torch.as_tensor(np.ascontiguousarray(leaf, np.int32), device=X.device)
+            elif leaf.dtype != torch.int32 or not leaf.is_contiguous() or leaf.device != X.device:
+                leaf = leaf.to(device=X.device, dtype=torch.int32).contiguous()
+            if leaf.numel() < m:
+                raise N.DimensionMismatch(f"leaf holds {leaf.numel()} ids, {m} needed")
             val = torch.empty(m, dtype=torch.float64, device=X.device) if val is None else val
             N.dchk(N.dev().csp_eval_dev(self.h, _ptr(X), _ptr(leaf), m, _ptr(val), _stream_ptr(stream)))
         else:
             X = np.ascontiguousarray(X, np.float64)
             leaf = np.ascontiguousarray(leaf, np.int32)
+            if leaf.size < m:
+                raise N.DimensionMismatch(f"leaf holds {leaf.size} ids, {m} needed")
             val = np.empty(m, np.float64) if val is None else val
             N.dchk(N.dev().csp_eval(self.h, _ptr(X), _ptr(leaf), m, _ptr(val)))
         return val

@@ -1,13 +1,24 @@
-"""Multi-GPU plumbing (one process per GPU, torch.distributed): the path shards with no exchange step.
+"""Multi-GPU plumbing.  The path shards with no exchange step; the collectives are the library's own, behind the
+C ABI (csrc/comm.cu, NCCL over NVLink):
 
-  C1  the flattened tree blob is broadcast ONCE from the rank that grew the tree (NCCL over NVLink on GPUs; the same code
-      runs over gloo with CPU tensors in the CPU tests);
-  --  queries are split into contiguous ranges, leaves into contiguous leaf-id ranges: no communication;
-  C2  results (leaf id int32 + value f64 per query) are gathered to rank 0 on request.
+  C1  csp_shard_tree_broadcast   the flattened tree blob, ONCE per tree version, uploaded on every GPU from the device buffer;
+  --  csp_shard_fit              leaf fits sharded by contiguous leaf-id range, fitted records all-gathered;
+  --  queries split into contiguous ranges: no communication;
+  C2  csp_shard_locate_eval_dev  (leaf id int32, value f64) gathered to one rank, pipelined behind the next chunk's kernels.
 
-Nothing here computes: kernels are reached through device.py.
+Two ways to form the clique: `init_single_process(ndev)` (one process drives every GPU -- what a Julia host does) and
+`init_from_torch_distributed()` (one process per GPU under torchrun: torch.distributed only carries the 128-byte NCCL id and
+the barriers; the data path never goes through it).  Nothing in this file computes.
+
+The torch.distributed helpers at the end (`broadcast_blob`, `gather_results`) are the host-side equivalents used by the CPU
+(gloo) tests of the partition logic; the GPU path does not call them.
 """
+import ctypes as C
+
 import numpy as np
+
+from . import _native as N
+from .device import DeviceTree, LeafModels, _is_cuda_tensor, _ptr, _stream_ptr
 
 
 def shard_range(total, world, rank):
@@ -17,9 +28,193 @@ def shard_range(total, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def shard_counts(total, world):
+    return [shard_range(total, world, r)[1] - shard_range(total, world, r)[0] for r in range(world)]
+
+
+# ---- clique ---------------------------------------------------------------------------------------------------------------
+def init_single_process(ndev, devices=None):
+    """csp_init: GPUs devices[i] (default 0..ndev-1) become ranks 0..ndev-1, all driven by this process."""
+    devs = None if devices is None else (C.c_int32 * ndev)(*devices)
+    N.dchk(N.dev().csp_init(int(ndev), devs))
+    return comm_info()
+
+
+def init_from_torch_distributed(device):
+    """csp_init_rank with the world / rank of the initialised torch.distributed group (NCCL or gloo); the 128-byte NCCL unique id
+    travels from rank 0 by a torch.distributed broadcast."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    ident = (C.c_char * 128)()
+    if world > 1:
+        if rank == 0:
+            N.dchk(N.dev().csp_comm_unique_id(ident))
+        backend = dist.get_backend()
+        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).clone()
+        if backend == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, 0)
+        ident = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+    N.dchk(N.dev().csp_init_rank(world, rank, int(device), ident))
+    return comm_info()
+
+
+def shutdown():
+    N.dchk(N.dev().csp_shutdown())
+
+
+def comm_info():
+    info = (C.c_int64 * 4)()
+    N.dchk(N.dev().csp_comm_info(info))
+    return dict(world=int(info[0]), local=int(info[1]), first_rank=int(info[2]), nccl_version=int(info[3]))
+
+
+def synchronize():
+    N.dchk(N.dev().csp_shard_synchronize())
+
+
+TIMING_KEYS = ("blob_h2d_ms", "tree_broadcast_ms", "upload_ms", "fit_ms", "allgather_ms", "gather_ms")
+
+
+def timing():
+    ms = (C.c_double * 6)()
+    N.dchk(N.dev().csp_shard_timing(ms))
+    return {k: float(ms[i]) for i, k in enumerate(TIMING_KEYS)}
+
+
+def _ptr_array(items):
+    if items is None:
+        return None
+    arr = (C.c_void_p * len(items))()
+    for i, it in enumerate(items):
+        arr[i] = None if it is None else (_ptr(it) if hasattr(it, "shape") else it)
+    return arr
+
+
+def _stream_array(streams, nlocal):
+    if streams is None:
+        return None
+    arr = (C.c_void_p * nlocal)()
+    for i, s in enumerate(streams):
+        arr[i] = _stream_ptr(s)
+    return arr
+
+
+class _Borrowed:
+    """A DeviceTree / LeafModels view over a handle owned by a sharded object."""
+
+    @staticmethod
+    def tree(h):
+        t = DeviceTree.__new__(DeviceTree)
+        t.h = h
+        info = (C.c_int64 * 8)()
+        N.dchk(N.dev().csp_tree_info(h, info))
+        t.n, t.p, t.n_nodes, t.n_internal, t.n_leaves, t.device, t.max_depth, t.kib = [int(v) for v in info]
+        t.close = lambda: None
+        return t
+
+    @staticmethod
+    def models(h):
+        m = LeafModels(h)
+        m.close = lambda: None
+        return m
+
+
+class ShardedTree:
+    """csp_shard_tree: the tree replicated on every GPU of the clique by one NCCL broadcast (collective constructor)."""
+
+    def __init__(self, blob=None, root=0):
+        info = comm_info()
+        self.nlocal, self.world, self.first_rank = info["local"], info["world"], info["first_rank"]
+        h = C.c_void_p()
+        if blob is not None:
+            blob = np.ascontiguousarray(blob, np.uint8)
+            N.dchk(N.dev().csp_shard_tree_broadcast(blob.ctypes.data, blob.nbytes, int(root), C.byref(h)))
+        else:
+            N.dchk(N.dev().csp_shard_tree_broadcast(None, 0, int(root), C.byref(h)))
+        self.h = h
+        self.local = []
+        for i in range(self.nlocal):
+            th = C.c_void_p()
+            N.dchk(N.dev().csp_shard_tree_get(h, i, C.byref(th)))
+            self.local.append(_Borrowed.tree(th))
+        t0 = self.local[0]
+        self.n, self.p, self.n_leaves = t0.n, t0.p, t0.n_leaves
+
+    def fit(self, models=None, skip=0, streams=None):
+        """Leaf fits sharded by leaf-id range over the ranks + all-gather of the records (collective).  models=None allocates."""
+        h = models.h if models is not None else C.c_void_p()
+        N.dchk(N.dev().csp_shard_fit(self.h, skip, C.byref(h), _stream_array(streams, self.nlocal)))
+        return models if models is not None else ShardedModels(h, self.nlocal)
+
+    def locate_eval_resident(self, models, X, counts, leaf, val, status=None, gather_root=-1, leaf_all=None, val_all=None, chunk=0,
+                             streams=None):
+        """Per local rank i: locate + evaluate the resident shard X[i] (counts[rank] queries) into leaf[i] / val[i] / status[i];
+        with gather_root >= 0 also gather every rank's (leaf, val) into leaf_all / val_all on that rank (collective)."""
+        cnt = (C.c_int64 * self.world)(*[int(c) for c in counts])
+        N.dchk(N.dev().csp_shard_locate_eval_dev(self.h, models.h, _ptr_array(X), cnt, _ptr_array(leaf), _ptr_array(val),
+                                                 _ptr_array(status) if status is not None else None, int(gather_root),
+                                                 None if leaf_all is None else _ptr(leaf_all), None if val_all is None else _ptr(val_all),
+                                                 int(chunk), _stream_array(streams, self.nlocal)))
+
+    def gather_resident(self, leaf, val, counts, gather_root, leaf_all, val_all, streams=None):
+        cnt = (C.c_int64 * self.world)(*[int(c) for c in counts])
+        N.dchk(N.dev().csp_shard_gather_dev(_ptr_array(leaf), _ptr_array(val), cnt, int(gather_root),
+                                            None if leaf_all is None else _ptr(leaf_all), None if val_all is None else _ptr(val_all),
+                                            _stream_array(streams, self.nlocal)))
+
+    def locate_eval(self, models, X, leaf=None, val=None, status=None):
+        """Host buffers: this process's queries split over its local GPUs; results in host arrays (leaf, val, status)."""
+        X = np.ascontiguousarray(X, np.float64)
+        if X.ndim != 2 or X.shape[1] != self.n:
+            raise N.DimensionMismatch(f"tree has {self.n} dimensions, got a query array of shape {X.shape}")
+        m = X.shape[0]
+        leaf = np.empty(m, np.int32) if leaf is None else leaf
+        val = np.empty(m, np.float64) if val is None else val
+        status = np.empty(m, np.uint8) if status is None else status
+        N.dchk(N.dev().csp_shard_locate_eval(self.h, models.h, X.ctypes.data, m, leaf.ctypes.data, val.ctypes.data, status.ctypes.data))
+        return leaf, val, status
+
+    def close(self):
+        if self.h:
+            N.dev().csp_shard_tree_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ShardedModels:
+    """csp_shard_models: every GPU holds every leaf model; each rank fitted its own leaf-id range."""
+
+    def __init__(self, h, nlocal):
+        self.h = h
+        self.local = []
+        for i in range(nlocal):
+            mh = C.c_void_p()
+            N.dchk(N.dev().csp_shard_models_get(h, i, C.byref(mh)))
+            self.local.append(_Borrowed.models(mh))
+
+    def close(self):
+        if self.h:
+            N.dev().csp_shard_models_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- torch.distributed equivalents (CPU / gloo tests of the partition logic) ---------------------------------------------------
 def broadcast_blob(blob, src=0, device=None):
-    """Broadcast a packed tree blob (numpy uint8 on `src`, None elsewhere).  Returns a torch uint8 tensor on `device`
-    (CUDA for NCCL, CPU for gloo) holding the blob on every rank."""
+    """Broadcast a packed tree blob (numpy uint8 on `src`, None elsewhere) with torch.distributed.  Returns a torch uint8 tensor on
+    `device` (CPU for gloo) holding the blob on every rank."""
     import torch
     import torch.distributed as dist
     rank = dist.get_rank()

@@ -34,6 +34,7 @@ extern "C" {
 #define CSP_ERR_NOMEM (-3)
 #define CSP_ERR_UNSUPPORTED (-4) /* degree / dimension outside what the kernels cover (p in {1,2}; fits need p == 2) */
 #define CSP_ERR_NO_DEVICE (-5)
+#define CSP_ERR_NCCL (-6)        /* NCCL could not be loaded, or a collective failed */
 
 /* per-query status written by csp_find_leaf* / csp_locate_eval* */
 #define CSP_Q_OK 0
@@ -130,6 +131,14 @@ int csp_models_fit(const csp_tree* tree, int32_t skip, csp_models** out);
 /* Re-fit into an existing handle obtained from csp_models_fit on the same tree (asynchronous on `stream`; no allocation):
  * what a caller that re-fits every iteration uses. */
 int csp_models_refit(const csp_tree* tree, int32_t skip, csp_models* models, void* stream);
+/* An unfitted handle for this tree (records zeroed): the target of csp_models_refit / csp_models_refit_range. */
+int csp_models_alloc(const csp_tree* tree, csp_models** out);
+/* Re-fit only the leaves [leaf_lo, leaf_hi) (ids in leaves(root) order) into an existing handle; the other records are left
+ * untouched.  This is the per-GPU piece of a leaf-sharded fit (csp_shard_fit).  Asynchronous on `stream`. */
+int csp_models_refit_range(const csp_tree* tree, int32_t skip, csp_models* models, int64_t leaf_lo, int64_t leaf_hi, void* stream);
+/* The records of the listed leaves only (nb ids), outputs as in csp_models_download (any may be NULL). */
+int csp_models_download_rows(const csp_models* models, const int32_t* leaf_ids, int64_t nb, double* c, double* g, double* Q,
+                             double* b, uint8_t* status);
 /* Models supplied by the caller (host arrays, layouts as in csp_fit_boxes; Q may be NULL for degree-1 models). */
 int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double* g, const double* Q, const double* b,
                       csp_models** out);
@@ -142,7 +151,8 @@ int csp_models_info(const csp_models* models, int64_t info[4]);
 int csp_models_free(csp_models* models);
 
 /* ---- K3: batched evaluation; replaces modelvalue(c, g, Q, b, x) (src/cs2.jl:155-159) ----------------------------- */
-/* val[i] = c_l + g_l'(x_i - b_l) + (x_i - b_l)' Q_l (x_i - b_l) / 2 with l = leaf[i] (leaf[i] < 0 gives NaN). */
+/* val[i] = c_l + g_l'(x_i - b_l) + (x_i - b_l)' Q_l (x_i - b_l) / 2 with l = leaf[i]; a leaf id outside
+ * [0, n_models) -- negative (out-of-world marker) or too large -- gives NaN on every evaluation path. */
 int csp_eval(const csp_models* models, const double* X, const int32_t* leaf, int64_t m, double* val);
 int csp_eval_dev(const csp_models* models, const double* dX, const int32_t* dleaf, int64_t m, double* dval, void* stream);
 /* find_leaf_at followed by modelvalue of that leaf's model, fused.  leaf / status may be NULL. */
@@ -156,6 +166,62 @@ int csp_locate_eval_dev(const csp_tree* tree, const csp_models* models, const do
  * Q: n*n in the .data layout, prec: n*n column-major bytes.  Host buffers. */
 int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q, const double* b, const double* y,
                           const uint8_t* prec, const double* X, int64_t m, double* val);
+
+/* ---- multi-GPU: the tree replicated on every GPU, queries and leaf fits sharded, results gathered ------
+ * The reference is single-threaded and has no counterpart; the partition is BASELINE.json's (configs[2], configs[4]): the
+ * flattened tree is NCCL-broadcast once, query batches shard by contiguous ranges and leaf fits by contiguous leaf-id ranges with
+ * no exchange between ranks except the all-gather of the fitted records, and (leaf id, value) results are gathered to one rank.
+ * NCCL (libnccl.so.2) is loaded when the first of these functions is called.
+ *
+ * Two ways to form the clique.  Single process: csp_init makes the listed GPUs ranks 0..ndev-1 (ncclCommInitAll), all driven by
+ * the calling thread -- what a Julia host uses.  One process per GPU (torchrun): rank 0 obtains 128 bytes from
+ * csp_comm_unique_id, hands them to the other ranks by any side channel, and every rank calls csp_init_rank (ncclCommInitRank).
+ * Every csp_shard_* call is collective: each process calls it with the same arguments; per-rank arrays (`dX`, `dleaf`, `streams`
+ * ...) have one entry per LOCAL rank (ndev in the first mode, 1 in the second).  `streams` may be NULL (library streams) or hold
+ * one cudaStream_t per local rank; the call's work, communication included, is ordered on those streams and is asynchronous. */
+int csp_init(int ndev, const int* devs); /* devs == NULL: devices 0..ndev-1 */
+int csp_comm_unique_id(void* id128);
+int csp_init_rank(int world, int rank, int device, const void* id128);
+int csp_shutdown(void);
+/* info[0..3] = world size, local ranks, first local rank, NCCL version code (0 before initialisation) */
+int csp_comm_info(int64_t info[4]);
+
+typedef struct csp_shard_tree csp_shard_tree;     /* one csp_tree replica per local rank */
+typedef struct csp_shard_models csp_shard_models; /* one csp_models replica per local rank */
+
+/* C1: broadcast the packed tree (csp_tree_pack) from rank `root` and upload it on every GPU straight from the device buffer the
+ * broadcast landed in.  `blob`/`bytes` are read only by the process that owns rank `root`. */
+int csp_shard_tree_broadcast(const void* blob, size_t bytes, int root, csp_shard_tree** out);
+int csp_shard_tree_get(const csp_shard_tree* st, int local_index, csp_tree** tree); /* borrowed: do not free */
+int csp_shard_tree_free(csp_shard_tree* st);
+/* Leaf fits sharded by contiguous leaf-id range over the ranks (csp_models_refit_range), then the fitted records are all-gathered
+ * (one in-place ncclBroadcast per owner range, grouped) so that every GPU holds every model.  *models == NULL allocates the
+ * replicas, otherwise they are re-fitted in place. */
+int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** models, void* const* streams);
+int csp_shard_models_get(const csp_shard_models* sm, int local_index, csp_models** models); /* borrowed */
+int csp_shard_models_free(csp_shard_models* sm);
+/* Resident shards: rank r holds counts[r] queries (counts has WORLD entries, identical on every process); local rank i reads
+ * dX[i] and writes dleaf[i] / dval[i] / dstatus[i] (dstatus may be NULL or hold NULLs).  With gather_root >= 0 the (leaf, value)
+ * pairs of all ranks are also gathered, in rank order, into dleaf_all / dval_all on rank gather_root's GPU (C2: grouped
+ * ncclSend/ncclRecv, pipelined chunk by chunk behind the kernels of the next chunk; chunk = queries per pipeline step, 0 = default).
+ * dleaf_all / dval_all are read only by the process that owns gather_root. */
+int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* sm, const double* const* dX, const int64_t* counts,
+                              int32_t* const* dleaf, double* const* dval, uint8_t* const* dstatus, int gather_root,
+                              int32_t* dleaf_all, double* dval_all, int64_t chunk, void* const* streams);
+/* The gather alone (results already computed): what csp_shard_locate_eval_dev does after its kernels. */
+int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, int gather_root,
+                         int32_t* dleaf_all, double* dval_all, void* const* streams);
+/* Host buffers: the calling process's m queries are split over its local GPUs (contiguous ranges, one host thread and one copy /
+ * compute pipeline per GPU) and the results land in the caller's arrays -- in single-process mode that is the whole batch
+ * gathered on the host.  Returns when the results are complete. */
+int csp_shard_locate_eval(const csp_shard_tree* st, const csp_shard_models* sm, const double* X, int64_t m, int32_t* leaf,
+                          double* val, uint8_t* status);
+/* Wait for the library streams of every local rank. */
+int csp_shard_synchronize(void);
+/* Device milliseconds of the last collective of each kind, measured with CUDA events on local rank 0's stream (synchronizes):
+ * ms[0] tree blob host->device on the root, ms[1] tree ncclBroadcast, ms[2] per-GPU upload + derived arrays (host wall clock),
+ * ms[3] sharded fit kernels, ms[4] all-gather of the records, ms[5] gather of the results (csp_shard_gather_dev). */
+int csp_shard_timing(double ms[6]);
 
 /* ---- instrumentation -------------------------------------------------------------------------------------------- */
 /* Number of kernels this library has launched in this process since load (bench.py reports it as gpu_launches). */

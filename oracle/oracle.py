@@ -495,11 +495,14 @@ def tridiagonal_pattern(n):
     return [(i, i + 1) for i in range(1, n)]
 
 
-def locate_eval_batch(root, X, c, g, Qdata, b, nthreads=1):
-    """Qdata: (nl, n, n) with Qdata[l][i][j] = SymmetricArray .data[i,j] (as returned by fit_boxes_batch)."""
+def locate_eval_batch(root, X, c, g, Qdata, b, nthreads=1, Qf=None):
+    """Qdata: (nl, n, n) with Qdata[l][i][j] = SymmetricArray .data[i,j] (as returned by fit_boxes_batch); or pass Qf, the same
+    already in the library's column-major per-leaf layout (Qf[l][j][i] = .data[i,j]), to skip the conversion copy."""
     X = np.ascontiguousarray(X, np.float64)
     m, n = X.shape
-    Qf = np.ascontiguousarray(np.asarray(Qdata).transpose(0, 2, 1))  # back to column-major per leaf
+    if Qf is None:
+        Qf = np.ascontiguousarray(np.asarray(Qdata).transpose(0, 2, 1))  # back to column-major per leaf
+    assert Qf.flags.c_contiguous and Qf.dtype == np.float64
     leaf, val, st = np.zeros(m, np.int32), np.zeros(m), np.zeros(m, np.uint8)
     sec = C.c_double()
     _chk(lib().cspo_locate_eval_batch(C.c_void_p(root.h), _dp(X), C.c_long(m), n, _dp(np.ascontiguousarray(c)),

@@ -39,3 +39,52 @@ def assert_flat_equal(a, b):
         assert a[k] == b[k], k
     for k in FLAT_KEYS:
         assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+
+
+def grow_config_both(name):
+    """BASELINE config `name` (cb.synthetic.CONFIGS) grown identically in the product's host tree and in the oracle's pointer tree
+    (same seed, points, dimlists and compiled objective as cb.synthetic.config_tree).  Returns (root, oroot, objective)."""
+    c = cb.synthetic.CONFIGS[name]
+    n, p = c["n"], c["p"]
+    root, obj = cb.synthetic.config_tree(name)
+    rng = np.random.default_rng(1000)
+    lo, up = np.full(n, float(c.get("lower", -1.0))), np.full(n, float(c.get("upper", 1.0)))
+    base = c.get("base", 0.0)
+    pos = np.full(n, float(base)) if np.isscalar(base) else np.asarray(base, np.float64)
+    X = lo + (up - lo) * rng.random((c["npoints"], n))
+    cycle = cb.synthetic.cs1_dimlists(n) if p == 1 else cb.synthetic.round_robin_dimlists(n)
+    oroot = O.Box(O.World(lo, up, pos, obj(pos)), p)
+    fp, ctx = oracle_objective(obj)
+    O.addpoints_cycle(oroot, X, cycle, fp, ctx)
+    O.index_tree(oroot)
+    return root, oroot, obj
+
+
+WELL_CONDITIONED = 16.0  # a value is "well conditioned" when the summed magnitudes are at most this multiple of |value|
+
+
+def eval_errors(val, oval, X, leaf, c, g, Q, b):
+    """Error summary of evaluated values against the oracle's (finite entries only).  Q: (nl, n, n) in the .data layout or None.
+    scale = |c| + |g|.|dx| + |dx|'|Q||dx|/2 bounds the magnitude of the terms modelvalue sums (reference src/cs2.jl:155-159), so
+    |err| <= 1e-12 * scale is the backward-stable bar; on well-conditioned values (scale <= 16 |value|) the plain relative error
+    |err| / |value| is reported as well."""
+    fin = np.isfinite(oval)
+    lf = leaf[fin]
+    dx = np.abs(X[fin] - b[lf])
+    scale = np.abs(c[lf]) + (np.abs(g[lf]) * dx).sum(1)
+    if Q is not None:
+        step = 200000
+        quad = np.empty(len(lf))
+        for o in range(0, len(lf), step):
+            Qs = np.abs(np.nan_to_num(Q[lf[o:o + step]]))
+            Qs = np.triu(Qs) + np.triu(Qs, 1).transpose(0, 2, 1)
+            quad[o:o + step] = np.einsum("qi,qij,qj->q", dx[o:o + step], Qs, dx[o:o + step]) / 2
+        scale = scale + quad
+    err = np.abs(val[fin] - oval[fin])
+    scaled = err / np.maximum(scale, 1e-300)
+    av = np.abs(oval[fin])
+    well = scale <= WELL_CONDITIONED * av
+    rel = err[well] / av[well]
+    return dict(max_scaled=float(scaled.max()) if err.size else 0.0, max_rel_wellcond=float(rel.max()) if rel.size else 0.0,
+                frac_wellcond=float(well.mean()) if err.size else 0.0, n=int(err.size),
+                nan_pattern_equal=bool(np.array_equal(np.isfinite(val), fin)))
