@@ -120,10 +120,10 @@ def dev():
         L.csp_tree_free.argtypes = [vp]
         L.csp_find_leaf.argtypes = [vp, vp, C.c_int64, vp, vp]
         L.csp_find_leaf_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
-        L.csp_fit_boxes.argtypes = [vp, vp, C.c_int64, C.c_int32] + [vp] * 8
-        L.csp_coefficients_p.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp]
+        L.csp_fit_boxes.argtypes = [vp, vp, C.c_int64, C.c_int32] + [vp] * 9
+        L.csp_coefficients_p.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, vp]
         L.csp_fit_gdiag.argtypes = [vp, vp, C.c_int64, C.c_int32, vp, vp, vp, vp]
-        L.csp_coefficients_p_sparse.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp]
+        L.csp_coefficients_p_sparse.argtypes = [vp, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]
         L.csp_models_fit.argtypes = [vp, C.c_int32, vpp]
         L.csp_models_refit.argtypes = [vp, C.c_int32, vp, vp]
         L.csp_models_possemidef.argtypes = [vp, vp]
@@ -138,6 +138,10 @@ def dev():
         L.csp_models_alloc.argtypes = [vp, vpp]
         L.csp_models_refit_range.argtypes = [vp, C.c_int32, vp, C.c_int64, C.c_int64, vp]
         L.csp_models_download_rows.argtypes = [vp, vp, C.c_int64, vp, vp, vp, vp, vp]
+        L.csp_find_leaf_from.argtypes = [vp, C.c_int32, vp, C.c_int64, vp, vp]
+        L.csp_find_leaf_from_dev.argtypes = [vp, C.c_int32, vp, C.c_int64, vp, vp, vp]
+        L.csp_boxbounds.argtypes = [vp, C.c_int32, vp, vp]
+        L.csp_tree_extrema.argtypes = [vp, C.c_int32, vp, vp, vp, vp]
         # multi-GPU layer (comm.cu)
         L.csp_init.argtypes = [C.c_int, c_i32p]
         L.csp_comm_unique_id.argtypes = [vp]
@@ -168,6 +172,7 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
            "csp_timing_read", "csp_modelvalue_native", "csp_coefficients_p_sparse",
            "csp_models_possemidef", "csp_fit_gdiag", "csp_models_alloc", "csp_models_refit_range", "csp_models_download_rows",
+           "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
            "csp_init", "csp_comm_unique_id", "csp_init_rank", "csp_shutdown", "csp_comm_info", "csp_shard_tree_broadcast",
            "csp_shard_tree_get", "csp_shard_tree_free", "csp_shard_fit", "csp_shard_models_get", "csp_shard_models_free",
            "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]

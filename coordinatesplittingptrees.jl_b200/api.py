@@ -53,21 +53,20 @@ def device_tree(root):
 
 
 def find_leaf_at(root, x):
-    """find_leaf_at(root, x).  1-D x (or a scalar for 1-d trees): returns the leaf Box, raising like the reference.
-    2-D X of shape (m, n): returns the int32 array of leaf ids (ranks in leaves(root)); out-of-world rows raise."""
-    if root.id != 0:
-        raise NotImplementedError("the accelerated find_leaf_at starts at the root box")
+    """find_leaf_at(box, x), `box` being the root or any other box of the tree (the reference accepts any, src/tree.jl:351-360).
+    1-D x (or a scalar for 1-d trees): returns the leaf Box, raising like the reference.  2-D X of shape (m, n): returns the int32
+    array of leaf ids (ranks in leaves(getroot(box))); rows outside boxbounds(box) raise."""
     X = np.asarray(x, np.float64)
     single = X.ndim <= 1
     X = np.ascontiguousarray(np.atleast_1d(X).reshape(1, -1) if single else X)
     n = root.n
     if X.shape[1] != n:
         raise N.DimensionMismatch(f"tree has {n} dimensions, got {X.shape[1]}")
-    leaf, status = device_tree(root).find_leaf(X)
+    leaf, status = device_tree(root).find_leaf(X, start=T.node_id(root) if root.id != 0 else None)
     bad = np.flatnonzero(status == Q_OUTSIDE)
     if bad.size:
         i = int(bad[0])
-        raise N.ErrorException(f"{X[i].tolist()} not within the world bounds (query {i})")
+        raise N.ErrorException(f"{X[i].tolist()} not within the bounds of the box (query {i})")
     if single:
         f = root.tree.flat()
         return root._mk(f["box_of_pre"][f["leaf_nodes"][leaf[0]]])
@@ -95,13 +94,8 @@ def fit_quadratic_native(box, skip=0):
     _require_cs2(box)
     r = device_tree(box).fit_boxes([T.node_id(box)], skip=skip, native=True)
     _raise_fit(r["status"][0], box)
-    prec = r["prec"][0]
-    n = box.n
-    firstmatch = np.zeros(n, np.int64)
-    for d in range(n):  # partner of d in its chain split: the other dimension split "with" it, else the fictive n+1
-        partner = [k for k in range(n) if k != d and prec[d, k] and prec[k, d]]
-        firstmatch[d] = partner[0] + 1 if partner else n + 1
-    return float(r["c"][0]), r["gnat"][0], SymmetricArray(r["Q"][0]), r["b"][0], r["y"][0], prec, firstmatch
+    return (float(r["c"][0]), r["gnat"][0], SymmetricArray(r["Q"][0]), r["b"][0], r["y"][0], r["prec"][0],
+            r["firstmatch"][0].astype(np.int64))
 
 
 def fit_quadratic(box, skip=0):
@@ -112,10 +106,14 @@ def fit_quadratic(box, skip=0):
     return float(r["c"][0]), r["g"][0], SymmetricArray(r["Q"][0]), r["b"][0]
 
 
-def coefficients_p(box, skip=0):
+def coefficients_p(box, callback=None, skip=0):
     """Highest-order coefficients (reference src/polynomials.jl:127-230): SymmetricArray of off-diagonal Hessian entries
-    for p=2 (diagonal NaN), the gradient vector for p=1."""
-    Cp, _ = device_tree(box).coefficients_p([T.node_id(box)], skip=skip)
+    for p=2 (diagonal NaN), the gradient vector for p=1, the p-dimensional array of mixed coefficients for p>2.
+    The reference's `callback(child, value)` runs once per child of every split that supplies a coefficient; the kernels do not
+    call back into the host, so a callback here receives the total number of such invocations, callback(count)."""
+    Cp, _, used = device_tree(box).coefficients_p([T.node_id(box)], skip=skip, counts=True)
+    if callback is not None:
+        callback(int(used[0]) << box.p)
     return SymmetricArray(Cp[0])
 
 
@@ -127,13 +125,15 @@ def fit_quadratic_gdiag(box, skip=0):
     return float(r["c"][0]), r["g"][0], SymmetricArray(r["Q"][0]), r["b"][0]
 
 
-def coefficients_p_sparse(box, pattern, skip=0):
+def coefficients_p_sparse(box, pattern, callback=None, skip=0):
     """coefficients_p!(Cp, box) with a sparse symmetric Cp (reference src/polynomials.jl:161-230, :244-271): `pattern` is either
     the string "tridiagonal" (SymTridiagonal: returns its off-diagonal vector ev) or a list of above-diagonal positions (i, j),
     1-based, i < j (returns {(i, j): value}).  Only those coefficients are determined and the traversal stops once they are."""
     tri = isinstance(pattern, str) and pattern == "tridiagonal"
     pat = [(i, i + 1) for i in range(1, box.n)] if tri else [tuple(sorted(p)) for p in pattern]
-    vals, _ = device_tree(box).coefficients_p_sparse(pat, [T.node_id(box)], skip=skip)
+    vals, _, used = device_tree(box).coefficients_p_sparse(pat, [T.node_id(box)], skip=skip, counts=True)
+    if callback is not None:  # total number of reference callback invocations (4 per split that supplied a coefficient)
+        callback(int(used[0]) << box.p)
     return vals[0] if tri else {p: float(v) for p, v in zip(pat, vals[0])}
 
 
@@ -199,11 +199,26 @@ def possemidef(Q):
     return U + np.triu(out, 1).T
 
 
-def minimum(root):
-    """minimum(root): the leaf with the smallest value (reference src/CoordinateSplittingPTrees.jl:64-66)."""
-    f = root.tree.flat()
-    v = f["val"][f["leaf_nodes"]]
-    return root._mk(f["box_of_pre"][f["leaf_nodes"][int(np.argmin(v))]])
+def _leaf_box(box, leaf):
+    f = box.tree.flat()
+    return box._mk(f["box_of_pre"][f["leaf_nodes"][leaf]])
+
+
+def extrema(box):
+    """extrema(box) = (minimum(box), maximum(box)) over leaves(box) (reference src/CoordinateSplittingPTrees.jl:64-68: isless on
+    value, the first of equal leaves): a reduction on the device over the resident values."""
+    lmin, _, lmax, _ = device_tree(box).extrema(T.node_id(box))
+    return _leaf_box(box, lmin), _leaf_box(box, lmax)
+
+
+def minimum(box):
+    """minimum(box): the leaf with the smallest value (reference src/CoordinateSplittingPTrees.jl:66)."""
+    return extrema(box)[0]
+
+
+def maximum(box):
+    """maximum(box): the leaf with the largest value (reference src/CoordinateSplittingPTrees.jl:67)."""
+    return extrema(box)[1]
 
 
 def fit_leaves(root, skip=0):

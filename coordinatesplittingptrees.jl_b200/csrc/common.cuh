@@ -200,4 +200,30 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- splits(box) (reference src/tree.jl:461-540) as preorder range scans, any degree p ------------------------------
+// The ids splits(box) yields for one ancestor (or for the box's own subtree): up to three ascending ranges, visited in
+// this order.  Scanning them as ONE virtual sequence keeps the lanes of a chunk busy (the ranges are mostly tiny).
+struct RangeGroup {
+    int lo1, n1, lo2, n2, lo3, n3;
+    __device__ __forceinline__ int total() const { return n1 + n2 + n3; }
+    __device__ __forceinline__ int id(int v) const { return v < n1 ? lo1 + v : (v < n1 + n2 ? lo2 + (v - n1) : lo3 + (v - n1 - n2)); }
+};
+// Drives `fn(group)` over splits(box) in iteration order until fn returns true (done).
+template <class F>
+__device__ __forceinline__ void for_split_groups(const TreeView& t, int box, F&& fn) {
+    int cnode = box;
+    int4 ci = t.ninfo[box];
+    if (!(ci.w & CSP_NF_LEAF))
+        if (fn(RangeGroup{ci.y, ci.z, 0, 0, 0, 0})) return;  // own split, then its subtree in preorder
+    while (ci.x != cnode) {
+        const int a = ci.x;
+        const int4 ai = t.ninfo[a];
+        // subtrees of a's children before c, those after c, then a's own split
+        if (fn(RangeGroup{ai.y + 1, ci.y - (ai.y + 1), ci.y + ci.z, ai.y + ai.z - (ci.y + ci.z), ai.y, 1})) return;
+        cnode = a;
+        ci = ai;
+    }
+}
+
 #endif

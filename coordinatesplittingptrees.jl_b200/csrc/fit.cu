@@ -42,8 +42,10 @@ struct FitParams {
     double* gnat; double* y; uint8_t* prec;       // optional native-form extras (dense, box-major)
     uint8_t* status;
     long long* visited;
+    long long* used;     // optional: number of splits that supplied a coefficient (2^p callback invocations each, src/polynomials.jl:222)
+    int* firstmatch;     // optional [nb*n]: fit_poly1's firstmatch (src/cs2.jl:173,191-193), 1-based partner dimension (n+1: fictive)
     // results of the chain pre-pass (k_fit_chain), box-major
-    int* ch_status; int* ch_itop; double* ch_c; double* ch_y; double* ch_g; int* ch_step;
+    int* ch_status; int* ch_itop; double* ch_c; double* ch_y; double* ch_g; int* ch_step; int* ch_fm;
     // sparse-pattern coefficients_p (FIT_MODE_COEF, p == 2): slotmap[i*n+j] (i<j, 0-based) = output slot or -1; npat slots; the
     // output row of a box is then Q[bi*Q_stride + slot]
     const int* slotmap; int npat; const int* pat_ij;
@@ -154,36 +156,12 @@ __device__ int chaintop_dev(const TreeView& t, int box, int* covered, int* top_o
     return CSP_FIT_OK;
 }
 
-// The ids splits(box) yields for one ancestor (or for the box's own subtree): up to three ascending ranges, visited in
-// this order.  Scanning them as ONE virtual sequence keeps the lanes of a chunk busy (the ranges are mostly tiny).
-struct RangeGroup {
-    int lo1, n1, lo2, n2, lo3, n3;
-    __device__ __forceinline__ int total() const { return n1 + n2 + n3; }
-    __device__ __forceinline__ int id(int v) const { return v < n1 ? lo1 + v : (v < n1 + n2 ? lo2 + (v - n1) : lo3 + (v - n1 - n2)); }
-};
-// Drives `fn(group)` over splits(box) in iteration order until fn returns true (done).
-template <class F>
-__device__ __forceinline__ void for_split_groups(const TreeView& t, int box, F&& fn) {
-    int cnode = box;
-    int4 ci = t.ninfo[box];
-    if (!(ci.w & CSP_NF_LEAF))
-        if (fn(RangeGroup{ci.y, ci.z, 0, 0, 0, 0})) return;  // own split, then its subtree in preorder
-    while (ci.x != cnode) {
-        const int a = ci.x;
-        const int4 ai = t.ninfo[a];
-        // subtrees of a's children before c, those after c, then a's own split
-        if (fn(RangeGroup{ai.y + 1, ci.y - (ai.y + 1), ci.y + ci.z, ai.y + ai.z - (ci.y + ci.z), ai.y, 1})) return;
-        cnode = a;
-        ci = ai;
-    }
-}
-
 // Chain pre-pass, one THREAD per box: getleaf + chaintop (src/polynomials.jl:22-98) + the chain walk of fit_poly1
 // (src/cs2.jl:183-203).  Both are short sequential integer walks; running them on one lane of a warp-per-box kernel left
 // 31 lanes idle for a fifth of that kernel's instructions.
 __global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* __restrict__ node_ids, long long row_lo, long long nb, int* __restrict__ ch_status,
                                                    int* __restrict__ ch_itop, double* __restrict__ ch_c, double* __restrict__ ch_y,
-                                                   double* __restrict__ ch_g, int* __restrict__ ch_step) {
+                                                   double* __restrict__ ch_g, int* __restrict__ ch_step, int* __restrict__ ch_fm) {
     const int n = t.n;
     for (long long bi = row_lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; bi < nb; bi += (long long)gridDim.x * blockDim.x) {
         const int box = node_ids ? node_ids[bi] : t.lnode[bi];
@@ -215,7 +193,8 @@ __global__ void __launch_bounds__(128) k_fit_chain(const TreeView t, const int* 
                 const double x1 = t.ixs[2 * I], x2 = t.ixs[2 * I + 1];
                 const double f0 = t.icval[4 * I], f1 = t.icval[4 * I + 1], f2 = t.icval[4 * I + 2];
                 y[d1 - 1] = x1; step[d1 - 1] = k;
-                if (d2 <= n) { y[d2 - 1] = x2; step[d2 - 1] = k; }
+                if (ch_fm) ch_fm[bi * n + d1 - 1] = d2;
+                if (d2 <= n) { y[d2 - 1] = x2; step[d2 - 1] = k; if (ch_fm) ch_fm[bi * n + d2 - 1] = d1; }
                 g[d1 - 1] = (f1 - f0) / (x1 - b[d1 - 1]);
                 if (d2 <= n) g[d2 - 1] = (f2 - f0) / (x2 - b[d2 - 1]);
                 cur = t.ichild[4 * I + 3];
@@ -581,7 +560,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
         int tpos, foundp, sw_cnt = 0, sw_total = 0;
         fit_scan<P, false, BIG>(prm, w, box, npairs, tpos, foundp, sw_cnt, sw_total);
         FIT_TICK(1);
-        long long nvisited;
+        long long nvisited, nused = foundp;  // every filled slot was set by exactly one split
         {   // number of splits coefficients_p examined (after `skip`): up to the one that filled the last slot
             int mx = -1;
             if (w.plist) {  // four independent gathers in flight per lane
@@ -666,7 +645,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
                 // sequential behaviour exactly with one lane (rare path).
                 if (lane == 0) {
                     for (long long e = 0; e < qlen; ++e) Qo[e] = dnan();
-                    long long nrem = npairs, tp = 0, examined = 0;
+                    long long nrem = npairs, tp = 0, examined = 0, nset = 0;
                     for_split_groups(t, box, [&](const RangeGroup& grp) -> bool {
                         const int total = grp.total();
                         for (int v = 0; v < total; ++v, ++tp) {
@@ -692,6 +671,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
                                 if (cur != cur) {
                                     Qo[slot] = P == 2 ? coef_value<2>(t, id) : coef_value<1>(t, id);
                                     nrem -= 1;
+                                    nset += 1;
                                 }
                             }
                             if (nrem <= 0) return true;
@@ -699,8 +679,10 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
                         return false;
                     });
                     nvisited = examined;
+                    nused = nset;
                 }
                 nvisited = __shfl_sync(FULL, nvisited, 0);
+                nused = __shfl_sync(FULL, nused, 0);
                 __syncwarp();
             }
 
@@ -926,6 +908,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
                     if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
                     if (prm.gnat) prm.gnat[bi * n + i] = ok ? w.sg[i] : dnan();
                     if (prm.y) prm.y[bi * n + i] = ok ? w.sy[i] : dnan();
+                    if (prm.firstmatch) prm.firstmatch[bi * n + i] = ok ? prm.ch_fm[bi * n + i] : 0;
                 }
                 if (prm.prec)
                     for (int e = lane; e < n * n; e += 32) {
@@ -971,6 +954,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             if (lane == 0) {
                 if (prm.status) prm.status[bi] = (uint8_t)status;
                 if (prm.visited) prm.visited[bi] = nvisited;
+                if (prm.used) prm.used[bi] = nused;
             }
             __syncwarp();
             FIT_TICK(4);
@@ -1216,7 +1200,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     }
     if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
         const size_t nb = (size_t)prm.nb;
-        const size_t need = nb * ((size_t)n * 20 + 16) + 64 + 64;  // chain rows + alignment slack + the work counter
+        const size_t need = nb * ((size_t)n * (prm.firstmatch ? 24 : 20) + 16) + 64 + 64;  // chain rows + alignment slack + the work counter
         if (need > t->fit_ws_bytes) {
             if (t->fit_ws) { CSP_CUDA(cudaDeviceSynchronize()); csp_dev_free(t->fit_ws); t->fit_ws = nullptr; t->fit_ws_bytes = 0; }
             CSP_CHECK(csp_dev_alloc(&t->fit_ws, need));
@@ -1229,6 +1213,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         prm.ch_step = (int*)base_p; base_p += nb * n * 4;
         prm.ch_status = (int*)base_p; base_p += nb * 4;
         prm.ch_itop = (int*)base_p; base_p += nb * 4;
+        if (prm.firstmatch) { prm.ch_fm = (int*)base_p; base_p += nb * n * 4; }
         prm.work_counter = (unsigned long long*)(((uintptr_t)base_p + 63) & ~(uintptr_t)63);
         if (getenv("CSP_FIT_DYNAMIC") && atoi(getenv("CSP_FIT_DYNAMIC")) == 0) prm.work_counter = nullptr;
         else CSP_CUDA(cudaMemsetAsync(prm.work_counter, 0, sizeof(unsigned long long), st));
@@ -1236,7 +1221,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         {
             CspTimed tm(CSP_K_FIT, st);
             k_fit_chain<<<(unsigned)blocks, 128, 0, st>>>(prm.t, prm.node_ids, prm.row_lo, prm.row_hi, prm.ch_status, prm.ch_itop, prm.ch_c, prm.ch_y,
-                                                         prm.ch_g, prm.ch_step);
+                                                         prm.ch_g, prm.ch_step, prm.ch_fm);
         }
         CSP_LAUNCHED();
         CSP_CUDA(cudaGetLastError());
@@ -1304,7 +1289,7 @@ struct DevBuf {
 extern "C" {
 
 int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q, double* b,
-                  double* g_native, double* y, uint8_t* prec, uint8_t* status) {
+                  double* g_native, double* y, uint8_t* prec, int32_t* firstmatch, uint8_t* status) {
     CSP_CHECK(check_nodes(t, node_ids, nb));
     if (t->v.p != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "fit_quadratic is defined for Box{2} only (reference src/cs2.jl:89); tree has p=%d", t->v.p);
     if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
@@ -1315,8 +1300,9 @@ int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
     // chunk the boxes so that the dense Q workspace stays below ~2 GiB
     const long long per = (long long)n * n * 8;
     const long long chunk = std::max<long long>(1, std::min<long long>(nb, (2LL << 30) / per));
-    DevBuf dids, dc, dg_, dQ, db, dgn, dy, dprec, dst;
+    DevBuf dids, dc, dg_, dQ, db, dgn, dy, dprec, dst, dfm;
     if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
+    if (firstmatch) CSP_CHECK(dfm.alloc(chunk * n * 4));
     CSP_CHECK(dc.alloc(chunk * 8)); CSP_CHECK(dg_.alloc(chunk * n * 8)); CSP_CHECK(dQ.alloc(chunk * per)); CSP_CHECK(db.alloc(chunk * n * 8));
     if (g_native) CSP_CHECK(dgn.alloc(chunk * n * 8));
     if (y) CSP_CHECK(dy.alloc(chunk * n * 8));
@@ -1338,6 +1324,7 @@ int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
         prm.Q = (double*)dQ.p; prm.Q_stride = (long long)n * n; prm.q_packed = 0;
         prm.b = (double*)db.p; prm.b_stride = n;
         prm.gnat = (double*)dgn.p; prm.y = (double*)dy.p; prm.prec = (uint8_t*)dprec.p; prm.status = (uint8_t*)dst.p;
+        prm.firstmatch = (int*)dfm.p;
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "fit kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1351,23 +1338,28 @@ int csp_fit_boxes(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
         if (y) CSP_CUDA(cudaMemcpy(y + off * n, dy.p, cnt * n * 8, cudaMemcpyDeviceToHost));
         if (prec) CSP_CUDA(cudaMemcpy(prec + off * (long long)n * n, dprec.p, cnt * (long long)n * n, cudaMemcpyDeviceToHost));
         if (status) CSP_CUDA(cudaMemcpy(status + off, dst.p, cnt, cudaMemcpyDeviceToHost));
+        if (firstmatch) CSP_CUDA(cudaMemcpy(firstmatch + off * n, dfm.p, cnt * n * 4, cudaMemcpyDeviceToHost));
     }
     return CSP_OK;
 }
 
-int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited) {
+int csp_coefficients_generic(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited, int64_t* used);  // extras.cu
+
+int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited, int64_t* used) {
     CSP_CHECK(check_nodes(t, node_ids, nb));
     if (skip < 0 || !Cp) return csp_set_error(CSP_ERR_INVALID, "bad argument");
     if (nb == 0) return CSP_OK;
     CSP_CHECK(csp_require_device());
+    if (t->v.p > 2 || (getenv("CSP_COEF_GENERIC") && atoi(getenv("CSP_COEF_GENERIC")))) return csp_coefficients_generic(t, node_ids, nb, skip, Cp, visited, used);
     DeviceGuard dg(t->device);
     const int n = t->v.n;
     const long long per = (t->v.p == 2 ? (long long)n * n : n) * 8;
     const long long chunk = std::max<long long>(1, std::min<long long>(nb, (2LL << 30) / per));
-    DevBuf dids, dQ, dvis;
+    DevBuf dids, dQ, dvis, dused;
     if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
     CSP_CHECK(dQ.alloc(chunk * per));
     CSP_CHECK(dvis.alloc(chunk * 8));
+    CSP_CHECK(dused.alloc(chunk * 8));
     for (long long off = 0; off < nb; off += chunk) {
         const long long cnt = std::min(chunk, nb - off);
         FitParams prm{};
@@ -1380,7 +1372,7 @@ int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, i
             prm.node_ids = t->v.lnode + off;
         }
         prm.Q = (double*)dQ.p; prm.Q_stride = per / 8; prm.q_packed = 0;
-        prm.visited = (long long*)dvis.p;
+        prm.visited = (long long*)dvis.p; prm.used = (long long*)dused.p;
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1388,12 +1380,13 @@ int csp_coefficients_p(const csp_tree* t, const int32_t* node_ids, int64_t nb, i
         CSP_CHECK(rc);
         CSP_CUDA(cudaMemcpy(Cp + off * (per / 8), dQ.p, cnt * per, cudaMemcpyDeviceToHost));
         if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
+        if (used) CSP_CUDA(cudaMemcpy(used + off, dused.p, cnt * 8, cudaMemcpyDeviceToHost));
     }
     return CSP_OK;
 }
 
 int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_t skip, int32_t npat, const int32_t* pat_i,
-                              const int32_t* pat_j, double* vals, int64_t* visited) {
+                              const int32_t* pat_j, double* vals, int64_t* visited, int64_t* used) {
     CSP_CHECK(check_nodes(t, node_ids, nb));
     if (t->v.p != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "sparse coefficients_p output is defined for p == 2 (symmetric matrices)");
     if (skip < 0 || npat < 0 || (npat > 0 && (!pat_i || !pat_j || !vals))) return csp_set_error(CSP_ERR_INVALID, "bad argument");
@@ -1409,10 +1402,11 @@ int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_
     DeviceGuard dg(t->device);
     const long long per = std::max(npat, 1);
     const long long chunk = std::max<long long>(1, std::min<long long>(nb, (1LL << 30) / (per * 8)));
-    DevBuf dids, dQ, dvis, dslot;
+    DevBuf dids, dQ, dvis, dslot, dused;
     if (node_ids) CSP_CHECK(dids.alloc(chunk * 4));
     CSP_CHECK(dQ.alloc(chunk * per * 8));
     CSP_CHECK(dvis.alloc(chunk * 8));
+    CSP_CHECK(dused.alloc(chunk * 8));
     CSP_CHECK(dslot.alloc((size_t)n * n * 4));
     CSP_CUDA(cudaMemcpy(dslot.p, slot.data(), (size_t)n * n * 4, cudaMemcpyHostToDevice));
     for (long long off = 0; off < nb; off += chunk) {
@@ -1428,7 +1422,7 @@ int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_
         }
         prm.Q = (double*)dQ.p; prm.Q_stride = per; prm.q_packed = 0;
         prm.slotmap = (const int*)dslot.p; prm.npat = npat;
-        prm.visited = (long long*)dvis.p;
+        prm.visited = (long long*)dvis.p; prm.used = (long long*)dused.p;
         void* scratch = nullptr;
         int rc = launch_fit(t, prm, 0, &scratch);
         if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "coefficients kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1436,6 +1430,7 @@ int csp_coefficients_p_sparse(const csp_tree* t, const int32_t* node_ids, int64_
         CSP_CHECK(rc);
         if (npat > 0) CSP_CUDA(cudaMemcpy(vals + off * npat, dQ.p, cnt * (long long)npat * 8, cudaMemcpyDeviceToHost));
         if (visited) CSP_CUDA(cudaMemcpy(visited + off, dvis.p, cnt * 8, cudaMemcpyDeviceToHost));
+        if (used) CSP_CUDA(cudaMemcpy(used + off, dused.p, cnt * 8, cudaMemcpyDeviceToHost));
     }
     return CSP_OK;
 }
@@ -1464,6 +1459,7 @@ int csp_models_fit(const csp_tree* t, int32_t skip, csp_models** out) {
     if (!t || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     *out = nullptr;
     if (skip < 0) return csp_set_error(CSP_ERR_INVALID, "skip < 0");
+    if (t->v.p > 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "models exist for degrees p <= 2 only (the tree has p=%d)", t->v.p);
     CSP_CHECK(csp_require_device());
     DeviceGuard dg(t->device);
     const int n = t->v.n;
@@ -1575,6 +1571,7 @@ int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q,
 int csp_models_alloc(const csp_tree* t, csp_models** out) {
     if (!t || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     *out = nullptr;
+    if (t->v.p > 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "models exist for degrees p <= 2 only (the tree has p=%d)", t->v.p);
     CSP_CHECK(csp_require_device());
     DeviceGuard dg(t->device);
     csp_models* mo = new csp_models();

@@ -777,6 +777,7 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
 static int check_pair(const csp_tree* t, const csp_models* mo) {
     if (!t) return csp_set_error(CSP_ERR_INVALID, "tree is NULL");
     if (mo) {
+        if (t->v.p > 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "models exist for degrees p <= 2 only (the tree has p=%d)", t->v.p);
         if (mo->device != t->device) return csp_set_error(CSP_ERR_INVALID, "tree and models live on different devices");
         if (mo->n != t->v.n) return csp_set_error(CSP_ERR_INVALID, "models have n=%d, tree has n=%d", mo->n, t->v.n);
         if (mo->n_models != t->v.n_leaves)
@@ -813,6 +814,7 @@ extern "C" {
 int csp_find_leaf_dev(const csp_tree* t, const double* dX, int64_t m, int32_t* dleaf, uint8_t* dstatus, void* stream) {
     CSP_CHECK(check_pair(t, nullptr));
     if (m < 0 || (m > 0 && !dX)) return csp_set_error(CSP_ERR_INVALID, "bad query buffer");
+    if (t->v.p > 2) return csp_find_leaf_from_dev(t, 0, dX, m, dleaf, dstatus, stream);  // no packed descent records for p > 2
     DeviceGuard g(t->device);
     return launch_locate(t, nullptr, dX, m, dleaf, nullptr, dstatus, (cudaStream_t)stream);
 }
@@ -859,6 +861,7 @@ int csp_eval_dev(const csp_models* mo, const double* dX, const int32_t* dleaf, i
 int csp_find_leaf(const csp_tree* t, const double* X, int64_t m, int32_t* leaf, uint8_t* status) {
     CSP_CHECK(check_pair(t, nullptr));
     if (m < 0 || (m > 0 && (!X || !leaf))) return csp_set_error(CSP_ERR_INVALID, "bad buffer");
+    if (t->v.p > 2) return csp_find_leaf_from(t, 0, X, m, leaf, status);
     return run_host(t, nullptr, false, X, nullptr, m, leaf, nullptr, status);
 }
 

@@ -105,7 +105,7 @@ int csp_timing_read(double* ms, int64_t* launches) {
     g_timed.clear();
     return CSP_OK;
 }
-int csp_version(void) { return 100; }
+int csp_version(void) { return 200; }
 const char* csp_last_error(void) { return g_last_error.c_str(); }
 int csp_device_count(int* count) {
     if (!count) return csp_set_error(CSP_ERR_INVALID, "count is NULL");
@@ -152,8 +152,8 @@ static int validate_desc(const csp_tree_desc* d) {
     if (d->n > CSP_MAX_DIM) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d exceeds the supported maximum %d", d->n, CSP_MAX_DIM);
     if (d->p == 1 && d->n_internal >= (1 << 24))
         return csp_set_error(CSP_ERR_UNSUPPORTED, "CS1 trees are limited to 2^24 splits by the 16-byte descent record");
-    if (d->p != 1 && d->p != 2)
-        return csp_set_error(CSP_ERR_UNSUPPORTED, "degree p=%d is not supported by the sm_100a kernels (p must be 1 or 2)", d->p);
+    if (d->p < 1 || d->p > 8)
+        return csp_set_error(CSP_ERR_UNSUPPORTED, "degree p=%d is outside 1..8 (reference src/types.jl:194-201)", d->p);
     if (d->n_nodes < 1 || d->n_internal < 0 || d->n_leaves < 1 || d->n_internal >= d->n_nodes)
         return csp_set_error(CSP_ERR_INVALID, "inconsistent counts: nodes=%d internal=%d leaves=%d", d->n_nodes, d->n_internal, d->n_leaves);
     const void* ptrs[] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val};
@@ -263,8 +263,8 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     std::vector<DRec2> r2(p == 2 ? ni : 0);
     std::vector<int> dleaf;
     dleaf.reserve((size_t)ni * (C - 1) + 1);
-    if (ni == 0) dleaf.push_back(0);  // the root is the only leaf
-    {
+    if (ni == 0 || p > 2) dleaf.push_back(0);  // the root is the only leaf / no packed records for p > 2 (generic kernels, extras.cu)
+    if (p <= 2) {
         std::vector<int> bfs;  // preorder internal ids in BFS order
         bfs.reserve(ni);
         if (ni > 0) bfs.push_back(0);
@@ -309,7 +309,8 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     CSP_CHECK(to_device(t, std::vector<double>(d->lower, d->lower + n), &v.lower));
     CSP_CHECK(to_device(t, std::vector<double>(d->upper, d->upper + n), &v.upper));
     if (p == 1) { const DRec1* q; CSP_CHECK(to_device(t, r1, &q)); v.drec = q; }
-    else { const DRec2* q; CSP_CHECK(to_device(t, r2, &q)); v.drec = q; }
+    else if (p == 2) { const DRec2* q; CSP_CHECK(to_device(t, r2, &q)); v.drec = q; }
+    else v.drec = nullptr;
     CSP_CHECK(to_device(t, dleaf, &v.dleaf));
     CSP_CHECK(to_device(t, ninfo, &v.ninfo));
     CSP_CHECK(to_device(t, nleaf, &v.nleaf));
@@ -341,7 +342,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     {   // fit work units: the real leaves that are children of the same split share their splits() traversal
         std::vector<int4> units;
         units.reserve((size_t)ni);
-        for (int I = 0; I < ni; ++I) {
+        for (int I = 0; I < ni && p == 2; ++I) {
             int m[4] = {-1, -1, -1, -1}, cnt = 0;
             for (int k = 0; k < C && cnt < 4; ++k) {
                 const int c = d->child[(size_t)I * C + k];
@@ -349,7 +350,7 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             }
             if (cnt) units.push_back(make_int4(m[0], m[1], m[2], m[3]));
         }
-        if (ni == 0 && nl == 1) units.push_back(make_int4(0, -1, -1, -1));  // the root is the only leaf
+        if (ni == 0 && nl == 1 && p == 2) units.push_back(make_int4(0, -1, -1, -1));  // the root is the only leaf
         CSP_CHECK(to_device(t, units, &t->fit_units));
         t->n_fit_units = (long long)units.size();
     }

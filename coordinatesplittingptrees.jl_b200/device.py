@@ -127,9 +127,10 @@ class DeviceTree:
             pass
 
     # ---- K1 -------------------------------------------------------------------------------------------------
-    def find_leaf(self, X, leaf=None, status=None, stream=None):
+    def find_leaf(self, X, leaf=None, status=None, stream=None, start=None):
         """Batched find_leaf_at.  X: (m, n) float64 numpy array (host path) or torch CUDA tensor (resident path).
-        Returns (leaf ids int32, status uint8)."""
+        start: node id of the box the search starts from (None / 0: the root; any other box uses the general boxbounds check of
+        the reference, csp_find_leaf_from).  Returns (leaf ids int32, status uint8)."""
         m = self._check_X(X)
         _check_buf(leaf, m, "int32", X, "leaf")
         _check_buf(status, m, "uint8", X, "status")
@@ -137,13 +138,32 @@ class DeviceTree:
             import torch
             leaf = torch.empty(m, dtype=torch.int32, device=X.device) if leaf is None else leaf
             status = torch.empty(m, dtype=torch.uint8, device=X.device) if status is None else status
-            N.dchk(N.dev().csp_find_leaf_dev(self.h, _ptr(X), m, _ptr(leaf), _ptr(status), _stream_ptr(stream)))
+            if start:
+                N.dchk(N.dev().csp_find_leaf_from_dev(self.h, int(start), _ptr(X), m, _ptr(leaf), _ptr(status), _stream_ptr(stream)))
+            else:
+                N.dchk(N.dev().csp_find_leaf_dev(self.h, _ptr(X), m, _ptr(leaf), _ptr(status), _stream_ptr(stream)))
         else:
             X = np.ascontiguousarray(X, np.float64)
             leaf = np.empty(m, np.int32) if leaf is None else leaf
             status = np.empty(m, np.uint8) if status is None else status
-            N.dchk(N.dev().csp_find_leaf(self.h, _ptr(X), m, _ptr(leaf), _ptr(status)))
+            if start:
+                N.dchk(N.dev().csp_find_leaf_from(self.h, int(start), _ptr(X), m, _ptr(leaf), _ptr(status)))
+            else:
+                N.dchk(N.dev().csp_find_leaf(self.h, _ptr(X), m, _ptr(leaf), _ptr(status)))
         return leaf, status
+
+    def boxbounds(self, node_id):
+        """boxbounds(box) of any node, computed on the device (csp_boxbounds): (lower[n], upper[n])."""
+        lo, hi = np.empty(self.n), np.empty(self.n)
+        N.dchk(N.dev().csp_boxbounds(self.h, int(node_id), _ptr(lo), _ptr(hi)))
+        return lo, hi
+
+    def extrema(self, node_id=0):
+        """(leaf_min, value_min, leaf_max, value_max) over leaves(box) (csp_tree_extrema, isless order, first leaf wins ties)."""
+        lmin, lmax = C.c_int32(), C.c_int32()
+        vmin, vmax = C.c_double(), C.c_double()
+        N.dchk(N.dev().csp_tree_extrema(self.h, int(node_id), C.byref(lmin), C.byref(vmin), C.byref(lmax), C.byref(vmax)))
+        return lmin.value, vmin.value, lmax.value, vmax.value
 
     def _check_X(self, X):
         shape = tuple(X.shape)
@@ -159,7 +179,7 @@ class DeviceTree:
     def fit_boxes(self, node_ids=None, skip=0, native=False):
         """fit_quadratic for the listed node ids (None: every leaf).  Returns a dict of host arrays:
         c (nb,), g (nb,n), Q (nb,n,n) with Q[l,i,j] = SymmetricArray .data[i,j], b (nb,n), status (nb,);
-        with native=True also gnat, y, prec (nb,n,n bool)."""
+        with native=True also gnat, y, prec (nb,n,n bool), firstmatch (nb,n int32)."""
         n = self.n
         if node_ids is None:
             nb, ids = self.n_leaves, None
@@ -171,11 +191,12 @@ class DeviceTree:
         gn = np.empty((nb, n)) if native else None
         y = np.empty((nb, n)) if native else None
         prec = np.empty((nb, n * n), np.uint8) if native else None
+        fm = np.empty((nb, n), np.int32) if native else None
         N.dchk(N.dev().csp_fit_boxes(self.h, _ptr(ids), nb, skip, _ptr(c), _ptr(g), _ptr(Q), _ptr(b), _ptr(gn), _ptr(y), _ptr(prec),
-                                     _ptr(st)))
+                                     _ptr(fm), _ptr(st)))
         out = dict(c=c, g=g, Q=Q.reshape(nb, n, n).transpose(0, 2, 1), b=b, status=st)
         if native:
-            out.update(gnat=gn, y=y, prec=prec.reshape(nb, n, n).transpose(0, 2, 1).astype(bool))
+            out.update(gnat=gn, y=y, prec=prec.reshape(nb, n, n).transpose(0, 2, 1).astype(bool), firstmatch=fm)
         return out
 
     def fit_gdiag(self, node_ids=None, skip=0):
@@ -190,26 +211,27 @@ class DeviceTree:
         N.dchk(N.dev().csp_fit_gdiag(self.h, _ptr(ids), nb, skip, _ptr(c), _ptr(g), _ptr(Q), _ptr(b)))
         return dict(c=c, g=g, Q=Q.reshape(nb, n, n).transpose(0, 2, 1), b=b)
 
-    def coefficients_p(self, node_ids=None, skip=0):
-        """coefficients_p for the listed node ids (None: every leaf): (Cp, visited); Cp is (nb,n) for p=1 and (nb,n,n)
-        (.data layout, Cp[l,i,j] = data[i,j]) for p=2."""
+    def coefficients_p(self, node_ids=None, skip=0, counts=False):
+        """coefficients_p for the listed node ids (None: every leaf): (Cp, visited) -- with counts=True (Cp, visited, used), used =
+        number of splits that supplied a coefficient (the reference's callback runs 2^p times for each).  Cp is (nb,n) for p=1,
+        (nb,n,n) (.data layout, Cp[l,i,j] = data[i,j]) for p=2 and (nb,)+(n,)*p with Cp[l,i1,..,ip] = data[i1,..,ip] for p>2."""
         n = self.n
         if node_ids is None:
             nb, ids = self.n_leaves, None
         else:
             ids = np.ascontiguousarray(node_ids, np.int32)
             nb = len(ids)
-        per = n * n if self.p == 2 else n
+        per = n ** self.p
         Cp = np.empty((nb, per))
-        vis = np.empty(nb, np.int64)
-        N.dchk(N.dev().csp_coefficients_p(self.h, _ptr(ids), nb, skip, _ptr(Cp), _ptr(vis)))
-        if self.p == 2:
-            Cp = Cp.reshape(nb, n, n).transpose(0, 2, 1)
-        return Cp, vis
+        vis, used = np.empty(nb, np.int64), np.empty(nb, np.int64)
+        N.dchk(N.dev().csp_coefficients_p(self.h, _ptr(ids), nb, skip, _ptr(Cp), _ptr(vis), _ptr(used)))
+        if self.p >= 2:  # column-major .data per box -> numpy index order
+            Cp = Cp.reshape((nb,) + (n,) * self.p).transpose((0,) + tuple(range(self.p, 0, -1)))
+        return (Cp, vis, used) if counts else (Cp, vis)
 
-    def coefficients_p_sparse(self, pattern, node_ids=None, skip=0):
+    def coefficients_p_sparse(self, pattern, node_ids=None, skip=0, counts=False):
         """coefficients_p! into a sparse symmetric output: pattern = [(i, j), ...] above-diagonal positions (1-based, i < j).
-        Returns (values (nb, npat) in pattern order, visited (nb,))."""
+        Returns (values (nb, npat) in pattern order, visited (nb,)) and, with counts=True, also used (nb,)."""
         if node_ids is None:
             nb, ids = self.n_leaves, None
         else:
@@ -218,9 +240,10 @@ class DeviceTree:
         pi = np.ascontiguousarray([p[0] for p in pattern], np.int32)
         pj = np.ascontiguousarray([p[1] for p in pattern], np.int32)
         vals = np.empty((nb, len(pattern)))
-        vis = np.empty(nb, np.int64)
-        N.dchk(N.dev().csp_coefficients_p_sparse(self.h, _ptr(ids), nb, skip, len(pattern), _ptr(pi), _ptr(pj), _ptr(vals), _ptr(vis)))
-        return vals, vis
+        vis, used = np.empty(nb, np.int64), np.empty(nb, np.int64)
+        N.dchk(N.dev().csp_coefficients_p_sparse(self.h, _ptr(ids), nb, skip, len(pattern), _ptr(pi), _ptr(pj), _ptr(vals), _ptr(vis),
+                                                 _ptr(used)))
+        return (vals, vis, used) if counts else (vals, vis)
 
     def fit_models(self, skip=0):
         """Fit every leaf and keep the canonical models on the device (csp_models_fit)."""

@@ -32,7 +32,7 @@ extern "C" {
 #define CSP_ERR_INVALID (-1)     /* bad argument; DimensionMismatch / ArgumentError on the host side */
 #define CSP_ERR_CUDA (-2)        /* a CUDA runtime call failed */
 #define CSP_ERR_NOMEM (-3)
-#define CSP_ERR_UNSUPPORTED (-4) /* degree / dimension outside what the kernels cover (p in {1,2}; fits need p == 2) */
+#define CSP_ERR_UNSUPPORTED (-4) /* degree / dimension outside what the kernels cover (fits need p == 2, models p <= 2) */
 #define CSP_ERR_NO_DEVICE (-5)
 #define CSP_ERR_NCCL (-6)        /* NCCL could not be loaded, or a collective failed */
 
@@ -56,7 +56,7 @@ typedef struct csp_models csp_models; /* device-resident per-leaf models (c, g, 
  * the library at upload. */
 typedef struct csp_tree_desc {
     int32_t n;          /* ndims(root) */
-    int32_t p;          /* degree(root): 1 or 2 */
+    int32_t p;          /* degree(root): 1..8 (src/types.jl:194-201); fits and models need p <= 2 */
     int32_t n_nodes;    /* length(root) */
     int32_t n_internal; /* number of non-leaf boxes */
     int32_t n_leaves;   /* length(leaves(root)) */
@@ -96,6 +96,20 @@ int csp_tree_free(csp_tree* tree);
 /* leaf[i] = leaf id of the leaf containing X[:,i], or -1 with status[i] = CSP_Q_OUTSIDE.  status may be NULL. */
 int csp_find_leaf(const csp_tree* tree, const double* X, int64_t m, int32_t* leaf, uint8_t* status);
 int csp_find_leaf_dev(const csp_tree* tree, const double* dX, int64_t m, int32_t* dleaf, uint8_t* dstatus, void* stream);
+/* find_leaf_at(box, x) with ANY box of the tree as the starting point (the reference accepts one, and addpoint! calls it that way:
+ * src/CoordinateSplittingPTrees.jl:106-108): the general bounds check of src/tree.jl:357-360 against boxbounds(box, i)
+ * (src/tree.jl:146-171) -- lower <= x < upper, the upper edge allowed only where it is the world's -- then the descent from
+ * that box.  node_id = 0 is the root. */
+int csp_find_leaf_from(const csp_tree* tree, int32_t node_id, const double* X, int64_t m, int32_t* leaf, uint8_t* status);
+int csp_find_leaf_from_dev(const csp_tree* tree, int32_t node_id, const double* dX, int64_t m, int32_t* dleaf, uint8_t* dstatus,
+                           void* stream);
+/* boxbounds(box) (src/tree.jl:136-171) of any box, computed on the device: lower[n], upper[n] (host arrays). */
+int csp_boxbounds(const csp_tree* tree, int32_t node_id, double* lower, double* upper);
+/* minimum(box) / maximum(box) / extrema(box) (src/CoordinateSplittingPTrees.jl:64-68: isless on value over leaves(box)): ids
+ * and values of the first minimal and the first maximal real leaf under node_id (NaN sorts last, -0.0 before 0.0, as isless does).
+ * A device reduction over the resident values: it can follow an upload or a fit without the values visiting the host.
+ * Any output may be NULL. */
+int csp_tree_extrema(const csp_tree* tree, int32_t node_id, int32_t* leaf_min, double* val_min, int32_t* leaf_max, double* val_max);
 
 /* ---- K2: batched model fits ------------------------------------------------------------------------------------- */
 /* fit_quadratic(value, box; skip) for each listed box (src/cs2.jl:89-93: fit_poly1 :162-205, coefficients_p
@@ -104,14 +118,19 @@ int csp_find_leaf_dev(const csp_tree* tree, const double* dX, int64_t m, int32_t
  *   c[nb], g[nb*n] canonical gradient, Q[nb*n*n] in the layout of SymmetricArray .data (column-major, values at
  *   [i,j] with i<=j, the strictly lower triangle keeps the NaN fill; src/types.jl:432-454, src/polynomials.jl:232-233),
  *   b[nb*n]; native-form extras of fit_quadratic_native (src/cs2.jl:115-121): g_native[nb*n], y[nb*n],
- *   prec[nb*n*n] (column-major Bool matrix, prec[i,j] <=> i was split before-or-with j); status[nb] CSP_FIT_*.
+ *   prec[nb*n*n] (column-major Bool matrix, prec[i,j] <=> i was split before-or-with j), firstmatch[nb*n] (src/cs2.jl:173,
+ *   191-193: the 1-based dimension split together with each dimension in the chain, n+1 for a fictive partner); status[nb] CSP_FIT_*.
  * Boxes whose status is not CSP_FIT_OK get NaN outputs.  Requires p == 2. */
 int csp_fit_boxes(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* c, double* g, double* Q,
-                  double* b, double* g_native, double* y, uint8_t* prec, uint8_t* status);
-/* coefficients_p(value, box; skip) (src/polynomials.jl:127-230), dense output Cp[nb*n^p]: p == 2 gives the
- * off-diagonal Hessian entries (.data layout as above, diagonal NaN), p == 1 the gradient vector.
- * visited[nb] (may be NULL) = number of splits the traversal examined. */
-int csp_coefficients_p(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited);
+                  double* b, double* g_native, double* y, uint8_t* prec, int32_t* firstmatch, uint8_t* status);
+/* coefficients_p(value, box; skip) (src/polynomials.jl:127-230), dense output Cp[nb*n^p] in the column-major .data layout of the
+ * p-dimensional SymmetricArray (values at sorted index tuples, NaN elsewhere): p == 2 gives the off-diagonal Hessian entries
+ * (diagonal NaN), p == 1 the gradient vector, 3 <= p <= 8 the p-th order mixed coefficients (test/runtests.jl:593-648).
+ * visited[nb] (may be NULL) = number of splits the traversal examined; used[nb] (may be NULL) = number of splits that supplied a
+ * coefficient -- the reference invokes its callback 2^p times for each of them (src/polynomials.jl:222, counts at
+ * test/runtests.jl:652-700). */
+int csp_coefficients_p(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, double* Cp, int64_t* visited,
+                       int64_t* used);
 
 /* Q = coefficients_p(value, box; skip) followed by fit_quadratic_gdiag!(value, Q, box; skip) (src/cs2.jl:332-384): the chain-free
  * fit -- gradient and diagonal from two 1-d difference equations per dimension, b = position(box), c = value(box).  It never
@@ -122,7 +141,7 @@ int csp_fit_gdiag(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int
  * as all of them are; a SymTridiagonal output is the pattern (i, i+1).  vals[nb*npat] in pattern order (NaN where no split supplies
  * the pair).  Requires p == 2. */
 int csp_coefficients_p_sparse(const csp_tree* tree, const int32_t* node_ids, int64_t nb, int32_t skip, int32_t npat,
-                              const int32_t* pat_i, const int32_t* pat_j, double* vals, int64_t* visited);
+                              const int32_t* pat_i, const int32_t* pat_j, double* vals, int64_t* visited, int64_t* used);
 
 /* ---- per-leaf models resident on the device ---------------------------------------------------------------------- */
 /* Fit every leaf and keep the canonical models (c, g, Q, b) on the device for evaluation.  p == 2: fit_quadratic;

@@ -115,7 +115,7 @@ def test_cabi_library_exports_every_declared_symbol():
     L = N.dev()
     for name in declared:
         assert hasattr(L, name), name
-    assert L.csp_version() == 100
+    assert L.csp_version() == 200
 
 
 def test_cabi_fails_loudly_without_device():
