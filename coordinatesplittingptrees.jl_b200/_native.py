@@ -117,6 +117,7 @@ def dev():
         L.csp_tree_pack.argtypes = [C.POINTER(TreeDesc), vp, C.c_size_t]
         L.csp_tree_upload_blob.argtypes = [vp, C.c_size_t, vpp]
         L.csp_tree_info.argtypes = [vp, c_i64p]
+        L.csp_tree_export_derived.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.csp_tree_free.argtypes = [vp]
         L.csp_find_leaf.argtypes = [vp, vp, C.c_int64, vp, vp]
         L.csp_find_leaf_dev.argtypes = [vp, vp, C.c_int64, vp, vp, vp]
@@ -172,7 +173,7 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
            "csp_timing_read", "csp_modelvalue_native", "csp_coefficients_p_sparse",
            "csp_models_possemidef", "csp_fit_gdiag", "csp_models_alloc", "csp_models_refit_range", "csp_models_download_rows",
-           "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
+           "csp_tree_export_derived", "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
            "csp_init", "csp_comm_unique_id", "csp_init_rank", "csp_shutdown", "csp_comm_info", "csp_shard_tree_broadcast",
            "csp_shard_tree_get", "csp_shard_tree_free", "csp_shard_fit", "csp_shard_models_get", "csp_shard_models_free",
            "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]

@@ -111,7 +111,7 @@ int need_init() {
     if (!G.init) return csp_set_error(CSP_ERR_INVALID, "call csp_init or csp_init_rank first");
     return CSP_OK;
 }
-cudaStream_t stream_of(void* const* streams, size_t i) { return streams && streams[i] ? (cudaStream_t)streams[i] : G.local[i].st; }
+cudaStream_t stream_of(void* const* streams, size_t i) { return streams ? (cudaStream_t)streams[i] : G.local[i].st; }
 void tbegin(int k, cudaStream_t st) { DeviceGuard g(G.local[0].device); cudaEventRecord(G.tev[k][0], st); }
 void tend(int k, cudaStream_t st) { DeviceGuard g(G.local[0].device); cudaEventRecord(G.tev[k][1], st); G.tset[k] = true; }
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }

@@ -198,6 +198,23 @@ static int validate_desc(const csp_tree_desc* d) {
     return CSP_OK;
 }
 
+// tree_build.cu
+struct RawTree {
+    int n, p, nn, ni, nl;
+    const double *lower, *upper;
+    const int* parent;
+    const uint8_t* childindex;
+    const int* internal_id;
+    const int* leaf_id;
+    const double* val;
+    const int* inode;
+    const int* dims;
+    const double* xs;
+    const int* child;
+    const double* pos;
+};
+int csp_tree_build_device(csp_tree* t, const RawTree& r);
+
 template <class T>
 static int to_device(csp_tree* t, const std::vector<T>& h, const T** out) {
     void* p = nullptr;
@@ -359,6 +376,57 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
     return CSP_OK;
 }
 
+// Host-side construction of the derived arrays (upload_impl above): kept for A/B checks of the device builder only
+// (CSP_UPLOAD_HOST=1; tests/test_gpu_parity.py compares the two bit for bit).
+static bool host_builder() { return getenv("CSP_UPLOAD_HOST") && atoi(getenv("CSP_UPLOAD_HOST")); }
+
+static csp_tree* new_tree() {
+    csp_tree* t = new csp_tree();
+    t->device = csp_current_device();
+    int sms = 0;  // (cudaGetDeviceProperties costs milliseconds per call)
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device) == cudaSuccess) t->n_sm = sms;
+    return t;
+}
+
+static int check_header(int n, int p, int nn, int ni, int nl) {
+    if (n < 1) return csp_set_error(CSP_ERR_INVALID, "n must be >= 1 (got %d)", n);
+    if (n > CSP_MAX_DIM) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d exceeds the supported maximum %d", n, CSP_MAX_DIM);
+    if (p < 1 || p > 8) return csp_set_error(CSP_ERR_UNSUPPORTED, "degree p=%d is outside 1..8 (reference src/types.jl:194-201)", p);
+    if (p == 1 && ni >= (1 << 24)) return csp_set_error(CSP_ERR_UNSUPPORTED, "CS1 trees are limited to 2^24 splits by the 16-byte descent record");
+    if (nn < 1 || ni < 0 || nl < 1 || ni >= nn) return csp_set_error(CSP_ERR_INVALID, "inconsistent counts: nodes=%d internal=%d leaves=%d", nn, ni, nl);
+    if ((long long)nn != 1 + (long long)ni * (1 << p))
+        return csp_set_error(CSP_ERR_INVALID, "n_nodes=%d is not 1 + n_internal*2^p = %lld", nn, 1 + (long long)ni * (1 << p));
+    return CSP_OK;
+}
+
+// The tree owns one device buffer in the blob layout; `fill` puts the description into it; the rest is derived on the device.
+template <class Fill>
+static int upload_device(int n, int p, int nn, int ni, int nl, Fill&& fill, csp_tree** out) {
+    CSP_CHECK(check_header(n, p, nn, ni, nl));
+    csp_tree* t = new_tree();
+    DeviceGuard g(t->device);
+    Section s[12];
+    const size_t need = blob_layout(n, p, nn, ni, s);
+    void* dblob = nullptr;
+    int rc = csp_dev_alloc(&dblob, need);
+    if (rc == CSP_OK) {
+        t->allocs.push_back(dblob);
+        t->bytes += need;
+        rc = fill((char*)dblob, s, need);
+    }
+    if (rc == CSP_OK) {
+        const char* b = (const char*)dblob;
+        RawTree r{n, p, nn, ni, nl,
+                  (const double*)(b + s[0].off), (const double*)(b + s[1].off), (const int*)(b + s[2].off), (const uint8_t*)(b + s[3].off),
+                  (const int*)(b + s[4].off), (const int*)(b + s[5].off), (const double*)(b + s[6].off), (const int*)(b + s[7].off),
+                  (const int*)(b + s[8].off), (const double*)(b + s[9].off), (const int*)(b + s[10].off), (const double*)(b + s[11].off)};
+        rc = csp_tree_build_device(t, r);
+    }
+    if (rc != CSP_OK) { csp_tree_free(t); return rc; }
+    *out = t;
+    return CSP_OK;
+}
+
 extern "C" {
 
 int csp_tree_free(csp_tree* tree) {
@@ -382,17 +450,30 @@ int csp_tree_free(csp_tree* tree) {
 int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out) {
     if (!out) return csp_set_error(CSP_ERR_INVALID, "out is NULL");
     *out = nullptr;
-    CSP_CHECK(validate_desc(desc));
+    if (!desc) return csp_set_error(CSP_ERR_INVALID, "desc is NULL");
     CSP_CHECK(csp_require_device());
-    csp_tree* t = new csp_tree();
-    t->device = csp_current_device();
-    DeviceGuard g(t->device);
-    int sms = 0;  // (cudaGetDeviceProperties costs milliseconds per call)
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device) == cudaSuccess) t->n_sm = sms;
-    int rc = upload_impl(desc, t);
-    if (rc != CSP_OK) { csp_tree_free(t); return rc; }
-    *out = t;
-    return CSP_OK;
+    if (host_builder()) {
+        CSP_CHECK(validate_desc(desc));
+        csp_tree* t = new_tree();
+        DeviceGuard g(t->device);
+        int rc = upload_impl(desc, t);
+        if (rc != CSP_OK) { csp_tree_free(t); return rc; }
+        *out = t;
+        return CSP_OK;
+    }
+    const csp_tree_desc* d = desc;
+    const void* ptrs[] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val};
+    for (const void* q : ptrs)
+        if (!q) return csp_set_error(CSP_ERR_INVALID, "a per-node array of the tree descriptor is NULL");
+    if (d->n_internal > 0 && (!d->inode || !d->dims || !d->xs || !d->child || !d->pos))
+        return csp_set_error(CSP_ERR_INVALID, "a per-internal-node array of the tree descriptor is NULL");
+    return upload_device(d->n, d->p, d->n_nodes, d->n_internal, d->n_leaves, [&](char* dblob, const Section* s, size_t) -> int {
+        const void* src[12] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val,
+                               d->inode, d->dims, d->xs, d->child, d->pos};
+        for (int i = 0; i < 12; ++i)
+            if (s[i].bytes) CSP_CUDA(cudaMemcpyAsync(dblob + s[i].off, src[i], s[i].bytes, cudaMemcpyHostToDevice, 0));
+        return CSP_OK;
+    }, out);
 }
 
 int csp_tree_blob_size(const csp_tree_desc* d, size_t* bytes) {
@@ -422,39 +503,63 @@ int csp_tree_pack(const csp_tree_desc* d, void* blob, size_t bytes) {
 
 int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out) {
     if (!blob || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    *out = nullptr;
     if (bytes < sizeof(BlobHeader)) return csp_set_error(CSP_ERR_INVALID, "blob shorter than its header");
     CSP_CHECK(csp_require_device());
-    std::vector<char> host;
-    const char* base = (const char*)blob;
     cudaPointerAttributes attr{};
-    if (cudaPointerGetAttributes(&attr, blob) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
-        host.resize(bytes);  // e.g. the buffer an NCCL broadcast landed in
-        CSP_CUDA(cudaMemcpy(host.data(), blob, bytes, cudaMemcpyDeviceToHost));
-        base = host.data();
-    } else {
-        cudaGetLastError();
-    }
+    const bool on_device = cudaPointerGetAttributes(&attr, blob) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
     BlobHeader h;
-    memcpy(&h, base, sizeof h);
+    if (on_device) CSP_CUDA(cudaMemcpy(&h, blob, sizeof h, cudaMemcpyDeviceToHost));  // e.g. the buffer an NCCL broadcast landed in
+    else memcpy(&h, blob, sizeof h);
     if (memcmp(h.magic, "CSPB200", 8) != 0 || h.version != 1) return csp_set_error(CSP_ERR_INVALID, "not a CSPB200 v1 blob");
+    CSP_CHECK(check_header(h.n, h.p, h.n_nodes, h.n_internal, h.n_leaves));
     Section s[12];
-    size_t need = blob_layout(h.n, h.p, h.n_nodes, h.n_internal, s);
+    const size_t need = blob_layout(h.n, h.p, h.n_nodes, h.n_internal, s);
     if (bytes < need) return csp_set_error(CSP_ERR_INVALID, "blob truncated: %zu < %zu", bytes, need);
-    csp_tree_desc d{};
-    d.n = h.n; d.p = h.p; d.n_nodes = h.n_nodes; d.n_internal = h.n_internal; d.n_leaves = h.n_leaves;
-    d.lower = (const double*)(base + s[0].off);
-    d.upper = (const double*)(base + s[1].off);
-    d.parent = (const int32_t*)(base + s[2].off);
-    d.childindex = (const uint8_t*)(base + s[3].off);
-    d.internal_id = (const int32_t*)(base + s[4].off);
-    d.leaf_id = (const int32_t*)(base + s[5].off);
-    d.val = (const double*)(base + s[6].off);
-    d.inode = (const int32_t*)(base + s[7].off);
-    d.dims = (const int32_t*)(base + s[8].off);
-    d.xs = (const double*)(base + s[9].off);
-    d.child = (const int32_t*)(base + s[10].off);
-    d.pos = (const double*)(base + s[11].off);
-    return csp_tree_upload(&d, out);
+    if (host_builder()) {
+        std::vector<char> host;
+        const char* base = (const char*)blob;
+        if (on_device) {
+            host.resize(need);
+            CSP_CUDA(cudaMemcpy(host.data(), blob, need, cudaMemcpyDeviceToHost));
+            base = host.data();
+        }
+        csp_tree_desc d{};
+        d.n = h.n; d.p = h.p; d.n_nodes = h.n_nodes; d.n_internal = h.n_internal; d.n_leaves = h.n_leaves;
+        d.lower = (const double*)(base + s[0].off); d.upper = (const double*)(base + s[1].off);
+        d.parent = (const int32_t*)(base + s[2].off); d.childindex = (const uint8_t*)(base + s[3].off);
+        d.internal_id = (const int32_t*)(base + s[4].off); d.leaf_id = (const int32_t*)(base + s[5].off);
+        d.val = (const double*)(base + s[6].off); d.inode = (const int32_t*)(base + s[7].off);
+        d.dims = (const int32_t*)(base + s[8].off); d.xs = (const double*)(base + s[9].off);
+        d.child = (const int32_t*)(base + s[10].off); d.pos = (const double*)(base + s[11].off);
+        return csp_tree_upload(&d, out);
+    }
+    // one copy of the blob (device-to-device when it already is on a GPU: no host bounce), everything else derived on the device
+    return upload_device(h.n, h.p, h.n_nodes, h.n_internal, h.n_leaves, [&](char* dblob, const Section*, size_t nbytes) -> int {
+        CSP_CUDA(cudaMemcpyAsync(dblob, blob, nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, 0));
+        return CSP_OK;
+    }, out);
+}
+
+// Diagnostic: a derived device array back on the host, so that tests can compare the device builder with the host builder.
+// which: 0 ninfo, 1 drec, 2 dleaf, 3 ixself, 4 icval, 5 lnode, 6 lpoff, 7 lpath, 8 fit_units.  *bytes = size of the array.
+int csp_tree_export_derived(const csp_tree* t, int which, void* out, size_t cap, size_t* bytes) {
+    if (!t || !bytes) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
+    const TreeView& v = t->v;
+    const size_t C = size_t(1) << v.p, ni = v.n_internal, nl = v.n_leaves;
+    long long ptotal = 0;
+    DeviceGuard g(t->device);
+    CSP_CUDA(cudaMemcpy(&ptotal, v.lpoff + nl, 8, cudaMemcpyDeviceToHost));
+    const void* src[9] = {v.ninfo, v.drec, v.dleaf, v.ixself, v.icval, v.lnode, v.lpoff, v.lpath, t->fit_units};
+    const size_t sz[9] = {(size_t)v.n_nodes * 16, v.p == 2 ? ni * sizeof(DRec2) : (v.p == 1 ? ni * sizeof(DRec1) : 0), (ni * (C - 1) + 1) * 4,
+                          ni * v.p * 8, ni * C * 8, nl * 4, (nl + 1) * 8, (size_t)ptotal * 8, (size_t)t->n_fit_units * 16};
+    if (which < 0 || which > 8) return csp_set_error(CSP_ERR_INVALID, "which out of range");
+    *bytes = sz[which];
+    if (!out) return CSP_OK;
+    if (cap < sz[which]) return csp_set_error(CSP_ERR_INVALID, "buffer too small: %zu < %zu", cap, sz[which]);
+    if (sz[which]) CSP_CUDA(cudaMemcpy(out, src[which], sz[which], cudaMemcpyDeviceToHost));
+    return CSP_OK;
 }
 
 int csp_tree_info(const csp_tree* t, int64_t info[8]) {

@@ -115,6 +115,15 @@ class DeviceTree:
         N.dchk(L.csp_tree_info(h, info))
         self.n, self.p, self.n_nodes, self.n_internal, self.n_leaves, self.device, self.max_depth, self.kib = [int(v) for v in info]
 
+    def export_derived(self, which):
+        """Diagnostic (csp_tree_export_derived): one of the device-derived arrays as raw bytes (numpy uint8)."""
+        sz = C.c_size_t()
+        N.dchk(N.dev().csp_tree_export_derived(self.h, int(which), None, 0, C.byref(sz)))
+        out = np.zeros(sz.value, np.uint8)
+        if sz.value:
+            N.dchk(N.dev().csp_tree_export_derived(self.h, int(which), out.ctypes.data, sz.value, C.byref(sz)))
+        return out
+
     def close(self):
         if self.h:
             N.dev().csp_tree_free(self.h)

@@ -88,6 +88,11 @@ int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out);
 int csp_tree_blob_size(const csp_tree_desc* desc, size_t* bytes);
 int csp_tree_pack(const csp_tree_desc* desc, void* blob, size_t bytes);
 int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out);
+/* Diagnostic: one of the arrays the library derives on the device at upload, copied back to the host (tests compare the device
+ * builder with the host-side construction, CSP_UPLOAD_HOST=1).  which: 0 node records, 1 descent records, 2 descent leaf table,
+ * 3 split-box coordinates, 4 child values, 5 leaf nodes, 6 path offsets, 7 ancestor paths, 8 fit units.  *bytes = its size; out may
+ * be NULL to query it. */
+int csp_tree_export_derived(const csp_tree* tree, int which, void* out, size_t cap, size_t* bytes);
 /* info[0..7] = n, p, n_nodes, n_internal, n_leaves, device, max leaf depth, bytes resident (KiB) */
 int csp_tree_info(const csp_tree* tree, int64_t info[8]);
 int csp_tree_free(csp_tree* tree);
@@ -196,8 +201,9 @@ int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q,
  * the calling thread -- what a Julia host uses.  One process per GPU (torchrun): rank 0 obtains 128 bytes from
  * csp_comm_unique_id, hands them to the other ranks by any side channel, and every rank calls csp_init_rank (ncclCommInitRank).
  * Every csp_shard_* call is collective: each process calls it with the same arguments; per-rank arrays (`dX`, `dleaf`, `streams`
- * ...) have one entry per LOCAL rank (ndev in the first mode, 1 in the second).  `streams` may be NULL (library streams) or hold
- * one cudaStream_t per local rank; the call's work, communication included, is ordered on those streams and is asynchronous. */
+ * ...) have one entry per LOCAL rank (ndev in the first mode, 1 in the second).  `streams` may be NULL (the library's own
+ * non-blocking stream per rank) or hold one cudaStream_t per local rank (a NULL entry is that device's default stream, as in the
+ * *_dev calls); the call's work, communication included, is ordered on those streams and is asynchronous. */
 int csp_init(int ndev, const int* devs); /* devs == NULL: devices 0..ndev-1 */
 int csp_comm_unique_id(void* id128);
 int csp_init_rank(int world, int rank, int device, const void* id128);

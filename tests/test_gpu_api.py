@@ -238,3 +238,45 @@ def test_extrema_on_device():
         assert same(vmin, cb.value(bmin)) and same(vmax, cb.value(bmax))
         gmin, gmax = cb.extrema(box)
         assert gmin == bmin and gmax == bmax and cb.minimum(box) == bmin and cb.maximum(box) == bmax
+
+
+DERIVED = ("node records", "descent records", "descent leaf table", "split-box coordinates", "child values", "leaf nodes",
+           "path offsets", "ancestor paths", "fit units")
+
+
+@pytest.mark.parametrize("n,p,npoints", [(1, 1, 30), (2, 1, 200), (3, 2, 0), (2, 2, 150), (5, 2, 90), (10, 2, 400), (7, 3, 20), (40, 1, 25)])
+def test_device_builder_equals_host_builder(n, p, npoints, monkeypatch):
+    """Every array the library derives at upload (tree_build.cu, on the device, straight from the blob sections) equals the
+    host-side construction bit for bit -- from a descriptor, from a host blob and from a device blob (the NCCL broadcast buffer)."""
+    import torch
+    from csp_b200.device import DeviceTree
+    if p == 3:
+        root, _, _ = grow_degree(n, p, npoints, seed=5)
+    else:
+        root, _, _ = grow_both(n, p, npoints, seed=600 + n)
+    flat = root.tree.flat()
+    blob = cb.pack_blob(flat)
+    monkeypatch.setenv("CSP_UPLOAD_HOST", "1")
+    ref = DeviceTree(flat)
+    want = [ref.export_derived(k) for k in range(9)]
+    monkeypatch.delenv("CSP_UPLOAD_HOST")
+    for how in ("desc", "host blob", "device blob"):
+        dt = DeviceTree(flat) if how == "desc" else DeviceTree(blob=blob if how == "host blob" else torch.from_numpy(blob).cuda())
+        assert (dt.n, dt.p, dt.n_nodes, dt.n_internal, dt.n_leaves, dt.max_depth) == (ref.n, ref.p, ref.n_nodes, ref.n_internal, ref.n_leaves, ref.max_depth)
+        for k in range(9):
+            if p > 2 and k in (1, 2):
+                continue  # no packed descent records for p > 2
+            assert np.array_equal(dt.export_derived(k), want[k]), (how, DERIVED[k])
+        dt.close()
+    ref.close()
+
+
+def test_device_builder_rejects_bad_descriptions():
+    from csp_b200.device import DeviceTree
+    root, _, _ = grow_both(4, 2, 30, seed=9)
+    good = root.tree.flat()
+    for key, idx, val in (("parent", 5, 7), ("child", 3, 1), ("internal_id", 0, 3), ("dims", 2, 99), ("leaf_id", 4, 77)):
+        bad = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in good.items()}
+        bad[key][idx] = val
+        with pytest.raises(cb.CspError):
+            DeviceTree(bad)

@@ -85,8 +85,10 @@ def test_c2_all_fits_and_queries_full():
     assert same(leaf.cpu().numpy(), oleaf) and same(status.cpu().numpy(), ostatus)
     e = check_values(val.cpu().numpy(), oval, X, oleaf, mo, ofit["Q"])
     print("C2 value errors:", e)
-    leaf_h, val_h, status_h = dt.locate_eval(models, X[:300_000])  # host-buffer path
-    assert same(leaf_h, oleaf[:300_000]) and same(val_h, val[:300_000].cpu().numpy())
+    k = 300_000  # host-buffer path (a batch this small is evaluated inside the locate kernel: another summation order)
+    leaf_h, val_h, status_h = dt.locate_eval(models, X[:k])
+    assert same(leaf_h, oleaf[:k]) and same(status_h, ostatus[:k])
+    check_values(val_h, oval[:k], X[:k], oleaf[:k], mo, ofit["Q"])
 
 
 def test_c3_all_fits_and_queries_full():
