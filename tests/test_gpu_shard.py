@@ -43,8 +43,11 @@ def test_leaf_range_fits_equal_full_fit(n, npoints, monkeypatch):
         assert same(part[k], full[k][rows]), k
 
 
-def test_single_process_clique_matches_single_gpu():
+def test_single_process_clique_matches_single_gpu(monkeypatch):
     import torch
+    # per-query evaluation inside the locate kernel: the summation order does not depend on how the batch is split, so the
+    # sharded / chunked results can be compared with the one-batch answer bit for bit
+    monkeypatch.setenv("CSP_EVAL_MODE", "direct")
     ndev = min(cb.device_count(), 8)
     root, _, _ = grow_both(8, 2, 400, seed=77)
     dt = cb.device_tree(root)
@@ -109,7 +112,7 @@ def test_multiprocess_clique():
     ndev = min(cb.device_count(), 4)
     if ndev < 2:
         pytest.skip("needs at least two GPUs")
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", CSP_EVAL_MODE="direct")  # batch-split-independent summation order
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ndev}", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.join(ROOT, "tests", "mp_shard_worker.py")], capture_output=True, text=True,
                        env=env, timeout=600)
