@@ -563,18 +563,25 @@ def main():
         Xk = torch.empty((max(rows, 1), n), dtype=torch.float64, device=dev)
         fill_uniform(torch, Xk, 1234 + 131 * rank + k)
         Xres.append(Xk)
-    leaf = torch.empty(max(mine, 1), dtype=torch.int32, device=dev)
-    val = torch.empty(max(mine, 1), dtype=torch.float64, device=dev)
     status = torch.empty(max(mine, 1), dtype=torch.uint8, device=dev)
     gather = world > 1
     leaf_all = torch.empty(M, dtype=torch.int32, device=dev) if (gather and rank == 0) else None
     val_all = torch.empty(M, dtype=torch.float64, device=dev) if (gather and rank == 0) else None
+    inplace = gather and rank == 0   # rank 0 computes straight into its slots of the gathered arrays: no copy of its own part
+    leaf = None if inplace else torch.empty(max(mine, 1), dtype=torch.int32, device=dev)
+    val = None if inplace else torch.empty(max(mine, 1), dtype=torch.float64, device=dev)
     sm = st.fit(streams=[cur])
     torch.cuda.synchronize()
 
     # per call j: every rank processes queries [j*chunk, (j+1)*chunk) of its shard; rank 0 receives them chunk-major
     call_counts = [[max(0, min(chunk, c - j * chunk)) for c in counts] for j in range(ncalls)]
     call_base = [sum(sum(cc) for cc in call_counts[:j]) for j in range(ncalls)]
+
+    def out_slices(j):
+        """(leaf, val) output buffers of call j on this rank."""
+        if inplace:
+            return leaf_all[call_base[j]:], val_all[call_base[j]:]
+        return leaf[j * chunk:], val[j * chunk:]
 
     def locate_all(with_gather):
         for j in range(ncalls):
@@ -584,7 +591,8 @@ def main():
             groot = 0 if (with_gather and gather) else -1
             la = leaf_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             va = val_all[call_base[j]:] if (groot == 0 and rank == 0) else None
-            st.locate_eval_resident(sm, [Xj], cc, [leaf[o:]], [val[o:]], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
+            lj, vj = out_slices(j)
+            st.locate_eval_resident(sm, [Xj], cc, [lj], [vj], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
                                     chunk=args.gather_chunk, streams=[cur])
 
     def step(evs=None, with_gather=True):
@@ -633,17 +641,25 @@ def main():
         a.record()
         for _ in range(nx):
             for j in range(ncalls):
-                o = j * chunk
-                st.gather_resident([leaf[o:]], [val[o:]], call_counts[j], 0, leaf_all[call_base[j]:] if rank == 0 else None,
+                lj, vj = out_slices(j)
+                st.gather_resident([lj], [vj], call_counts[j], 0, leaf_all[call_base[j]:] if rank == 0 else None,
                                    val_all[call_base[j]:] if rank == 0 else None, streams=[cur])
         b.record()
         barrier()
         gather_ms = maxranks([a.elapsed_time(b) / nx])[0]
-    # gathered results equal the per-rank results (rank 0 checks its own slice of every call)
+    # the gathered arrays hold what the owners computed: every rank's checksums of its own results against rank 0's copy
     gather_ok = None
-    if gather and rank == 0:
-        gather_ok = all(bool(torch.equal(leaf_all[call_base[j]: call_base[j] + call_counts[j][0]], leaf[j * chunk: j * chunk + call_counts[j][0]]))
-                        for j in range(ncalls))
+    if gather:
+        lj, vj = out_slices(0)
+        k0 = call_counts[0][rank]
+        mine_ck = torch.stack([lj[:k0].sum(dtype=torch.int64).double(), vj[:k0].nan_to_num().sum()])
+        cks = [torch.zeros_like(mine_ck) for _ in range(world)]
+        dist.all_gather(cks, mine_ck)
+        if rank == 0:
+            offs = np.concatenate([[0], np.cumsum(call_counts[0])])
+            gather_ok = all(bool(torch.equal(torch.stack([leaf_all[offs[r]:offs[r + 1]].sum(dtype=torch.int64).double(),
+                                                          val_all[offs[r]:offs[r + 1]].nan_to_num().sum()]), cks[r])) for r in range(world))
+        lj = vj = None
 
     # ---- instrumented pass: per-kernel device times (rank-local)
     cdev.timing_read()
@@ -655,9 +671,11 @@ def main():
     cdev.timing_enable(False)
     barrier()
 
-    touched = int(torch.unique(leaf[: min(mine, 20_000_000)]).numel()) if mine else 0
+    l0, v0 = out_slices(0)
+    k0 = min(call_counts[0][rank], 20_000_000)
+    touched = int(torch.unique(l0[:k0]).numel()) if k0 else 0
     bad = int((status[:mine] != 0).sum().item())
-    nanvals = int(torch.isnan(val[:mine]).sum().item())
+    nanvals = int(torch.isnan(v0[:call_counts[0][rank]]).sum().item())
 
     # ---- e2e: the same metric through the host-buffer C-ABI call, pinned host memory, copies inside the timed region
     e2e = None
@@ -680,7 +698,7 @@ def main():
                 st.locate_eval(sm, Xn, leaf=ln, val=vn, status=sn)  # csp_shard_locate_eval: returns when the results are in host memory
             torch.cuda.synchronize()
             dt = maxranks([time.perf_counter() - t0e])[0]
-            same = bool(np.array_equal(ln[:100000], leaf[:100000].cpu().numpy()))  # the same queries as the first resident chunk
+            same = bool(np.array_equal(ln[:100000], l0[:100000].cpu().numpy()))  # the same queries as the first resident chunk
             e2e = {"value": world * me * esteps / dt, "unit": "queries/s", "h2d_bytes_per_step": int(world * me * n * 8),
                    "d2h_bytes_per_step": int(world * me * 13), "steps": esteps, "queries_per_step": int(world * me),
                    "queries_per_step_per_gpu": int(me), "matches_resident_path": same,
@@ -693,7 +711,7 @@ def main():
     # ---- secondary: C5 fits sharded over the same GPUs (collective: every rank takes part)
     c5 = None
     if not args.no_secondary:
-        del Xres, leaf_all, val_all
+        del Xres, leaf_all, val_all, l0, v0, leaf, val
         Xres = None
         torch.cuda.empty_cache()
         try:

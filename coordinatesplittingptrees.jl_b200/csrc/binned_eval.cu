@@ -117,6 +117,36 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, l
     }
 }
 
+// The same without atomics: the query's rank inside its leaf's bin came back from the histogram atomic of the descent kernel
+// (slot_of holds it on entry); the sorted position is the bin offset plus that rank.
+__global__ void __launch_bounds__(256) k_scatter_ranked(const int* __restrict__ leaf, long long m, int n_models, const int* __restrict__ off,
+                                                        int2* __restrict__ perm, int* __restrict__ slot_of) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
+        int lf[4], rk[4], o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            lf[u] = q < m ? leaf[q] : -2;
+            rk[u] = q < m ? slot_of[q] : -1;
+            if (lf[u] >= n_models || rk[u] < 0) lf[u] = lf[u] == -2 ? -2 : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) o[u] = lf[u] >= 0 ? __ldg(off + lf[u]) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long q = q0 + u * stride;
+            if (lf[u] >= 0) {
+                const int s = o[u] + rk[u];
+                perm[s] = make_int2((int)q, lf[u]);
+                slot_of[q] = s;
+            } else if (lf[u] == -1) {
+                slot_of[q] = -1;
+            }
+        }
+    }
+}
+
 // values come back from leaf-sorted order to query order: a gather (reads hit L2: the chunk's sorted values were just
 // written) followed by coalesced writes -- instead of scattered 8-byte writes, which cost a sector read-modify-write each
 __global__ void __launch_bounds__(256) k_unpermute(const int* __restrict__ slot_of, const double* __restrict__ vsorted, long long m,
@@ -218,6 +248,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, co
     for (; s0 < end; s0 += 32) {
         const bool valid = ql.y >= 0;
         const int2 qn = s0 + 32 + lane < end ? perm[s0 + 32 + lane] : make_int2(0, -1);
+        if (qn.y >= 0 && (mv.flags & 1)) prefetch_row_l2(X + (size_t)(unsigned)qn.x * N, N * 8);  // the next iteration's gathers then hit L2
         unsigned todo = __ballot_sync(FULL, valid);
         while (todo) {
             const int lf = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
@@ -359,6 +390,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
         const bool valid = ql.y >= 0;
         const long long sn = s + 32;
         const int2 qn = sn < end ? perm[sn] : make_int2(0, -1);  // the next 32 positions, in flight during this iteration
+        if (qn.y >= 0 && (mv.flags & 1)) prefetch_row_l2(X + (size_t)(unsigned)qn.x * N, N * 8);  // ... and their rows on the way to L2
         double x[N + 1];
         if (valid) {
             const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
@@ -510,6 +542,7 @@ struct BinWorkspace {
     double* vsorted = nullptr;  // [m] values in leaf-sorted order
     int* leaf = nullptr;     // [m] when the caller did not ask for leaf ids
     int epoch = 0;
+    bool ranked = false;     // slot already holds each query's rank inside its leaf's bin (returning histogram atomics)
 };
 
 int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w) {
@@ -572,7 +605,8 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * (8 / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_SCATTER, st);
-        k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->cursor, w->perm, w->slot);
+        if (w->ranked) k_scatter_ranked<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->off, w->perm, w->slot);
+        else k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->cursor, w->perm, w->slot);
     }
     CSP_LAUNCHED();
     auto unpermute = [&]() -> int {
@@ -586,7 +620,8 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         CSP_CHECK(csp_dense_eval(mo, n_sm, dX, w->perm, w->off + nl, m, w->vsorted, st));
         return unpermute();
     }
-    ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
+    ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data, 0};
+    if (!(getenv("CSP_EVAL_PREFETCH") && atoi(getenv("CSP_EVAL_PREFETCH")) == 0)) mv.flags |= 1;
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)

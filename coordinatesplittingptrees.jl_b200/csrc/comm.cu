@@ -496,6 +496,10 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
             CSP_CUDA(cudaStreamWaitEvent(cs[i], G.local[i].fork, 0));
         }
     }
+    // NCCL's send / receive kernels need room beside the persistent grids of the pipeline, or they only run between kernels
+    const char* renv = getenv("CSP_GATHER_SM_RESERVE");
+    struct Reserve { ~Reserve() { g_csp_sm_reserve = 0; } } reserve_guard;
+    g_csp_sm_reserve = gather ? (renv ? atoi(renv) : 8) : 0;
     int step = 0;
     for (long long off = 0; off < mx; off += chunk, ++step) {
         for (size_t i = 0; i < nl; ++i) {

@@ -74,6 +74,7 @@ struct ModelsView {
     int n, degree, stride;
     long long n_models;
     const double* data;
+    int flags;  // bit 0: prefetch the next rows into L2 (binned evaluation)
 };
 static inline long long csp_model_len(int n, int degree) {
     return n + (degree == 2 ? (long long)(n + 1) * (n + 2) / 2 : (long long)n + 1);
@@ -145,6 +146,8 @@ void csp_dev_free(void* p);
 enum { CSP_K_LOCATE = 0, CSP_K_LOCATE_EVAL, CSP_K_SCAN, CSP_K_SCATTER, CSP_K_EVAL_BINNED, CSP_K_EVAL, CSP_K_FIT, CSP_K_CLASSES };
 extern bool g_csp_timing;
 extern int g_csp_grid_div;  // >1 while two chunks are in flight on two streams: persistent grids shrink so that both fit on the SMs
+extern int g_csp_sm_reserve;  // SMs' worth of CTAs the persistent grids leave free while NCCL kernels run beside them (comm.cu)
+inline int csp_grid_sms(int n_sm) { return std::max(1, std::max(n_sm, 1) - g_csp_sm_reserve); }
 void csp_timing_begin(int cls, cudaStream_t st);
 void csp_timing_end(cudaStream_t st);
 struct CspTimed {
@@ -199,6 +202,16 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Pull one query row (bytes, any alignment) towards L2 ahead of its use: one bulk prefetch when the row is 16-byte granular
+// (cp.async.bulk.prefetch.L2, SASS UBLKPF), else one prefetch per 32-byte sector it touches.
+__device__ __forceinline__ void prefetch_row_l2(const double* row, int bytes) {
+    const unsigned long long a = (unsigned long long)row;
+    if (((a | (unsigned)bytes) & 15u) == 0) {
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(bytes) : "memory");
+    } else {
+        for (unsigned long long q = a & ~31ull; q < a + bytes; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- splits(box) (reference src/tree.jl:461-540) as preorder range scans, any degree p ------------------------------

@@ -388,10 +388,13 @@ __global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) 
 }
 
 // per-leaf histogram for the evaluate-only entry point (leaf ids supplied by the caller)
-__global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long long m, long long n_models, int* __restrict__ cnt) {
+__global__ void __launch_bounds__(256) k_hist(const int* __restrict__ leaf, long long m, long long n_models, int* __restrict__ cnt,
+                                              int* __restrict__ rank) {
     for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < m; q += (long long)gridDim.x * blockDim.x) {
         const int lf = leaf[q];
-        if (lf >= 0 && lf < n_models) atomicAdd(cnt + lf, 1);
+        const bool ok = lf >= 0 && lf < n_models;
+        if (rank) rank[q] = ok ? atomicAdd(cnt + lf, 1) : -1;
+        else if (ok) atomicAdd(cnt + lf, 1);
     }
 }
 
@@ -471,9 +474,9 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
     }
 }
 
-int csp_hist_launch(const int* dleaf, long long m, long long n_models, int* cnt, int n_sm, cudaStream_t st) {
+int csp_hist_launch(const int* dleaf, long long m, long long n_models, int* cnt, int* rank, int n_sm, cudaStream_t st) {
     const long long blocks = std::min<long long>((m + 255) / 256, (long long)std::max(n_sm, 1) * 8);
-    k_hist<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, st>>>(dleaf, m, n_models, cnt);
+    k_hist<<<(unsigned)std::max<long long>(blocks, 1), 256, 0, st>>>(dleaf, m, n_models, cnt, rank);
     CSP_LAUNCHED();
     CSP_CUDA(cudaGetLastError());
     return CSP_OK;

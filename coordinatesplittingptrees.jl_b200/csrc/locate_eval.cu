@@ -30,6 +30,7 @@ struct LocateParams {
     int bulk;         // X is 16-byte aligned: TMA bulk copies allowed
     int top;          // number of BFS-first descent records staged in shared memory
     int* hist;        // optional: per-leaf query counts (binned evaluation, binned_eval.cu)
+    int* rank;        // optional, with hist: the count the query found (its rank inside its leaf's bin), -1 outside the world
 };
 
 __device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -274,7 +275,8 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
             if (ok) lf = descend<P>(prm.t, xr, 1, s_top, prm.top);
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+            if (prm.rank) prm.rank[q] = lf >= 0 ? atomicAdd(prm.hist + lf, 1) : -1;  // returning: the scatter needs no atomics
+            else if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
         if constexpr (EVAL) {
             __syncwarp();
@@ -306,6 +308,7 @@ struct LocateOnlyParams {
     int* leaf;
     uint8_t* status;
     int* hist;
+    int* rank;
     int tile, bulk, top, bounds_in_params;
     double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
 };
@@ -394,7 +397,8 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
             const long long q = tl * tile + tid;
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+            if (prm.rank) prm.rank[q] = lf >= 0 ? atomicAdd(prm.hist + lf, 1) : -1;  // returning: the scatter needs no atomics
+            else if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
         // xT is private per thread column: no barrier needed before the next tile's transpose
     }
@@ -459,7 +463,8 @@ __global__ void __launch_bounds__(256) k_locate_wide(const __grid_constant__ Loc
             const long long q = q0 + lane;
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
-            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+            if (prm.rank) prm.rank[q] = lf >= 0 ? atomicAdd(prm.hist + lf, 1) : -1;
+            else if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
         }
     }
 }
@@ -540,7 +545,7 @@ static int launch_locate_t(const csp_tree* t, LocateParams& prm, cudaStream_t st
     }
     prm.tile = g->tile; prm.stages = g->stages; prm.top = g->top;
     long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
-    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * g->occ);
+    long long grid = std::min<long long>(ntiles, (long long)csp_grid_sms(t->n_sm) * g->occ);
     {
         CspTimed tm(EG >= 0 ? CSP_K_LOCATE_EVAL : CSP_K_LOCATE, st);
         kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
@@ -572,10 +577,10 @@ static int launch_locate_wide(const csp_tree* t, const LocateParams& lp, cudaStr
         g = &t->geo.back().second;
     }
     LocateOnlyParams prm{};
-    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist; prm.rank = lp.rank;
     prm.tile = 256; prm.bulk = lp.bulk; prm.top = g->top;
     const long long nbatch = (prm.m + 31) / 32;
-    const long long grid = std::min<long long>((nbatch + 7) / 8, (long long)std::max(t->n_sm, 1) * std::max(1, g->occ / g_csp_grid_div));
+    const long long grid = std::min<long long>((nbatch + 7) / 8, (long long)csp_grid_sms(t->n_sm) * std::max(1, g->occ / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_LOCATE, st);
         kern<<<(unsigned)grid, 256, g->smem, st>>>(prm);
@@ -631,13 +636,13 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
         g = &t->geo.back().second;
     }
     LocateOnlyParams prm{};
-    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist; prm.rank = lp.rank;
     prm.tile = g->tile; prm.bulk = lp.bulk; prm.top = g->top;
     prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
     if (prm.bounds_in_params)
         for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
     long long ntiles = (prm.m + prm.tile - 1) / prm.tile;
-    long long grid = std::min<long long>(ntiles, (long long)std::max(t->n_sm, 1) * std::max(1, g->occ / g_csp_grid_div));
+    long long grid = std::min<long long>(ntiles, (long long)csp_grid_sms(t->n_sm) * std::max(1, g->occ / g_csp_grid_div));
     {
         CspTimed tm(CSP_K_LOCATE, st);
         kern<<<(unsigned)grid, prm.tile, g->smem, st>>>(prm);
@@ -668,6 +673,7 @@ struct BinWorkspace {
     double* vsorted = nullptr;
     int* leaf = nullptr;
     int epoch = 0;
+    bool ranked = false;
 };
 int csp_bin_alloc(int nl, long long m, bool need_leaf, cudaStream_t st, BinWorkspace* w);
 int csp_bin_alloc_sync(int nl, long long m, BinWorkspace* w);
@@ -676,7 +682,7 @@ void csp_bin_free(BinWorkspace* w, cudaStream_t st);
 int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long m, const int* dleaf, double* dval, BinWorkspace* w,
                     cudaStream_t st);
 bool csp_dense_supported(const csp_models* mo);  // dense_eval.cu
-int csp_hist_launch(const int* dleaf, long long m, long long n_models, int* cnt, int n_sm, cudaStream_t st);
+int csp_hist_launch(const int* dleaf, long long m, long long n_models, int* cnt, int* rank, int n_sm, cudaStream_t st);
 
 // Evaluation strategy: with many queries per leaf, bin the located queries by leaf and evaluate model-stationary
 // (binned_eval.cu); otherwise evaluate inside the locate kernel, fetching each query's model record.
@@ -756,8 +762,12 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             cp.status = dstatus ? dstatus + off : nullptr;
             cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
             cp.hist = w[k].cnt;
+            // ranks from K1's (returning) histogram atomics: the scatter then only adds the bin offset (CSP_BIN_RANKED=0: a
+            // second round of atomics in the scatter instead)
+            w[k].ranked = !(getenv("CSP_BIN_RANKED") && atoi(getenv("CSP_BIN_RANKED")) == 0);
+            cp.rank = w[k].ranked ? w[k].slot : nullptr;
             rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
-            if (rc == CSP_OK) rc = csp_binned_eval(mo, t->n_sm, cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
+            if (rc == CSP_OK) rc = csp_binned_eval(mo, csp_grid_sms(t->n_sm), cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
         }
         g_csp_grid_div = 1;
         if (preset) preset->epoch = w[0].epoch;
@@ -840,7 +850,8 @@ int csp_eval_dev(const csp_models* mo, const double* dX, const int32_t* dleaf, i
         cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, mo->device);
         BinWorkspace w;
         int rc = csp_bin_alloc((int)mo->n_models, m, false, st, &w);
-        if (rc == CSP_OK) rc = csp_hist_launch(dleaf, m, mo->n_models, w.cnt, nsm, st);
+        w.ranked = true;
+        if (rc == CSP_OK) rc = csp_hist_launch(dleaf, m, mo->n_models, w.cnt, w.slot, nsm, st);
         if (rc == CSP_OK) rc = csp_binned_eval(mo, nsm, dX, m, dleaf, dval, &w, st);
         csp_bin_free(&w, st);
         return rc;

@@ -74,6 +74,7 @@ int csp_require_device() {
 
 bool g_csp_timing = false;
 int g_csp_grid_div = 1;
+int g_csp_sm_reserve = 0;
 namespace {
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 std::vector<TimedLaunch> g_timed;
@@ -552,7 +553,7 @@ int csp_tree_export_derived(const csp_tree* t, int which, void* out, size_t cap,
     DeviceGuard g(t->device);
     CSP_CUDA(cudaMemcpy(&ptotal, v.lpoff + nl, 8, cudaMemcpyDeviceToHost));
     const void* src[9] = {v.ninfo, v.drec, v.dleaf, v.ixself, v.icval, v.lnode, v.lpoff, v.lpath, t->fit_units};
-    const size_t sz[9] = {(size_t)v.n_nodes * 16, v.p == 2 ? ni * sizeof(DRec2) : (v.p == 1 ? ni * sizeof(DRec1) : 0), (ni * (C - 1) + 1) * 4,
+    const size_t sz[9] = {(size_t)v.n_nodes * 16, v.p == 2 ? ni * sizeof(DRec2) : (v.p == 1 ? ni * sizeof(DRec1) : 0), (v.p <= 2 ? ni * (C - 1) + 1 : 1) * 4,
                           ni * v.p * 8, ni * C * 8, nl * 4, (nl + 1) * 8, (size_t)ptotal * 8, (size_t)t->n_fit_units * 16};
     if (which < 0 || which > 8) return csp_set_error(CSP_ERR_INVALID, "which out of range");
     *bytes = sz[which];
