@@ -154,3 +154,13 @@ def test_blob_file_roundtrip(tmp_path):
     assert np.array_equal(blob, cb.pack_blob(flat))
     hdr = np.frombuffer(blob[:32].tobytes(), dtype=np.int32)
     assert [int(v) for v in hdr[3:8]] == [flat["n"], flat["p"], flat["n_nodes"], flat["n_internal"], flat["n_leaves"]]
+
+
+def test_julia_binding_covers_every_export():
+    """julia/CSpB200.jl (the reference-side binding; not executable here, Julia is absent) binds every entry point the header
+    declares and nothing the header does not."""
+    hdr = open(os.path.join(ROOT, "include", "csp_b200.h")).read()
+    declared = set(re.findall(r"\b(csp_[a-z_0-9]+)\s*\(", hdr))
+    jl = open(os.path.join(ROOT, "julia", "CSpB200.jl")).read()
+    bound = set(re.findall(r"\(:(csp_[a-z_0-9]+), LIB\)", jl))
+    assert bound == declared, bound ^ declared
