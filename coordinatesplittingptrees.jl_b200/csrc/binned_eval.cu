@@ -220,35 +220,73 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
 // and are re-read from the staged record (same double-buffered cp.async slots as below) only when the leaf changes.
 // W = Z U, then the row dot with z (re-read from L1) and a quad reduction.  A group that straddles two leaves is computed
 // once per leaf with the other rows masked at the store.
+// Row stride (doubles) of the staged x rows: 16-byte granular (TMA destination) and (stride in words) mod 32 in {8, 24}, so that the
+// 16 lanes of a half-warp -- 4 rows x 4 consecutive doubles -- read 16 distinct bank pairs when the A fragments are loaded.
+__host__ __device__ constexpr int mma_row_stride(int n) {
+    int rs = n;  // even
+    while (((2 * rs) % 32) != 8 && ((2 * rs) % 32) != 24) rs += 2;
+    return rs;
+}
+
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, const double* __restrict__ X,
                                                         const int2* __restrict__ perm, const int* __restrict__ total,
                                                         double* __restrict__ val) {
     static_assert((N & 1) == 0 && N >= 2 && N <= 30, "even n only");
     constexpr int NP = (N + 1 + 7) / 8 * 8, KS = NP / 4, NT = NP / 8;
-    extern __shared__ __align__(16) double s_rec[];  // [warps][2][stride]
+    constexpr int RS = mma_row_stride(N);
+    extern __shared__ __align__(16) double s_rec[];  // per warp: [2][stride] records, [2][32][RS] staged rows; then [warps][2] mbarriers
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, stride = mv.stride;
+    const int lane = threadIdx.x & 31, stride = mv.stride, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
     const int r = lane >> 2, t = lane & 3;
-    double* slot = s_rec + (size_t)(threadIdx.x >> 5) * 2 * stride;
+    const size_t per_warp = (size_t)2 * stride + (size_t)2 * 32 * RS;
+    double* slot = s_rec + (size_t)wib * per_warp;
+    double* rows = slot + (size_t)2 * stride;
+    uint64_t* bars = (uint64_t*)(s_rec + (size_t)nwb * per_warp) + 2 * wib;
     const long long tot = *total;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long per = ((tot + 31) / 32 + nwarps - 1) / nwarps * 32;
     const long long start = wid * per, end = start + per < tot ? start + per : tot;
     if (start >= end) return;
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     auto fetch = [&](int lf, int b) {
         const double* __restrict__ M = mv.data + (size_t)lf * stride;
         double* dst = slot + (size_t)b * stride;
         for (int k = lane * 2; k < stride; k += 64) cp_async16(dst + k, M + k);
     };
+    // x rows of 32 sorted positions -> stage st: one TMA bulk copy per row (each lane gathers its own), all completing on the
+    // stage's mbarrier; issued one iteration ahead, so the gather latency (DRAM: these rows are scattered over the whole chunk)
+    // is covered by the previous iteration's tensor-core work instead of stalling it
+    auto stage_rows = [&](const int2& q, int st) {
+        const bool v = q.y >= 0;
+        const unsigned vm = __ballot_sync(FULL, v);
+        if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(__popc(vm) * N * 8));
+        __syncwarp();
+        if (v) {
+            fence_proxy_async();
+            bulk_g2s(rows + ((size_t)st * 32 + lane) * RS, X + (size_t)(unsigned)q.x * N, N * 8, &bars[st]);
+        }
+    };
     int cur = 0, staged = -1, pre = -1;
     double uf[KS][NT], bA[KS], bE[NT][2];  // per-leaf fragments (registers)
     long long s0 = start;
     int2 ql = s0 + lane < end ? perm[s0 + lane] : make_int2(0, -1);
-    for (; s0 < end; s0 += 32) {
+    int2 qn = s0 + 32 + lane < end ? perm[s0 + 32 + lane] : make_int2(0, -1);
+    stage_rows(ql, 0);
+    uint32_t ph0 = 0, ph1 = 0;
+    int cs = 0;
+    for (; s0 < end; s0 += 32, cs ^= 1) {
         const bool valid = ql.y >= 0;
-        const int2 qn = s0 + 32 + lane < end ? perm[s0 + 32 + lane] : make_int2(0, -1);
-        if (qn.y >= 0 && (mv.flags & 1)) prefetch_row_l2(X + (size_t)(unsigned)qn.x * N, N * 8);  // the next iteration's gathers then hit L2
+        if (s0 + 32 < end) stage_rows(qn, cs ^ 1);  // the next iteration's rows start moving now
+        const int2 qnn = s0 + 64 + lane < end ? perm[s0 + 64 + lane] : make_int2(0, -1);  // and the one after's perm entries
+        if (cs == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1; }
+        else { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+        const double* crow = rows + (size_t)cs * 32 * RS;
         unsigned todo = __ballot_sync(FULL, valid);
         while (todo) {
             const int lf = __shfl_sync(FULL, ql.y, __ffs(todo) - 1);
@@ -299,61 +337,47 @@ __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, co
                     pre = nl;
                 }
             }
-            // groups in batches: all the global loads of a batch are issued before its first MMA
-            constexpr int GB = KS <= 4 ? 4 : 2;
 #pragma unroll
-            for (int g0 = 0; g0 < 4; g0 += GB) {
-                double a[GB][KS];
-                const double* xps[GB];
-                bool rm[GB];
+            for (int g = 0; g < 4; ++g) {
+                if (!((minemask >> (8 * g)) & 0xffu)) continue;  // warp-uniform: no row of this group belongs to lf
+                const bool rm = (minemask >> (8 * g + r)) & 1u;
+                const double* srow = crow + (size_t)(8 * g + r) * RS;
+                double a[KS];
 #pragma unroll
-                for (int gg = 0; gg < GB; ++gg) {
-                    const int g = g0 + gg;
-                    const int rq = __shfl_sync(FULL, ql.x, 8 * g + r);
-                    rm[gg] = (minemask >> (8 * g + r)) & 1u;
-                    xps[gg] = X + (size_t)(unsigned)rq * N;
-#pragma unroll
-                    for (int ks = 0; ks < KS; ++ks) {
-                        const int k = 4 * ks + t;
-                        double v = 0.0;
-                        if (k < N) { if (rm[gg]) v = __ldg(xps[gg] + k); }
-                        else if (k == N) v = 1.0;
-                        a[gg][ks] = v;
-                    }
+                for (int ks = 0; ks < KS; ++ks) {
+                    const int k = 4 * ks + t;
+                    double v = 0.0;
+                    if (k < N) { if (rm) v = srow[k] - bA[ks]; }
+                    else if (k == N) v = 1.0;
+                    a[ks] = v;
                 }
+                double w[NT][2];
 #pragma unroll
-                for (int gg = 0; gg < GB; ++gg) {
-                    const int g = g0 + gg;
-                    if (!((minemask >> (8 * g)) & 0xffu)) continue;  // warp-uniform: no row of this group belongs to lf
+                for (int J = 0; J < NT; ++J) { w[J][0] = 0.0; w[J][1] = 0.0; }
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-                        if (4 * ks + t < N && rm[gg]) a[gg][ks] -= bA[ks];
-                    double w[NT][2];
+                for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
-                    for (int J = 0; J < NT; ++J) { w[J][0] = 0.0; w[J][1] = 0.0; }
+                    for (int J = ks / 2; J < NT; ++J) dmma884(w[J][0], w[J][1], a[ks], uf[ks][J]);
+                double dot = 0.0;
 #pragma unroll
-                    for (int ks = 0; ks < KS; ++ks)
-#pragma unroll
-                        for (int J = ks / 2; J < NT; ++J) dmma884(w[J][0], w[J][1], a[gg][ks], uf[ks][J]);
-                    double dot = 0.0;
-#pragma unroll
-                    for (int J = 0; J < NT; ++J) {
-                        const int col = 8 * J + 2 * t;
-                        double z0 = 0.0, z1 = 0.0;
-                        if (col + 1 < N) {
-                            if (rm[gg]) { const double2 xv = __ldg((const double2*)(xps[gg] + col)); z0 = xv.x - bE[J][0]; z1 = xv.y - bE[J][1]; }
-                        } else if (col == N) {
-                            z0 = 1.0;
-                        }
-                        dot = fma(w[J][0], z0, fma(w[J][1], z1, dot));
+                for (int J = 0; J < NT; ++J) {
+                    const int col = 8 * J + 2 * t;
+                    double z0 = 0.0, z1 = 0.0;
+                    if (col + 1 < N) {
+                        if (rm) { const double2 xv = *(const double2*)(srow + col); z0 = xv.x - bE[J][0]; z1 = xv.y - bE[J][1]; }
+                    } else if (col == N) {
+                        z0 = 1.0;
                     }
-                    dot += __shfl_xor_sync(FULL, dot, 1);
-                    dot += __shfl_xor_sync(FULL, dot, 2);
-                    if (t == 0 && rm[gg]) val[s0 + 8 * g + r] = dot;
+                    dot = fma(w[J][0], z0, fma(w[J][1], z1, dot));
                 }
+                dot += __shfl_xor_sync(FULL, dot, 1);
+                dot += __shfl_xor_sync(FULL, dot, 2);
+                if (t == 0 && rm) val[s0 + 8 * g + r] = dot;
             }
         }
+        __syncwarp();  // every lane is done with stage cs before the next iteration refills it
         ql = qn;
+        qn = qnn;
     }
     cp_async_wait_all();
 }
@@ -621,7 +645,9 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         return unpermute();
     }
     ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data, 0};
-    if (!(getenv("CSP_EVAL_PREFETCH") && atoi(getenv("CSP_EVAL_PREFETCH")) == 0)) mv.flags |= 1;
+    // CSP_EVAL_PREFETCH=1: bulk L2 prefetch of the next iteration's rows.  Measured per 1e8 queries: n=20 7.51 -> 7.21 ms, n=10 4.06 ->
+    // 4.64 ms (the FMA kernel is already DRAM-bound; extra requests only queue).  Off by default.
+    if (getenv("CSP_EVAL_PREFETCH") && atoi(getenv("CSP_EVAL_PREFETCH")) == 1) mv.flags |= 1;
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)
@@ -639,12 +665,27 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         const bool mma = !(getenv("CSP_EVAL_MMA") && atoi(getenv("CSP_EVAL_MMA")) == 0);
         // FP64 tensor cores from n = 16 up (measured, 1e8 queries: n = 20 10.4 -> 7.5 ms; n = 10 4.0 -> 7.7 ms: too little MMA work
         // per 8-row group to pay for the fragment bookkeeping, so small n keeps the FMA kernel)
-        switch (mma ? n : -1) {
-            case 16: launch(k_eval_binned_mma<16>); return unpermute();
-            case 20: launch(k_eval_binned_mma<20>); return unpermute();
-            case 24: launch(k_eval_binned_mma<24>); return unpermute();
-            case 30: launch(k_eval_binned_mma<30>); return unpermute();
-            default: break;
+        if (mma && (n == 16 || n == 20 || n == 24 || n == 30)) {
+            // per warp: two record slots + two stages of 32 staged rows; as many warps per CTA as keep two CTAs on an SM
+            const size_t per_warp = ((size_t)2 * mo->stride + (size_t)2 * 32 * mma_row_stride(n)) * sizeof(double);
+            int warps = 8;
+            while (warps > 2 && 2 * (warps * (per_warp + 16) + 1024) > 226 * 1024) warps -= 2;
+            const size_t smem = warps * (per_warp + 16);
+            const long long mblocks = std::min<long long>((m + 32 * warps - 1) / (32 * warps), (long long)std::max(n_sm, 1) * 2);
+            auto launch_mma = [&](auto kern) {
+                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                CspTimed tm(CSP_K_EVAL_BINNED, st);
+                kern<<<(unsigned)mblocks, warps * 32, smem, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
+                CSP_LAUNCHED();
+            };
+            switch (n) {
+                case 16: launch_mma(k_eval_binned_mma<16>); break;
+                case 20: launch_mma(k_eval_binned_mma<20>); break;
+                case 24: launch_mma(k_eval_binned_mma<24>); break;
+                default: launch_mma(k_eval_binned_mma<30>); break;
+            }
+            CSP_CUDA(cudaGetLastError());
+            return unpermute();
         }
         switch (n) {
             case 2: launch(k_eval_binned_exact<2>); break;

@@ -762,9 +762,10 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             cp.status = dstatus ? dstatus + off : nullptr;
             cp.bulk = ((uintptr_t)cp.X % 16 == 0) ? 1 : 0;
             cp.hist = w[k].cnt;
-            // ranks from K1's (returning) histogram atomics: the scatter then only adds the bin offset (CSP_BIN_RANKED=0: a
-            // second round of atomics in the scatter instead)
-            w[k].ranked = !(getenv("CSP_BIN_RANKED") && atoi(getenv("CSP_BIN_RANKED")) == 0);
+            // CSP_BIN_RANKED=1: bin ranks from returning histogram atomics in K1, so that the scatter only adds the bin offset.
+            // Measured on B200 per 1e8 queries: C3 locate 6.33 -> 7.31 ms and scatter+unpermute 3.31 -> 4.90 ms (the rank array and the
+            // offset gather cost more than the atomics they replace); C2 locate 4.47 -> 5.37, scatter 2.37 -> 1.96.  Off by default.
+            w[k].ranked = getenv("CSP_BIN_RANKED") && atoi(getenv("CSP_BIN_RANKED")) == 1;
             cp.rank = w[k].ranked ? w[k].slot : nullptr;
             rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
             if (rc == CSP_OK) rc = csp_binned_eval(mo, csp_grid_sms(t->n_sm), cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
