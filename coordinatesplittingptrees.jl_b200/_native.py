@@ -85,6 +85,8 @@ def host():
         L.csph_boxbounds.argtypes = [C.c_void_p, C.c_int, C.c_int, c_f64p]
         L.csph_flatten.argtypes = [C.c_void_p, c_f64p, c_f64p, c_i32p, c_u8p, c_i32p, c_i32p, c_f64p, c_i32p, c_i32p, c_f64p, c_i32p,
                                    c_f64p, c_i32p, c_i32p]
+        L.csph_split_count.argtypes = [C.c_void_p, c_i32p]
+        L.csph_split_log.argtypes = [C.c_void_p, C.c_int, C.c_int, c_i32p, c_i32p, c_f64p, c_f64p]
         L.csph_quadnoise_new.argtypes = [C.c_int, c_f64p, C.c_double, C.c_uint64]
         L.csph_quadnoise_new.restype = C.c_void_p
         L.csph_quadnoise_free.argtypes = [C.c_void_p]
@@ -117,6 +119,9 @@ def dev():
         L.csp_tree_pack.argtypes = [C.POINTER(TreeDesc), vp, C.c_size_t]
         L.csp_tree_upload_blob.argtypes = [vp, C.c_size_t, vpp]
         L.csp_tree_info.argtypes = [vp, c_i64p]
+        L.csp_tree_create_live.argtypes = [C.c_int32, C.c_int32, vp, vp, vp, C.c_double, vpp]
+        L.csp_tree_append_splits.argtypes = [vp, C.c_int64, vp, vp, vp, vp]
+        L.csp_tree_live_maps.argtypes = [vp, vp, vp]
         L.csp_tree_export_derived.argtypes = [vp, C.c_int, vp, C.c_size_t, C.POINTER(C.c_size_t)]
         L.csp_tree_free.argtypes = [vp]
         L.csp_find_leaf.argtypes = [vp, vp, C.c_int64, vp, vp]
@@ -173,7 +178,7 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_models_free", "csp_eval", "csp_eval_dev", "csp_locate_eval", "csp_locate_eval_dev", "csp_kernel_launches", "csp_timing_enable",
            "csp_timing_read", "csp_modelvalue_native", "csp_coefficients_p_sparse",
            "csp_models_possemidef", "csp_fit_gdiag", "csp_models_alloc", "csp_models_refit_range", "csp_models_download_rows",
-           "csp_tree_export_derived", "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
+           "csp_tree_export_derived", "csp_tree_create_live", "csp_tree_append_splits", "csp_tree_live_maps", "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
            "csp_init", "csp_comm_unique_id", "csp_init_rank", "csp_shutdown", "csp_comm_info", "csp_shard_tree_broadcast",
            "csp_shard_tree_get", "csp_shard_tree_free", "csp_shard_fit", "csp_shard_models_get", "csp_shard_models_free",
            "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]

@@ -41,9 +41,22 @@ class SymmetricArray:
         return self.full() if self.data.ndim == 2 else self.data
 
 
-def device_tree(root):
-    """The tree of `root`, resident on the current GPU; re-uploaded when addpoint!/split changed it."""
+def device_tree(root, live=False):
+    """The tree of `root`, resident on the current GPU.  live=False: re-flattened on the host and re-uploaded whenever
+    addpoint!/split changed it.  live=True: the device copy grows with the tree -- only the splits made since the last
+    call are sent (the split log) and the flattening is re-derived on the device (csp_tree_append_splits): what an optimiser loop
+    that alternates addpoint! with queries and fits uses.  Node / leaf ids are preorder ids of the current version either way."""
     t = root.tree
+    if live:
+        if t._live is None:
+            w = t.world
+            t._live = DeviceTree.live(t.n, t.p, w.lower, w.upper, w.position, w.meta)
+            t._live_splits = 0
+        ns = t.split_count()
+        if ns > t._live_splits:
+            t._live.append_splits(*t.split_log(t._live_splits, ns))
+            t._live_splits = ns
+        return t._live
     if t._device is None or t._device_version != t.version:
         if t._device is not None:
             t._device.close()

@@ -393,42 +393,71 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
                                                           double* __restrict__ val) {
     constexpr int NC = (N + 1) * (N + 2) / 2;  // coefficients of the packed (N+1)x(N+1) triangle
     constexpr bool VEC = (N & 1) == 0;         // A block and x rows are 16-byte aligned
-    extern __shared__ __align__(16) double s_rec[];  // [warps][2][stride]
+    // Even N: the x rows of the NEXT 32 positions are gathered into shared memory by one TMA bulk copy per row while the current
+    // ones are evaluated (two stages per warp, one mbarrier each), so the scattered-row latency is off the critical path.
+    constexpr int RS = VEC ? N : 0;            // staged row stride (doubles): 16-byte granular
+    extern __shared__ __align__(16) double s_rec[];  // per warp: [2][stride] records, [2][32][RS] rows; then [warps][2] mbarriers
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, stride = mv.stride;
-    double* slot = s_rec + (size_t)(threadIdx.x >> 5) * 2 * stride;
+    const int lane = threadIdx.x & 31, stride = mv.stride, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
+    const size_t per_warp = (size_t)2 * stride + (size_t)2 * 32 * RS;
+    double* slot = s_rec + (size_t)wib * per_warp;
+    double* rows = slot + (size_t)2 * stride;
+    uint64_t* bars = (uint64_t*)(s_rec + (size_t)nwb * per_warp) + 2 * wib;
     const long long tot = *total;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long per = ((tot + 31) / 32 + nwarps - 1) / nwarps * 32;  // positions per warp, a multiple of 32
     const long long start = wid * per, end = start + per < tot ? start + per : tot;
     if (start >= end) return;
+    if (VEC && lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
     auto fetch = [&](int lf, int b) {  // whole record (stride % 4 == 0 doubles, 32-byte aligned) into slot b
         const double* __restrict__ M = mv.data + (size_t)lf * stride;
         double* dst = slot + (size_t)b * stride;
         for (int k = lane * 2; k < stride; k += 64) cp_async16(dst + k, M + k);
     };
+    auto stage_rows = [&](const int2& q, int st) {
+        const bool v = q.y >= 0;
+        const unsigned vm = __ballot_sync(FULL, v);
+        if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(__popc(vm) * N * 8));
+        __syncwarp();
+        if (v) {
+            fence_proxy_async();
+            bulk_g2s(rows + ((size_t)st * 32 + lane) * RS, X + (size_t)(unsigned)q.x * N, N * 8, &bars[st]);
+        }
+    };
     int cur = 0, staged = -1, pre = -1;  // slot in use, leaf it holds, leaf in flight into the other slot (warp-uniform)
     long long s = start + lane;
     int2 ql = s < end ? perm[s] : make_int2(0, -1);
-    for (; s - lane < end; s += 32) {
+    int2 qn = s + 32 < end ? perm[s + 32] : make_int2(0, -1);
+    if constexpr (VEC) stage_rows(ql, 0);
+    uint32_t ph0 = 0, ph1 = 0;
+    int cs = 0;
+    for (; s - lane < end; s += 32, cs ^= 1) {
         const bool valid = ql.y >= 0;
-        const long long sn = s + 32;
-        const int2 qn = sn < end ? perm[sn] : make_int2(0, -1);  // the next 32 positions, in flight during this iteration
-        if (qn.y >= 0 && (mv.flags & 1)) prefetch_row_l2(X + (size_t)(unsigned)qn.x * N, N * 8);  // ... and their rows on the way to L2
+        if constexpr (VEC)
+            if (s - lane + 32 < end) stage_rows(qn, cs ^ 1);
+        const int2 qnn = s + 64 < end ? perm[s + 64] : make_int2(0, -1);  // perm entries two iterations ahead
         double x[N + 1];
-        if (valid) {
-            const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
-            if constexpr (VEC) {
+        if constexpr (VEC) {
+            if (cs == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1; }
+            else { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
+            if (valid) {
+                const double* srow = rows + ((size_t)cs * 32 + lane) * RS;
 #pragma unroll
                 for (int i = 0; i < N; i += 2) {
-                    const double2 v = __ldg((const double2*)(xp + i));
+                    const double2 v = *(const double2*)(srow + i);
                     x[i] = v.x;
                     x[i + 1] = v.y;
                 }
-            } else {
-#pragma unroll
-                for (int i = 0; i < N; ++i) x[i] = __ldg(xp + i);
             }
+        } else if (valid) {
+            const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
+#pragma unroll
+            for (int i = 0; i < N; ++i) x[i] = __ldg(xp + i);
         }
         unsigned todo = __ballot_sync(FULL, valid);
         double result = 0.0;
@@ -521,6 +550,7 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
         }
         if (valid) val[s] = result;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
         ql = qn;
+        qn = qnn;
     }
     cp_async_wait_all();  // a prefetch may still be in flight
 }
@@ -644,10 +674,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         CSP_CHECK(csp_dense_eval(mo, n_sm, dX, w->perm, w->off + nl, m, w->vsorted, st));
         return unpermute();
     }
-    ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data, 0};
-    // CSP_EVAL_PREFETCH=1: bulk L2 prefetch of the next iteration's rows.  Measured per 1e8 queries: n=20 7.51 -> 7.21 ms, n=10 4.06 ->
-    // 4.64 ms (the FMA kernel is already DRAM-bound; extra requests only queue).  Off by default.
-    if (getenv("CSP_EVAL_PREFETCH") && atoi(getenv("CSP_EVAL_PREFETCH")) == 1) mv.flags |= 1;
+    ModelsView mv{mo->n, mo->degree, mo->stride, mo->n_models, mo->data};
     const int n = mo->n;
     const bool aligned = ((uintptr_t)dX % 16 == 0);
     size_t dyn_smem = 0;  // only the exact-n kernels stage records in shared memory (8 warps x one record)
@@ -661,7 +688,8 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     bool done = false;
     if (mo->degree == 2 && vec_ok) {
         done = true;
-        dyn_smem = (size_t)8 * 2 * mo->stride * sizeof(double);  // 8 warps x two record slots
+        // 8 warps x (two record slots + two stages of 32 staged x rows when n is even) + two mbarriers per warp
+        dyn_smem = (size_t)8 * ((size_t)2 * mo->stride + ((n & 1) ? 0 : (size_t)2 * 32 * n)) * sizeof(double) + 8 * 16;
         const bool mma = !(getenv("CSP_EVAL_MMA") && atoi(getenv("CSP_EVAL_MMA")) == 0);
         // FP64 tensor cores from n = 16 up (measured, 1e8 queries: n = 20 10.4 -> 7.5 ms; n = 10 4.0 -> 7.7 ms: too little MMA work
         // per 8-row group to pay for the fragment bookkeeping, so small n keeps the FMA kernel)

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdint>
@@ -74,7 +75,6 @@ struct ModelsView {
     int n, degree, stride;
     long long n_models;
     const double* data;
-    int flags;  // bit 0: prefetch the next rows into L2 (binned evaluation)
 };
 static inline long long csp_model_len(int n, int degree) {
     return n + (degree == 2 ? (long long)(n + 1) * (n + 2) / 2 : (long long)n + 1);
@@ -87,6 +87,7 @@ __host__ __device__ static inline long long csp_a_index(int n, int i, int j) {
     return (long long)i * (n + 1) - (long long)i * (i - 1) / 2 + (j - i);
 }
 
+struct LiveState;  // live.cu
 struct csp_tree {
     int device = 0;
     TreeView v{};
@@ -105,6 +106,7 @@ struct csp_tree {
     mutable double* fit_coef = nullptr;  // [n_internal] highest-order coefficient of every split (built on the first fit)
     mutable void* fit_ws = nullptr;  // grow-only scratch of the fit pre-pass (chain results), one fit call at a time per handle
     mutable size_t fit_ws_bytes = 0;
+    LiveState* live = nullptr;  // set for trees grown by appending to the split log (live.cu)
     mutable cudaStream_t pipe_st[2] = {nullptr, nullptr};
     mutable cudaEvent_t pipe_fork = nullptr, pipe_join[2] = {nullptr, nullptr};
 };
@@ -115,6 +117,53 @@ struct csp_models {
     double* data = nullptr;    // device, n_models*stride
     uint8_t* status = nullptr; // device, n_models (CSP_FIT_*)
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// wire format (csp_tree_pack / csp_tree_upload_blob): a 64-byte header, then the csp_tree_desc arrays in declaration order,
+// each padded to 16 bytes.  The device copy of a tree keeps this layout; RawTree points into it.
+// ---------------------------------------------------------------------------------------------------------------
+struct BlobHeader {
+    char magic[8];  // "CSPB200\0"
+    int32_t version, n, p, n_nodes, n_internal, n_leaves;
+    int32_t reserved[8];
+};
+static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
+
+struct Section { size_t off, bytes; };
+inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+inline size_t blob_layout(int n, int p, int nn, int ni, Section s[12]) {
+    size_t C = size_t(1) << p;
+    size_t sz[12] = {size_t(n) * 8, size_t(n) * 8, size_t(nn) * 4, size_t(nn), size_t(nn) * 4, size_t(nn) * 4, size_t(nn) * 8,
+                     size_t(ni) * 4, size_t(ni) * p * 4, size_t(ni) * p * 8, size_t(ni) * C * 4, size_t(ni) * n * 8};
+    size_t off = sizeof(BlobHeader);
+    for (int i = 0; i < 12; ++i) { s[i] = {off, sz[i]}; off = align16(off + sz[i]); }
+    return off;
+}
+
+struct RawTree {  // device pointers to the description arrays (sections of the blob)
+    int n, p, nn, ni, nl;
+    const double *lower, *upper;
+    const int* parent;
+    const uint8_t* childindex;
+    const int* internal_id;
+    const int* leaf_id;
+    const double* val;
+    const int* inode;
+    const int* dims;
+    const double* xs;
+    const int* child;
+    const double* pos;
+};
+inline RawTree raw_tree_at(const char* b, const Section* s, int n, int p, int nn, int ni, int nl) {
+    return RawTree{n, p, nn, ni, nl,
+                   (const double*)(b + s[0].off), (const double*)(b + s[1].off), (const int*)(b + s[2].off), (const uint8_t*)(b + s[3].off),
+                   (const int*)(b + s[4].off), (const int*)(b + s[5].off), (const double*)(b + s[6].off), (const int*)(b + s[7].off),
+                   (const int*)(b + s[8].off), (const double*)(b + s[9].off), (const int*)(b + s[10].off), (const double*)(b + s[11].off)};
+}
+struct csp_tree;
+int csp_tree_build_device(csp_tree* t, const RawTree& r);  // tree_build.cu
+struct LiveState;                                          // live.cu
+void csp_live_free(LiveState* ls);
 
 // ---------------------------------------------------------------------------------------------------------------
 // error plumbing / launch accounting
@@ -202,16 +251,6 @@ __device__ __forceinline__ void cp_async8(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-// Pull one query row (bytes, any alignment) towards L2 ahead of its use: one bulk prefetch when the row is 16-byte granular
-// (cp.async.bulk.prefetch.L2, SASS UBLKPF), else one prefetch per 32-byte sector it touches.
-__device__ __forceinline__ void prefetch_row_l2(const double* row, int bytes) {
-    const unsigned long long a = (unsigned long long)row;
-    if (((a | (unsigned)bytes) & 15u) == 0) {
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(bytes) : "memory");
-    } else {
-        for (unsigned long long q = a & ~31ull; q < a + bytes; q += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
-    }
-}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // ---- splits(box) (reference src/tree.jl:461-540) as preorder range scans, any degree p ------------------------------

@@ -38,6 +38,7 @@ struct HostTree {
     // per split
     std::vector<int> sdims;         // p per split, 1-based, > n fictive
     std::vector<double> sxs;        // p per split
+    std::vector<int> sbox;          // the box each split divides: with sdims / sxs / the children's values this is the split log
     int n_fake_leaves = 0;
 
     int nboxes() const { return (int)parent.size(); }
@@ -138,6 +139,7 @@ int do_split(HostTree& t, int par, int k, const int* dims, const double* xs, int
     const int s = (int)(t.sdims.size() / p);
     t.sdims.insert(t.sdims.end(), d.begin(), d.end());
     t.sxs.insert(t.sxs.end(), x.begin(), x.end());
+    t.sbox.push_back(par);
     std::vector<double> cp(t.pos.begin() + (size_t)par * n, t.pos.begin() + (size_t)(par + 1) * n);
     const int first = t.nboxes();
     for (int c = 0; c <= L; ++c) {
@@ -290,6 +292,27 @@ int csph_boxbounds(void* tp, int box, int d, double* out2) {
     if (box < 0 || box >= t.nboxes()) return fail(E_BOUNDS, "box id out of range");
     if (d < 1 || d > t.n) return fail(E_BOUNDS, "dimension out of range");
     t.boxbounds(box, d, out2[0], out2[1]);
+    return 0;
+}
+
+// The split log (creation order), entries [s0, s1): what csp_tree_append_splits consumes.  The children of the s-th split are
+// the boxes 1 + s*2^p + (0 .. 2^p-1); child_val[(s-s0)*2^p + c] = value(child c).
+int csph_split_count(void* tp, int* nsplits) {
+    HostTree& t = *(HostTree*)tp;
+    *nsplits = (int)t.sbox.size();
+    return 0;
+}
+int csph_split_log(void* tp, int s0, int s1, int* split_box, int* dims, double* xs, double* child_val) {
+    HostTree& t = *(HostTree*)tp;
+    const int p = t.p, C = t.C;
+    if (s0 < 0 || s1 < s0 || s1 > (int)t.sbox.size()) return fail(E_BOUNDS, "split range out of bounds");
+    for (int s = s0; s < s1; ++s) {
+        const int k = s - s0, par = t.sbox[s], first = t.first_child[par];
+        if (first != 1 + s * C) return fail(E_ERROR, "internal error: children of a split are not at 1 + s*2^p");
+        split_box[k] = par;
+        for (int j = 0; j < p; ++j) { dims[(size_t)k * p + j] = t.sdims[(size_t)s * p + j]; xs[(size_t)k * p + j] = t.sxs[(size_t)s * p + j]; }
+        for (int c = 0; c < C; ++c) child_val[(size_t)k * C + c] = t.val[first + c];
+    }
     return 0;
 }
 

@@ -129,24 +129,6 @@ int64_t csp_kernel_launches(void) { return g_csp_launches.load(); }
 // ---------------------------------------------------------------------------------------------------------------
 // blob format: 64-byte header followed by the desc arrays in declaration order, each padded to 16 bytes
 // ---------------------------------------------------------------------------------------------------------------
-struct BlobHeader {
-    char magic[8];  // "CSPB200\0"
-    int32_t version, n, p, n_nodes, n_internal, n_leaves;
-    int32_t reserved[8];
-};
-static_assert(sizeof(BlobHeader) == 64, "blob header is 64 bytes");
-
-struct Section { size_t off, bytes; };
-static size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-static size_t blob_layout(int n, int p, int nn, int ni, Section s[12]) {
-    size_t C = size_t(1) << p;
-    size_t sz[12] = {size_t(n) * 8, size_t(n) * 8, size_t(nn) * 4, size_t(nn), size_t(nn) * 4, size_t(nn) * 4, size_t(nn) * 8,
-                     size_t(ni) * 4, size_t(ni) * p * 4, size_t(ni) * p * 8, size_t(ni) * C * 4, size_t(ni) * n * 8};
-    size_t off = sizeof(BlobHeader);
-    for (int i = 0; i < 12; ++i) { s[i] = {off, sz[i]}; off = align16(off + sz[i]); }
-    return off;
-}
-
 static int validate_desc(const csp_tree_desc* d) {
     if (!d) return csp_set_error(CSP_ERR_INVALID, "desc is NULL");
     if (d->n < 1) return csp_set_error(CSP_ERR_INVALID, "n must be >= 1 (got %d)", d->n);
@@ -200,21 +182,6 @@ static int validate_desc(const csp_tree_desc* d) {
 }
 
 // tree_build.cu
-struct RawTree {
-    int n, p, nn, ni, nl;
-    const double *lower, *upper;
-    const int* parent;
-    const uint8_t* childindex;
-    const int* internal_id;
-    const int* leaf_id;
-    const double* val;
-    const int* inode;
-    const int* dims;
-    const double* xs;
-    const int* child;
-    const double* pos;
-};
-int csp_tree_build_device(csp_tree* t, const RawTree& r);
 
 template <class T>
 static int to_device(csp_tree* t, const std::vector<T>& h, const T** out) {
@@ -416,12 +383,7 @@ static int upload_device(int n, int p, int nn, int ni, int nl, Fill&& fill, csp_
         rc = fill((char*)dblob, s, need);
     }
     if (rc == CSP_OK) {
-        const char* b = (const char*)dblob;
-        RawTree r{n, p, nn, ni, nl,
-                  (const double*)(b + s[0].off), (const double*)(b + s[1].off), (const int*)(b + s[2].off), (const uint8_t*)(b + s[3].off),
-                  (const int*)(b + s[4].off), (const int*)(b + s[5].off), (const double*)(b + s[6].off), (const int*)(b + s[7].off),
-                  (const int*)(b + s[8].off), (const double*)(b + s[9].off), (const int*)(b + s[10].off), (const double*)(b + s[11].off)};
-        rc = csp_tree_build_device(t, r);
+        rc = csp_tree_build_device(t, raw_tree_at((const char*)dblob, s, n, p, nn, ni, nl));
     }
     if (rc != CSP_OK) { csp_tree_free(t); return rc; }
     *out = t;
@@ -438,6 +400,7 @@ int csp_tree_free(csp_tree* tree) {
         for (void* p : tree->allocs) csp_dev_free(p);
         csp_dev_free(tree->fit_ws);
         csp_dev_free(tree->fit_coef);
+        if (tree->live) csp_live_free(tree->live);
         for (int i = 0; i < 2; ++i) {
             if (tree->pipe_st[i]) cudaStreamDestroy(tree->pipe_st[i]);
             if (tree->pipe_join[i]) cudaEventDestroy(tree->pipe_join[i]);

@@ -8,21 +8,6 @@
 
 #include "common.cuh"
 
-struct RawTree {  // device pointers to the description arrays (sections of the blob); same definition in tree.cu
-    int n, p, nn, ni, nl;
-    const double *lower, *upper;
-    const int* parent;
-    const uint8_t* childindex;
-    const int* internal_id;
-    const int* leaf_id;
-    const double* val;
-    const int* inode;
-    const int* dims;
-    const double* xs;
-    const int* child;
-    const double* pos;
-};
-
 enum { E_PARENT = 1, E_INTERNAL_ID, E_LEAF_ID, E_CHILD, E_DIM, E_END };
 __device__ __forceinline__ void flag_error(int* err, int code, int where) {
     if (atomicCAS(err, 0, code) == 0) err[1] = where;

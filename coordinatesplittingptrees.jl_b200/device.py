@@ -124,6 +124,41 @@ class DeviceTree:
             N.dchk(N.dev().csp_tree_export_derived(self.h, int(which), out.ctypes.data, sz.value, C.byref(sz)))
         return out
 
+    # ---- incremental residency (live trees: csp_tree_create_live / csp_tree_append_splits) -----------------------------
+    @classmethod
+    def live(cls, n, p, lower, upper, root_position, root_value, device=None):
+        """A tree that grows on the device from its split log (include/csp_b200.h, "incremental residency")."""
+        L = N.dev()
+        if device is not None:
+            N.dchk(L.csp_set_device(int(device)))
+        lo, up, pos = (np.ascontiguousarray(a, np.float64) for a in (lower, upper, root_position))
+        h = C.c_void_p()
+        N.dchk(L.csp_tree_create_live(int(n), int(p), _ptr(lo), _ptr(up), _ptr(pos), float(root_value), C.byref(h)))
+        t = cls.__new__(cls)
+        t.h = h
+        t._refresh()
+        return t
+
+    def _refresh(self):
+        info = (C.c_int64 * 8)()
+        N.dchk(N.dev().csp_tree_info(self.h, info))
+        self.n, self.p, self.n_nodes, self.n_internal, self.n_leaves, self.device, self.max_depth, self.kib = [int(v) for v in info]
+
+    def append_splits(self, split_box, dims, xs, child_val):
+        """Append splits (creation order) to a live tree and re-derive the flattening on the device."""
+        sb = np.ascontiguousarray(split_box, np.int32)
+        d = np.ascontiguousarray(dims, np.int32)
+        x = np.ascontiguousarray(xs, np.float64)
+        cv = np.ascontiguousarray(child_val, np.float64)
+        N.dchk(N.dev().csp_tree_append_splits(self.h, len(sb), _ptr(sb), _ptr(d), _ptr(x), _ptr(cv)))
+        self._refresh()
+
+    def live_maps(self):
+        """(node_of_box, box_of_node) of a live tree: creation-order box ids <-> current preorder node ids."""
+        a, b = np.empty(self.n_nodes, np.int32), np.empty(self.n_nodes, np.int32)
+        N.dchk(N.dev().csp_tree_live_maps(self.h, _ptr(a), _ptr(b)))
+        return a, b
+
     def close(self):
         if self.h:
             N.dev().csp_tree_free(self.h)

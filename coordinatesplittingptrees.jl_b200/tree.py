@@ -102,12 +102,16 @@ class _Tree:
         self._flat = None
         self._device = None
         self._device_version = -1
+        self._live = None      # device copy grown from the split log (api.device_tree(root, live=True))
+        self._live_splits = 0  # splits already appended to it
         self._keep = []
 
     def __del__(self):
         try:
             if self._device is not None:
                 self._device.close()
+            if self._live is not None:
+                self._live.close()
             N.host().csph_tree_free(self.h)
         except Exception:
             pass
@@ -116,6 +120,19 @@ class _Tree:
         v = [C.c_int32() for _ in range(5)]
         N.hchk(N.host().csph_counts(self.h, *[C.byref(x) for x in v]))
         return dict(n=v[0].value, p=v[1].value, n_nodes=v[2].value, n_internal=v[3].value, n_leaves=v[4].value)
+
+    def split_count(self):
+        v = C.c_int32()
+        N.hchk(N.host().csph_split_count(self.h, C.byref(v)))
+        return v.value
+
+    def split_log(self, s0, s1):
+        """Entries [s0, s1) of the split log (creation order): (split_box, dims, xs, child_val) as csp_tree_append_splits takes them."""
+        k, p, Cn = s1 - s0, self.p, 1 << self.p
+        sb, d, x, cv = np.zeros(k, np.int32), np.zeros(k * p, np.int32), np.zeros(k * p), np.zeros(k * Cn)
+        if k:
+            N.hchk(N.host().csph_split_log(self.h, s0, s1, _p(sb, c_i32p), _p(d, c_i32p), _p(x, c_f64p), _p(cv, c_f64p)))
+        return sb, d, x, cv
 
     def flat(self):
         """Preorder SoA arrays == the fields of csp_tree_desc (include/csp_b200.h), plus the box<->node id maps."""

@@ -88,6 +88,22 @@ int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out);
 int csp_tree_blob_size(const csp_tree_desc* desc, size_t* bytes);
 int csp_tree_pack(const csp_tree_desc* desc, void* blob, size_t bytes);
 int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out);
+/* ---- incremental residency: a tree that grows on the device ------------------------------------------------
+ * addpoint! (src/CoordinateSplittingPTrees.jl:94-142) appends ceil(n/p) splits per call and shifts the preorder ids of everything
+ * behind them; re-flattening and re-uploading the whole tree per call is O(tree).  A LIVE tree is fed the SPLIT LOG instead -- the
+ * splits in creation order, where ids never change: box 0 is the root and the s-th split of the tree (0-based) creates the boxes
+ * 1 + s*2^p + (0 .. 2^p-1), child index = offset.  An append sends only the new splits; the library re-derives the preorder
+ * flattening and everything else on the device.  All other entry points work on a live tree as on an uploaded one (node and
+ * leaf ids are the preorder ids of the CURRENT version; csp_tree_live_maps translates box ids). */
+int csp_tree_create_live(int32_t n, int32_t p, const double* lower, const double* upper, const double* root_position,
+                         double root_value, csp_tree** out);
+/* The splits made since the last call, in creation order: entry k divides box split_box[k] along dims[k*p ..] (1-based, > n
+ * fictive) at xs[k*p ..]; child_val[k*2^p + c] = value(child c) (child 0 = split.self repeats the divided box's value). */
+int csp_tree_append_splits(csp_tree* tree, int64_t nsplits, const int32_t* split_box, const int32_t* dims, const double* xs,
+                           const double* child_val);
+/* node_of_box[b] = current preorder node id of box b, box_of_node[v] = box id of node v (n_nodes entries each; either may be NULL). */
+int csp_tree_live_maps(const csp_tree* tree, int32_t* node_of_box, int32_t* box_of_node);
+
 /* Diagnostic: one of the arrays the library derives on the device at upload, copied back to the host (tests compare the device
  * builder with the host-side construction, CSP_UPLOAD_HOST=1).  which: 0 node records, 1 descent records, 2 descent leaf table,
  * 3 split-box coordinates, 4 child values, 5 leaf nodes, 6 path offsets, 7 ancestor paths, 8 fit units.  *bytes = its size; out may

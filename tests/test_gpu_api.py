@@ -280,3 +280,70 @@ def test_device_builder_rejects_bad_descriptions():
         bad[key][idx] = val
         with pytest.raises(cb.CspError):
             DeviceTree(bad)
+
+
+RAW_SECTIONS = ("parent", "childindex", "internal_id", "leaf_id", "val", "inode", "dims", "xs", "child", "pos")
+
+
+@pytest.mark.parametrize("n,p,npoints", [(1, 1, 25), (2, 1, 60), (3, 2, 40), (6, 2, 60), (10, 2, 120), (7, 3, 12)])
+def test_live_tree_equals_full_upload(n, p, npoints):
+    """a device tree grown from the split log (csp_tree_append_splits, flattening re-derived on the device) is, after
+    every addpoint!, bit for bit the tree a full host re-flatten + upload produces: derived arrays, ids, query and fit results."""
+    from csp_b200.device import DeviceTree
+    if p == 3:
+        root, _, _ = grow_degree(n, p, 3, seed=11)
+        f = lambda y: float(np.sum(np.asarray(y) ** 3))
+        cyc = None
+    else:
+        root, _, f = grow_both(n, p, 5, seed=700 + n)
+        cyc = cb.synthetic.cs1_dimlists(n) if p == 1 else cb.synthetic.round_robin_dimlists(n)
+    rng = np.random.default_rng(n + p)
+    X = cb.synthetic.uniform_queries(root, 3000, seed=4)
+    live = cb.device_tree(root, live=True)
+    for it in range(npoints):
+        x = rng.uniform(root.world.lower, root.world.upper)
+        if p == 3:
+            order = rng.permutation(n) + 1
+            dimlists = [tuple(int(d) for d in order[i:i + p]) for i in range(0, n, p)]
+        else:
+            dimlists = cyc[it % len(cyc)]
+        cb.addpoint(root, x, dimlists, f)
+        live = cb.device_tree(root, live=True)          # appends the new splits only
+        if it % 7 and it != npoints - 1:
+            continue
+        flat = root.tree.flat()
+        ref = DeviceTree(flat)
+        assert (live.n_nodes, live.n_internal, live.n_leaves, live.max_depth) == (ref.n_nodes, ref.n_internal, ref.n_leaves, ref.max_depth)
+        for k in range(9):
+            if p > 2 and k in (1, 2):
+                continue
+            assert np.array_equal(live.export_derived(k), ref.export_derived(k)), (it, DERIVED[k])
+        node_of_box, box_of_node = live.live_maps()
+        assert same(node_of_box, flat["pre_of_box"]) and same(box_of_node, flat["box_of_pre"])
+        l1, s1 = live.find_leaf(X)
+        l2, s2 = ref.find_leaf(X)
+        assert same(l1, l2) and same(s1, s2)
+        if p == 2:
+            a, b = live.fit_models().download(), ref.fit_models().download()
+            for key in ("status", "c", "g", "Q", "b"):
+                assert same(a[key], b[key]), key
+        else:
+            a, b = live.coefficients_p(counts=True), ref.coefficients_p(counts=True)
+            for u, w in zip(a, b):
+                assert same(u, w)
+        ref.close()
+
+
+def test_live_tree_rejects_bad_log():
+    from csp_b200.device import DeviceTree
+    t = DeviceTree.live(2, 2, [-1, -1], [1, 1], [0, 0], 0.5)
+    assert (t.n_nodes, t.n_leaves) == (1, 1)
+    t.append_splits([0], [1, 2], [0.5, 0.5], [0.5, 1, 2, 3])
+    assert (t.n_nodes, t.n_internal, t.n_leaves) == (5, 1, 4)
+    with pytest.raises(cb.CspError):
+        t.append_splits([9], [1, 2], [0.1, 0.1], [0, 0, 0, 0])   # box 9 does not exist yet
+    with pytest.raises(cb.CspError):
+        t.append_splits([0], [1, 2], [0.1, 0.1], [0, 0, 0, 0])   # box 0 is split already
+    assert (t.n_nodes, t.n_internal, t.n_leaves) == (5, 1, 4)     # the handle survived
+    leaf, status = t.find_leaf(np.array([[0.9, 0.9], [-0.9, -0.9]]))
+    assert (status == 0).all() and leaf[0] != leaf[1]
