@@ -94,8 +94,10 @@ __global__ void __launch_bounds__(SCAN_T) k_scan(int* __restrict__ cnt, int nl, 
 
 // ---- scatter: perm[slot] = (query, leaf), slot = cursor[leaf]++ ------------------------------------------------------
 // Leaf ids outside [0, n_models) (caller-supplied ids of csp_eval*) are treated like "outside the world": slot -1, value NaN.
+// valq != null ("direct" mode): the evaluation kernel writes each value straight to its query's place, so no slot is recorded and
+// the queries without a leaf get their NaN here.
 __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, long long m, int n_models, int* __restrict__ cursor,
-                                                 int2* __restrict__ perm, int* __restrict__ slot_of) {
+                                                 int2* __restrict__ perm, int* __restrict__ slot_of, double* __restrict__ valq) {
     // four independent atomics in flight per thread (the returning atomic's L2 round trip is the critical path)
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; q0 < m; q0 += 4 * stride) {
@@ -112,7 +114,8 @@ __global__ void __launch_bounds__(256) k_scatter(const int* __restrict__ leaf, l
         for (int u = 0; u < 4; ++u) {
             const long long q = q0 + u * stride;
             if (lf[u] >= 0) perm[slot[u]] = make_int2((int)q, lf[u]);
-            if (lf[u] != -2) slot_of[q] = slot[u];  // -1: outside the world (the reference throws, src/tree.jl:359)
+            if (valq) { if (lf[u] == -1) valq[q] = dnan_b(); }
+            else if (lf[u] != -2) slot_of[q] = slot[u];  // -1: outside the world (the reference throws, src/tree.jl:359)
         }
     }
 }
@@ -231,7 +234,7 @@ __host__ __device__ constexpr int mma_row_stride(int n) {
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, const double* __restrict__ X,
                                                         const int2* __restrict__ perm, const int* __restrict__ total,
-                                                        double* __restrict__ val) {
+                                                        double* __restrict__ val, const int direct) {
     static_assert((N & 1) == 0 && N >= 2 && N <= 30, "even n only");
     constexpr int NP = (N + 1 + 7) / 8 * 8, KS = NP / 4, NT = NP / 8;
     constexpr int RS = mma_row_stride(N);
@@ -372,7 +375,8 @@ __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, co
                 }
                 dot += __shfl_xor_sync(FULL, dot, 1);
                 dot += __shfl_xor_sync(FULL, dot, 2);
-                if (t == 0 && rm) val[s0 + 8 * g + r] = dot;
+                const int rq = __shfl_sync(FULL, ql.x, 8 * g + r);
+                if (t == 0 && rm) val[direct ? (long long)(unsigned)rq : s0 + 8 * g + r] = dot;
             }
         }
         __syncwarp();  // every lane is done with stage cs before the next iteration refills it
@@ -390,74 +394,44 @@ __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, co
 template <int N>
 __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, const double* __restrict__ X,
                                                           const int2* __restrict__ perm, const int* __restrict__ total,
-                                                          double* __restrict__ val) {
+                                                          double* __restrict__ val, const int direct) {
     constexpr int NC = (N + 1) * (N + 2) / 2;  // coefficients of the packed (N+1)x(N+1) triangle
     constexpr bool VEC = (N & 1) == 0;         // A block and x rows are 16-byte aligned
-    // Even N: the x rows of the NEXT 32 positions are gathered into shared memory by one TMA bulk copy per row while the current
-    // ones are evaluated (two stages per warp, one mbarrier each), so the scattered-row latency is off the critical path.
-    constexpr int RS = VEC ? N : 0;            // staged row stride (doubles): 16-byte granular
-    extern __shared__ __align__(16) double s_rec[];  // per warp: [2][stride] records, [2][32][RS] rows; then [warps][2] mbarriers
+    extern __shared__ __align__(16) double s_rec[];  // [warps][2][stride]
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, stride = mv.stride, wib = threadIdx.x >> 5, nwb = blockDim.x >> 5;
-    const size_t per_warp = (size_t)2 * stride + (size_t)2 * 32 * RS;
-    double* slot = s_rec + (size_t)wib * per_warp;
-    double* rows = slot + (size_t)2 * stride;
-    uint64_t* bars = (uint64_t*)(s_rec + (size_t)nwb * per_warp) + 2 * wib;
+    const int lane = threadIdx.x & 31, stride = mv.stride;
+    double* slot = s_rec + (size_t)(threadIdx.x >> 5) * 2 * stride;
     const long long tot = *total;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5, wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long per = ((tot + 31) / 32 + nwarps - 1) / nwarps * 32;  // positions per warp, a multiple of 32
     const long long start = wid * per, end = start + per < tot ? start + per : tot;
     if (start >= end) return;
-    if (VEC && lane == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
     auto fetch = [&](int lf, int b) {  // whole record (stride % 4 == 0 doubles, 32-byte aligned) into slot b
         const double* __restrict__ M = mv.data + (size_t)lf * stride;
         double* dst = slot + (size_t)b * stride;
         for (int k = lane * 2; k < stride; k += 64) cp_async16(dst + k, M + k);
     };
-    auto stage_rows = [&](const int2& q, int st) {
-        const bool v = q.y >= 0;
-        const unsigned vm = __ballot_sync(FULL, v);
-        if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(__popc(vm) * N * 8));
-        __syncwarp();
-        if (v) {
-            fence_proxy_async();
-            bulk_g2s(rows + ((size_t)st * 32 + lane) * RS, X + (size_t)(unsigned)q.x * N, N * 8, &bars[st]);
-        }
-    };
     int cur = 0, staged = -1, pre = -1;  // slot in use, leaf it holds, leaf in flight into the other slot (warp-uniform)
     long long s = start + lane;
     int2 ql = s < end ? perm[s] : make_int2(0, -1);
-    int2 qn = s + 32 < end ? perm[s + 32] : make_int2(0, -1);
-    if constexpr (VEC) stage_rows(ql, 0);
-    uint32_t ph0 = 0, ph1 = 0;
-    int cs = 0;
-    for (; s - lane < end; s += 32, cs ^= 1) {
+    for (; s - lane < end; s += 32) {
         const bool valid = ql.y >= 0;
-        if constexpr (VEC)
-            if (s - lane + 32 < end) stage_rows(qn, cs ^ 1);
-        const int2 qnn = s + 64 < end ? perm[s + 64] : make_int2(0, -1);  // perm entries two iterations ahead
+        const long long sn = s + 32;
+        const int2 qn = sn < end ? perm[sn] : make_int2(0, -1);  // the next 32 positions, in flight during this iteration
         double x[N + 1];
-        if constexpr (VEC) {
-            if (cs == 0) { mbar_wait(&bars[0], ph0); ph0 ^= 1; }
-            else { mbar_wait(&bars[1], ph1); ph1 ^= 1; }
-            if (valid) {
-                const double* srow = rows + ((size_t)cs * 32 + lane) * RS;
+        if (valid) {
+            const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
+            if constexpr (VEC) {
 #pragma unroll
                 for (int i = 0; i < N; i += 2) {
-                    const double2 v = *(const double2*)(srow + i);
+                    const double2 v = __ldg((const double2*)(xp + i));
                     x[i] = v.x;
                     x[i + 1] = v.y;
                 }
-            }
-        } else if (valid) {
-            const double* __restrict__ xp = X + (size_t)(unsigned)ql.x * N;
+            } else {
 #pragma unroll
-            for (int i = 0; i < N; ++i) x[i] = __ldg(xp + i);
+                for (int i = 0; i < N; ++i) x[i] = __ldg(xp + i);
+            }
         }
         unsigned todo = __ballot_sync(FULL, valid);
         double result = 0.0;
@@ -548,9 +522,8 @@ __global__ void __launch_bounds__(256) k_eval_binned_exact(const ModelsView mv, 
             }
             __syncwarp();
         }
-        if (valid) val[s] = result;  // leaf-sorted position: coalesced; k_unpermute brings it back to query order
+        if (valid) val[direct ? (long long)(unsigned)ql.x : s] = result;  // sorted position (coalesced; k_unpermute follows) or the query's own
         ql = qn;
-        qn = qnn;
     }
     cp_async_wait_all();  // a prefetch may still be in flight
 }
@@ -650,6 +623,15 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
                     cudaStream_t st) {
     const int nl = (int)mo->n_models;
     const int nblocks = (nl + SCAN_T * SCAN_PER - 1) / (SCAN_T * SCAN_PER);
+    // "direct": the exact-n evaluation kernels write val[query] themselves (scattered 8-byte stores that merge in L2 while the
+    // chunk's value range fits there) instead of sorted values + a k_unpermute pass; see DESIGN.md for the measurements
+    const int n_ = mo->n;
+    const bool mma_on = !(getenv("CSP_EVAL_MMA") && atoi(getenv("CSP_EVAL_MMA")) == 0);
+    const bool exact_kernel = mo->degree == 2 && !csp_dense_supported(mo) && (((uintptr_t)dX % 16 == 0) || (n_ & 1)) &&
+                              (n_ == 2 || n_ == 3 || n_ == 4 || n_ == 5 || n_ == 6 || n_ == 8 || n_ == 10 || n_ == 12 || n_ == 16 || n_ == 20 ||
+                               (mma_on && (n_ == 24 || n_ == 30)));
+    const char* denv = getenv("CSP_EVAL_DIRECT_WRITE");
+    const bool direct = exact_kernel && !w->ranked && (denv ? atoi(denv) != 0 : false);
     w->epoch += 1;
     {
         CspTimed tm(CSP_K_SCAN, st);
@@ -660,7 +642,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     {
         CspTimed tm(CSP_K_SCATTER, st);
         if (w->ranked) k_scatter_ranked<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->off, w->perm, w->slot);
-        else k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->cursor, w->perm, w->slot);
+        else k_scatter<<<(unsigned)blocks, 256, 0, st>>>(dleaf, m, nl, w->cursor, w->perm, w->slot, direct ? dval : nullptr);
     }
     CSP_LAUNCHED();
     auto unpermute = [&]() -> int {
@@ -681,16 +663,22 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
     auto launch = [&](auto kern) {
         if (dyn_smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
         CspTimed tm(CSP_K_EVAL_BINNED, st);
-        kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
+        kern<<<(unsigned)blocks, 256, dyn_smem, st>>>(mv, dX, w->perm, w->off + nl, direct ? dval : w->vsorted, direct ? 1 : 0);
+        CSP_LAUNCHED();
+    };
+    auto launch_plain = [&](auto kern) {  // kernels without the direct-write mode
+        CspTimed tm(CSP_K_EVAL_BINNED, st);
+        kern<<<(unsigned)blocks, 256, 0, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
         CSP_LAUNCHED();
     };
     const bool vec_ok = aligned || (n & 1);
     bool done = false;
     if (mo->degree == 2 && vec_ok) {
         done = true;
-        // 8 warps x (two record slots + two stages of 32 staged x rows when n is even) + two mbarriers per warp
-        dyn_smem = (size_t)8 * ((size_t)2 * mo->stride + ((n & 1) ? 0 : (size_t)2 * 32 * n)) * sizeof(double) + 8 * 16;
-        const bool mma = !(getenv("CSP_EVAL_MMA") && atoi(getenv("CSP_EVAL_MMA")) == 0);
+        // 8 warps x two record slots.  (Staging the x rows through shared memory with TMA, as k_eval_binned_mma does, was measured
+        // on this kernel too: n = 10, 1e8 queries 4.06 -> 4.42 ms -- it is DRAM-bound already, the extra pass only adds work.)
+        dyn_smem = (size_t)8 * 2 * mo->stride * sizeof(double);
+        const bool mma = mma_on;
         // FP64 tensor cores from n = 16 up (measured, 1e8 queries: n = 20 10.4 -> 7.5 ms; n = 10 4.0 -> 7.7 ms: too little MMA work
         // per 8-row group to pay for the fragment bookkeeping, so small n keeps the FMA kernel)
         if (mma && (n == 16 || n == 20 || n == 24 || n == 30)) {
@@ -703,7 +691,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
             auto launch_mma = [&](auto kern) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 CspTimed tm(CSP_K_EVAL_BINNED, st);
-                kern<<<(unsigned)mblocks, warps * 32, smem, st>>>(mv, dX, w->perm, w->off + nl, w->vsorted);
+                kern<<<(unsigned)mblocks, warps * 32, smem, st>>>(mv, dX, w->perm, w->off + nl, direct ? dval : w->vsorted, direct ? 1 : 0);
                 CSP_LAUNCHED();
             };
             switch (n) {
@@ -713,7 +701,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
                 default: launch_mma(k_eval_binned_mma<30>); break;
             }
             CSP_CUDA(cudaGetLastError());
-            return unpermute();
+            return direct ? CSP_OK : unpermute();
         }
         switch (n) {
             case 2: launch(k_eval_binned_exact<2>); break;
@@ -731,14 +719,14 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
         if (!done) dyn_smem = 0;
     }
     if (done) {}
-    else if (n <= 4 && vec_ok) launch(k_eval_binned<4>);
-    else if (n <= 8 && vec_ok) launch(k_eval_binned<8>);
-    else if (n <= 12 && vec_ok) launch(k_eval_binned<12>);
-    else if (n <= 16 && vec_ok) launch(k_eval_binned<16>);
-    else if (n <= 20 && vec_ok) launch(k_eval_binned<20>);
-    else if (n <= 24 && vec_ok) launch(k_eval_binned<24>);
-    else if (n <= 32 && vec_ok) launch(k_eval_binned<32>);
-    else launch(k_eval_binned_generic);
+    else if (n <= 4 && vec_ok) launch_plain(k_eval_binned<4>);
+    else if (n <= 8 && vec_ok) launch_plain(k_eval_binned<8>);
+    else if (n <= 12 && vec_ok) launch_plain(k_eval_binned<12>);
+    else if (n <= 16 && vec_ok) launch_plain(k_eval_binned<16>);
+    else if (n <= 20 && vec_ok) launch_plain(k_eval_binned<20>);
+    else if (n <= 24 && vec_ok) launch_plain(k_eval_binned<24>);
+    else if (n <= 32 && vec_ok) launch_plain(k_eval_binned<32>);
+    else launch_plain(k_eval_binned_generic);
     CSP_CUDA(cudaGetLastError());
-    return unpermute();
+    return (direct && done) ? CSP_OK : unpermute();
 }

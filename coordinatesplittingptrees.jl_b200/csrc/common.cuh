@@ -161,7 +161,7 @@ inline RawTree raw_tree_at(const char* b, const Section* s, int n, int p, int nn
                    (const int*)(b + s[8].off), (const double*)(b + s[9].off), (const int*)(b + s[10].off), (const double*)(b + s[11].off)};
 }
 struct csp_tree;
-int csp_tree_build_device(csp_tree* t, const RawTree& r);  // tree_build.cu
+int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower = nullptr, const double* h_upper = nullptr);  // tree_build.cu
 struct LiveState;                                          // live.cu
 void csp_live_free(LiveState* ls);
 
@@ -176,6 +176,14 @@ int csp_require_device();  // CSP_OK or CSP_ERR_NO_DEVICE
 // pool, whose release threshold is raised once so that freed blocks are reused -- re-uploading a tree or re-fitting models
 // every optimiser iteration then costs no cudaMalloc / cudaFree.  Callers synchronise before freeing memory other streams used.
 int csp_dev_alloc(void** p, size_t bytes);
+// While set (by a builder whose work is all on the legacy default stream and which synchronises at its end), csp_dev_alloc skips
+// its per-allocation stream synchronisation.
+extern thread_local bool g_csp_alloc_nosync;
+struct AllocNoSync {
+    bool prev;
+    AllocNoSync() : prev(g_csp_alloc_nosync) { g_csp_alloc_nosync = true; }
+    ~AllocNoSync() { g_csp_alloc_nosync = prev; }
+};
 void csp_dev_free(void* p);
 
 #define CSP_CUDA(call)                                                                                         \

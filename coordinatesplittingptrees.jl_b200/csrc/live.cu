@@ -22,6 +22,7 @@ struct LiveState {
     double* base = nullptr;          // [n] position(root)
     double root_val = 0.0;
     std::vector<double> lower, upper;
+    std::vector<char> is_split;      // host: box already divided (a box is split at most once)
     char* blob = nullptr;            // description arrays in the blob layout, re-derived after every append
     size_t blob_cap = 0;
     int* node_of_box = nullptr;      // [cap boxes] preorder node id of every box (creation-order id)
@@ -144,6 +145,7 @@ inline unsigned nblk(long long items) { return (unsigned)std::max<long long>(1, 
 
 // Re-derive the description (blob layout) from the split log, then everything else (tree_build.cu).
 int rebuild(csp_tree* t) {
+    AllocNoSync nosync;  // all on the legacy default stream; the builder synchronises at its end
     LiveState& L = *t->live;
     const int n = L.n, p = L.p, C = 1 << p;
     const long long S = L.S, nb = 1 + S * C;
@@ -210,7 +212,7 @@ int rebuild(csp_tree* t) {
     int nl = 0;
     CSP_CUDA(cudaMemcpy(&nl, lscan + nb, 4, cudaMemcpyDeviceToHost));  // synchronises
     CSP_CUDA(cudaGetLastError());
-    return csp_tree_build_device(t, raw_tree_at(B, sec, n, p, (int)nb, (int)S, nl));
+    return csp_tree_build_device(t, raw_tree_at(B, sec, n, p, (int)nb, (int)S, nl), L.lower.data(), L.upper.data());
 }
 
 }  // namespace
@@ -252,12 +254,23 @@ int csp_tree_append_splits(csp_tree* t, int64_t ns, const int32_t* split_box, co
     const int p = L.p, C = 1 << p, n = L.n;
     const int maxdim = (n + p - 1) / p * p;
     {   // the log must describe a tree: a box is split once, after it was created
-        std::vector<char> seen;
-        for (int64_t k = 0; k < ns; ++k) {
+        L.is_split.resize((size_t)(1 + (L.S + ns) * C), 0);
+        int64_t k = 0;
+        const char* why = nullptr;
+        for (; k < ns && !why; ++k) {
             const long long limit = 1 + (L.S + k) * C;  // boxes that exist when split S+k is made
-            if (split_box[k] < 0 || split_box[k] >= limit) return csp_set_error(CSP_ERR_INVALID, "split %lld divides box %d, which does not exist yet", (long long)(L.S + k), split_box[k]);
-            for (int j = 0; j < p; ++j)
-                if (dims[k * p + j] < 1 || dims[k * p + j] > maxdim) return csp_set_error(CSP_ERR_INVALID, "split %lld: dimension %d out of range", (long long)(L.S + k), dims[k * p + j]);
+            if (split_box[k] < 0 || split_box[k] >= limit) why = "divides a box that does not exist yet";
+            else if (L.is_split[split_box[k]]) why = "divides a box that is split already";
+            else {
+                for (int j = 0; j < p; ++j)
+                    if (dims[k * p + j] < 1 || dims[k * p + j] > maxdim) why = "has a dimension out of range";
+                if (!why) L.is_split[split_box[k]] = 1;
+            }
+        }
+        if (why) {
+            for (int64_t u = 0; u + 1 < k; ++u) L.is_split[split_box[u]] = 0;  // undo the marks of this call
+            L.is_split.resize((size_t)(1 + L.S * C));
+            return csp_set_error(CSP_ERR_INVALID, "split %lld (box %d) %s", (long long)(L.S + k - 1), split_box[k - 1], why);
         }
     }
     DeviceGuard g(t->device);
@@ -276,8 +289,10 @@ int csp_tree_append_splits(csp_tree* t, int64_t ns, const int32_t* split_box, co
     CSP_CUDA(cudaMemcpyAsync(L.sp_cval + L.S * C, child_val, (size_t)ns * C * 8, cudaMemcpyHostToDevice, 0));
     L.S += ns;
     int rc = rebuild(t);
-    if (rc != CSP_OK) {  // e.g. a box split twice: drop the entries again so that the handle stays usable
+    if (rc != CSP_OK) {  // drop the entries again so that the handle stays usable
+        for (int64_t u = 0; u < ns; ++u) L.is_split[split_box[u]] = 0;
         L.S -= ns;
+        L.is_split.resize((size_t)(1 + L.S * C));
         rebuild(t);
     }
     return rc;

@@ -55,7 +55,7 @@ int csp_dev_alloc(void** p, size_t bytes) {
         *p = nullptr;
         return csp_set_error(CSP_ERR_NOMEM, "cannot allocate %zu bytes of device memory: %s", bytes, cudaGetErrorString(e));
     }
-    cudaStreamSynchronize((cudaStream_t)0);  // the block may be used from any stream right away
+    if (!g_csp_alloc_nosync) cudaStreamSynchronize((cudaStream_t)0);  // the block may be used from any stream right away
     return CSP_OK;
 }
 void csp_dev_free(void* p) {
@@ -75,6 +75,7 @@ int csp_require_device() {
 bool g_csp_timing = false;
 int g_csp_grid_div = 1;
 int g_csp_sm_reserve = 0;
+thread_local bool g_csp_alloc_nosync = false;
 namespace {
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 std::vector<TimedLaunch> g_timed;
@@ -369,7 +370,7 @@ static int check_header(int n, int p, int nn, int ni, int nl) {
 
 // The tree owns one device buffer in the blob layout; `fill` puts the description into it; the rest is derived on the device.
 template <class Fill>
-static int upload_device(int n, int p, int nn, int ni, int nl, Fill&& fill, csp_tree** out) {
+static int upload_device(int n, int p, int nn, int ni, int nl, const double* h_lower, const double* h_upper, Fill&& fill, csp_tree** out) {
     CSP_CHECK(check_header(n, p, nn, ni, nl));
     csp_tree* t = new_tree();
     DeviceGuard g(t->device);
@@ -383,7 +384,7 @@ static int upload_device(int n, int p, int nn, int ni, int nl, Fill&& fill, csp_
         rc = fill((char*)dblob, s, need);
     }
     if (rc == CSP_OK) {
-        rc = csp_tree_build_device(t, raw_tree_at((const char*)dblob, s, n, p, nn, ni, nl));
+        rc = csp_tree_build_device(t, raw_tree_at((const char*)dblob, s, n, p, nn, ni, nl), h_lower, h_upper);
     }
     if (rc != CSP_OK) { csp_tree_free(t); return rc; }
     *out = t;
@@ -431,7 +432,7 @@ int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out) {
         if (!q) return csp_set_error(CSP_ERR_INVALID, "a per-node array of the tree descriptor is NULL");
     if (d->n_internal > 0 && (!d->inode || !d->dims || !d->xs || !d->child || !d->pos))
         return csp_set_error(CSP_ERR_INVALID, "a per-internal-node array of the tree descriptor is NULL");
-    return upload_device(d->n, d->p, d->n_nodes, d->n_internal, d->n_leaves, [&](char* dblob, const Section* s, size_t) -> int {
+    return upload_device(d->n, d->p, d->n_nodes, d->n_internal, d->n_leaves, d->lower, d->upper, [&](char* dblob, const Section* s, size_t) -> int {
         const void* src[12] = {d->lower, d->upper, d->parent, d->childindex, d->internal_id, d->leaf_id, d->val,
                                d->inode, d->dims, d->xs, d->child, d->pos};
         for (int i = 0; i < 12; ++i)
@@ -500,7 +501,9 @@ int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out) {
         return csp_tree_upload(&d, out);
     }
     // one copy of the blob (device-to-device when it already is on a GPU: no host bounce), everything else derived on the device
-    return upload_device(h.n, h.p, h.n_nodes, h.n_internal, h.n_leaves, [&](char* dblob, const Section*, size_t nbytes) -> int {
+    const double* hl = on_device ? nullptr : (const double*)((const char*)blob + s[0].off);
+    const double* hu = on_device ? nullptr : (const double*)((const char*)blob + s[1].off);
+    return upload_device(h.n, h.p, h.n_nodes, h.n_internal, h.n_leaves, hl, hu, [&](char* dblob, const Section*, size_t nbytes) -> int {
         CSP_CUDA(cudaMemcpyAsync(dblob, blob, nbytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, 0));
         return CSP_OK;
     }, out);

@@ -217,7 +217,8 @@ inline unsigned blocks_for(long long items) { return (unsigned)std::max<long lon
 }  // namespace
 
 // r: device pointers of the description (inside a buffer the tree already owns).  Fills t->v and the derived arrays.
-int csp_tree_build_device(csp_tree* t, const RawTree& r) {
+int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower, const double* h_upper) {
+    AllocNoSync nosync;  // everything below runs on the legacy default stream and ends with a device synchronisation
     const int n = r.n, p = r.p, C = 1 << p, nn = r.nn, ni = r.ni, nl = r.nl;
     cudaStream_t st = 0;
     // CUB temporary storage: the largest request of the calls below
@@ -314,8 +315,13 @@ int csp_tree_build_device(csp_tree* t, const RawTree& r) {
     CSP_LAUNCHED();
     CSP_CUDA(cudaGetLastError());
     t->h_lower.resize(n); t->h_upper.resize(n);
-    CSP_CUDA(cudaMemcpy(t->h_lower.data(), r.lower, (size_t)n * 8, cudaMemcpyDeviceToHost));
-    CSP_CUDA(cudaMemcpy(t->h_upper.data(), r.upper, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    if (h_lower && h_upper) {
+        std::copy(h_lower, h_lower + n, t->h_lower.begin());
+        std::copy(h_upper, h_upper + n, t->h_upper.begin());
+    } else {
+        CSP_CUDA(cudaMemcpy(t->h_lower.data(), r.lower, (size_t)n * 8, cudaMemcpyDeviceToHost));
+        CSP_CUDA(cudaMemcpy(t->h_upper.data(), r.upper, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    }
     v.drec = drec; v.dleaf = dleaf; v.ninfo = ninfo; v.ixself = ixself; v.icval = icval; v.lnode = lnode; v.lpoff = lpoff; v.lpath = lpath;
     t->fit_units = units;
     t->n_fit_units = p == 2 ? (ni == 0 && nl == 1 ? 1 : h.n_units) : 0;
