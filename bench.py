@@ -480,7 +480,7 @@ def main():
     ap.add_argument("--queries", type=int, default=None, help="queries per step, whole job (default 1e9 for C3, 1e8 for C2)")
     ap.add_argument("--chunk", type=int, default=100_000_000, help="resident chunk per GPU (queries)")
     ap.add_argument("--resident-chunks", type=int, default=4, help="distinct resident chunks per GPU when a shard exceeds them (cycled)")
-    ap.add_argument("--gather-chunk", type=int, default=1 << 24, help="queries per gather pipeline step")
+    ap.add_argument("--gather-chunk", type=int, default=25_000_000, help="queries per gather pipeline step (also the binning chunk)")
     ap.add_argument("--e2e-queries", type=int, default=None)
     ap.add_argument("--ref-queries", type=int, default=20_000_000)
     ap.add_argument("--ref-fits", type=int, default=100_000)

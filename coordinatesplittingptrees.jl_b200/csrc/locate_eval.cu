@@ -717,10 +717,11 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         // HBM; chunks must stay large enough to amortise the four launches and to keep many queries per leaf.
         // Measured on B200 (C2, 1e8 queries): 0.5M 17.8 ms, 1M 14.5, 2M 12.8, 4M 12.6, 8M 13.2, unchunked 17.0.
         const char* cenv = getenv("CSP_BIN_CHUNK");
-        // With many leaves the runs per leaf must stay long enough to amortise a record fetch per warp (C3, 1e6 leaves, 5e7
-        // queries: 2M chunks 19.4 ms, 8M 11.8, 16M 10.7, unchunked 10.4), hence at least 40 queries per leaf per chunk.
+        // With many leaves the runs per leaf must stay long enough to amortise a record fetch per warp, while the scatter and the
+        // un-permute get slower as the chunk (the range their random accesses cover) grows.  C3, 1e6 leaves, per 1e8 queries
+        // (round 2 kernels): 4M chunks 18.1 ms, 8M 15.9, 16M 14.8, 25M 14.3, 40M 14.9, 50M 15.3, 100M 16.1: 25 queries per leaf per chunk.
         long long chunk = cenv ? atoll(cenv)
-                               : std::max<long long>(std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24)), 40LL * mo->n_models);
+                               : std::max<long long>(std::max<long long>(1 << 18, (416LL << 20) / (8LL * t->v.n + 24)), 25LL * mo->n_models);
         // The tensor-core evaluation reads every x row exactly once (TMA / cp.async gathers) and expands a leaf's record per
         // run of tiles: nothing is gained from L2-sized chunks, and small chunks shorten the runs (C4, 2e7 queries: 0.5M-query
         // chunks 29.8 ms, one chunk 19.9 ms); only the workspace (24 B/query) bounds the chunk.
