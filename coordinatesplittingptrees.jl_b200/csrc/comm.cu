@@ -93,7 +93,11 @@ int finish_init() {
     for (Rank& r : G.local) {
         DeviceGuard g(r.device);
         CSP_CUDA(cudaStreamCreateWithFlags(&r.st, cudaStreamNonBlocking));
-        CSP_CUDA(cudaStreamCreateWithFlags(&r.cst, cudaStreamNonBlocking));
+        // the communication stream outranks the compute streams: NCCL's send / receive CTAs are placed as soon as a kernel of
+        // the pipeline retires some of its own, instead of queueing behind the next kernel's persistent grid
+        int prio_lo = 0, prio_hi = 0;
+        CSP_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CSP_CUDA(cudaStreamCreateWithPriority(&r.cst, cudaStreamNonBlocking, prio_hi));
         CSP_CUDA(cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming));
         CSP_CUDA(cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming));
         for (auto& e : r.chunk_ev) CSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -499,7 +503,7 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
     // NCCL's send / receive kernels need room beside the persistent grids of the pipeline, or they only run between kernels
     const char* renv = getenv("CSP_GATHER_SM_RESERVE");
     struct Reserve { ~Reserve() { g_csp_sm_reserve = 0; } } reserve_guard;
-    g_csp_sm_reserve = gather ? (renv ? atoi(renv) : 8) : 0;
+    g_csp_sm_reserve = gather ? (renv ? atoi(renv) : 0) : 0;  // measured at N=2 (C3): 0 / 8 / 16 SMs reserved -> 87.4 / 91.0 / 86.9 ms per step: no gain
     int step = 0;
     for (long long off = 0; off < mx; off += chunk, ++step) {
         for (size_t i = 0; i < nl; ++i) {

@@ -475,8 +475,19 @@ int csp_tree_upload_blob(const void* blob, size_t bytes, csp_tree** out) {
     const bool on_device = cudaPointerGetAttributes(&attr, blob) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
     cudaGetLastError();
     BlobHeader h;
-    if (on_device) CSP_CUDA(cudaMemcpy(&h, blob, sizeof h, cudaMemcpyDeviceToHost));  // e.g. the buffer an NCCL broadcast landed in
-    else memcpy(&h, blob, sizeof h);
+    std::vector<char> bounce;
+    if (on_device) {  // e.g. the buffer an NCCL broadcast landed in
+        DeviceGuard gsrc(attr.device);  // (pool memory is only accessible from its own device)
+        if (attr.device == csp_current_device()) {
+            CSP_CUDA(cudaMemcpy(&h, blob, sizeof h, cudaMemcpyDeviceToHost));
+        } else {  // a blob on another GPU than the target: through the host
+            bounce.resize(bytes);
+            CSP_CUDA(cudaMemcpy(bounce.data(), blob, bytes, cudaMemcpyDeviceToHost));
+            return csp_tree_upload_blob(bounce.data(), bytes, out);
+        }
+    } else {
+        memcpy(&h, blob, sizeof h);
+    }
     if (memcmp(h.magic, "CSPB200", 8) != 0 || h.version != 1) return csp_set_error(CSP_ERR_INVALID, "not a CSPB200 v1 blob");
     CSP_CHECK(check_header(h.n, h.p, h.n_nodes, h.n_internal, h.n_leaves));
     Section s[12];
