@@ -565,8 +565,19 @@ def main():
         Xres.append(Xk)
     status = torch.empty(max(mine, 1), dtype=torch.uint8, device=dev)
     gather = world > 1
-    leaf_all = torch.empty(M, dtype=torch.int32, device=dev) if (gather and rank == 0) else None
-    val_all = torch.empty(M, dtype=torch.float64, device=dev) if (gather and rank == 0) else None
+    leaf_all = val_all = None
+    gather_path = "none"
+    if gather:
+        try:     # library-owned gather buffers: the blocks move with the copy engines (peer DMA over NVLink), no SMs involved
+            leaf_all, val_all = shard.gather_alloc(M, root=0, device=local)
+            gather_path = "copy engines (csp_shard_gather_alloc: device-to-device DMA over NVLink into rank 0's arrays; NCCL carries one completion word per call)"
+        except cb.CspError:
+            if rank == 0:
+                leaf_all = torch.empty(M, dtype=torch.int32, device=dev)
+                val_all = torch.empty(M, dtype=torch.float64, device=dev)
+            gather_path = "NCCL send/recv kernels"
+        if os.environ.get("CSP_GATHER") == "nccl":
+            gather_path = "NCCL send/recv kernels (CSP_GATHER=nccl)"
     inplace = gather and rank == 0   # rank 0 computes straight into its slots of the gathered arrays: no copy of its own part
     leaf = None if inplace else torch.empty(max(mine, 1), dtype=torch.int32, device=dev)
     val = None if inplace else torch.empty(max(mine, 1), dtype=torch.float64, device=dev)
@@ -593,7 +604,7 @@ def main():
             va = val_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             lj, vj = out_slices(j)
             st.locate_eval_resident(sm, [Xj], cc, [lj], [vj], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
-                                    chunk=args.gather_chunk, streams=[cur])
+                                    chunk=args.gather_chunk, streams=[cur], gather_base=call_base[j])
 
     def step(evs=None, with_gather=True):
         if evs: evs[0].record()
@@ -643,7 +654,7 @@ def main():
             for j in range(ncalls):
                 lj, vj = out_slices(j)
                 st.gather_resident([lj], [vj], call_counts[j], 0, leaf_all[call_base[j]:] if rank == 0 else None,
-                                   val_all[call_base[j]:] if rank == 0 else None, streams=[cur])
+                                   val_all[call_base[j]:] if rank == 0 else None, streams=[cur], gather_base=call_base[j])
         b.record()
         barrier()
         gather_ms = maxranks([a.elapsed_time(b) / nx])[0]
@@ -713,6 +724,8 @@ def main():
     if not args.no_secondary:
         del Xres, leaf_all, val_all, l0, v0, leaf, val
         Xres = None
+        if gather:
+            shard.gather_free()
         torch.cuda.empty_cache()
         try:
             c5 = run_c5_fits(cb, torch, shard, rank, world, max(2, min(args.steps, 5)), cur, dist)
@@ -747,8 +760,8 @@ def main():
                "resident_chunk_queries": int(chunk), "calls_per_step": int(ncalls), "distinct_resident_chunks_per_gpu": int(nres),
                "resident": "every query of the batch distinct and resident" if nres == ncalls else
                            f"the shard exceeds HBM: {nres} distinct resident chunks of {chunk} queries cycled over the {ncalls} passes of a step",
-               "gather": "(leaf:int32, value:f64) of every query to rank 0, NCCL send/recv inside the timed region, pipelined in steps of "
-                         f"{args.gather_chunk} queries behind the kernels" if gather else "single GPU: results already on rank 0"},
+               "gather": "(leaf:int32, value:f64) of every query to rank 0 inside the timed region, pipelined in steps of "
+                         f"{args.gather_chunk} queries behind the kernels; transport: {gather_path}" if gather else "single GPU: results already on rank 0"},
            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "fits": fits,
            "locate_eval_ms": loc_ms, "fit_ms": fit_ms,
            "gather_ms": gather_ms, "value_without_gather": M / (nogather_ms * 1e-3), "ms_per_step_without_gather": nogather_ms,

@@ -28,6 +28,7 @@ struct NcclApi {
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 NcclApi N;
@@ -52,6 +53,7 @@ int load_nccl() {
     N.Broadcast = (decltype(N.Broadcast))sym("ncclBroadcast");
     N.Send = (decltype(N.Send))sym("ncclSend");
     N.Recv = (decltype(N.Recv))sym("ncclRecv");
+    N.AllReduce = (decltype(N.AllReduce))sym("ncclAllReduce");
     N.GetErrorString = (decltype(N.GetErrorString))sym("ncclGetErrorString");
     if (!ok) return csp_set_error(CSP_ERR_NCCL, "libnccl.so.2 lacks a required symbol");
     N.h = h;
@@ -73,8 +75,21 @@ struct Rank {
     cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
+// Gather buffers owned by the library (csp_shard_gather_alloc): plain cudaMalloc memory on the root's GPU that every other rank
+// can write with its copy engines -- through the unified address space in single-process mode (peer access enabled), through a
+// CUDA IPC mapping in one-process-per-GPU mode.
+struct GatherBuf {
+    int root = -1;
+    long long cap = 0;
+    bool owner = false;                 // this process allocated them (it owns the root rank)
+    int32_t* leaf = nullptr;            // address usable by this process's ranks (the allocation itself, or the IPC mapping)
+    double* val = nullptr;
+    int* flag = nullptr;                // per local rank a 4-byte device word for the completion signal
+};
 struct Ctx {
     bool init = false;
+    GatherBuf gb;
+    std::vector<int*> sig;              // per local rank: small device scratch for the completion signals
     int world = 0, version = 0;
     std::vector<Rank> local;
     cudaEvent_t tev[6][2] = {};  // timing events on local rank 0's streams
@@ -196,8 +211,11 @@ int csp_init_rank(int world, int rank, int device, const void* id128) {
     return finish_init();
 }
 
+int csp_shard_gather_free(void);
 int csp_shutdown(void) {
     if (!G.init) return CSP_OK;
+    csp_shard_gather_free();
+    for (size_t i = 0; i < G.sig.size(); ++i) { DeviceGuard g(G.local[i].device); if (G.sig[i]) cudaFree(G.sig[i]); }
     for (Rank& r : G.local) {
         DeviceGuard g(r.device);
         cudaDeviceSynchronize();
@@ -405,6 +423,56 @@ int csp_shard_models_free(csp_shard_models* sm) {
 // ---- C2: gather of (leaf id, value) to one rank ---------------------------------------------------------------------------
 // One pipeline step: queries [off, off + cnt_r) of every rank r that still has some.  Sends / receives of all local ranks are one
 // NCCL group (a single thread may drive several GPUs); the root copies its own part with a device-to-device copy.
+// Copy-engine variant (library-owned gather buffers): every rank pushes its block straight into the root's arrays with
+// device-to-device DMA over NVLink on its communication stream -- no SMs, so it runs beside the pipeline's kernels.
+static int gather_step_ce(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, long long off, long long chunk,
+                          int root, long long gbase, const std::vector<cudaStream_t>& cs) {
+    const size_t nl = G.local.size();
+    int root_dev = -1;
+    for (size_t i = 0; i < nl; ++i)
+        if (G.local[i].rank == root) root_dev = G.local[i].device;
+    for (size_t i = 0; i < nl; ++i) {
+        const Rank& rk = G.local[i];
+        const long long cnt = std::min<long long>(chunk, counts[rk.rank] - off);
+        if (cnt <= 0) continue;
+        long long base = gbase;
+        for (int r = 0; r < rk.rank; ++r) base += counts[r];
+        int32_t* dl = G.gb.leaf + base + off;
+        double* dv = G.gb.val + base + off;
+        DeviceGuard g(rk.device);
+        if (dl != dleaf[i] + off) {
+            if (root_dev >= 0 && root_dev != rk.device) CSP_CUDA(cudaMemcpyPeerAsync(dl, root_dev, dleaf[i] + off, rk.device, (size_t)cnt * 4, cs[i]));
+            else CSP_CUDA(cudaMemcpyAsync(dl, dleaf[i] + off, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, cs[i]));
+        }
+        if (dv != dval[i] + off) {
+            if (root_dev >= 0 && root_dev != rk.device) CSP_CUDA(cudaMemcpyPeerAsync(dv, root_dev, dval[i] + off, rk.device, (size_t)cnt * 8, cs[i]));
+            else CSP_CUDA(cudaMemcpyAsync(dv, dval[i] + off, (size_t)cnt * 8, cudaMemcpyDeviceToDevice, cs[i]));
+        }
+    }
+    return CSP_OK;
+}
+// ... and its completion signal, once per call: every sender's communication stream, behind its copies, sends one word to the
+// root, whose communication stream receives them all: when that stream is joined the gathered block is complete on the root.
+static int gather_signal_ce(int root, const std::vector<cudaStream_t>& cs) {
+    if (G.world <= 1) return CSP_OK;
+    const size_t nl = G.local.size();
+    ncclResult_t r1 = N.GroupStart();
+    for (size_t i = 0; i < nl && r1 == ncclSuccess; ++i) {
+        const Rank& rk = G.local[i];
+        if (rk.rank != root) {
+            r1 = N.Send(G.sig[i], 1, ncclInt32, root, rk.comm, cs[i]);
+        } else {
+            for (int r = 0; r < G.world && r1 == ncclSuccess; ++r)
+                if (r != root) r1 = N.Recv(G.sig[i] + 1 + r, 1, ncclInt32, r, rk.comm, cs[i]);
+        }
+    }
+    ncclResult_t r2 = N.GroupEnd();
+    if (r1 != ncclSuccess || r2 != ncclSuccess)
+        return csp_set_error(CSP_ERR_NCCL, "gather completion signal failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+    return CSP_OK;
+}
+static bool gather_uses_ce(int root) { return G.gb.leaf != nullptr && G.gb.root == root && !(getenv("CSP_GATHER") && !strcmp(getenv("CSP_GATHER"), "nccl")); }
+
 static int gather_step(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, long long off, long long chunk,
                        int root, int32_t* dleaf_all, double* dval_all, const std::vector<cudaStream_t>& cs) {
     const size_t nl = G.local.size();
@@ -455,14 +523,23 @@ static int check_counts(const int64_t* counts, int gather_root, const void* a, c
     for (int r = 0; r < G.world; ++r)
         if (counts[r] < 0) return csp_set_error(CSP_ERR_INVALID, "counts[%d] < 0", r);
     if (gather_root >= G.world) return csp_set_error(CSP_ERR_INVALID, "gather_root %d out of range", gather_root);
-    if (gather_root >= 0)
+    if (gather_root >= 0 && !gather_uses_ce(gather_root))
         for (const Rank& rk : G.local)
             if (rk.rank == gather_root && (!a || !b)) return csp_set_error(CSP_ERR_INVALID, "the gather root needs dleaf_all and dval_all");
     return CSP_OK;
 }
 
+static int check_gather_base(const int64_t* counts, int64_t gather_base) {
+    long long tot = 0;
+    for (int r = 0; r < G.world; ++r) tot += counts[r];
+    if (gather_base < 0 || gather_base + tot > G.gb.cap)
+        return csp_set_error(CSP_ERR_INVALID, "gather block [%lld, %lld) outside the gather buffers (capacity %lld)", (long long)gather_base,
+                             (long long)(gather_base + tot), G.gb.cap);
+    return CSP_OK;
+}
+
 int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, int gather_root,
-                         int32_t* dleaf_all, double* dval_all, void* const* streams) {
+                         int32_t* dleaf_all, double* dval_all, int64_t gather_base, void* const* streams) {
     CSP_CHECK(need_init());
     if (!dleaf || !dval || gather_root < 0) return csp_set_error(CSP_ERR_INVALID, "bad argument");
     CSP_CHECK(check_counts(counts, gather_root, dleaf_all, dval_all));
@@ -471,15 +548,25 @@ int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval,
     long long mx = 0;
     for (size_t i = 0; i < nl; ++i) s[i] = stream_of(streams, i);
     for (int r = 0; r < G.world; ++r) mx = std::max<long long>(mx, counts[r]);
+    const bool ce = gather_uses_ce(gather_root);
+    if (ce) CSP_CHECK(check_gather_base(counts, gather_base));
     tbegin(5, s[0]);
-    int rc = mx > 0 ? gather_step(dleaf, dval, counts, 0, mx, gather_root, dleaf_all, dval_all, s) : CSP_OK;
+    int rc = CSP_OK;
+    if (mx > 0) {
+        if (ce) {
+            rc = gather_step_ce(dleaf, dval, counts, 0, mx, gather_root, gather_base, s);
+            if (rc == CSP_OK) rc = gather_signal_ce(gather_root, s);
+        } else {
+            rc = gather_step(dleaf, dval, counts, 0, mx, gather_root, dleaf_all, dval_all, s);
+        }
+    }
     tend(5, s[0]);
     return rc;
 }
 
 int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* sm, const double* const* dX, const int64_t* counts,
                               int32_t* const* dleaf, double* const* dval, uint8_t* const* dstatus, int gather_root,
-                              int32_t* dleaf_all, double* dval_all, int64_t chunk, void* const* streams) {
+                              int32_t* dleaf_all, double* dval_all, int64_t gather_base, int64_t chunk, void* const* streams) {
     CSP_CHECK(need_init());
     if (!st || !sm || !dX || !dleaf || !dval) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     const size_t nl = G.local.size();
@@ -491,6 +578,8 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
     for (int r = 0; r < G.world; ++r) mx = std::max<long long>(mx, counts[r]);
     std::vector<cudaStream_t> s(nl), cs(nl);
     const bool gather = gather_root >= 0 && G.world > 1;
+    const bool ce = gather_root >= 0 && gather_uses_ce(gather_root);
+    if (ce) CSP_CHECK(check_gather_base(counts, gather_base));
     for (size_t i = 0; i < nl; ++i) {
         s[i] = stream_of(streams, i);
         cs[i] = gather ? G.local[i].cst : s[i];
@@ -519,15 +608,134 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
                 CSP_CUDA(cudaStreamWaitEvent(cs[i], ev, 0));
             }
         }
-        if (gather_root >= 0)
-            CSP_CHECK(gather_step((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, dleaf_all, dval_all, cs));
+        if (gather_root >= 0) {
+            if (ce) CSP_CHECK(gather_step_ce((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, gather_base, cs));
+            else CSP_CHECK(gather_step((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, dleaf_all, dval_all, cs));
+        }
     }
+    if (ce && gather) CSP_CHECK(gather_signal_ce(gather_root, cs));
     if (gather)
         for (size_t i = 0; i < nl; ++i) {  // the caller's stream ends behind the last gather step
             DeviceGuard g(G.local[i].device);
             CSP_CUDA(cudaEventRecord(G.local[i].join, cs[i]));
             CSP_CUDA(cudaStreamWaitEvent(s[i], G.local[i].join, 0));
         }
+    return CSP_OK;
+}
+
+// ---- library-owned gather buffers: the copy-engine path -------------------------------------------------------------------------
+// a few bytes from the root's process to every other process: through a device word and ncclBroadcast (set-up only)
+static int bcast_bytes(void* host, size_t n, int root) {
+    const size_t nl = G.local.size();
+    if (G.world <= 1 || nl == (size_t)G.world) return CSP_OK;  // single process: nothing to exchange
+    std::vector<void*> d(nl, nullptr);
+    int root_local = -1;
+    for (size_t i = 0; i < nl; ++i) {
+        DeviceGuard g(G.local[i].device);
+        CSP_CUDA(cudaMalloc(&d[i], n));
+        if (G.local[i].rank == root) { root_local = (int)i; CSP_CUDA(cudaMemcpy(d[i], host, n, cudaMemcpyHostToDevice)); }
+    }
+    CSP_NCCL(N.GroupStart());
+    for (size_t i = 0; i < nl; ++i) CSP_NCCL(N.Broadcast(d[i], d[i], n, ncclUint8, root, G.local[i].comm, G.local[i].st));
+    CSP_NCCL(N.GroupEnd());
+    for (size_t i = 0; i < nl; ++i) {
+        DeviceGuard g(G.local[i].device);
+        CSP_CUDA(cudaStreamSynchronize(G.local[i].st));
+        if (root_local < 0 && i == 0) CSP_CUDA(cudaMemcpy(host, d[i], n, cudaMemcpyDeviceToHost));
+        cudaFree(d[i]);
+    }
+    return CSP_OK;
+}
+
+int csp_shard_gather_free(void) {
+    if (!G.init || !G.gb.leaf) return CSP_OK;
+    for (Rank& r : G.local) { DeviceGuard g(r.device); cudaDeviceSynchronize(); }
+    if (G.gb.owner) {
+        cudaFree(G.gb.leaf);
+        cudaFree(G.gb.val);
+    } else {
+        DeviceGuard g(G.local[0].device);
+        cudaIpcCloseMemHandle(G.gb.leaf);
+        cudaIpcCloseMemHandle(G.gb.val);
+    }
+    G.gb = GatherBuf();
+    return CSP_OK;
+}
+
+int csp_shard_gather_alloc(int64_t capacity, int root, int32_t** dleaf_all, double** dval_all) {
+    CSP_CHECK(need_init());
+    if (capacity < 1 || root < 0 || root >= G.world) return csp_set_error(CSP_ERR_INVALID, "bad argument");
+    csp_shard_gather_free();
+    const size_t nl = G.local.size();
+    int root_local = -1;
+    for (size_t i = 0; i < nl; ++i)
+        if (G.local[i].rank == root) root_local = (int)i;
+    if (G.sig.empty()) {
+        G.sig.assign(nl, nullptr);
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            CSP_CUDA(cudaMalloc((void**)&G.sig[i], (size_t)(G.world + 2) * 4));
+            CSP_CUDA(cudaMemset(G.sig[i], 0, (size_t)(G.world + 2) * 4));
+        }
+    }
+    struct Handles { cudaIpcMemHandle_t leaf, val; int ok; } hd{};
+    if (root_local >= 0) {
+        DeviceGuard g(G.local[root_local].device);
+        cudaError_t e = cudaMalloc((void**)&G.gb.leaf, (size_t)capacity * 4);  // plain cudaMalloc: shareable, unlike pool memory
+        if (e == cudaSuccess) e = cudaMalloc((void**)&G.gb.val, (size_t)capacity * 8);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (G.gb.leaf) cudaFree(G.gb.leaf);
+            G.gb = GatherBuf();
+        } else {
+            G.gb.owner = true;
+            hd.ok = 1;
+            if (nl < (size_t)G.world) {
+                if (cudaIpcGetMemHandle(&hd.leaf, G.gb.leaf) != cudaSuccess || cudaIpcGetMemHandle(&hd.val, G.gb.val) != cudaSuccess) { cudaGetLastError(); hd.ok = 2; }
+            }
+        }
+    }
+    CSP_CHECK(bcast_bytes(&hd, sizeof hd, root));
+    if (root_local < 0) {
+        if (hd.ok == 1) {
+            DeviceGuard g(G.local[0].device);
+            if (cudaIpcOpenMemHandle((void**)&G.gb.leaf, hd.leaf, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                cudaIpcOpenMemHandle((void**)&G.gb.val, hd.val, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                G.gb = GatherBuf();
+                hd.ok = 2;
+            }
+        }
+    } else if (hd.ok == 1) {  // single process: the other local GPUs reach the root's memory through peer access
+        for (size_t i = 0; i < nl; ++i) {
+            if ((int)i == root_local) continue;
+            DeviceGuard g(G.local[i].device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(G.local[root_local].device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) hd.ok = 2;
+            cudaGetLastError();
+        }
+    }
+    // every rank must agree on the path: minimum over the ranks of "my mapping works"
+    int ok = (hd.ok == 1 && G.gb.leaf && G.gb.val) ? 1 : 0;
+    if (G.world > 1 && nl < (size_t)G.world) {
+        int* d = G.sig[0] + G.world + 1;
+        DeviceGuard g(G.local[0].device);
+        CSP_CUDA(cudaMemcpy(d, &ok, 4, cudaMemcpyHostToDevice));
+        CSP_NCCL(N.AllReduce(d, d, 1, ncclInt32, ncclMin, G.local[0].comm, G.local[0].st));
+        CSP_CUDA(cudaStreamSynchronize(G.local[0].st));
+        CSP_CUDA(cudaMemcpy(&ok, d, 4, cudaMemcpyDeviceToHost));
+    }
+    if (!ok) {
+        G.gb.root = root;  // so that csp_shard_gather_free releases whatever this rank holds
+        if (G.gb.leaf) csp_shard_gather_free();
+        G.gb = GatherBuf();
+        return csp_set_error(CSP_ERR_UNSUPPORTED, "gather buffers cannot be shared between the GPUs (peer access / CUDA IPC unavailable); "
+                                                  "pass your own dleaf_all / dval_all: the NCCL send / receive path is used then");
+    }
+    G.gb.root = root;
+    G.gb.cap = capacity;
+    if (dleaf_all) *dleaf_all = root_local >= 0 ? G.gb.leaf : nullptr;
+    if (dval_all) *dval_all = root_local >= 0 ? G.gb.val : nullptr;
     return CSP_OK;
 }
 

@@ -103,7 +103,7 @@ struct csp_tree {
     // L1-bound descent of one chunk overlaps the DRAM-bound evaluation of the previous one
     const int4* fit_units = nullptr;  // [n_fit_units] leaf ids (-1 padded) of the real leaves under each split that has any (fit.cu)
     long long n_fit_units = 0;
-    mutable double* fit_coef = nullptr;  // [n_internal] highest-order coefficient of every split (built on the first fit)
+    double* fit_coef = nullptr;  // [n_internal] highest-order coefficient of every split (built with the tree: csp_fit_build_coef)
     mutable void* fit_ws = nullptr;  // grow-only scratch of the fit pre-pass (chain results), one fit call at a time per handle
     mutable size_t fit_ws_bytes = 0;
     LiveState* live = nullptr;  // set for trees grown by appending to the split log (live.cu)
@@ -162,6 +162,7 @@ inline RawTree raw_tree_at(const char* b, const Section* s, int n, int p, int nn
 }
 struct csp_tree;
 int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower = nullptr, const double* h_upper = nullptr);  // tree_build.cu
+int csp_fit_build_coef(csp_tree* t);                       // fit.cu
 struct LiveState;                                          // live.cu
 void csp_live_free(LiveState* ls);
 

@@ -1160,6 +1160,21 @@ __global__ void __launch_bounds__(256) k_modelvalue_native(int n, double c, cons
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
+// Highest-order coefficient of every split (src/polynomials.jl:212-224), once per tree version; on the legacy default stream,
+// before the builder's final synchronisation.
+int csp_fit_build_coef(csp_tree* t) {
+    if (t->v.n_internal <= 0 || t->v.p > 2) return CSP_OK;
+    void* pc = nullptr;
+    CSP_CHECK(csp_dev_alloc(&pc, (size_t)t->v.n_internal * sizeof(double)));
+    const int blocks = std::min(4096, (t->v.n_internal + 255) / 256);
+    if (t->v.p == 2) k_coef_table<2><<<blocks, 256>>>(t->v, (double*)pc);
+    else k_coef_table<1><<<blocks, 256>>>(t->v, (double*)pc);
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
+    t->fit_coef = (double*)pc;
+    return CSP_OK;
+}
+
 static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void** scratch_out) {
     *scratch_out = nullptr;
     if (prm.nb == 0) return CSP_OK;
@@ -1185,19 +1200,9 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         prm.units = t->fit_units;  // all leaves: sibling leaves share the off-diagonal work
         prm.n_units = t->n_fit_units;
     }
-    if (t->v.n_internal > 0 && !(getenv("CSP_FIT_COEF_TABLE") && atoi(getenv("CSP_FIT_COEF_TABLE")) == 0)) {
-        if (!t->fit_coef) {
-            void* pc = nullptr;
-            CSP_CHECK(csp_dev_alloc(&pc, (size_t)t->v.n_internal * sizeof(double)));
-            const int blocks = std::min(4096, (t->v.n_internal + 255) / 256);
-            if (P == 2) k_coef_table<2><<<blocks, 256, 0, st>>>(t->v, (double*)pc);
-            else k_coef_table<1><<<blocks, 256, 0, st>>>(t->v, (double*)pc);
-            CSP_LAUNCHED();
-            CSP_CUDA(cudaGetLastError());
-            t->fit_coef = (double*)pc;
-        }
-        prm.coef = t->fit_coef;
-    }
+    // the per-split coefficient table is built with the tree (csp_fit_build_coef, called by the device builder): no lazy
+    // initialisation here, so concurrent fits on different streams only ever read it
+    if (t->fit_coef && !(getenv("CSP_FIT_COEF_TABLE") && atoi(getenv("CSP_FIT_COEF_TABLE")) == 0)) prm.coef = t->fit_coef;
     if (prm.mode == FIT_MODE_FULL) {  // chain pre-pass: one thread per box
         const size_t nb = (size_t)prm.nb;
         const size_t need = nb * ((size_t)n * (prm.firstmatch ? 24 : 20) + 16) + 64 + 64;  // chain rows + alignment slack + the work counter

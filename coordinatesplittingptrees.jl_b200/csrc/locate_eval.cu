@@ -703,15 +703,6 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
     prm.X = dX; prm.m = m; prm.leaf = dleaf; prm.val = dval; prm.status = dstatus;
     prm.bulk = ((uintptr_t)dX % 16 == 0) ? 1 : 0;
     if (mo && use_binned(mo, m)) {
-        static bool pool_ready[64] = {};
-        if (t->device < 64 && !pool_ready[t->device]) {  // keep stream-ordered allocations cached between calls
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, t->device) == cudaSuccess) {
-                unsigned long long thr = ~0ULL;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-            pool_ready[t->device] = true;
-        }
         // The pipeline runs chunk by chunk: between the kernels of a chunk its leaf ids, permutation, values and (partly)
         // coordinates are still in the 126 MB L2, so the evaluation's gathers and scattered value writes mostly avoid
         // HBM; chunks must stay large enough to amortise the four launches and to keep many queries per leaf.

@@ -3,6 +3,7 @@
 #include <cstring>
 
 #include <chrono>
+#include <mutex>
 #include <cstdio>
 #include <cstdlib>
 
@@ -23,17 +24,17 @@ int csp_set_error(int code, const char* fmt, ...) {
 }
 int csp_current_device() { return g_device; }
 int csp_dev_alloc(void** p, size_t bytes) {
-    static bool ready[64] = {};
+    static std::once_flag ready[64];
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long thr = ~0ULL;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-        }
-        ready[dev] = true;
-    }
+    if (dev >= 0 && dev < 64)
+        std::call_once(ready[dev], [dev] {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                unsigned long long thr = ~0ULL;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+        });
     *p = nullptr;
     // size classes (x1.125 steps, 64 KB aligned): a tree that grows a little every optimiser iteration keeps landing in the
     // blocks its previous version released instead of making the pool map new memory
@@ -79,15 +80,20 @@ thread_local bool g_csp_alloc_nosync = false;
 namespace {
 struct TimedLaunch { int cls; cudaEvent_t a, b; };
 std::vector<TimedLaunch> g_timed;
+std::mutex g_timed_mu;  // held from csp_timing_begin to csp_timing_end: instrumented launches are serialised across host threads
 }
 void csp_timing_begin(int cls, cudaStream_t st) {
+    g_timed_mu.lock();
     TimedLaunch t{cls, nullptr, nullptr};
     cudaEventCreate(&t.a);
     cudaEventCreate(&t.b);
     cudaEventRecord(t.a, st);
     g_timed.push_back(t);
 }
-void csp_timing_end(cudaStream_t st) { cudaEventRecord(g_timed.back().b, st); }
+void csp_timing_end(cudaStream_t st) {
+    cudaEventRecord(g_timed.back().b, st);
+    g_timed_mu.unlock();
+}
 
 extern "C" {
 int csp_timing_enable(int on) {
@@ -97,6 +103,7 @@ int csp_timing_enable(int on) {
 int csp_timing_read(double* ms, int64_t* launches) {
     if (!ms || !launches) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     for (int i = 0; i < CSP_K_CLASSES; ++i) { ms[i] = 0; launches[i] = 0; }
+    std::lock_guard<std::mutex> lock(g_timed_mu);
     if (!g_timed.empty()) CSP_CUDA(cudaDeviceSynchronize());
     for (auto& t : g_timed) {
         float e = 0;
@@ -422,6 +429,8 @@ int csp_tree_upload(const csp_tree_desc* desc, csp_tree** out) {
         csp_tree* t = new_tree();
         DeviceGuard g(t->device);
         int rc = upload_impl(desc, t);
+        if (rc == CSP_OK) rc = csp_fit_build_coef(t);
+        if (rc == CSP_OK && cudaDeviceSynchronize() != cudaSuccess) rc = csp_set_error(CSP_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (rc != CSP_OK) { csp_tree_free(t); return rc; }
         *out = t;
         return CSP_OK;

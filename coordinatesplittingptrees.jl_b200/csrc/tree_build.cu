@@ -330,6 +330,7 @@ int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower, 
         CSP_CUDA(cudaMemcpy(units, &u, sizeof u, cudaMemcpyHostToDevice));
     }
     t->max_depth = (int)h.max_depth;
+    CSP_CHECK(csp_fit_build_coef(t));
     CSP_CUDA(cudaDeviceSynchronize());
     return CSP_OK;
 }

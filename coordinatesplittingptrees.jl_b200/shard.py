@@ -83,6 +83,33 @@ def timing():
     return {k: float(ms[i]) for i, k in enumerate(TIMING_KEYS)}
 
 
+class _RawCuda:
+    """A device buffer owned by the library, exposed through __cuda_array_interface__ so that torch.as_tensor can view it."""
+
+    def __init__(self, ptr, count, typestr):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def gather_alloc(capacity, root=0, device=None):
+    """csp_shard_gather_alloc: library-owned gather buffers on rank `root` (collective).  Returns (leaf_all, val_all) as torch views
+    on the process that owns the root rank, (None, None) elsewhere.  Gathers to that root then move their blocks with the copy
+    engines (peer DMA over NVLink) at the element offset `gather_base` the calls are given."""
+    import torch
+    pl, pv = C.c_void_p(), C.c_void_p()
+    N.dchk(N.dev().csp_shard_gather_alloc(int(capacity), int(root), C.byref(pl), C.byref(pv)))
+    if not pl.value:
+        return None, None
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    with torch.cuda.device(dev):
+        leaf = torch.as_tensor(_RawCuda(pl.value, capacity, "<i4"), device=dev)
+        val = torch.as_tensor(_RawCuda(pv.value, capacity, "<f8"), device=dev)
+    return leaf, val
+
+
+def gather_free():
+    N.dchk(N.dev().csp_shard_gather_free())
+
+
 def _ptr_array(items):
     if items is None:
         return None
@@ -149,20 +176,21 @@ class ShardedTree:
         return models if models is not None else ShardedModels(h, self.nlocal)
 
     def locate_eval_resident(self, models, X, counts, leaf, val, status=None, gather_root=-1, leaf_all=None, val_all=None, chunk=0,
-                             streams=None):
+                             streams=None, gather_base=0):
         """Per local rank i: locate + evaluate the resident shard X[i] (counts[rank] queries) into leaf[i] / val[i] / status[i];
-        with gather_root >= 0 also gather every rank's (leaf, val) into leaf_all / val_all on that rank (collective)."""
+        with gather_root >= 0 also gather every rank's (leaf, val) into leaf_all / val_all on that rank (collective) -- or, when
+        gather_alloc() buffers exist, into those at element offset gather_base (copy-engine path)."""
         cnt = (C.c_int64 * self.world)(*[int(c) for c in counts])
         N.dchk(N.dev().csp_shard_locate_eval_dev(self.h, models.h, _ptr_array(X), cnt, _ptr_array(leaf), _ptr_array(val),
                                                  _ptr_array(status) if status is not None else None, int(gather_root),
                                                  None if leaf_all is None else _ptr(leaf_all), None if val_all is None else _ptr(val_all),
-                                                 int(chunk), _stream_array(streams, self.nlocal)))
+                                                 int(gather_base), int(chunk), _stream_array(streams, self.nlocal)))
 
-    def gather_resident(self, leaf, val, counts, gather_root, leaf_all, val_all, streams=None):
+    def gather_resident(self, leaf, val, counts, gather_root, leaf_all, val_all, streams=None, gather_base=0):
         cnt = (C.c_int64 * self.world)(*[int(c) for c in counts])
         N.dchk(N.dev().csp_shard_gather_dev(_ptr_array(leaf), _ptr_array(val), cnt, int(gather_root),
                                             None if leaf_all is None else _ptr(leaf_all), None if val_all is None else _ptr(val_all),
-                                            _stream_array(streams, self.nlocal)))
+                                            int(gather_base), _stream_array(streams, self.nlocal)))
 
     def locate_eval(self, models, X, leaf=None, val=None, status=None):
         """Host buffers: this process's queries split over its local GPUs; results in host arrays (leaf, val, status)."""

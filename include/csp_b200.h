@@ -10,7 +10,10 @@
  *     failure on the calling thread.  No exceptions cross this boundary; the host wrapper re-raises the reference's
  *     exception types from the status codes documented below.
  *   - the caller owns every host buffer; the library owns device memory behind the opaque handles.
- *   - one caller thread per handle at a time; concurrent readers of one csp_tree are safe.
+ *   - threads: point location and evaluation only read a csp_tree / csp_models and may run concurrently on one handle (from
+ *     different host threads and streams); the fit entry points share a per-tree scratch buffer and are NOT reentrant on one
+ *     handle; handles are created / freed / re-fitted by one thread at a time; the multi-GPU layer and the timing switch are
+ *     process-wide and driven by one thread.
  *   - a query matrix X holds m queries of n doubles each, each query contiguous (Julia: an n x m column-major Matrix).
  *   - `*_dev` variants take DEVICE pointers on the handle's device plus a cudaStream_t (as void*; NULL = default stream),
  *     are asynchronous, and are what a caller with resident data uses.  The plain variants take HOST buffers, move them
@@ -248,10 +251,20 @@ int csp_shard_models_free(csp_shard_models* sm);
  * dleaf_all / dval_all are read only by the process that owns gather_root. */
 int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* sm, const double* const* dX, const int64_t* counts,
                               int32_t* const* dleaf, double* const* dval, uint8_t* const* dstatus, int gather_root,
-                              int32_t* dleaf_all, double* dval_all, int64_t chunk, void* const* streams);
+                              int32_t* dleaf_all, double* dval_all, int64_t gather_base, int64_t chunk, void* const* streams);
 /* The gather alone (results already computed): what csp_shard_locate_eval_dev does after its kernels. */
 int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, int gather_root,
-                         int32_t* dleaf_all, double* dval_all, void* const* streams);
+                         int32_t* dleaf_all, double* dval_all, int64_t gather_base, void* const* streams);
+/* Gather buffers owned by the library, `capacity` results on rank `root`'s GPU (collective; *dleaf_all / *dval_all are set on the
+ * process that owns `root`, NULL elsewhere).  While they exist, a gather to that root ignores the dleaf_all / dval_all arguments
+ * and writes the call's block at element offset `gather_base` of these buffers (every process passes the same gather_base),
+ * moving it with the GPUs' COPY ENGINES -- device-to-device DMA over NVLink straight into the root's memory (peer access in
+ * single-process mode, a CUDA IPC mapping with one process per GPU) -- so that no SM is taken from the kernels the transfer
+ * overlaps; NCCL only carries one completion word per call.  Without them the gather runs as NCCL send / receive kernels.
+ * A rank may compute straight into its own block of the buffers (then nothing is copied for it).  CSP_ERR_UNSUPPORTED when the
+ * GPUs cannot map each other's memory. */
+int csp_shard_gather_alloc(int64_t capacity, int root, int32_t** dleaf_all, double** dval_all);
+int csp_shard_gather_free(void);
 /* Host buffers: the calling process's m queries are split over its local GPUs (contiguous ranges, one host thread and one copy /
  * compute pipeline per GPU) and the results land in the caller's arrays -- in single-process mode that is the whole batch
  * gathered on the host.  Returns when the results are complete. */

@@ -145,6 +145,54 @@ end
 nodeid(t::DeviceTree, box) = t.flat.nodeid[box]
 leafbox(t::DeviceTree, leaf::Integer) = t.flat.leafboxes[leaf + 1]
 
+# ---- live trees: the device copy grows with the tree (include/csp_b200.h, "incremental residency") ------------------------------------------
+"""
+A device tree fed the SPLIT LOG instead of whole flattenings: `LiveTree(root)` replays the splits of `root` in creation order and
+`update!(lt)` sends only the splits `addpoint!` made since the last call; the preorder flattening is re-derived on the device.
+Box ids here are creation-order ids (root 0; the children of the s-th split are 1 + s*2^p + (0:2^p-1)).
+"""
+mutable struct LiveTree
+    tree::DeviceTree
+    root::Box
+    boxid::IdDict{Any,Int32}   # Box -> creation-order id
+    nsplits::Int
+end
+function LiveTree(root::Box{p,Float64}) where p
+    w = root.world; n = ndims(root)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:csp_tree_create_live, LIB), Cint, (Int32, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Float64, Ref{Ptr{Cvoid}}),
+                n, p, collect(Float64, w.lower), collect(Float64, w.upper), collect(Float64, position(root)), value(root), h))
+    lt = LiveTree(finalizer(free!, DeviceTree(h[], nothing, true)), root, IdDict{Any,Int32}(root => Int32(0)), 0)
+    update!(lt)
+end
+"Append the splits made since the last call.  The reference keeps no log, so they are found by walking the boxes that were leaves."
+function update!(lt::LiveTree)
+    p = CSp.degree(lt.root); C = 1 << p
+    sb = Int32[]; dims = Int32[]; xs = Float64[]; cv = Float64[]
+    frontier = [b for b in keys(lt.boxid) if !isleaf(b) && !haskey(lt.boxid, CSp.getchild(b.split, 0))]
+    sort!(frontier; by = b -> lt.boxid[b])
+    while !isempty(frontier)
+        b = popfirst!(frontier)
+        push!(sb, lt.boxid[b]); append!(dims, b.split.dims); append!(xs, b.split.xs)
+        for k in 0:C-1
+            c = CSp.getchild(b.split, k)
+            lt.boxid[c] = Int32(1 + (lt.nsplits + length(sb) - 1) * C + k)
+            push!(cv, value(c))
+            isleaf(c) || push!(frontier, c)
+        end
+    end
+    isempty(sb) || check(ccall((:csp_tree_append_splits, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}, Ptr{Float64}),
+                               lt.tree.h, length(sb), sb, dims, xs, cv))
+    lt.nsplits += length(sb)
+    lt
+end
+"(node_of_box, box_of_node): creation-order box ids <-> the current preorder node ids."
+function live_maps(lt::LiveTree)
+    nn = info(lt.tree)[3]; a = Vector{Int32}(undef, nn); b = Vector{Int32}(undef, nn)
+    check(ccall((:csp_tree_live_maps, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), lt.tree.h, a, b))
+    (a, b)
+end
+
 "Diagnostic: one of the arrays derived on the device at upload, as raw bytes (csp_tree_export_derived)."
 function export_derived(t::DeviceTree, which::Integer)
     sz = Ref{Csize_t}(0)
@@ -430,16 +478,25 @@ end
 "Resident shards (device pointers per local GPU); with gather_root >= 0 the (leaf, value) pairs are gathered on that rank (C2)."
 function locate_eval_dev!(s::ShardedTree, sm::ShardedModels, dX::Vector{Ptr{Cvoid}}, counts::Vector{Int64}, dleaf::Vector{Ptr{Cvoid}},
                           dval::Vector{Ptr{Cvoid}}, dstatus::Vector{Ptr{Cvoid}}; gather_root::Integer=-1, dleaf_all::Ptr{Cvoid}=C_NULL,
-                          dval_all::Ptr{Cvoid}=C_NULL, chunk::Integer=0, streams::Union{Vector{Ptr{Cvoid}},Nothing}=nothing)
+                          dval_all::Ptr{Cvoid}=C_NULL, gather_base::Integer=0, chunk::Integer=0,
+                          streams::Union{Vector{Ptr{Cvoid}},Nothing}=nothing)
     check(ccall((:csp_shard_locate_eval_dev, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Cint, Ptr{Cvoid}, Ptr{Cvoid},
-                 Int64, Ptr{Ptr{Cvoid}}),
-                s.h, sm.h, dX, counts, dleaf, dval, dstatus, gather_root, dleaf_all, dval_all, chunk, streams === nothing ? C_NULL : streams))
+                 Int64, Int64, Ptr{Ptr{Cvoid}}),
+                s.h, sm.h, dX, counts, dleaf, dval, dstatus, gather_root, dleaf_all, dval_all, gather_base, chunk,
+                streams === nothing ? C_NULL : streams))
 end
 gather_dev!(dleaf::Vector{Ptr{Cvoid}}, dval::Vector{Ptr{Cvoid}}, counts::Vector{Int64}, gather_root::Integer, dleaf_all::Ptr{Cvoid},
-            dval_all::Ptr{Cvoid}; streams::Union{Vector{Ptr{Cvoid}},Nothing}=nothing) =
-    check(ccall((:csp_shard_gather_dev, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}),
-                dleaf, dval, counts, gather_root, dleaf_all, dval_all, streams === nothing ? C_NULL : streams))
+            dval_all::Ptr{Cvoid}; gather_base::Integer=0, streams::Union{Vector{Ptr{Cvoid}},Nothing}=nothing) =
+    check(ccall((:csp_shard_gather_dev, LIB), Cint, (Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Ptr{Int64}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Ptr{Cvoid}}),
+                dleaf, dval, counts, gather_root, dleaf_all, dval_all, gather_base, streams === nothing ? C_NULL : streams))
+"Library-owned gather buffers on rank `root` (copy-engine gather: peer DMA over NVLink); returns (dleaf_all, dval_all) device pointers."
+function gather_alloc(capacity::Integer; root::Integer=0)
+    pl = Ref{Ptr{Cvoid}}(C_NULL); pv = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:csp_shard_gather_alloc, LIB), Cint, (Int64, Cint, Ref{Ptr{Cvoid}}, Ref{Ptr{Cvoid}}), capacity, root, pl, pv))
+    (pl[], pv[])
+end
+gather_free() = check(ccall((:csp_shard_gather_free, LIB), Cint, ()))
 synchronize() = check(ccall((:csp_shard_synchronize, LIB), Cint, ()))
 "(blob h2d, tree broadcast, upload, fit kernels, record all-gather, result gather) in milliseconds"
 function shard_timing()

@@ -56,6 +56,20 @@ def main():
     assert same(leaf.cpu().numpy(), rleaf[lo:hi]) and same(val.cpu().numpy(), rval[lo:hi])
     if rank == 0:
         assert same(leaf_all.cpu().numpy(), rleaf) and same(val_all.cpu().numpy(), rval)
+    # the same gather through library-owned buffers and the copy engines (CUDA IPC mapping of rank 0's arrays)
+    gl, gv = shard.gather_alloc(m + 500, root=0, device=local)
+    if rank == 0:
+        gl.fill_(-7)
+    torch.cuda.synchronize()
+    dist.barrier()
+    for _ in range(2):
+        st.locate_eval_resident(sm, [Xd], counts, [leaf], [val], [status], gather_root=0, chunk=40_000, streams=[stream], gather_base=500)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        assert same(gl[500:].cpu().numpy(), rleaf) and same(gv[500:].cpu().numpy(), rval) and int(gl[:500].max()) == -7
+    dist.barrier()
+    shard.gather_free()
     dist.barrier()
     sm.close()
     st.close()

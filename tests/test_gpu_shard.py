@@ -98,6 +98,17 @@ def test_single_process_clique_matches_single_gpu(monkeypatch):
         assert same(la.cpu().numpy(), rleaf) and same(va.cpu().numpy(), rval)
         t = shard.timing()
         assert t["fit_ms"] > 0
+        # library-owned gather buffers: the same gather through the copy engines (peer DMA), at an offset into the buffers
+        gl, gv = shard.gather_alloc(m + 1000, root=root2, device=st.local[root2].device)
+        gl.fill_(-7)
+        st.locate_eval_resident(sm, Xd, counts, leaf, val, status, gather_root=root2, chunk=70_000, gather_base=1000)
+        shard.synchronize()
+        assert same(gl[1000:].cpu().numpy(), rleaf) and same(gv[1000:].cpu().numpy(), rval) and int(gl[:1000].max()) == -7
+        gl.fill_(-7)
+        st.gather_resident(leaf, val, counts, root2, None, None, gather_base=0)
+        shard.synchronize()
+        assert same(gl[:m].cpu().numpy(), rleaf) and same(gv[:m].cpu().numpy(), rval)
+        shard.gather_free()
         # host buffers, split over the local GPUs by one thread per GPU
         hleaf, hval, hstatus = st.locate_eval(sm, X)
         assert same(hleaf, rleaf) and same(hval, rval) and same(hstatus, rstatus)
