@@ -594,6 +594,9 @@ def main():
             return leaf_all[call_base[j]:], val_all[call_base[j]:]
         return leaf[j * chunk:], val[j * chunk:]
 
+    if gather:
+        shard.defer_join(True)   # the calls of a step write disjoint result ranges: one join per step instead of one per call
+
     def locate_all(with_gather):
         for j in range(ncalls):
             cc = call_counts[j]
@@ -605,6 +608,8 @@ def main():
             lj, vj = out_slices(j)
             st.locate_eval_resident(sm, [Xj], cc, [lj], [vj], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
                                     chunk=args.gather_chunk, streams=[cur], gather_base=call_base[j])
+        if with_gather and gather:
+            shard.join([cur])
 
     def step(evs=None, with_gather=True):
         if evs: evs[0].record()

@@ -162,6 +162,8 @@ def dev():
         L.csp_shard_locate_eval_dev.argtypes = [vp, vp, vpp, c_i64p, vpp, vpp, vpp, C.c_int, vp, vp, C.c_int64, C.c_int64, vpp]
         L.csp_shard_gather_dev.argtypes = [vpp, vpp, c_i64p, C.c_int, vp, vp, C.c_int64, vpp]
         L.csp_shard_gather_alloc.argtypes = [C.c_int64, C.c_int, vpp, vpp]
+        L.csp_shard_defer_join.argtypes = [C.c_int]
+        L.csp_shard_join.argtypes = [vpp]
         L.csp_shard_locate_eval.argtypes = [vp, vp, vp, C.c_int64, vp, vp, vp]
         L.csp_shard_timing.argtypes = [c_f64p]
         _dev = L
@@ -182,4 +184,4 @@ EXPORTS = ["csp_version", "csp_last_error", "csp_device_count", "csp_set_device"
            "csp_tree_export_derived", "csp_tree_create_live", "csp_tree_append_splits", "csp_tree_live_maps", "csp_find_leaf_from", "csp_find_leaf_from_dev", "csp_boxbounds", "csp_tree_extrema",
            "csp_init", "csp_comm_unique_id", "csp_init_rank", "csp_shutdown", "csp_comm_info", "csp_shard_tree_broadcast",
            "csp_shard_tree_get", "csp_shard_tree_free", "csp_shard_fit", "csp_shard_models_get", "csp_shard_models_free",
-           "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_gather_alloc", "csp_shard_gather_free", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]
+           "csp_shard_locate_eval_dev", "csp_shard_gather_dev", "csp_shard_gather_alloc", "csp_shard_gather_free", "csp_shard_defer_join", "csp_shard_join", "csp_shard_locate_eval", "csp_shard_synchronize", "csp_shard_timing"]

@@ -88,6 +88,7 @@ struct GatherBuf {
 };
 struct Ctx {
     bool init = false;
+    bool defer_join = false;            // csp_shard_defer_join: gathers are joined by csp_shard_join instead of by every call
     GatherBuf gb;
     std::vector<int*> sig;              // per local rank: small device scratch for the completion signals
     int world = 0, version = 0;
@@ -614,12 +615,28 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
         }
     }
     if (ce && gather) CSP_CHECK(gather_signal_ce(gather_root, cs));
-    if (gather)
+    if (gather && !G.defer_join)
         for (size_t i = 0; i < nl; ++i) {  // the caller's stream ends behind the last gather step
             DeviceGuard g(G.local[i].device);
             CSP_CUDA(cudaEventRecord(G.local[i].join, cs[i]));
             CSP_CUDA(cudaStreamWaitEvent(s[i], G.local[i].join, 0));
         }
+    return CSP_OK;
+}
+
+int csp_shard_defer_join(int on) {
+    CSP_CHECK(need_init());
+    G.defer_join = on != 0;
+    return CSP_OK;
+}
+
+int csp_shard_join(void* const* streams) {
+    CSP_CHECK(need_init());
+    for (size_t i = 0; i < G.local.size(); ++i) {
+        DeviceGuard g(G.local[i].device);
+        CSP_CUDA(cudaEventRecord(G.local[i].join, G.local[i].cst));
+        CSP_CUDA(cudaStreamWaitEvent(stream_of(streams, i), G.local[i].join, 0));
+    }
     return CSP_OK;
 }
 

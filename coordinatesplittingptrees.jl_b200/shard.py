@@ -106,6 +106,17 @@ def gather_alloc(capacity, root=0, device=None):
     return leaf, val
 
 
+def defer_join(on=True):
+    """csp_shard_defer_join: resident locate+evaluate calls stop waiting for their own last gather step; join() does it once."""
+    N.dchk(N.dev().csp_shard_defer_join(1 if on else 0))
+
+
+def join(streams=None):
+    """csp_shard_join: the given streams (one per local rank; None: the library's) wait for every gather issued so far."""
+    nlocal = comm_info()["local"]
+    N.dchk(N.dev().csp_shard_join(_stream_array(streams, nlocal)))
+
+
 def gather_free():
     N.dchk(N.dev().csp_shard_gather_free())
 

@@ -255,6 +255,11 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
 /* The gather alone (results already computed): what csp_shard_locate_eval_dev does after its kernels. */
 int csp_shard_gather_dev(const int32_t* const* dleaf, const double* const* dval, const int64_t* counts, int gather_root,
                          int32_t* dleaf_all, double* dval_all, int64_t gather_base, void* const* streams);
+/* By default every csp_shard_locate_eval_dev call ends with the callers' streams waiting for its last gather step.  With
+ * csp_shard_defer_join(1) they do not: consecutive calls then overlap the previous call's last transfer with their own kernels
+ * (the calls must write disjoint result ranges), and csp_shard_join makes the streams wait for every gather issued so far. */
+int csp_shard_defer_join(int on);
+int csp_shard_join(void* const* streams);
 /* Gather buffers owned by the library, `capacity` results on rank `root`'s GPU (collective; *dleaf_all / *dval_all are set on the
  * process that owns `root`, NULL elsewhere).  While they exist, a gather to that root ignores the dleaf_all / dval_all arguments
  * and writes the call's block at element offset `gather_base` of these buffers (every process passes the same gather_base),

@@ -497,6 +497,9 @@ function gather_alloc(capacity::Integer; root::Integer=0)
     (pl[], pv[])
 end
 gather_free() = check(ccall((:csp_shard_gather_free, LIB), Cint, ()))
+"Let consecutive resident calls overlap the previous call's last gather step; `join()` then waits for all gathers issued so far."
+defer_join(on::Bool=true) = check(ccall((:csp_shard_defer_join, LIB), Cint, (Cint,), on))
+join(streams::Union{Vector{Ptr{Cvoid}},Nothing}=nothing) = check(ccall((:csp_shard_join, LIB), Cint, (Ptr{Ptr{Cvoid}},), streams === nothing ? C_NULL : streams))
 synchronize() = check(ccall((:csp_shard_synchronize, LIB), Cint, ()))
 "(blob h2d, tree broadcast, upload, fit kernels, record all-gather, result gather) in milliseconds"
 function shard_timing()
