@@ -270,10 +270,9 @@ __global__ void __launch_bounds__(256) k_eval_binned_mma(const ModelsView mv, co
         const unsigned vm = __ballot_sync(FULL, v);
         if (lane == 0) mbar_expect_tx(&bars[st], (uint32_t)(__popc(vm) * N * 8));
         __syncwarp();
-        if (v) {
-            fence_proxy_async();
-            bulk_g2s(rows + ((size_t)st * 32 + lane) * RS, X + (size_t)(unsigned)q.x * N, N * 8, &bars[st]);
-        }
+        // (no proxy fence: the stage being refilled was only READ through the generic proxy, and those reads completed -- their
+        // values fed the MMAs -- before the __syncwarp that closed the previous iteration)
+        if (v) bulk_g2s(rows + ((size_t)st * 32 + lane) * RS, X + (size_t)(unsigned)q.x * N, N * 8, &bars[st]);
     };
     int cur = 0, staged = -1, pre = -1;
     double uf[KS][NT], bA[KS], bE[NT][2];  // per-leaf fragments (registers)

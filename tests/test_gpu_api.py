@@ -347,3 +347,27 @@ def test_live_tree_rejects_bad_log():
     assert (t.n_nodes, t.n_internal, t.n_leaves) == (5, 1, 4)     # the handle survived
     leaf, status = t.find_leaf(np.array([[0.9, 0.9], [-0.9, -0.9]]))
     assert (status == 0).all() and leaf[0] != leaf[1]
+
+
+@pytest.mark.parametrize("n,nl,m", [(40, 9, 20000), (10, 7, 300000), (6, 5, 2000)])
+def test_eval_leaf_ids_out_of_range_give_nan(n, nl, m):
+    """csp_eval[_dev] takes caller-supplied leaf ids: an id outside [0, n_models) -- negative or too large -- gives NaN on every
+    evaluation path (grouped dense n > 32, binned n <= 32, one-thread-per-query), never an out-of-bounds access."""
+    import torch
+    from csp_b200.device import LeafModels
+    rng = np.random.default_rng(n)
+    c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))
+    Q = np.triu(rng.standard_normal((nl, n, n)) / n)
+    models = LeafModels.upload(c, g, Q, b)
+    X = rng.uniform(-1, 1, (m, n))
+    leaf = rng.integers(0, nl, m).astype(np.int32)
+    bad = rng.random(m) < 0.1
+    leaf[bad] = rng.choice(np.array([-1, -5, nl, nl + 3, 2 ** 30], np.int32), int(bad.sum()))
+    oval, _ = O.eval_batch(c, g, Q, b, X[~bad], leaf[~bad])
+    for where in ("host", "device"):
+        if where == "host":
+            val = models.evaluate(X, leaf)
+        else:
+            val = models.evaluate(torch.from_numpy(X).cuda(), torch.from_numpy(leaf).cuda()).cpu().numpy()
+        assert np.isnan(val[bad]).all() and np.isfinite(val[~bad]).all()
+        assert np.allclose(val[~bad], oval, rtol=1e-12, atol=1e-12 * np.abs(oval).max())
