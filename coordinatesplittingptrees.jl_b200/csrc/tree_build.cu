@@ -225,7 +225,9 @@ int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower, 
     size_t tmp_scan_i = 0, tmp_scan_l = 0, tmp_sort = 0, tmp_max = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan_i, (const int*)nullptr, (int*)nullptr, nn + 1, st);
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan_l, (const long long*)nullptr, (long long*)nullptr, nl + 1, st);
-    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, std::max(ni, 1), 0, 32, st);
+    int depth_bits = 1;  // a depth is below the number of splits: sort only the bits that can be set
+    while (depth_bits < 31 && (1LL << depth_bits) <= (long long)ni) ++depth_bits;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const int*)nullptr, (int*)nullptr, (const int*)nullptr, (int*)nullptr, std::max(ni, 1), 0, depth_bits, st);
     cub::DeviceReduce::Max(nullptr, tmp_max, (const long long*)nullptr, (long long*)nullptr, std::max(nl, 1), st);
     const size_t tmp_bytes = std::max(std::max(tmp_scan_i, tmp_scan_l), std::max(tmp_sort, tmp_max)) + 256;
 
@@ -283,7 +285,7 @@ int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower, 
     if (ni > 0 && p <= 2) {
         // BFS order == internal nodes sorted by depth, preorder within a depth (a stable sort of the preorder sequence)
         tb = tmp_bytes;
-        cub::DeviceRadixSort::SortPairs(tmp, tb, idepth, keys_out, iota, bfs, ni, 0, 32, st);
+        cub::DeviceRadixSort::SortPairs(tmp, tb, idepth, keys_out, iota, bfs, ni, 0, depth_bits, st);
         kb_bfs_counts<<<blocks_for(ni + 1), 256, 0, st>>>(r, bfs, nint, nlf);
         tb = tmp_bytes;
         cub::DeviceScan::ExclusiveSum(tmp, tb, nint, Fex, ni + 1, st);
