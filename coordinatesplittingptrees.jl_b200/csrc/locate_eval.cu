@@ -773,6 +773,17 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         }
         return rc;
     }
+    if (mo && t->v.n > 256) {
+        // Large n, small batch: the fused kernel would need a shared-memory tile of whole rows (it stops fitting near n = 700).
+        // Locate with the streaming descent kernel (any n), then evaluate from the leaf ids (grouped dense / per-query kernel).
+        int* lbuf = dleaf;
+        if (!lbuf) CSP_CUDA(cudaMallocAsync((void**)&lbuf, (size_t)m * 4, st));
+        prm.leaf = lbuf;
+        int rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, prm, st) : launch_locate_p<1>(t, nullptr, prm, st);
+        if (rc == CSP_OK) rc = csp_eval_dev(mo, dX, lbuf, m, dval, st);
+        if (!dleaf) cudaFreeAsync(lbuf, st);
+        return rc;
+    }
     if (mo) { prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data; }
     return t->v.p == 2 ? launch_locate_p<2>(t, mo, prm, st) : launch_locate_p<1>(t, mo, prm, st);
 }

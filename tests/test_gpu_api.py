@@ -371,3 +371,24 @@ def test_eval_leaf_ids_out_of_range_give_nan(n, nl, m):
             val = models.evaluate(torch.from_numpy(X).cuda(), torch.from_numpy(leaf).cuda()).cpu().numpy()
         assert np.isnan(val[bad]).all() and np.isfinite(val[~bad]).all()
         assert np.allclose(val[~bad], oval, rtol=1e-12, atol=1e-12 * np.abs(oval).max())
+
+
+def test_locate_eval_very_large_n_small_batch():
+    """n beyond what the fused locate+evaluate kernel can tile in shared memory: a small batch falls back to the
+    streaming descent kernel followed by the evaluate-from-leaf-ids path instead of failing."""
+    from csp_b200.device import LeafModels
+    n = 900
+    root, oroot, _ = grow_both(n, 1, 1, seed=31, sigma=0.0)
+    dt = cb.device_tree(root)
+    nl = dt.n_leaves
+    rng = np.random.default_rng(2)
+    c, g, b = rng.standard_normal(nl), rng.standard_normal((nl, n)), 0.1 * rng.standard_normal((nl, n))
+    models = LeafModels.upload(c, g, None, b)
+    X = cb.synthetic.uniform_queries(root, 500, seed=8)
+    X[3, 7] = 5.0
+    leaf, val, status = dt.locate_eval(models, X)
+    oleaf, ostatus, _ = O.find_leaf_batch(oroot, X)
+    assert same(leaf, oleaf) and same(status, ostatus) and status[3] == 1 and np.isnan(val[3])
+    ok = oleaf >= 0
+    want = c[oleaf[ok]] + np.einsum("qi,qi->q", g[oleaf[ok]], X[ok] - b[oleaf[ok]])
+    assert np.allclose(val[ok], want, rtol=1e-11, atol=1e-11 * np.abs(want).max())
