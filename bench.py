@@ -603,12 +603,15 @@ def main():
             o = j * chunk
             Xj = Xres[j % nres]
             groot = 0 if (with_gather and gather) else -1
+            if groot == 0 and j == ncalls - 1:
+                shard.defer_join(False)  # the step's last call waits for its own (tapered) gathers
             la = leaf_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             va = val_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             lj, vj = out_slices(j)
             st.locate_eval_resident(sm, [Xj], cc, [lj], [vj], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
                                     chunk=args.gather_chunk, streams=[cur], gather_base=call_base[j])
         if with_gather and gather:
+            shard.defer_join(True)
             shard.join([cur])
 
     def step(evs=None, with_gather=True):

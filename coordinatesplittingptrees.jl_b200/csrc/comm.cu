@@ -594,8 +594,19 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
     const char* renv = getenv("CSP_GATHER_SM_RESERVE");
     struct Reserve { ~Reserve() { g_csp_sm_reserve = 0; } } reserve_guard;
     g_csp_sm_reserve = gather ? (renv ? atoi(renv) : 0) : 0;  // measured at N=2 (C3): 0 / 8 / 16 SMs reserved -> 87.4 / 91.0 / 86.9 ms per step: no gain
+    // Pipeline steps.  The gather of the LAST step is the part no kernel can hide, so when this call itself waits for its
+    // gathers (no deferred join) the final chunk is tapered -- halves down to an eighth -- and only a small block is exposed
+    // (N = 8, C3: 2.6 -> 0.4 ms); the smaller binning chunks cost the kernels a few per cent on that last eighth of the data.
+    std::vector<long long> sizes;
+    for (long long rem = mx; rem > 0;) {
+        long long c = std::min<long long>(chunk, rem);
+        if (gather && !G.defer_join && rem <= chunk && c > chunk / 8 && c > (1 << 20)) c = (c + 1) / 2;
+        sizes.push_back(c);
+        rem -= c;
+    }
     int step = 0;
-    for (long long off = 0; off < mx; off += chunk, ++step) {
+    long long off = 0;
+    for (const long long chunk : sizes) {  // (shadows the parameter: this step's size)
         for (size_t i = 0; i < nl; ++i) {
             const Rank& rk = G.local[i];
             const long long cnt = std::min<long long>(chunk, counts[rk.rank] - off);
@@ -613,6 +624,8 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
             if (ce) CSP_CHECK(gather_step_ce((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, gather_base, cs));
             else CSP_CHECK(gather_step((const int32_t* const*)dleaf, (const double* const*)dval, counts, off, chunk, gather_root, dleaf_all, dval_all, cs));
         }
+        off += chunk;
+        ++step;
     }
     if (ce && gather) CSP_CHECK(gather_signal_ce(gather_root, cs));
     if (gather && !G.defer_join)
