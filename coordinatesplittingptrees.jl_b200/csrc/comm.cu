@@ -143,6 +143,11 @@ struct csp_shard_tree {
 };
 struct csp_shard_models {
     std::vector<csp_models*> models;
+    // copy-engine all-gather of the fitted records: every rank's record / status arrays mapped by every other rank
+    bool ce = false;
+    std::vector<std::vector<double*>> peer_data;     // [local rank][rank] -> that rank's record array, as addressable here
+    std::vector<std::vector<uint8_t*>> peer_status;
+    std::vector<void*> ipc_opened;                   // mappings to close
 };
 
 extern "C" {
@@ -351,6 +356,93 @@ int csp_shard_tree_free(csp_shard_tree* st) {
     return CSP_OK;
 }
 
+// Map every rank's record and status arrays on every other rank (peer access inside a process, CUDA IPC between processes).
+// Collective; false (on every rank alike) when some rank cannot map some other.
+static int bcast_bytes(void* host, size_t n, int root);
+static int setup_models_ce(csp_shard_models* sm) {
+    const size_t nl = G.local.size();
+    const int W = G.world;
+    sm->peer_data.assign(nl, std::vector<double*>(W, nullptr));
+    sm->peer_status.assign(nl, std::vector<uint8_t*>(W, nullptr));
+    int ok = 1;
+    for (int r = 0; r < W; ++r) {
+        int owner = -1;
+        for (size_t i = 0; i < nl; ++i)
+            if (G.local[i].rank == r) owner = (int)i;
+        struct Handles { cudaIpcMemHandle_t data, status; int ok; } hd{};
+        if (owner >= 0) {
+            hd.ok = 1;
+            if (nl < (size_t)W) {
+                DeviceGuard g(G.local[owner].device);
+                if (cudaIpcGetMemHandle(&hd.data, sm->models[owner]->data) != cudaSuccess ||
+                    cudaIpcGetMemHandle(&hd.status, sm->models[owner]->status) != cudaSuccess) { cudaGetLastError(); hd.ok = 0; }
+            }
+        }
+        CSP_CHECK(bcast_bytes(&hd, sizeof hd, r));
+        if (!hd.ok) ok = 0;
+        for (size_t i = 0; i < nl && hd.ok; ++i) {
+            if ((int)i == owner) {
+                sm->peer_data[i][r] = sm->models[i]->data;
+                sm->peer_status[i][r] = sm->models[i]->status;
+            } else if (owner >= 0) {  // same process: the unified address space, peer access enabled
+                DeviceGuard g(G.local[i].device);
+                cudaError_t e = cudaDeviceEnablePeerAccess(G.local[owner].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+                sm->peer_data[i][r] = sm->models[owner]->data;
+                sm->peer_status[i][r] = sm->models[owner]->status;
+            } else {  // another process
+                DeviceGuard g(G.local[i].device);
+                void *pd = nullptr, *ps = nullptr;
+                if (cudaIpcOpenMemHandle(&pd, hd.data, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+                    cudaIpcOpenMemHandle(&ps, hd.status, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    ok = 0;
+                }
+                if (pd) sm->ipc_opened.push_back(pd);
+                if (ps) sm->ipc_opened.push_back(ps);
+                sm->peer_data[i][r] = (double*)pd;
+                sm->peer_status[i][r] = (uint8_t*)ps;
+            }
+        }
+    }
+    if (W > 1 && nl < (size_t)W) {  // agree: minimum over the ranks
+        int* d = G.sig[0] + G.world + 1;
+        DeviceGuard g(G.local[0].device);
+        CSP_CUDA(cudaMemcpy(d, &ok, 4, cudaMemcpyHostToDevice));
+        CSP_NCCL(N.AllReduce(d, d, 1, ncclInt32, ncclMin, G.local[0].comm, G.local[0].st));
+        CSP_CUDA(cudaStreamSynchronize(G.local[0].st));
+        CSP_CUDA(cudaMemcpy(&ok, d, 4, cudaMemcpyDeviceToHost));
+    }
+    sm->ce = ok != 0;
+    if (sm->ce)
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            CSP_CUDA(cudaEventCreateWithFlags(&sm->models[i]->ready, cudaEventDisableTiming));
+        }
+    return CSP_OK;
+}
+static int ensure_sig() {
+    if (!G.sig.empty()) return CSP_OK;
+    const size_t nl = G.local.size();
+    G.sig.assign(nl, nullptr);
+    for (size_t i = 0; i < nl; ++i) {
+        DeviceGuard g(G.local[i].device);
+        CSP_CUDA(cudaMalloc((void**)&G.sig[i], (size_t)(G.world + 2) * 4));
+        CSP_CUDA(cudaMemset(G.sig[i], 0, (size_t)(G.world + 2) * 4));
+    }
+    return CSP_OK;
+}
+// a barrier on the communication streams: one word all-reduced (every rank's kernel is ordered behind what its stream holds)
+static int comm_barrier(const std::vector<cudaStream_t>& cs) {
+    ncclResult_t r1 = N.GroupStart();
+    for (size_t i = 0; i < G.local.size() && r1 == ncclSuccess; ++i)
+        r1 = N.AllReduce(G.sig[i], G.sig[i], 1, ncclInt32, ncclSum, G.local[i].comm, cs[i]);
+    ncclResult_t r2 = N.GroupEnd();
+    if (r1 != ncclSuccess || r2 != ncclSuccess) return csp_set_error(CSP_ERR_NCCL, "barrier failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2));
+    return CSP_OK;
+}
+
 // ---- leaf-sharded fit + all-gather of the records -------------------------------------------------------------------------
 int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** models, void* const* streams) {
     if (!st || !models) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
@@ -359,11 +451,17 @@ int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** mod
     if (st->trees.size() != nl) return csp_set_error(CSP_ERR_INVALID, "sharded tree does not belong to this clique");
     csp_shard_models* sm = *models;
     const bool fresh = sm == nullptr;
+    const bool want_ce = G.world > 1 && !(getenv("CSP_ALLGATHER") && !strcmp(getenv("CSP_ALLGATHER"), "nccl"));
     if (fresh) {
         sm = new csp_shard_models();
         sm->models.assign(nl, nullptr);
         for (size_t i = 0; i < nl; ++i) {
-            int rc = csp_models_alloc(st->trees[i], &sm->models[i]);
+            int rc = csp_models_alloc_ex(st->trees[i], want_ce, &sm->models[i]);
+            if (rc != CSP_OK) { csp_shard_models_free(sm); return rc; }
+        }
+        if (want_ce) {
+            int rc = ensure_sig();
+            if (rc == CSP_OK) rc = setup_models_ce(sm);
             if (rc != CSP_OK) { csp_shard_models_free(sm); return rc; }
         }
     } else if (sm->models.size() != nl) {
@@ -371,38 +469,80 @@ int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** mod
     }
     auto fail = [&](int rc) { if (fresh) csp_shard_models_free(sm); return rc; };
     const long long nleaves = sm->models[0]->n_models;
+    std::vector<cudaStream_t> s(nl), cs(nl);
+    for (size_t i = 0; i < nl; ++i) { s[i] = stream_of(streams, i); cs[i] = G.local[i].cst; }
+    if (sm->ce) {
+        // Copy-engine all-gather, off the callers' streams.  (1) The communication streams step behind everything queued so far
+        // (the previous evaluations) and meet in a barrier: no rank's records are overwritten while another still reads them.
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            CSP_CUDA(cudaEventRecord(G.local[i].fork, s[i]));
+            CSP_CUDA(cudaStreamWaitEvent(cs[i], G.local[i].fork, 0));
+        }
+        int rc = comm_barrier(cs);
+        if (rc != CSP_OK) return fail(rc);
+    }
     for (size_t i = 0; i < nl; ++i) {
         long long lo, hi;
         shard_range(nleaves, G.world, G.local[i].rank, &lo, &hi);
-        cudaStream_t s = stream_of(streams, i);
-        if (i == 0) tbegin(3, s);
-        int rc = csp_models_refit_range(st->trees[i], skip, sm->models[i], lo, hi, s);
-        if (i == 0) tend(3, s);
+        if (i == 0) tbegin(3, s[i]);
+        int rc = csp_models_refit_range(st->trees[i], skip, sm->models[i], lo, hi, s[i]);
+        if (i == 0) tend(3, s[i]);
         if (rc != CSP_OK) return fail(rc);
     }
-    if (G.world > 1) {
-        // "all-gather-v": every owner broadcasts its range of records (and status bytes) in place; one group
-        tbegin(4, stream_of(streams, 0));
+    if (sm->ce) {
+        // (2) behind the local fit, every rank pushes its record range into every other rank's array with its copy engines
+        // (device-to-device DMA over NVLink), (3) a second barrier tells everyone that all ranges have landed, (4) the
+        // models' `ready` event is recorded: the descent of the next batch runs meanwhile, its evaluation waits for the event.
+        for (size_t i = 0; i < nl; ++i) {
+            const Rank& rk = G.local[i];
+            csp_models* mo = sm->models[i];
+            long long lo, hi;
+            shard_range(nleaves, G.world, rk.rank, &lo, &hi);
+            DeviceGuard g(rk.device);
+            CSP_CUDA(cudaEventRecord(rk.join, s[i]));
+            CSP_CUDA(cudaStreamWaitEvent(cs[i], rk.join, 0));
+            if (i == 0) tbegin(4, cs[i]);
+            for (int d = 1; d < G.world && hi > lo; ++d) {
+                const int r = (rk.rank + d) % G.world;  // every rank starts with a different target
+                CSP_CUDA(cudaMemcpyAsync(sm->peer_data[i][r] + (size_t)lo * mo->stride, mo->data + (size_t)lo * mo->stride,
+                                         (size_t)(hi - lo) * mo->stride * 8, cudaMemcpyDeviceToDevice, cs[i]));
+                CSP_CUDA(cudaMemcpyAsync(sm->peer_status[i][r] + lo, mo->status + lo, (size_t)(hi - lo), cudaMemcpyDeviceToDevice, cs[i]));
+            }
+        }
+        int rc = comm_barrier(cs);
+        if (rc != CSP_OK) return fail(rc);
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            if (i == 0) tend(4, cs[i]);
+            CSP_CUDA(cudaEventRecord(sm->models[i]->ready, cs[i]));
+        }
+    } else if (G.world > 1) {
+        // "all-gather-v" with NCCL: every owner broadcasts its range of records (and status bytes) in place; one group
+        tbegin(4, s[0]);
         ncclResult_t r1 = N.GroupStart();
         for (size_t i = 0; i < nl && r1 == ncclSuccess; ++i) {
             csp_models* mo = sm->models[i];
-            cudaStream_t s = stream_of(streams, i);
             for (int r = 0; r < G.world && r1 == ncclSuccess; ++r) {
                 long long lo, hi;
                 shard_range(nleaves, G.world, r, &lo, &hi);
                 if (hi <= lo) continue;
                 double* p = mo->data + (size_t)lo * mo->stride;
-                r1 = N.Broadcast(p, p, (size_t)(hi - lo) * mo->stride, ncclDouble, r, G.local[i].comm, s);
-                if (r1 == ncclSuccess) r1 = N.Broadcast(mo->status + lo, mo->status + lo, (size_t)(hi - lo), ncclUint8, r, G.local[i].comm, s);
+                r1 = N.Broadcast(p, p, (size_t)(hi - lo) * mo->stride, ncclDouble, r, G.local[i].comm, s[i]);
+                if (r1 == ncclSuccess) r1 = N.Broadcast(mo->status + lo, mo->status + lo, (size_t)(hi - lo), ncclUint8, r, G.local[i].comm, s[i]);
             }
         }
         ncclResult_t r2 = N.GroupEnd();
-        tend(4, stream_of(streams, 0));
+        tend(4, s[0]);
         if (r1 != ncclSuccess || r2 != ncclSuccess)
             return fail(csp_set_error(CSP_ERR_NCCL, "record all-gather failed: %s", N.GetErrorString(r1 != ncclSuccess ? r1 : r2)));
     }
     if (fresh) {
-        for (size_t i = 0; i < nl; ++i) { DeviceGuard g(G.local[i].device); cudaStreamSynchronize(stream_of(streams, i)); }
+        for (size_t i = 0; i < nl; ++i) {
+            DeviceGuard g(G.local[i].device);
+            cudaStreamSynchronize(s[i]);
+            cudaStreamSynchronize(cs[i]);
+        }
         *models = sm;
     }
     return CSP_OK;
@@ -416,6 +556,11 @@ int csp_shard_models_get(const csp_shard_models* sm, int local_index, csp_models
 
 int csp_shard_models_free(csp_shard_models* sm) {
     if (!sm) return CSP_OK;
+    if (!sm->ipc_opened.empty()) {
+        for (Rank& r : G.local) { DeviceGuard g(r.device); cudaDeviceSynchronize(); }
+        DeviceGuard g(G.local[0].device);
+        for (void* q : sm->ipc_opened) cudaIpcCloseMemHandle(q);
+    }
     for (csp_models* m : sm->models) csp_models_free(m);
     delete sm;
     return CSP_OK;
@@ -700,14 +845,7 @@ int csp_shard_gather_alloc(int64_t capacity, int root, int32_t** dleaf_all, doub
     int root_local = -1;
     for (size_t i = 0; i < nl; ++i)
         if (G.local[i].rank == root) root_local = (int)i;
-    if (G.sig.empty()) {
-        G.sig.assign(nl, nullptr);
-        for (size_t i = 0; i < nl; ++i) {
-            DeviceGuard g(G.local[i].device);
-            CSP_CUDA(cudaMalloc((void**)&G.sig[i], (size_t)(G.world + 2) * 4));
-            CSP_CUDA(cudaMemset(G.sig[i], 0, (size_t)(G.world + 2) * 4));
-        }
-    }
+    CSP_CHECK(ensure_sig());
     struct Handles { cudaIpcMemHandle_t leaf, val; int ok; } hd{};
     if (root_local >= 0) {
         DeviceGuard g(G.local[root_local].device);

@@ -116,7 +116,14 @@ struct csp_models {
     long long n_models = 0;
     double* data = nullptr;    // device, n_models*stride
     uint8_t* status = nullptr; // device, n_models (CSP_FIT_*)
+    bool plain = false;        // data / status are plain cudaMalloc memory (shareable between GPUs / processes), not pool memory
+    // Set by the multi-GPU layer when other ranks deposit parts of the records asynchronously (copy-engine all-gather, comm.cu):
+    // recorded once everything has landed; every consumer of the records waits for it on its own stream first.
+    cudaEvent_t ready = nullptr;
 };
+inline void csp_models_wait_ready(const csp_models* mo, cudaStream_t st) {
+    if (mo && mo->ready) cudaStreamWaitEvent(st, mo->ready, 0);
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // wire format (csp_tree_pack / csp_tree_upload_blob): a 64-byte header, then the csp_tree_desc arrays in declaration order,
@@ -163,6 +170,8 @@ inline RawTree raw_tree_at(const char* b, const Section* s, int n, int p, int nn
 struct csp_tree;
 int csp_tree_build_device(csp_tree* t, const RawTree& r, const double* h_lower = nullptr, const double* h_upper = nullptr);  // tree_build.cu
 int csp_fit_build_coef(csp_tree* t);                       // fit.cu
+struct csp_models;
+extern "C" int csp_models_alloc_ex(const csp_tree* t, bool plain, csp_models** out);  // fit.cu (internal)
 struct LiveState;                                          // live.cu
 void csp_live_free(LiveState* ls);
 

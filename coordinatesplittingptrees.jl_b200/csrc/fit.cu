@@ -1538,6 +1538,7 @@ int csp_fit_gdiag(const csp_tree* t, const int32_t* node_ids, int64_t nb, int32_
 }
 
 int csp_models_possemidef(csp_models* mo, void* stream) {
+    csp_models_wait_ready(mo, (cudaStream_t)stream);
     if (!mo) return csp_set_error(CSP_ERR_INVALID, "models is NULL");
     if (mo->degree != 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "possemidef needs quadratic (degree-2) models");
     if (mo->n > 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "possemidef kernel supports n <= 1024");
@@ -1573,7 +1574,10 @@ int csp_modelvalue_native(int32_t n, double c, const double* g, const double* Q,
     return CSP_OK;
 }
 
-int csp_models_alloc(const csp_tree* t, csp_models** out) {
+int csp_models_alloc(const csp_tree* t, csp_models** out) { return csp_models_alloc_ex(t, false, out); }
+
+// plain: plain cudaMalloc memory (what cudaIpcGetMemHandle / peer copies need) instead of the stream-ordered pool
+int csp_models_alloc_ex(const csp_tree* t, bool plain, csp_models** out) {
     if (!t || !out) return csp_set_error(CSP_ERR_INVALID, "NULL argument");
     *out = nullptr;
     if (t->v.p > 2) return csp_set_error(CSP_ERR_UNSUPPORTED, "models exist for degrees p <= 2 only (the tree has p=%d)", t->v.p);
@@ -1583,7 +1587,9 @@ int csp_models_alloc(const csp_tree* t, csp_models** out) {
     mo->device = t->device; mo->n = t->v.n; mo->degree = t->v.p == 2 ? 2 : 1;
     mo->stride = csp_model_stride(mo->n, mo->degree);
     mo->n_models = t->v.n_leaves;
-    if (csp_dev_alloc((void**)&mo->data, (size_t)mo->n_models * mo->stride * 8) != CSP_OK || csp_dev_alloc((void**)&mo->status, (size_t)mo->n_models) != CSP_OK ||
+    mo->plain = plain;
+    auto alloc = [&](void** q, size_t bytes) { return plain ? (cudaMalloc(q, std::max<size_t>(bytes, 16)) == cudaSuccess ? CSP_OK : (cudaGetLastError(), CSP_ERR_NOMEM)) : csp_dev_alloc(q, bytes); };
+    if (alloc((void**)&mo->data, (size_t)mo->n_models * mo->stride * 8) != CSP_OK || alloc((void**)&mo->status, (size_t)mo->n_models) != CSP_OK ||
         cudaMemset(mo->data, 0, (size_t)mo->n_models * mo->stride * 8) != cudaSuccess || cudaMemset(mo->status, 0, (size_t)mo->n_models) != cudaSuccess) {
         csp_models_free(mo);
         return csp_set_error(CSP_ERR_NOMEM, "cannot allocate %d model records", t->v.n_leaves);

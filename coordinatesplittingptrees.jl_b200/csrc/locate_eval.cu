@@ -760,7 +760,10 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
             w[k].ranked = getenv("CSP_BIN_RANKED") && atoi(getenv("CSP_BIN_RANKED")) == 1;
             cp.rank = w[k].ranked ? w[k].slot : nullptr;
             rc = t->v.p == 2 ? launch_locate_p<2>(t, nullptr, cp, ss[k]) : launch_locate_p<1>(t, nullptr, cp, ss[k]);
-            if (rc == CSP_OK) rc = csp_binned_eval(mo, csp_grid_sms(t->n_sm), cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
+            if (rc == CSP_OK) {
+                csp_models_wait_ready(mo, ss[k]);  // the descent above did not need the records; everything below does
+                rc = csp_binned_eval(mo, csp_grid_sms(t->n_sm), cp.X, cnt, cp.leaf, dval + off, &w[k], ss[k]);
+            }
         }
         g_csp_grid_div = 1;
         if (preset) preset->epoch = w[0].epoch;
@@ -785,6 +788,7 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         return rc;
     }
     if (mo) { prm.mv.n = mo->n; prm.mv.degree = mo->degree; prm.mv.stride = mo->stride; prm.mv.n_models = mo->n_models; prm.mv.data = mo->data; }
+    csp_models_wait_ready(mo, st);
     return t->v.p == 2 ? launch_locate_p<2>(t, mo, prm, st) : launch_locate_p<1>(t, mo, prm, st);
 }
 
@@ -847,6 +851,7 @@ int csp_eval_dev(const csp_models* mo, const double* dX, const int32_t* dleaf, i
     if (m < 0 || (m > 0 && (!dX || !dleaf || !dval))) return csp_set_error(CSP_ERR_INVALID, "bad buffer");
     if (m == 0) return CSP_OK;
     DeviceGuard g(mo->device);
+    csp_models_wait_ready(mo, (cudaStream_t)stream);
     if (csp_dense_supported(mo) && m < (1LL << 31) && !(getenv("CSP_EVAL_MODE") && !strcmp(getenv("CSP_EVAL_MODE"), "direct"))) {
         // large n: group the queries by leaf (histogram, scan, scatter) and evaluate on the FP64 tensor cores (K3b)
         cudaStream_t st = (cudaStream_t)stream;

@@ -50,8 +50,9 @@ int csp_models_free(csp_models* mo) {
     {
         DeviceGuard g(mo->device);
         cudaDeviceSynchronize();
-        csp_dev_free(mo->data);
-        csp_dev_free(mo->status);
+        if (mo->plain) { cudaFree(mo->data); cudaFree(mo->status); }
+        else { csp_dev_free(mo->data); csp_dev_free(mo->status); }
+        if (mo->ready) cudaEventDestroy(mo->ready);
     }
     delete mo;
     return CSP_OK;
@@ -112,6 +113,7 @@ int csp_models_upload(int32_t n, int64_t n_models, const double* c, const double
 int csp_models_download(const csp_models* mo, double* c, double* g, double* Q, double* b, uint8_t* status) {
     if (!mo) return csp_set_error(CSP_ERR_INVALID, "models is NULL");
     DeviceGuard dg(mo->device);
+    if (mo->ready) CSP_CUDA(cudaEventSynchronize(mo->ready));
     const size_t S = mo->stride;
     const long long slab = std::max<long long>(1, (256LL << 20) / (long long)(S * 8));
     std::vector<double> stage((size_t)std::min<long long>(slab, mo->n_models) * S);
@@ -131,6 +133,7 @@ int csp_models_download_rows(const csp_models* mo, const int32_t* leaf_ids, int6
         if (leaf_ids[i] < 0 || leaf_ids[i] >= mo->n_models) return csp_set_error(CSP_ERR_INVALID, "leaf id %d out of range at %lld", leaf_ids[i], (long long)i);
     if (nb == 0) return CSP_OK;
     DeviceGuard dg(mo->device);
+    if (mo->ready) CSP_CUDA(cudaEventSynchronize(mo->ready));
     const size_t S = mo->stride;
     const long long slab = std::max<long long>(1, (128LL << 20) / (long long)(S * 8));
     const long long cap = std::min<long long>(slab, nb);
