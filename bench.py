@@ -603,15 +603,12 @@ def main():
             o = j * chunk
             Xj = Xres[j % nres]
             groot = 0 if (with_gather and gather) else -1
-            if groot == 0 and j == ncalls - 1:
-                shard.defer_join(False)  # the step's last call waits for its own (tapered) gathers
             la = leaf_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             va = val_all[call_base[j]:] if (groot == 0 and rank == 0) else None
             lj, vj = out_slices(j)
             st.locate_eval_resident(sm, [Xj], cc, [lj], [vj], [status[o:]], gather_root=groot, leaf_all=la, val_all=va,
                                     chunk=args.gather_chunk, streams=[cur], gather_base=call_base[j])
         if with_gather and gather:
-            shard.defer_join(True)
             shard.join([cur])
 
     def step(evs=None, with_gather=True):
@@ -742,6 +739,8 @@ def main():
 
     if rank != 0:
         dist.barrier()  # rank 0 still uses its replicas for the parity / CPU-baseline leg
+        sm.close()
+        st.close()
         shard.shutdown()
         dist.destroy_process_group()
         return
@@ -752,9 +751,15 @@ def main():
     V = mean_visited(tree, flat["leaf_nodes"], n)
     fit_kernel_ms = KT["fit"][0] / ni
     lo_r0, hi_r0 = shard.shard_range(nl, world, 0)
-    fits = {"value": nl / (fit_ms * 1e-3), "unit": "leaf fits/s", "what": "all leaves fitted ONCE per step, sharded by leaf-id range over the GPUs, "
-            "records all-gathered (value = leaves / (fit + all-gather time, max over ranks))", "leaves": nl, "ms_per_step": fit_ms,
-            "kernel_ms_rank0": fit_kernel_ms, "allgather_ms_rank0": tm_fit["allgather_ms"] if world > 1 else 0.0, "leaves_rank0": hi_r0 - lo_r0,
+    ag_ms = tm_fit["allgather_ms"] if world > 1 else 0.0
+    ag_overlapped = world > 1 and os.environ.get("CSP_ALLGATHER") != "nccl"
+    fit_total_ms = fit_ms + (ag_ms if ag_overlapped else 0.0)  # with the copy-engine all-gather fit_ms (stream time) holds the kernels only
+    fits = {"value": nl / (fit_total_ms * 1e-3), "unit": "leaf fits/s", "what": "all leaves fitted ONCE per step, sharded by leaf-id range over the GPUs, "
+            "records all-gathered (value = leaves / (fit kernels + all-gather), counted serially although the copy-engine all-gather "
+            "runs beside the next batch's descent)", "leaves": nl, "ms_per_step": fit_total_ms, "stream_ms_per_step": fit_ms,
+            "allgather": ("copy engines: every rank pushes its record range to every other rank (peer DMA over NVLink), overlapped"
+                          if ag_overlapped else ("NCCL broadcasts on the step's stream" if world > 1 else "single GPU")),
+            "kernel_ms_rank0": fit_kernel_ms, "allgather_ms_rank0": ag_ms, "leaves_rank0": hi_r0 - lo_r0,
             "mean_splits_examined": V, "algorithmic_bytes_per_leaf": fit_bytes(n, V) if V else None,
             "frac": (hi_r0 - lo_r0) * fit_bytes(n, V) / (max(fit_kernel_ms, 1e-9) * 1e-3) / 1e9 / peak if V else None,
             "frac_note": "per GPU: rank 0's leaves x SURVEY 8(d) bytes / its fit-kernel time / measured HBM peak",

@@ -556,9 +556,9 @@ int csp_shard_models_get(const csp_shard_models* sm, int local_index, csp_models
 
 int csp_shard_models_free(csp_shard_models* sm) {
     if (!sm) return CSP_OK;
-    if (!sm->ipc_opened.empty()) {
-        for (Rank& r : G.local) { DeviceGuard g(r.device); cudaDeviceSynchronize(); }
-        DeviceGuard g(G.local[0].device);
+    if (!sm->ipc_opened.empty() && !sm->models.empty() && sm->models[0]) {  // (may run after csp_shutdown: no use of the clique here)
+        DeviceGuard g(sm->models[0]->device);
+        cudaDeviceSynchronize();
         for (void* q : sm->ipc_opened) cudaIpcCloseMemHandle(q);
     }
     for (csp_models* m : sm->models) csp_models_free(m);
@@ -739,13 +739,11 @@ int csp_shard_locate_eval_dev(const csp_shard_tree* st, const csp_shard_models* 
     const char* renv = getenv("CSP_GATHER_SM_RESERVE");
     struct Reserve { ~Reserve() { g_csp_sm_reserve = 0; } } reserve_guard;
     g_csp_sm_reserve = gather ? (renv ? atoi(renv) : 0) : 0;  // measured at N=2 (C3): 0 / 8 / 16 SMs reserved -> 87.4 / 91.0 / 86.9 ms per step: no gain
-    // Pipeline steps.  The gather of the LAST step is the part no kernel can hide, so when this call itself waits for its
-    // gathers (no deferred join) the final chunk is tapered -- halves down to an eighth -- and only a small block is exposed
-    // (N = 8, C3: 2.6 -> 0.4 ms); the smaller binning chunks cost the kernels a few per cent on that last eighth of the data.
+    // Pipeline steps of `chunk` queries.  (Tapering the last chunk so that less of the final gather is exposed was measured and
+    // dropped: N = 2, C3: 78.4 -> 82.2 ms per step -- chunks of a few million queries on 1e6 leaves run the binned kernels badly.)
     std::vector<long long> sizes;
     for (long long rem = mx; rem > 0;) {
-        long long c = std::min<long long>(chunk, rem);
-        if (gather && !G.defer_join && rem <= chunk && c > chunk / 8 && c > (1 << 20)) c = (c + 1) / 2;
+        const long long c = std::min<long long>(chunk, rem);
         sizes.push_back(c);
         rem -= c;
     }
