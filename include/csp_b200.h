@@ -239,8 +239,13 @@ int csp_shard_tree_broadcast(const void* blob, size_t bytes, int root, csp_shard
 int csp_shard_tree_get(const csp_shard_tree* st, int local_index, csp_tree** tree); /* borrowed: do not free */
 int csp_shard_tree_free(csp_shard_tree* st);
 /* Leaf fits sharded by contiguous leaf-id range over the ranks (csp_models_refit_range), then the fitted records are all-gathered
- * (one in-place ncclBroadcast per owner range, grouped) so that every GPU holds every model.  *models == NULL allocates the
- * replicas, otherwise they are re-fitted in place. */
+ * so that every GPU holds every model.  *models == NULL allocates the replicas, otherwise they are re-fitted in place.
+ * The all-gather runs on the COPY ENGINES when the GPUs can map each other's memory (peer access / CUDA IPC; the replicas are
+ * plain cudaMalloc memory then): behind its own fit, every rank pushes its record range into every other replica by
+ * device-to-device DMA over NVLink on a communication stream, between two one-word barriers.  The call does NOT make the
+ * callers' streams wait for it: each csp_models carries a `ready` event that every consumer of the records (evaluation,
+ * download, possemidef) waits for, so the descent of the next batch overlaps the transfer.  Otherwise (CSP_ALLGATHER=nccl, or
+ * no peer mapping): one in-place ncclBroadcast per owner range, grouped, on the callers' streams. */
 int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** models, void* const* streams);
 int csp_shard_models_get(const csp_shard_models* sm, int local_index, csp_models** models); /* borrowed */
 int csp_shard_models_free(csp_shard_models* sm);
