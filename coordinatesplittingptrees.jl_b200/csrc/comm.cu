@@ -72,6 +72,8 @@ struct Rank {
     ncclComm_t comm = nullptr;
     cudaStream_t st = nullptr;   // library stream (used when the caller passes no stream)
     cudaStream_t cst = nullptr;  // communication stream: gathers run here behind the next chunk's kernels
+    cudaStream_t aux[2] = {nullptr, nullptr};  // two more copy streams: pushes to different peers run on different copy engines
+    cudaEvent_t aux_go = nullptr, aux_done[2] = {nullptr, nullptr};
     cudaEvent_t fork = nullptr, join = nullptr;
     cudaEvent_t chunk_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
@@ -117,6 +119,11 @@ int finish_init() {
         CSP_CUDA(cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming));
         CSP_CUDA(cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming));
         for (auto& e : r.chunk_ev) CSP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+            CSP_CUDA(cudaStreamCreateWithPriority(&r.aux[k], cudaStreamNonBlocking, prio_hi));
+            CSP_CUDA(cudaEventCreateWithFlags(&r.aux_done[k], cudaEventDisableTiming));
+        }
+        CSP_CUDA(cudaEventCreateWithFlags(&r.aux_go, cudaEventDisableTiming));
     }
     {
         DeviceGuard g(G.local[0].device);
@@ -231,6 +238,8 @@ int csp_shutdown(void) {
         if (r.fork) cudaEventDestroy(r.fork);
         if (r.join) cudaEventDestroy(r.join);
         for (auto& e : r.chunk_ev) if (e) cudaEventDestroy(e);
+        for (int k = 0; k < 2; ++k) { if (r.aux[k]) cudaStreamDestroy(r.aux[k]); if (r.aux_done[k]) cudaEventDestroy(r.aux_done[k]); }
+        if (r.aux_go) cudaEventDestroy(r.aux_go);
     }
     {
         DeviceGuard g(G.local[0].device);
@@ -503,11 +512,19 @@ int csp_shard_fit(const csp_shard_tree* st, int32_t skip, csp_shard_models** mod
             CSP_CUDA(cudaEventRecord(rk.join, s[i]));
             CSP_CUDA(cudaStreamWaitEvent(cs[i], rk.join, 0));
             if (i == 0) tbegin(4, cs[i]);
+            // the pushes to the different peers are spread over three streams, i.e. over several copy engines and NVLink ports
+            CSP_CUDA(cudaEventRecord(rk.aux_go, cs[i]));
+            for (int k = 0; k < 2; ++k) CSP_CUDA(cudaStreamWaitEvent(rk.aux[k], rk.aux_go, 0));
             for (int d = 1; d < G.world && hi > lo; ++d) {
                 const int r = (rk.rank + d) % G.world;  // every rank starts with a different target
+                cudaStream_t ps = d % 3 == 0 ? cs[i] : rk.aux[d % 3 - 1];
                 CSP_CUDA(cudaMemcpyAsync(sm->peer_data[i][r] + (size_t)lo * mo->stride, mo->data + (size_t)lo * mo->stride,
-                                         (size_t)(hi - lo) * mo->stride * 8, cudaMemcpyDeviceToDevice, cs[i]));
-                CSP_CUDA(cudaMemcpyAsync(sm->peer_status[i][r] + lo, mo->status + lo, (size_t)(hi - lo), cudaMemcpyDeviceToDevice, cs[i]));
+                                         (size_t)(hi - lo) * mo->stride * 8, cudaMemcpyDeviceToDevice, ps));
+                CSP_CUDA(cudaMemcpyAsync(sm->peer_status[i][r] + lo, mo->status + lo, (size_t)(hi - lo), cudaMemcpyDeviceToDevice, ps));
+            }
+            for (int k = 0; k < 2; ++k) {
+                CSP_CUDA(cudaEventRecord(rk.aux_done[k], rk.aux[k]));
+                CSP_CUDA(cudaStreamWaitEvent(cs[i], rk.aux_done[k], 0));
             }
         }
         int rc = comm_barrier(cs);

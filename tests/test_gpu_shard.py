@@ -104,6 +104,22 @@ def test_single_process_clique_matches_single_gpu(monkeypatch):
         st.locate_eval_resident(sm, Xd, counts, leaf, val, status, gather_root=root2, chunk=70_000, gather_base=1000)
         shard.synchronize()
         assert same(gl[1000:].cpu().numpy(), rleaf) and same(gv[1000:].cpu().numpy(), rval) and int(gl[:1000].max()) == -7
+        # deferred join: two calls over the two halves of every shard, one join at the end
+        shard.defer_join(True)
+        gl.fill_(-7)
+        h1 = [c // 2 for c in counts]
+        h2 = [c - a for c, a in zip(counts, h1)]
+        st.locate_eval_resident(sm, Xd, h1, leaf, val, status, gather_root=root2, chunk=40_000, gather_base=0)
+        st.locate_eval_resident(sm, [x[a:] for x, a in zip(Xd, h1)], h2, [l[a:] for l, a in zip(leaf, h1)], [v[a:] for v, a in zip(val, h1)],
+                                [t_[a:] for t_, a in zip(status, h1)], gather_root=root2, chunk=40_000, gather_base=sum(h1))
+        shard.join()
+        shard.defer_join(False)
+        shard.synchronize()
+        o1, o2 = np.concatenate([[0], np.cumsum(h1)]), np.concatenate([[0], np.cumsum(h2)])
+        got = gl.cpu().numpy()
+        for r in range(ndev):  # the first call's blocks, then the second call's, each in rank order
+            assert same(got[o1[r]:o1[r + 1]], rleaf[offs[r]:offs[r] + h1[r]])
+            assert same(got[sum(h1) + o2[r]: sum(h1) + o2[r + 1]], rleaf[offs[r] + h1[r]:offs[r + 1]])
         gl.fill_(-7)
         st.gather_resident(leaf, val, counts, root2, None, None, gather_base=0)
         shard.synchronize()
