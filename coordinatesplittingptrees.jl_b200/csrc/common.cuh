@@ -26,11 +26,42 @@
 //
 // degree 2: 32 bytes, one 256-bit load (LDG.E.256).  meta: d0 bits 0-11, d1 bits 12-23 (0-based dims), flip0 24, flip1 25,
 // fictive0 26, fictive1 27, internal-children mask bits 28-31.
+// G, H: the leaf ids of the node's leaf children without a table.  In preorder the leaf children of a node have consecutive
+// leaf ids except across an internal sibling, i.e. at most two runs among four children: leaf child k has the id
+// (an internal child lies between the first leaf child and k ? H : G) + (number of leaf children below k).  Nodes where this
+// does not hold for every reachable child (fake leaves between real ones: fictive first dimension) store G = ~(first descent
+// leaf id) < 0 and resolve the id through dleaf.
 struct __align__(32) DRec2 {
     double mid0, mid1;
     int F, G;
-    unsigned meta, pad;
+    unsigned meta;
+    int H;
 };
+// Encodes (G, H) of a degree-2 record: L[k] = leaf id of child k (< 0: fake leaf), mask = internal children, fict = fictive
+// flags of the two split dimensions, gdl = the node's first descent leaf id.  Used by both tree builders.
+__host__ __device__ inline void csp_encode_leaf_runs(const int L[4], unsigned mask, unsigned fict0, unsigned fict1, int gdl, int* G, int* H) {
+    const unsigned lead = mask & ~(mask + 1u) & 0xfu;
+    int g = -1, h = -1;
+    bool haveg = false, haveh = false, ok = true;
+    for (int k = 0; k < 4; ++k) {
+        if ((mask >> k) & 1u) continue;
+        if ((fict0 && (k & 1)) || (fict1 && (k & 2))) continue;  // never reached by a descent
+        const unsigned below = (1u << k) - 1u;
+        int cnt = 0;
+        for (int j = 0; j < k; ++j) cnt += !((mask >> j) & 1u);
+        const int base = L[k] - cnt;
+        if (L[k] < 0 || base < 0) { ok = false; break; }
+        if (mask & below & ~lead) {
+            if (haveh && h != base) ok = false;
+            h = base; haveh = true;
+        } else {
+            if (haveg && g != base) ok = false;
+            g = base; haveg = true;
+        }
+    }
+    if (ok) { *G = haveg ? g : 0; *H = haveh ? h : 0; }
+    else { *G = ~gdl; *H = 0; }
+}
 // degree 1: 16 bytes, one 128-bit load.  w0 = F (24 bits) | G low 8 bits << 24;  w1 = G >> 8 (16 bits) | d << 16 (12 bits)
 // | flip << 28 | internal-children mask << 29 (2 bits).  Limits CS1 trees to 2^24 internal nodes / leaves.
 struct __align__(16) DRec1 {

@@ -11,8 +11,9 @@
 //   * two Z buffers: while the MMAs of tile t run, the row gathers of tile t+1 are in flight (one TMA bulk copy per row,
 //     or 8-byte cp.async when the rows are not 16-byte granular; both complete on the buffer's mbarrier), and the perm
 //     entries of tile t+2 are already in registers;
-//   * no fix-up pass: Z holds the raw query rows, z = x - b is formed in registers when the A fragments are loaded (the
-//     padding columns [n] = 1, (n, LD) = 0 are written once per buffer; the gathers never touch them; b is padded with 0);
+//   * Z receives the raw query rows; z = x - b is formed in place, once per row, when the row's leaf segment starts (round 1
+//     subtracted in registers at every A-fragment load: four warps per slab redid it, and every DMMA waited for a DSUB queued
+//     on the same FP64 pipe); the padding columns [n] = 1, (n, LD) = 0 are written once per buffer, the gathers never touch them;
 //   * U is stored packed by 8-row blocks (block kb keeps columns >= 8 kb only): half the shared memory of the square
 //     layout, conflict-free fragment loads (LD = NP + 4, so every row stride is 4 mod 8 doubles);
 //   * JS warps share each 16-row slab, the warp of column group jg taking the column tiles J = jg (mod JS): TR/16*JS
@@ -50,52 +51,69 @@ __host__ __device__ __forceinline__ int dmma_ubase(int kb, int LD) { return 8 * 
 // One warp's share of a 16-row slab: W = z U over its NL column tiles J = jj*JS + jg, then the partial row dots W . z.
 // Column tile J is needed for k < 8 (J + 1) only (U is upper triangular): stage s runs the k range in which exactly the
 // tiles jj >= s are live, so the tile loops are unrolled and free of predicates.
-template <int NL, int JS>
+template <int NL, int JS, bool SUB>  // SUB: Z holds raw rows, z = x - b is formed in registers (else Z already holds z)
 __device__ __forceinline__ void dmma_slab(const double* __restrict__ Z, const double* __restrict__ U, const double* __restrict__ sb,
-                                          double* __restrict__ part, int r0, int jg, int NP, int LD, int lane) {
+                                          double* __restrict__ part, int r0, int jg, int nt, int LD, int lane) {
     double acc[2][NL][2];
 #pragma unroll
     for (int jj = 0; jj < NL; ++jj) { acc[0][jj][0] = acc[0][jj][1] = acc[1][jj][0] = acc[1][jj][1] = 0.0; }
-    const double* za = Z + (size_t)(r0 + (lane >> 2)) * LD + (lane & 3);
-    const double* sbk = sb + (lane & 3);
+    const int l3 = lane & 3, l2 = lane >> 2;
+    // A fragments: z rows r0 + l2 and r0 + 8 + l2, columns k0 + l3 (Z already holds z = x - b, see the kernel)
+    const double* za = Z + (size_t)(r0 + l2) * LD + l3;
+    const double* sbk = sb + l3;
+    // B fragments: row k0 + l3 of U's 8-row block kb (rows of LD - 8 kb doubles, columns >= 8 kb only), column 8 J + l2.  The
+    // pointer advances from block to block by increments (no per-step address arithmetic in the DMMA loop):
+    //   base(kb + 1) - base(kb) = 8 rowlen(kb)  [block size]  - 8 l3  [rows get 8 shorter]  - 8  [the kept columns start 8 later]
+    int rowlen = LD;
+    const double* ub = U + l3 * LD + l2 + 8 * jg;
+    int kb = 0;
 #pragma unroll
     for (int s2 = 0; s2 < NL; ++s2) {
-        const int k_lo = s2 == 0 ? 0 : 8 * ((s2 - 1) * JS + jg + 1);
-        int k_hi = 8 * (s2 * JS + jg + 1);
-        if (k_hi > NP) k_hi = NP;
-#pragma unroll 4
-        for (int k0 = k_lo; k0 < k_hi; k0 += 4) {
-            const int kb = k0 >> 3;
-            const double bk = sbk[k0];
-            const double a0 = za[k0] - bk, a1 = za[(size_t)8 * LD + k0] - bk;  // z = x - b, formed in registers
-            const double* ub = U + dmma_ubase(kb, LD) + ((k0 & 4) + (lane & 3)) * (LD - 8 * kb) + (lane >> 2) + 8 * (jg - kb);
-            double bf[NL];
+        int kb_hi = s2 * JS + jg + 1;
+        if (kb_hi > nt) kb_hi = nt;
+#pragma unroll 2
+        for (; kb < kb_hi; ++kb) {
+            double a00 = za[0], a01 = za[(size_t)8 * LD], a10 = za[4], a11 = za[(size_t)8 * LD + 4];
+            if (SUB) { const double b0 = sbk[8 * kb], b1 = sbk[8 * kb + 4]; a00 -= b0; a01 -= b0; a10 -= b1; a11 -= b1; }
+            const double* ub1 = ub + 4 * rowlen;
+            double bf0[NL], bf1[NL];
 #pragma unroll
-            for (int jj = s2; jj < NL; ++jj) bf[jj] = ub[8 * JS * jj];
+            for (int jj = s2; jj < NL; ++jj) { bf0[jj] = ub[8 * JS * jj]; bf1[jj] = ub1[8 * JS * jj]; }
 #pragma unroll
             for (int jj = s2; jj < NL; ++jj) {
-                dmma884(acc[0][jj][0], acc[0][jj][1], a0, bf[jj]);
-                dmma884(acc[1][jj][0], acc[1][jj][1], a1, bf[jj]);
+                dmma884(acc[0][jj][0], acc[0][jj][1], a00, bf0[jj]);
+                dmma884(acc[1][jj][0], acc[1][jj][1], a01, bf0[jj]);
             }
+#pragma unroll
+            for (int jj = s2; jj < NL; ++jj) {
+                dmma884(acc[0][jj][0], acc[0][jj][1], a10, bf1[jj]);
+                dmma884(acc[1][jj][0], acc[1][jj][1], a11, bf1[jj]);
+            }
+            za += 8;
+            ub += 8 * rowlen - 8 * l3 - 8;
+            rowlen -= 8;
         }
     }
     // thread holds W[row][8J + 2*(lane&3) + {0,1}] for row = r0 + 8h + lane/4
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-        const int row = r0 + 8 * h + (lane >> 2);
-        const double* zr = Z + (size_t)row * LD + 2 * (lane & 3) + 8 * jg;
-        const double* br = sb + 2 * (lane & 3) + 8 * jg;
+        const int row = r0 + 8 * h + l2;
+        const double* zr = Z + (size_t)row * LD + 2 * l3 + 8 * jg;
+        const double* br = sb + 2 * l3 + 8 * jg;
         double sacc = 0.0;
 #pragma unroll
-        for (int jj = 0; jj < NL; ++jj)
-            sacc = fma(acc[h][jj][0], zr[8 * JS * jj] - br[8 * JS * jj], fma(acc[h][jj][1], zr[8 * JS * jj + 1] - br[8 * JS * jj + 1], sacc));
+        for (int jj = 0; jj < NL; ++jj) {
+            double z0 = zr[8 * JS * jj], z1 = zr[8 * JS * jj + 1];
+            if (SUB) { z0 -= br[8 * JS * jj]; z1 -= br[8 * JS * jj + 1]; }
+            sacc = fma(acc[h][jj][0], z0, fma(acc[h][jj][1], z1, sacc));
+        }
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
         sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if ((lane & 3) == 0) part[row] = sacc;
+        if (l3 == 0) part[row] = sacc;
     }
 }
 
-template <int TR, int NTJ, int JS>  // NTJ = ceil(nt / JS): every warp owns NTJ or NTJ - 1 column tiles
+template <int TR, int NTJ, int JS, bool SUB>  // NTJ = ceil(nt / JS): every warp owns NTJ or NTJ - 1 column tiles
 __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm) {
     extern __shared__ __align__(16) double sm[];
     const int n = prm.mv.n, NP = prm.NP, LD = prm.LD, nt = NP / 8;
@@ -170,7 +188,7 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
         if (buf == 0) { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; }
         else { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
         CSP_TICK(1);
-        const double* Z = Zb + (size_t)buf * TR * LD;
+        double* Z = Zb + (size_t)buf * TR * LD;
         double* part = s_part + (size_t)buf * JS * TR;
         const int* leaf_of = s_leaf + buf * TR;
         int seg_start = 0;
@@ -202,11 +220,21 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
                 __syncthreads();
                 CSP_TICK(3);
             }
+            // z = x - b, once per row, in place (the JS warps of a slab would otherwise each redo the subtraction for every
+            // fragment they load, on the FP64 pipe the DMMAs are queued on: the dependent DSUB -> DMMA pairs left the pipe idle
+            // 48 % of the time).  The padding columns stay [n] = 1, (n, LD) = 0: the loop stops at n.
+            if (!SUB) {
+                for (int r = seg_start + warp; r < seg_end; r += nwarps) {
+                    double* zr = Z + (size_t)r * LD;
+                    for (int k = lane; k < n; k += 32) zr[k] = zr[k] - sb[k];
+                }
+                __syncthreads();
+            }
             const int r0 = rg * 16;
             const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
             if (active) {
-                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS>(Z, U, sb, part + jg * TR, r0, jg, NP, LD, lane);
-                else dmma_slab<NTJ - 1, JS>(Z, U, sb, part + jg * TR, r0, jg, NP, LD, lane);
+                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
+                else dmma_slab<NTJ - 1, JS, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
             }
             CSP_TICK(5);
             __syncthreads();
@@ -308,7 +336,13 @@ __global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) 
             const double* __restrict__ A = M + n;
             if (lf != cur_leaf) {
                 for (int i = tid; i < NP; i += blockDim.x) sb[i] = i < n ? __ldg(M + i) : 0.0;
-                cur_leaf = lf;  // made visible by the first panel barrier below
+                cur_leaf = lf;
+            }
+            __syncthreads();
+            // z = x - b in place, once per row of the segment (see k_eval_dmma); visible after the first panel barrier below
+            for (int r = seg_start + warp; r < seg_end; r += 16) {
+                double* zr = Z + (size_t)r * LD;
+                for (int k = lane; k < n; k += 32) zr[k] = zr[k] - sb[k];
             }
             // panel J -> buffer J & 1: rows k < 8 (J + 1), columns 8J .. 8J + 7 of U (zero below the diagonal and past n)
             auto issue_panel = [&](int J) {
@@ -323,7 +357,6 @@ __global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) 
             const int r0 = rg * 16;
             const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
             const double* za = Z + (size_t)(r0 + (lane >> 2)) * LD + (lane & 3);
-            const double* sbk = sb + (lane & 3);
             double sacc[2] = {0.0, 0.0};
             issue_panel(0);
             for (int J = 0; J < nt; ++J) {
@@ -338,9 +371,8 @@ __global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) 
                     int ks = ks0;
                     for (; ks + 1 < ks1; ks += 2) {
                         const int k0 = 4 * ks;
-                        const double bk0 = sbk[k0], bk1 = sbk[k0 + 4];
-                        const double a00 = za[k0] - bk0, a01 = za[(size_t)8 * LD + k0] - bk0;
-                        const double a10 = za[k0 + 4] - bk1, a11 = za[(size_t)8 * LD + k0 + 4] - bk1;
+                        const double a00 = za[k0], a01 = za[(size_t)8 * LD + k0];
+                        const double a10 = za[k0 + 4], a11 = za[(size_t)8 * LD + k0 + 4];
                         const double b0 = ub[k0 * PANEL_LD], b1 = ub[(k0 + 4) * PANEL_LD];
                         dmma884(acc[0][0][0], acc[0][0][1], a00, b0);
                         dmma884(acc[0][1][0], acc[0][1][1], a01, b0);
@@ -349,19 +381,17 @@ __global__ void __launch_bounds__(512) k_eval_dmma_panel(const DenseParams prm) 
                     }
                     if (ks < ks1) {
                         const int k0 = 4 * ks;
-                        const double bk0 = sbk[k0];
-                        const double a00 = za[k0] - bk0, a01 = za[(size_t)8 * LD + k0] - bk0;
+                        const double a00 = za[k0], a01 = za[(size_t)8 * LD + k0];
                         const double b0 = ub[k0 * PANEL_LD];
                         dmma884(acc[0][0][0], acc[0][0][1], a00, b0);
                         dmma884(acc[0][1][0], acc[0][1][1], a01, b0);
                     }
                     // fold into the running row dots: thread holds W[row][8J + 2*(lane&3) + {0,1}]
                     const int c = 8 * J + 2 * (lane & 3);
-                    const double bc0 = sb[c], bc1 = sb[c + 1];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const double* zr = Z + (size_t)(r0 + 8 * h + (lane >> 2)) * LD + c;
-                        sacc[h] = fma(acc[0][h][0] + acc[1][h][0], zr[0] - bc0, fma(acc[0][h][1] + acc[1][h][1], zr[1] - bc1, sacc[h]));
+                        sacc[h] = fma(acc[0][h][0] + acc[1][h][0], zr[0], fma(acc[0][h][1] + acc[1][h][1], zr[1], sacc[h]));
                     }
                 }
             }
@@ -468,9 +498,15 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
             return CSP_OK;
         };
         if (smem > 227 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the DMMA evaluation kernel", n);
-        if (nt <= 8) return launch2(k_eval_dmma<TR, 2, JS>);  // nt >= 5 (n > 32)
-        if (nt <= 12) return launch2(k_eval_dmma<TR, 3, JS>);
-        return launch2(k_eval_dmma<TR, 4, JS>);
+        const bool fix = getenv("CSP_DMMA_FIXUP") && atoi(getenv("CSP_DMMA_FIXUP"));  // z = x - b in place, once per row (A/B switch)
+        if (fix) {
+            if (nt <= 8) return launch2(k_eval_dmma<TR, 2, JS, false>);  // nt >= 5 (n > 32)
+            if (nt <= 12) return launch2(k_eval_dmma<TR, 3, JS, false>);
+            return launch2(k_eval_dmma<TR, 4, JS, false>);
+        }
+        if (nt <= 8) return launch2(k_eval_dmma<TR, 2, JS, true>);
+        if (nt <= 12) return launch2(k_eval_dmma<TR, 3, JS, true>);
+        return launch2(k_eval_dmma<TR, 4, JS, true>);
     }
 }
 

@@ -36,7 +36,7 @@ struct LocateParams {
 __device__ __forceinline__ double dnan_le() { return __longlong_as_double(0x7ff8000000000000LL); }
 
 // 256-bit read-only load of one degree-2 descent record (LDG.E.256)
-__device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid1, int& F, int& G, unsigned& meta) {
+__device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid1, int& F, int& G, unsigned& meta, int& H) {
     unsigned long long a, b, c, d;
     asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
     mid0 = __longlong_as_double((long long)a);
@@ -44,6 +44,7 @@ __device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid
     F = (int)(unsigned)(c & 0xffffffffu);
     G = (int)(unsigned)(c >> 32);
     meta = (unsigned)(d & 0xffffffffu);
+    H = (int)(unsigned)(d >> 32);
 }
 
 // Descent (reference src/tree.jl:362-386).  Returns the leaf id.  s_top: the first `top` records, in shared memory.
@@ -57,14 +58,14 @@ __device__ __forceinline__ int descend(const TreeView& t, const double* __restri
         const DRec2* stop = (const DRec2*)s_top;
         while (true) {
             double mid0, mid1;
-            int F, G;
+            int F, G, H;
             unsigned meta;
             if (cur < top) {
                 const double2 mm = *(const double2*)&stop[cur].mid0;
                 const int4 w = *(const int4*)&stop[cur].F;
-                mid0 = mm.x; mid1 = mm.y; F = w.x; G = w.y; meta = (unsigned)w.z;
+                mid0 = mm.x; mid1 = mm.y; F = w.x; G = w.y; meta = (unsigned)w.z; H = w.w;
             } else {
-                ldg256(recs + cur, mid0, mid1, F, G, meta);
+                ldg256(recs + cur, mid0, mid1, F, G, meta, H);
             }
             const double x0 = xr[(meta & 0xfffu) * xs];
             const double x1 = xr[((meta >> 12) & 0xfffu) * xs];
@@ -75,7 +76,16 @@ __device__ __forceinline__ int descend(const TreeView& t, const double* __restri
             if ((mask >> idx) & 1u) {
                 cur = F + __popc(mask & below);
             } else {
-                dl = G + __popc(~mask & below);
+                // Leaf children hold consecutive leaf ids (preorder) except across an internal sibling: at most two runs among
+                // four children.  G >= 0: the record carries the base of both runs (G: before the first internal child that
+                // follows a leaf child, H: after it) and the leaf id needs no table; G < 0 (fake leaves in between, odd n):
+                // ~G is the node's first descent leaf id and the id comes from the dleaf table.
+                const unsigned cnt = __popc(~mask & below & 0xfu);
+                if (G >= 0) {
+                    const unsigned lead = mask & ~(mask + 1u);  // the internal children before the first leaf child
+                    return ((mask & below & ~lead) ? H : G) + (int)cnt;
+                }
+                dl = ~G + (int)cnt;
                 break;
             }
         }
@@ -300,6 +310,10 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
 //     the kernel parameters (constant bank) when n <= CSP_BOUNDS_PARAM;
 //   * the raw tile is dead after the transpose, so a single raw stage is re-filled by the next TMA copy while the
 //     descent runs on the transposed copy.
+// Tried and rejected (round 2, C3, n = 20: rows 160 B apart put lanes t and t+4 of a quarter-warp into the same bank group
+// for the 128-bit row reads): lanes 4-7 walking their row one column pair ahead.  Locate 6.08 -> 7.05 ms per 1e8 queries with a
+// per-lane constant-bank index for the bounds, 6.75 -> 7.05 with uniform bounds selected per lane: the extra instructions
+// cost more than the two-way conflict.
 #define CSP_BOUNDS_PARAM 32
 struct LocateOnlyParams {
     TreeView t;

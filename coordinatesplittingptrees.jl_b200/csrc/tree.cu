@@ -265,10 +265,11 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             const int I = bfs[head];
             const int F = (int)bfs.size(), G = (int)dleaf.size();
             unsigned mask = 0;
+            int L[4] = {-1, -1, -1, -1};
             for (int k = 0; k < C; ++k) {
                 const int c = d->child[(size_t)I * C + k];
                 if (d->internal_id[c] >= 0) { mask |= 1u << k; bfs.push_back(d->internal_id[c]); }
-                else dleaf.push_back(d->leaf_id[c]);
+                else { dleaf.push_back(d->leaf_id[c]); L[k] = d->leaf_id[c]; }
             }
             double mid[2] = {0, 0};
             unsigned dim0[2] = {0, 0}, flip[2] = {0, 0}, fict[2] = {1, 1};
@@ -282,7 +283,8 @@ static int upload_impl(const csp_tree_desc* d, csp_tree* t) {
             }
             if (p == 2) {
                 DRec2 r{};
-                r.mid0 = mid[0]; r.mid1 = mid[1]; r.F = F; r.G = G;
+                r.mid0 = mid[0]; r.mid1 = mid[1]; r.F = F;
+                csp_encode_leaf_runs(L, mask, fict[0], fict[1], G, &r.G, &r.H);
                 r.meta = dim0[0] | (dim0[1] << 12) | (flip[0] << 24) | (flip[1] << 25) | (fict[0] << 26) | (fict[1] << 27) | (mask << 28);
                 r2[head] = r;
             } else {

@@ -112,10 +112,11 @@ __global__ void __launch_bounds__(256) kb_records(const RawTree r, const int* __
     const int F = 1 + Fex[h], G = Gex[h];
     unsigned mask = 0;
     int g = G;
+    int L[4] = {-1, -1, -1, -1};
     for (int k = 0; k < C; ++k) {
         const int c = r.child[(size_t)I * C + k];
         if (r.internal_id[c] >= 0) mask |= 1u << k;
-        else dleaf[g++] = r.leaf_id[c];
+        else { dleaf[g++] = r.leaf_id[c]; L[k] = r.leaf_id[c]; }
     }
     double mid[2] = {0, 0};
     unsigned dim0[2] = {0, 0}, flip[2] = {0, 0}, fict[2] = {1, 1};
@@ -129,7 +130,8 @@ __global__ void __launch_bounds__(256) kb_records(const RawTree r, const int* __
     }
     if (P == 2) {
         DRec2 q{};
-        q.mid0 = mid[0]; q.mid1 = mid[1]; q.F = F; q.G = G;
+        q.mid0 = mid[0]; q.mid1 = mid[1]; q.F = F;
+        csp_encode_leaf_runs(L, mask, fict[0], fict[1], G, &q.G, &q.H);
         q.meta = dim0[0] | (dim0[1] << 12) | (flip[0] << 24) | (flip[1] << 25) | (fict[0] << 26) | (fict[1] << 27) | (mask << 28);
         ((DRec2*)drec)[h] = q;
     } else {
