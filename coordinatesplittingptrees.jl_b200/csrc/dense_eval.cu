@@ -46,75 +46,20 @@ struct DenseParams {
     long long* prof;  // optional [grid][8] per-phase clock counters (CSP_DMMA_PROF=1), else nullptr
 };
 
-__host__ __device__ __forceinline__ int dmma_ubase(int kb, int LD) { return 8 * (kb * LD - 4 * kb * (kb - 1)); }
+#include "dmma_slab.cuh"
 
-// One warp's share of a 16-row slab: W = z U over its NL column tiles J = jj*JS + jg, then the partial row dots W . z.
-// Column tile J is needed for k < 8 (J + 1) only (U is upper triangular): stage s runs the k range in which exactly the
-// tiles jj >= s are live, so the tile loops are unrolled and free of predicates.
-template <int NL, int JS, bool SUB>  // SUB: Z holds raw rows, z = x - b is formed in registers (else Z already holds z)
-__device__ __forceinline__ void dmma_slab(const double* __restrict__ Z, const double* __restrict__ U, const double* __restrict__ sb,
-                                          double* __restrict__ part, int r0, int jg, int nt, int LD, int lane) {
-    double acc[2][NL][2];
-#pragma unroll
-    for (int jj = 0; jj < NL; ++jj) { acc[0][jj][0] = acc[0][jj][1] = acc[1][jj][0] = acc[1][jj][1] = 0.0; }
-    const int l3 = lane & 3, l2 = lane >> 2;
-    // A fragments: z rows r0 + l2 and r0 + 8 + l2, columns k0 + l3 (Z already holds z = x - b, see the kernel)
-    const double* za = Z + (size_t)(r0 + l2) * LD + l3;
-    const double* sbk = sb + l3;
-    // B fragments: row k0 + l3 of U's 8-row block kb (rows of LD - 8 kb doubles, columns >= 8 kb only), column 8 J + l2.  The
-    // pointer advances from block to block by increments (no per-step address arithmetic in the DMMA loop):
-    //   base(kb + 1) - base(kb) = 8 rowlen(kb)  [block size]  - 8 l3  [rows get 8 shorter]  - 8  [the kept columns start 8 later]
-    int rowlen = LD;
-    const double* ub = U + l3 * LD + l2 + 8 * jg;
-    int kb = 0;
-#pragma unroll
-    for (int s2 = 0; s2 < NL; ++s2) {
-        int kb_hi = s2 * JS + jg + 1;
-        if (kb_hi > nt) kb_hi = nt;
-#pragma unroll 2
-        for (; kb < kb_hi; ++kb) {
-            double a00 = za[0], a01 = za[(size_t)8 * LD], a10 = za[4], a11 = za[(size_t)8 * LD + 4];
-            if (SUB) { const double b0 = sbk[8 * kb], b1 = sbk[8 * kb + 4]; a00 -= b0; a01 -= b0; a10 -= b1; a11 -= b1; }
-            const double* ub1 = ub + 4 * rowlen;
-            double bf0[NL], bf1[NL];
-#pragma unroll
-            for (int jj = s2; jj < NL; ++jj) { bf0[jj] = ub[8 * JS * jj]; bf1[jj] = ub1[8 * JS * jj]; }
-#pragma unroll
-            for (int jj = s2; jj < NL; ++jj) {
-                dmma884(acc[0][jj][0], acc[0][jj][1], a00, bf0[jj]);
-                dmma884(acc[1][jj][0], acc[1][jj][1], a01, bf0[jj]);
-            }
-#pragma unroll
-            for (int jj = s2; jj < NL; ++jj) {
-                dmma884(acc[0][jj][0], acc[0][jj][1], a10, bf1[jj]);
-                dmma884(acc[1][jj][0], acc[1][jj][1], a11, bf1[jj]);
-            }
-            za += 8;
-            ub += 8 * rowlen - 8 * l3 - 8;
-            rowlen -= 8;
-        }
-    }
-    // thread holds W[row][8J + 2*(lane&3) + {0,1}] for row = r0 + 8h + lane/4
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int row = r0 + 8 * h + l2;
-        const double* zr = Z + (size_t)row * LD + 2 * l3 + 8 * jg;
-        const double* br = sb + 2 * l3 + 8 * jg;
-        double sacc = 0.0;
-#pragma unroll
-        for (int jj = 0; jj < NL; ++jj) {
-            double z0 = zr[8 * JS * jj], z1 = zr[8 * JS * jj + 1];
-            if (SUB) { z0 -= br[8 * JS * jj]; z1 -= br[8 * JS * jj + 1]; }
-            sacc = fma(acc[h][jj][0], z0, fma(acc[h][jj][1], z1, sacc));
-        }
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-        sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-        if (l3 == 0) part[row] = sacc;
-    }
-}
-
-template <int TR, int NTJ, int JS, bool SUB>  // NTJ = ceil(nt / JS): every warp owns NTJ or NTJ - 1 column tiles
-__global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm) {
+// TR rows per tile, RW rows per compute warp, JS column groups: CW = TR/RW*JS compute warps, plus PW producer warps.  The
+// producers work one tile ahead of the compute warps: they issue the next tile's row gathers (a TMA bulk copy costs its issuing
+// warp ~200 cycles and they serialise within a warp: with every warp issuing its share, 8 % of the tile time went there with
+// the DMMA pipe idle), wait for them to land and form z = x - b in place, each row against its own leaf's b read from the
+// record, so that the compute warps' loop holds nothing but fragment loads and DMMAs.  (A DADD takes ~4 cycles of the FP64
+// pipe the DMMAs are queued on -- tools/ubench/fp64_peaks.cu: a 2x1-blocked DMMA loop drops from 34.1 to 27.3 TFLOP/s with one
+// DADD per DMMA -- and with the subtraction in registers the JS warps of a slab each redo it: 12 % of the pipe at n = 100.)
+// PW = 0: every warp computes, issues its share of the gathers, waits for the tile itself and subtracts in registers.
+template <int TR, int RW, int NTJ, int JS, int PW>  // NTJ = ceil(nt / JS): every compute warp owns NTJ or NTJ - 1 column tiles
+__global__ void __launch_bounds__((TR / RW * JS + PW) * 32) k_eval_dmma(const DenseParams prm) {
+    constexpr int CW = TR / RW * JS;
+    constexpr bool SUB = PW == 0;
     extern __shared__ __align__(16) double sm[];
     const int n = prm.mv.n, NP = prm.NP, LD = prm.LD, nt = NP / 8;
     const int usz = dmma_ubase(nt, LD);
@@ -122,11 +67,17 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
     double* Zb = U + usz;                            // [2][TR][LD]
     double* sb = Zb + (size_t)2 * TR * LD;           // [NP]  (b, zero padded)
     double* s_part = sb + NP;                        // [2][JS][TR]  (alternating by tile: one barrier per tile)
-    int* s_q = (int*)(s_part + 2 * JS * TR);         // [2][TR]
-    int* s_leaf = s_q + 2 * TR;                      // [2][TR]
+    int* s_leaf = (int*)(s_part + 2 * JS * TR);      // [2][TR]
     uint64_t* bar = (uint64_t*)(s_leaf + 2 * TR);    // [2]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const int rg = warp / JS, jg = (warp + rg) % JS;  // rotated so that every SM sub-partition (warp % 4) sees all column groups
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool compute = warp < CW;
+    // Row group and column group of a compute warp.  The column groups differ in cost (group jg owns the tiles J = jg mod JS, tile
+    // J costs J + 1 k-blocks), and the warps of one SM sub-partition (warp mod 4) share a DMMA pipe: with 16-row warps every
+    // sub-partition sees all four groups; with 32-row warps (two per sub-partition) it sees groups {0, 1} or {2, 3}, whose costs
+    // add up to about the same (n = 100: 28 + 18 and 21 + 24 k-blocks).
+    int rg, jg;
+    if (RW == 16 || JS != 4) { rg = warp / JS; jg = (warp + rg) % JS; }
+    else { rg = warp >> 2; const int s4 = warp & 3; jg = rg == 0 ? ((s4 & 1) << 1 | (s4 >> 1)) : ((((s4 & 1) << 1) | (s4 >> 1)) ^ 1); }
     const long long tot = *prm.total;
     const long long ntiles = (tot + TR - 1) / TR;
     const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -140,53 +91,100 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
         const int r = i / (LD - n), k = n + (i - r * (LD - n));
         Zb[(size_t)r * LD + k] = k == n ? 1.0 : 0.0;
     }
+    constexpr int RPW = PW ? TR / PW : TR / CW;  // rows gathered per issuing warp
+    static_assert(RPW <= 32, "one lane per gathered row");
+    const bool issuer = PW ? !compute : true;
+    const int iw = PW ? warp - CW : warp;
     auto perm_at = [&](long long t) -> int2 {  // this thread's perm entry of tile t (rows past the end: leaf -1)
         const long long s = t * TR + tid;
         return (tid < TR && t < t1 && s < tot) ? prm.perm[s] : make_int2(0, -1);
     };
+    auto issue_at = [&](long long t) -> int2 {  // (query, leaf) of the row this lane gathers for tile t (query -1: none)
+        const long long s = t * TR + iw * RPW + lane;
+        return (issuer && lane < RPW && t < t1 && s < tot) ? prm.perm[s] : make_int2(-1, -1);
+    };
     auto tile_rows = [&](long long t) { const long long r = tot - t * TR; return (int)(r < TR ? r : TR); };
-    // publish tile t's perm entries, arm the barrier and start the row gathers into buffer `buf` (which must be free)
-    auto start_tile = [&](long long t, int buf, int2 ql) {
-        if (tid < TR) { s_q[buf * TR + tid] = ql.x; s_leaf[buf * TR + tid] = ql.y; }
+    // Publish tile t's leaf ids, arm the barrier and start the row gathers into buffer `buf`.  No CTA barrier: the buffer and
+    // s_leaf[buf] were last read before the slab barrier every thread has passed, the issuing lanes hold their rows' query
+    // indices in registers (qi, prefetched two tiles ahead like ql), and the leaf ids are read only after the next slab barrier.
+    auto start_tile = [&](long long t, int buf, int2 ql, int qi) {
+        if (!SUB) fence_proxy_async();  // the producers' in-place z (generic-proxy writes) precede the TMA writes into this buffer
+        if (tid < TR) s_leaf[buf * TR + tid] = ql.y;
         const int rows = tile_rows(t);
-        constexpr int RPW = TR / (TR / 16 * JS);  // rows per warp: TMA issue is serial within a warp, so spread it
         if (prm.bulk) {
-            fence_proxy_async();
             if (tid == 0) mbar_expect_tx(&bar[buf], (uint32_t)((size_t)rows * n * 8));
-            __syncthreads();
-            const int r = warp * RPW + lane;
-            if (lane < RPW && r < rows)
-                bulk_g2s(Zb + ((size_t)buf * TR + r) * LD, prm.X + (size_t)(unsigned)s_q[buf * TR + r] * n, (uint32_t)(n * 8), &bar[buf]);
+            if (qi >= 0)
+                bulk_g2s(Zb + ((size_t)buf * TR + iw * RPW + lane) * LD, prm.X + (size_t)(unsigned)qi * n, (uint32_t)(n * 8), &bar[buf]);
         } else {
-            __syncthreads();
-            for (int r = warp * RPW; r < warp * RPW + RPW && r < rows; ++r) {
-                const double* __restrict__ src = prm.X + (size_t)(unsigned)s_q[buf * TR + r] * n;
-                double* dst = Zb + ((size_t)buf * TR + r) * LD;
-                for (int k = lane; k < n; k += 32) cp_async8(dst + k, src + k);
+            if (issuer) {
+#pragma unroll 1
+                for (int j = 0; j < RPW; ++j) {
+                    const int q = __shfl_sync(0xffffffffu, qi, j);
+                    if (q < 0) continue;
+                    const double* __restrict__ src = prm.X + (size_t)(unsigned)q * n;
+                    double* dst = Zb + ((size_t)buf * TR + iw * RPW + j) * LD;
+                    for (int k = lane; k < n; k += 32) cp_async8(dst + k, src + k);
+                }
             }
             cp_async_arrive(&bar[buf]);
+        }
+    };
+    // producers: z = x - b in place for the rows this warp gathered into buffer `buf` (lane j holds row j's (query, leaf))
+    auto fixup_rows = [&](int buf, int2 qlv) {
+        double* Zt = Zb + ((size_t)buf * TR + iw * RPW) * LD;
+        int prev = -2;
+        double bc[4] = {0.0, 0.0, 0.0, 0.0};  // b at columns lane + 32 k  (NP <= 128 in this kernel)
+#pragma unroll 4
+        for (int j = 0; j < RPW; ++j) {
+            const int q = __shfl_sync(0xffffffffu, qlv.x, j), lf = __shfl_sync(0xffffffffu, qlv.y, j);
+            if (q < 0) continue;
+            if (lf != prev) {
+                const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) bc[k] = lane + 32 * k < n ? __ldg(M + lane + 32 * k) : 0.0;
+                prev = lf;
+            }
+            double* zr = Zt + (size_t)j * LD + lane;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (lane + 32 * k < n) zr[32 * k] = zr[32 * k] - bc[k];
         }
     };
     uint32_t phase[2] = {0, 0};
     int cur_leaf = -1;
     long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tk = clock64();
 #define CSP_TICK(k) do { if (prm.prof && tid == 0) { const long long now_ = clock64(); pc[k] += now_ - tk; tk = now_; } } while (0)
-    int2 nxt = make_int2(0, -1);
+    int2 nxt = make_int2(0, -1), nxt_q = make_int2(-1, -1);
     __syncthreads();
     if (t0 < t1) {
-        start_tile(t0, 0, perm_at(t0));
+        const int2 q0 = issue_at(t0);
+        start_tile(t0, 0, perm_at(t0), q0.x);
         nxt = perm_at(t0 + 1);
+        nxt_q = issue_at(t0 + 1);
+        if (!SUB) {  // the first tile's z, before anybody computes on it
+            if (!compute) { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; fixup_rows(0, q0); }
+            __syncthreads();
+        }
     }
     for (long long t = t0; t < t1; ++t) {
         const int buf = (int)((t - t0) & 1);
         const int rows = tile_rows(t);
         if (t + 1 < t1) {  // the other buffer was released by the barrier that ended the previous iteration
-            start_tile(t + 1, buf ^ 1, nxt);
+            start_tile(t + 1, buf ^ 1, nxt, nxt_q.x);
+            if (!SUB && !compute) {  // wait for the next tile's rows and form its z while the compute warps work on this tile;
+                                     // the tile barrier below publishes it
+                if (buf == 0) { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
+                else { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; }
+                fixup_rows(buf ^ 1, nxt_q);
+            }
             nxt = perm_at(t + 2);
+            nxt_q = issue_at(t + 2);
         }
         CSP_TICK(0);
-        if (buf == 0) { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; }
-        else { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
+        if (SUB) {
+            if (buf == 0) { mbar_wait(&bar[0], phase[0]); phase[0] ^= 1; }
+            else { mbar_wait(&bar[1], phase[1]); phase[1] ^= 1; }
+        }
         CSP_TICK(1);
         double* Z = Zb + (size_t)buf * TR * LD;
         double* part = s_part + (size_t)buf * JS * TR;
@@ -204,37 +202,28 @@ __global__ void __launch_bounds__(TR * 2 * JS) k_eval_dmma(const DenseParams prm
                 seg_end = hi;
             }
             CSP_TICK(2);
-            if (lf != cur_leaf) {  // expand the record: b (zero padded) and the packed U
+            if (lf != cur_leaf && compute) {  // expand the record: b (zero padded) and the packed U (compute warps: the
+                                              // producers are busy with the next tile; barrier 1 spans the compute warps only)
                 const double* __restrict__ M = prm.mv.data + (size_t)lf * prm.mv.stride;
-                for (int i = tid; i < usz; i += blockDim.x) U[i] = 0.0;
-                for (int i = tid; i < NP; i += blockDim.x) sb[i] = i < n ? __ldg(M + i) : 0.0;
-                __syncthreads();
+                for (int i = tid; i < usz; i += CW * 32) U[i] = 0.0;
+                for (int i = tid; i < NP; i += CW * 32) sb[i] = i < n ? __ldg(M + i) : 0.0;
+                asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
                 const double* __restrict__ A = M + n;
-                for (int i = warp; i <= n; i += nwarps) {  // row i of the packed triangle: n + 1 - i coefficients, coalesced
+                for (int i = warp; i <= n; i += CW) {  // row i of the packed triangle: n + 1 - i coefficients, coalesced
                     const double* __restrict__ Ar = A + (i * (n + 1) - i * (i - 1) / 2);
                     const int kb = i >> 3;
                     double* Ur = U + dmma_ubase(kb, LD) + (i & 7) * (LD - 8 * kb) + (i - 8 * kb);
                     for (int e = lane; e < n + 1 - i; e += 32) Ur[e] = __ldg(Ar + e);
                 }
-                cur_leaf = lf;
-                __syncthreads();
+                asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory");
                 CSP_TICK(3);
             }
-            // z = x - b, once per row, in place (the JS warps of a slab would otherwise each redo the subtraction for every
-            // fragment they load, on the FP64 pipe the DMMAs are queued on: the dependent DSUB -> DMMA pairs left the pipe idle
-            // 48 % of the time).  The padding columns stay [n] = 1, (n, LD) = 0: the loop stops at n.
-            if (!SUB) {
-                for (int r = seg_start + warp; r < seg_end; r += nwarps) {
-                    double* zr = Z + (size_t)r * LD;
-                    for (int k = lane; k < n; k += 32) zr[k] = zr[k] - sb[k];
-                }
-                __syncthreads();
-            }
-            const int r0 = rg * 16;
-            const bool active = r0 < seg_end && r0 + 16 > seg_start;  // warp-uniform
+            cur_leaf = lf;
+            const int r0 = rg * RW;
+            const bool active = compute && r0 < seg_end && r0 + RW > seg_start;  // warp-uniform
             if (active) {
-                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
-                else dmma_slab<NTJ - 1, JS, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
+                if ((NTJ - 1) * JS + jg < nt) dmma_slab<NTJ, JS, RW, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
+                else dmma_slab<NTJ - 1, JS, RW, SUB>(Z, U, sb, part + jg * TR, r0, jg, nt, LD, lane);
             }
             CSP_TICK(5);
             __syncthreads();
@@ -471,8 +460,19 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
         return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the DMMA evaluation kernels", n);
     }
     {
-        constexpr int TR = 64, JS = 4;  // 16 warps per CTA, one CTA per SM
-        const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + 2 * JS * TR) * 8 + (size_t)(4 * TR) * 4 + 16;
+        constexpr int JS = 4, TR = 64;
+        // One CTA per SM (shared-memory bound).  Default: 16 warps of 16 rows x a column group, every warp issues its share of the
+        // gathers and subtracts b in registers.  Measured alternatives (B200, n = 100, 2e7 queries; kernel ms): 10.87 default;
+        // CSP_DMMA_LAYOUT=320 (8 warps of 32 rows: 31 % fewer shared-memory wavefronts per DMMA) 11.78; CSP_DMMA_LAYOUT=32 (the
+        // same plus 4 producer warps that issue the gathers and form z in place one tile ahead) 13.26: the producers finish
+        // after the compute warps.  tools/ubench/slab_peak.cu times the block alone: 24.5 TFLOP/s issued as used here, 30.0 with
+        // z resident and no tile barrier, against 36-37 for an unstructured register-blocked DMMA loop (fp64_peaks.cu): the
+        // short triangular k-loop (13 k-blocks at n = 100) with its per-slab prologue, row-dot epilogue and barrier is what
+        // keeps the pipe at 0.57; a tile pipeline per row group (no CTA-wide barrier) is the next step.
+        const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + 2 * JS * TR) * 8 + (size_t)(2 * TR) * 4 + 16;
+        const char* lenv = getenv("CSP_DMMA_LAYOUT");
+        const int layout = lenv ? atoi(lenv) : 16;
+        const int nthreads = layout == 16 ? 512 : (layout == 320 ? 256 : 384);
         const unsigned grid2 = (unsigned)std::max<long long>(1, std::min<long long>((m + TR - 1) / TR, std::max(n_sm, 1)));
         auto launch2 = [&](auto kern) -> int {
             const bool prof = getenv("CSP_DMMA_PROF") && atoi(getenv("CSP_DMMA_PROF"));
@@ -480,7 +480,7 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
             CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             {
                 CspTimed tm(CSP_K_EVAL_BINNED, st);
-                kern<<<grid2, TR * 2 * JS, smem, st>>>(prm);
+                kern<<<grid2, nthreads, smem, st>>>(prm);
             }
             CSP_LAUNCHED();
             CSP_CUDA(cudaGetLastError());
@@ -498,15 +498,15 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
             return CSP_OK;
         };
         if (smem > 227 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the DMMA evaluation kernel", n);
-        const bool fix = getenv("CSP_DMMA_FIXUP") && atoi(getenv("CSP_DMMA_FIXUP"));  // z = x - b in place, once per row (A/B switch)
-        if (fix) {
-            if (nt <= 8) return launch2(k_eval_dmma<TR, 2, JS, false>);  // nt >= 5 (n > 32)
-            if (nt <= 12) return launch2(k_eval_dmma<TR, 3, JS, false>);
-            return launch2(k_eval_dmma<TR, 4, JS, false>);
-        }
-        if (nt <= 8) return launch2(k_eval_dmma<TR, 2, JS, true>);
-        if (nt <= 12) return launch2(k_eval_dmma<TR, 3, JS, true>);
-        return launch2(k_eval_dmma<TR, 4, JS, true>);
+        auto pick = [&](auto rwc, auto pwc) -> int {
+            constexpr int RW = decltype(rwc)::value, PW = decltype(pwc)::value;
+            if (nt <= 8) return launch2(k_eval_dmma<TR, RW, 2, JS, PW>);  // nt >= 5 (n > 32)
+            if (nt <= 12) return launch2(k_eval_dmma<TR, RW, 3, JS, PW>);
+            return launch2(k_eval_dmma<TR, RW, 4, JS, PW>);
+        };
+        if (layout == 16) return pick(std::integral_constant<int, 16>{}, std::integral_constant<int, 0>{});
+        if (layout == 320) return pick(std::integral_constant<int, 32>{}, std::integral_constant<int, 0>{});  // 32-row warps, no producers
+        return pick(std::integral_constant<int, 32>{}, std::integral_constant<int, 4>{});
     }
 }
 
