@@ -418,6 +418,130 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
     }
 }
 
+// ---- K1, warp-granular ring (default for 16 <= n <= 32) -------------------------------------------------------------------
+// k_locate_only keeps a raw tile AND a transposed tile per CTA: 16 n bytes of shared memory per resident query, which at n = 20
+// leaves 20 warps per SM and room for 85 top records only -- and the descent is latency bound on top of L1 bound (C3: 31 % of the
+// warp slots, long_scoreboard the first stall).  Here ONE persistent CTA per SM separates the two roles of that memory:
+//   * landing zone: a ring of S slots of 32 rows each, sized for the bytes in flight (S * 32 * 8n bytes, ~50 KB), filled by
+//     TMA bulk copies (one per slot: 32 rows are one contiguous block of HBM), each slot with its own mbarrier;
+//   * working set: one transposed 32-query tile per WARP (the warp's private xT[d][lane]), 8n bytes per resident query.
+// A warp claims the next mini-tile of the CTA from a shared counter, waits for its slot, transposes it into its own xT (bounds
+// check on that pass), hands the slot back by issuing the TMA copy of the mini-tile S claims ahead, and descends.  No CTA
+// barrier in steady state: the warps drift apart and cover each other's latencies.  C3: 32 warps and the 341-record top.
+struct LocateRingParams {
+    TreeView t;
+    const double* X;
+    long long m;
+    int* leaf;
+    uint8_t* status;
+    int* hist;
+    int top, slots, bounds_in_params;
+    double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
+};
+
+template <int P>
+__global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__ LocateRingParams prm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int n = prm.t.n, S = prm.slots;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const size_t rec_bytes = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+    const size_t mini = (size_t)32 * n;  // doubles per mini-tile
+    unsigned char* s_top = smem_raw;
+    double* ring = (double*)(smem_raw + (((size_t)prm.top * rec_bytes + 127) & ~(size_t)127));
+    double* xT = ring + (size_t)S * mini + (size_t)warp * mini;  // this warp's transposed tile
+    double* s_lower = ring + (size_t)S * mini + (size_t)nwarps * mini;
+    double* s_upper = s_lower + n;
+    uint64_t* bar = (uint64_t*)(s_upper + n);
+    int* s_next = (int*)(bar + S);
+    volatile int* s_armed = s_next + 1;  // [S] number of fills issued into each slot so far
+    const long long nmini = (prm.m + 31) / 32;
+    auto rows_of = [&](long long mt) -> int { const long long r = prm.m - mt * 32; return r < 32 ? (int)r : 32; };
+    auto bulk_ok = [&](long long mt) -> bool { return ((size_t)rows_of(mt) * n * 8) % 16 == 0; };
+    auto fill = [&](int slot, long long mt, int use) {  // one lane; use = how many times the slot was filled before
+        const uint32_t bytes = (uint32_t)((size_t)rows_of(mt) * n * 8);
+        fence_proxy_async();
+        mbar_expect_tx(&bar[slot], bytes);
+        bulk_g2s(ring + (size_t)slot * mini, prm.X + (size_t)mt * mini, bytes, &bar[slot]);
+        __threadfence_block();
+        s_armed[slot] = use + 1;
+    };
+    if (!prm.bounds_in_params)
+        for (int i = tid; i < n; i += blockDim.x) { s_lower[i] = prm.t.lower[i]; s_upper[i] = prm.t.upper[i]; }
+    {
+        const int4* src = (const int4*)prm.t.drec;
+        int4* dst = (int4*)s_top;
+        const int n16 = (int)((size_t)prm.top * rec_bytes / 16);
+        for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&bar[s], 1); s_armed[s] = 0; }
+        *s_next = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid < S) {  // the first S mini-tiles of this CTA
+        const long long mt = blockIdx.x + (long long)tid * gridDim.x;
+        if (mt < nmini && bulk_ok(mt)) fill(tid, mt, 0);
+    }
+    while (true) {
+        int k = 0;
+        if (lane == 0) k = atomicAdd(s_next, 1);
+        k = __shfl_sync(0xffffffffu, k, 0);
+        const long long mt = blockIdx.x + (long long)k * gridDim.x;
+        if (mt >= nmini) break;
+        const int slot = k % S, rows = rows_of(mt);
+        const double* raw;
+        if (bulk_ok(mt)) {
+            // Claims run ahead of the data (32 warps, S slots): the parity wait below is only meaningful once the fill of THIS
+            // use has been issued (a parity wait on a barrier that is still one phase behind returns at once), which the
+            // consumer of the slot's previous use announces in s_armed.
+            const int use = k / S;
+            while (s_armed[slot] <= use) __nanosleep(20);
+            mbar_wait(&bar[slot], (uint32_t)(use & 1));
+            raw = ring + (size_t)slot * mini;
+        } else {  // an odd number of odd-length rows (the batch's last mini-tile): not a whole number of 16-byte units.
+            raw = prm.X + (size_t)mt * mini;  // Its slot was never armed; the rows are read straight from global memory.
+        }
+        bool ok = true;
+        if (lane < rows) {
+            const double* xr = raw + (size_t)lane * n;
+            double* col = xT + lane;
+            if ((n & 1) == 0) {
+                for (int i = 0; i < n; i += 2) {
+                    const double2 v = *(const double2*)(xr + i);
+                    col[(size_t)i * 32] = v.x;
+                    col[(size_t)(i + 1) * 32] = v.y;
+                    if (prm.bounds_in_params)
+                        ok &= (v.x >= prm.lo[i]) & (v.x <= prm.hi[i]) & (v.y >= prm.lo[i + 1]) & (v.y <= prm.hi[i + 1]);
+                    else
+                        ok &= (v.x >= s_lower[i]) & (v.x <= s_upper[i]) & (v.y >= s_lower[i + 1]) & (v.y <= s_upper[i + 1]);
+                }
+            } else {
+                for (int i = 0; i < n; ++i) {
+                    const double v = xr[i];
+                    col[(size_t)i * 32] = v;
+                    if (prm.bounds_in_params) ok &= (v >= prm.lo[i]) & (v <= prm.hi[i]);
+                    else ok &= (v >= s_lower[i]) & (v <= s_upper[i]);
+                }
+            }
+        }
+        __syncwarp();  // every row of the slot has been consumed: hand it to the mini-tile S claims ahead
+        if (lane == 0) {
+            const long long mt2 = blockIdx.x + (long long)(k + S) * gridDim.x;
+            if (mt2 < nmini && bulk_ok(mt2)) fill(slot, mt2, k / S + 1);
+        }
+        if (lane < rows) {
+            int lf = -1;
+            if (ok) lf = descend<P>(prm.t, xT + lane, 32, s_top, prm.top);
+            const long long q = mt * 32 + lane;
+            if (prm.leaf) prm.leaf[q] = lf;
+            if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
+            if (prm.hist && lf >= 0) atomicAdd(prm.hist + lf, 1);
+        }
+        __syncwarp();  // xT is rewritten by the next claim
+    }
+}
+
 // K1 without staging: a warp takes 32 consecutive queries.  Their rows are one contiguous block of 32 n doubles, which the
 // warp streams once, fully coalesced, for the root bounds check (src/tree.jl:357-360; one 32-bit "bad row" mask per lane,
 // OR-reduced with redux.sync); each lane then descends for its own query reading the few coordinates it needs from the
@@ -604,6 +728,65 @@ static int launch_locate_wide(const csp_tree* t, const LocateParams& lp, cudaStr
     return CSP_OK;
 }
 
+#define CSP_RING_FROM 16
+template <int P>
+static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
+    auto kern = k_locate_ring<P>;
+    const int n = t->v.n;
+    const csp_tree::Geo* g = nullptr;
+    for (auto& e : t->geo)
+        if (e.first == (const void*)kern) g = &e.second;
+    if (!g) {
+        csp_tree::Geo ng{};
+        const size_t rec = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
+        const size_t mini = (size_t)32 * n * 8;
+        const char* wenv = getenv("CSP_RING_WARPS");
+        const char* tenv = getenv("CSP_TOP_RECORDS");
+        const char* senv = getenv("CSP_RING_SLOTS");
+        int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : 32;
+        const size_t budget = 227 * 1024;
+        auto fixed = [&](int w, int tp) { return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)w * mini + (size_t)2 * n * 8 + 64 * 8 + 65 * 4 + 16; };
+        // landing zone: ~48 KB in flight per SM (the HBM latency x the SM's share of the bandwidth), at least 4 slots
+        int slots = senv ? atoi(senv) : (int)std::max<size_t>(4, (48 * 1024 + mini - 1) / mini);
+        // Tree top in shared memory: a level there costs ~0.4 L1 wavefronts per query against 1.0 from L1/L2, so one more level
+        // (1365 records of a CS2 tree, 44 KB) is worth giving up warps for as long as 20 remain.  Measured on C3 (n = 20, ms per
+        // 1e8 queries): 32 warps + 85 records 6.17, 32 + 341 5.86, 28 + 341 5.94, 24 + 1365 5.74 (the tiled kernel: 6.28).
+        int top = P == 2 ? 341 : 255;
+        {
+            const int big = P == 2 ? 1365 : 1023;
+            int w = warps;
+            while (w > 4 && fixed(w, big) + (size_t)slots * mini > budget) --w;
+            if (w >= 20) top = big;
+        }
+        if (tenv) top = atoi(tenv);
+        top = std::max(0, std::min(top, t->v.n_internal));
+        while (warps > 4 && fixed(warps, top) + (size_t)slots * mini > budget) --warps;
+        while (slots > 2 && fixed(warps, top) + (size_t)slots * mini > budget) --slots;
+        if (fixed(warps, top) + (size_t)slots * mini > budget) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the ring descent kernel", n);
+        slots = std::min(slots, 64);
+        ng.tile = warps * 32; ng.stages = slots; ng.top = top; ng.smem = fixed(warps, top) + (size_t)slots * mini;
+        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
+        ng.occ = 1;
+        t->geo.emplace_back((const void*)kern, ng);
+        g = &t->geo.back().second;
+    }
+    LocateRingParams prm{};
+    prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
+    prm.top = g->top; prm.slots = g->stages;
+    prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
+    if (prm.bounds_in_params)
+        for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
+    const long long nmini = (prm.m + 31) / 32;
+    const long long grid = std::min<long long>(nmini, (long long)std::max(1, csp_grid_sms(t->n_sm) / g_csp_grid_div));
+    {
+        CspTimed tm(CSP_K_LOCATE, st);
+        kern<<<(unsigned)grid, g->tile, g->smem, st>>>(prm);
+    }
+    CSP_LAUNCHED();
+    CSP_CUDA(cudaGetLastError());
+    return CSP_OK;
+}
+
 template <int P>
 static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
     {
@@ -613,6 +796,12 @@ static int launch_locate_only(const csp_tree* t, const LocateParams& lp, cudaStr
         const char* wenv = getenv("CSP_LOCATE_WIDE");  // 1: always, 0: never, unset: by n
         const int wide_from = 33;
         if (wenv ? atoi(wenv) != 0 : t->v.n >= wide_from) return launch_locate_wide<P>(t, lp, st);
+    }
+    {
+        const char* renv = getenv("CSP_LOCATE_RING");  // 1: always (n <= 32), 0: never, unset: by n
+        const int n = t->v.n;
+        const bool ring = renv ? atoi(renv) != 0 : (n >= CSP_RING_FROM && n <= CSP_BOUNDS_PARAM);
+        if (ring && lp.bulk && !lp.rank && n <= 64 && lp.m >= 32) return launch_locate_ring<P>(t, lp, st);
     }
     auto kern = k_locate_only<P>;
     const int n = t->v.n;

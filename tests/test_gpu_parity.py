@@ -56,12 +56,14 @@ TREES = [  # (n, p, npoints)
 ]
 
 
-@pytest.mark.parametrize("kernel", ["default", "tiled", "wide"])
+@pytest.mark.parametrize("kernel", ["default", "tiled", "wide", "ring"])
 @pytest.mark.parametrize("n,p,npoints", TREES)
 def test_find_leaf_bit_exact(n, p, npoints, kernel, monkeypatch):
-    """Both descent kernels (TMA-staged transposed tile / streaming) on every tree, whatever the default choice for its n."""
+    """Every descent kernel (TMA-staged transposed CTA tile / streaming / warp-granular ring) on every tree, whatever the default
+    choice for its n (the ring kernel takes n <= 64; above that the request falls through to the tiled kernel)."""
     if kernel != "default":
         monkeypatch.setenv("CSP_LOCATE_WIDE", "1" if kernel == "wide" else "0")
+        monkeypatch.setenv("CSP_LOCATE_RING", "1" if kernel == "ring" else "0")
     root, oroot, _ = grow_both(n, p, npoints, seed=100 + n + p)
     rng = np.random.default_rng(n * 7 + p)
     X = edge_queries(root, oroot, rng, 20000)

@@ -8,8 +8,9 @@ $BENCH > $O/r2_launch_plain.json 2> $O/r2_launch_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/r2_launches_ncu.csv $BENCH > $O/r2_launch_ncu.log 2>&1
 for CFG in C3 C2; do
   CMD="python tools/bench_pipeline.py --config $CFG --queries 50000000 --steps 1"
-  KS="k_locate_only k_scatter k_unpermute"
-  [ $CFG = C3 ] && KS="$KS k_eval_binned_mma" || KS="$KS k_eval_binned_exact"
+  KS="k_scatter k_unpermute"
+  [ $CFG = C3 ] && KS="k_locate_ring $KS k_eval_binned_mma" || KS="k_locate_only $KS k_eval_binned_exact"
+  [ -n "$ONLY" ] && KS="$ONLY"
   for K in $KS; do
     $CMD > $O/r2_plain_${CFG}_$K.log 2>&1 &&
     ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 1 -o $O/r2_${K}_$CFG $CMD > $O/r2_ncu_${CFG}_$K.log 2>&1
