@@ -235,7 +235,7 @@ def kernel_table(KT, steps, m_per_step, n, touched, tree_bytes, peak, p_):
     eval_name = ("k_eval_dmma (FP64 tensor cores, grouped dense modelvalue)" if n > 32 else
                  "k_eval_binned_mma<%d> (model-stationary modelvalue on the FP64 tensor cores)" % n if (n >= 16 and n % 2 == 0) else
                  "k_eval_binned_exact<%d> (model-stationary modelvalue)" % n)
-    names = {"locate": ("k_locate_wide<%d>" if n > 32 else "k_locate_ring<%d>" if n >= 16 else "k_locate_only<%d>") % p_ +
+    names = {"locate": ("k_locate_wide<%d>" if n > 32 else "k_locate_ring<%d>" if n >= 8 else "k_locate_only<%d>") % p_ +
                        " (find_leaf_at descent + per-leaf histogram)",
              "eval_binned": eval_name, "locate_eval_fused": "k_locate<%d,...> (fused find_leaf_at + modelvalue)" % p_,
              "scatter": "k_scatter + k_unpermute", "scan": "k_scan", "eval": "k_eval"}

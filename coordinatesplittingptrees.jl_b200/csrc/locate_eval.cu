@@ -49,13 +49,27 @@ __device__ __forceinline__ void ldg256(const DRec2* p, double& mid0, double& mid
 
 // Descent (reference src/tree.jl:362-386).  Returns the leaf id.  s_top: the first `top` records, in shared memory.
 // Coordinate d of the query is xr[d * xs] (xs = 1: row-major row; xs = tile: the thread's column of a transposed tile).
+// topc > 0 (degree 2 only): the first topc BFS records form COMPLETE levels of the tree (every child internal), so the child
+// of record i is record 4 i + 1 + idx and neither F, G nor H is needed there: those levels read the midpoints (16 B) and a
+// 4-byte copy of meta from the compact array s_meta instead of the record's second 16 bytes -- a random 128-bit shared-memory
+// load costs a warp ~10 wavefronts, a random 32-bit one ~3.5.
 template <int P>
-__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr, const int xs, const void* s_top, int top) {
+__device__ __forceinline__ int descend(const TreeView& t, const double* __restrict__ xr, const int xs, const void* s_top, int top,
+                                       const unsigned* s_meta = nullptr, int topc = 0) {
     if (t.n_internal == 0) return 0;  // the root is the only leaf
     int cur = 0, dl;
     if (P == 2) {
         const DRec2* __restrict__ recs = (const DRec2*)t.drec;
         const DRec2* stop = (const DRec2*)s_top;
+        while (cur < topc) {
+            const double2 mm = *(const double2*)&stop[cur].mid0;
+            const unsigned meta = s_meta[cur];
+            const double x0 = xr[(meta & 0xfffu) * xs];
+            const double x1 = xr[((meta >> 12) & 0xfffu) * xs];
+            const unsigned b0 = (unsigned)(x0 >= mm.x) ^ ((meta >> 24) & 1u);
+            const unsigned b1 = (unsigned)(x1 >= mm.y) ^ ((meta >> 25) & 1u);
+            cur = 4 * cur + 1 + (int)((b0 & ~(meta >> 26) & 1u) | ((b1 & ~(meta >> 27) & 1u) << 1));
+        }
         while (true) {
             double mid0, mid1;
             int F, G, H;
@@ -313,7 +327,7 @@ __global__ void __launch_bounds__(256) k_locate(const LocateParams prm) {
 // Tried and rejected (round 2, C3, n = 20: rows 160 B apart put lanes t and t+4 of a quarter-warp into the same bank group
 // for the 128-bit row reads): lanes 4-7 walking their row one column pair ahead.  Locate 6.08 -> 7.05 ms per 1e8 queries with a
 // per-lane constant-bank index for the bounds, 6.75 -> 7.05 with uniform bounds selected per lane: the extra instructions
-// cost more than the two-way conflict.
+// cost more than the two-way conflict.  The same stagger in the ring kernel, whose L1 runs at 90 %: 5.53 -> 5.50 ms (nothing).
 #define CSP_BOUNDS_PARAM 32
 struct LocateOnlyParams {
     TreeView t;
@@ -418,7 +432,7 @@ __global__ void __launch_bounds__(256) k_locate_only(const __grid_constant__ Loc
     }
 }
 
-// ---- K1, warp-granular ring (default for 16 <= n <= 32) -------------------------------------------------------------------
+// ---- K1, warp-granular ring (default for 8 <= n <= 32) --------------------------------------------------------------------
 // k_locate_only keeps a raw tile AND a transposed tile per CTA: 16 n bytes of shared memory per resident query, which at n = 20
 // leaves 20 warps per SM and room for 85 top records only -- and the descent is latency bound on top of L1 bound (C3: 31 % of the
 // warp slots, long_scoreboard the first stall).  Here ONE persistent CTA per SM separates the two roles of that memory:
@@ -436,6 +450,7 @@ struct LocateRingParams {
     uint8_t* status;
     int* hist;
     int top, slots, bounds_in_params;
+    int topc;  // complete-level prefix of the staged top (degree 2), see descend()
     double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
 };
 
@@ -454,6 +469,7 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
     uint64_t* bar = (uint64_t*)(s_upper + n);
     int* s_next = (int*)(bar + S);
     volatile int* s_armed = s_next + 1;  // [S] number of fills issued into each slot so far
+    unsigned* s_meta = (unsigned*)(s_next + 1 + S);  // [topc]
     const long long nmini = (prm.m + 31) / 32;
     auto rows_of = [&](long long mt) -> int { const long long r = prm.m - mt * 32; return r < 32 ? (int)r : 32; };
     auto bulk_ok = [&](long long mt) -> bool { return ((size_t)rows_of(mt) * n * 8) % 16 == 0; };
@@ -473,6 +489,8 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
         const int n16 = (int)((size_t)prm.top * rec_bytes / 16);
         for (int i = tid; i < n16; i += blockDim.x) dst[i] = __ldg(src + i);
     }
+    if (P == 2)
+        for (int i = tid; i < prm.topc; i += blockDim.x) s_meta[i] = ((const DRec2*)prm.t.drec)[i].meta;
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&bar[s], 1); s_armed[s] = 0; }
         *s_next = 0;
@@ -483,10 +501,10 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
         const long long mt = blockIdx.x + (long long)tid * gridDim.x;
         if (mt < nmini && bulk_ok(mt)) fill(tid, mt, 0);
     }
+    int knext = 0;
+    if (lane == 0) knext = atomicAdd(s_next, 1);
     while (true) {
-        int k = 0;
-        if (lane == 0) k = atomicAdd(s_next, 1);
-        k = __shfl_sync(0xffffffffu, k, 0);
+        const int k = __shfl_sync(0xffffffffu, knext, 0);
         const long long mt = blockIdx.x + (long long)k * gridDim.x;
         if (mt >= nmini) break;
         const int slot = k % S, rows = rows_of(mt);
@@ -529,10 +547,11 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
         if (lane == 0) {
             const long long mt2 = blockIdx.x + (long long)(k + S) * gridDim.x;
             if (mt2 < nmini && bulk_ok(mt2)) fill(slot, mt2, k / S + 1);
+            knext = atomicAdd(s_next, 1);  // the next claim: its latency hides behind the descent
         }
         if (lane < rows) {
             int lf = -1;
-            if (ok) lf = descend<P>(prm.t, xT + lane, 32, s_top, prm.top);
+            if (ok) lf = descend<P>(prm.t, xT + lane, 32, s_top, prm.top, s_meta, prm.topc);
             const long long q = mt * 32 + lane;
             if (prm.leaf) prm.leaf[q] = lf;
             if (prm.status) prm.status[q] = ok ? CSP_Q_OK : CSP_Q_OUTSIDE;
@@ -728,7 +747,7 @@ static int launch_locate_wide(const csp_tree* t, const LocateParams& lp, cudaStr
     return CSP_OK;
 }
 
-#define CSP_RING_FROM 16
+#define CSP_RING_FROM 8
 template <int P>
 static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
     auto kern = k_locate_ring<P>;
@@ -745,7 +764,9 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         const char* senv = getenv("CSP_RING_SLOTS");
         int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : 32;
         const size_t budget = 227 * 1024;
-        auto fixed = [&](int w, int tp) { return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)w * mini + (size_t)2 * n * 8 + 64 * 8 + 65 * 4 + 16; };
+        auto fixed = [&](int w, int tp) {
+            return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)w * mini + (size_t)2 * n * 8 + 64 * 8 + 65 * 4 + (P == 2 ? (size_t)tp * 4 : 0) + 16;
+        };
         // landing zone: ~48 KB in flight per SM (the HBM latency x the SM's share of the bandwidth), at least 4 slots
         int slots = senv ? atoi(senv) : (int)std::max<size_t>(4, (48 * 1024 + mini - 1) / mini);
         // Tree top in shared memory: a level there costs ~0.4 L1 wavefronts per query against 1.0 from L1/L2, so one more level
@@ -766,13 +787,28 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         slots = std::min(slots, 64);
         ng.tile = warps * 32; ng.stages = slots; ng.top = top; ng.smem = fixed(warps, top) + (size_t)slots * mini;
         CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
-        ng.occ = 1;
+        // complete levels at the top of the tree (every child internal): read the staged records back once per tree
+        ng.occ = 0;  // (re-used as topc for this kernel: one CTA per SM always)
+        const char* cenv = getenv("CSP_RING_COMPACT");  // 0: plain records on every level (A/B)
+        if (P == 2 && top > 0 && !(cenv && atoi(cenv) == 0)) {
+            std::vector<DRec2> h((size_t)top);
+            CSP_CUDA(cudaMemcpy(h.data(), t->v.drec, (size_t)top * sizeof(DRec2), cudaMemcpyDeviceToHost));
+            int lvl_lo = 0, lvl_n = 1, topc = 0;
+            while (lvl_lo + lvl_n <= top) {
+                bool full = true;
+                for (int i = lvl_lo; i < lvl_lo + lvl_n && full; ++i) full = (h[i].meta >> 28) == 0xfu && h[i].F == 4 * i + 1;
+                if (!full) break;
+                topc = lvl_lo + lvl_n;
+                lvl_lo += lvl_n; lvl_n *= 4;
+            }
+            ng.occ = topc;
+        }
         t->geo.emplace_back((const void*)kern, ng);
         g = &t->geo.back().second;
     }
     LocateRingParams prm{};
     prm.t = t->v; prm.X = lp.X; prm.m = lp.m; prm.leaf = lp.leaf; prm.status = lp.status; prm.hist = lp.hist;
-    prm.top = g->top; prm.slots = g->stages;
+    prm.top = g->top; prm.slots = g->stages; prm.topc = g->occ;
     prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
     if (prm.bounds_in_params)
         for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
