@@ -451,6 +451,7 @@ struct LocateRingParams {
     int* hist;
     int top, slots, bounds_in_params;
     int topc;  // complete-level prefix of the staged top (degree 2), see descend()
+    int rotate;
     double lo[CSP_BOUNDS_PARAM], hi[CSP_BOUNDS_PARAM];
 };
 
@@ -508,23 +509,24 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
         const long long mt = blockIdx.x + (long long)k * gridDim.x;
         if (mt >= nmini) break;
         const int slot = k % S, rows = rows_of(mt);
-        const double* raw;
-        if (bulk_ok(mt)) {
-            // Claims run ahead of the data (32 warps, S slots): the parity wait below is only meaningful once the fill of THIS
-            // use has been issued (a parity wait on a barrier that is still one phase behind returns at once), which the
-            // consumer of the slot's previous use announces in s_armed.
-            const int use = k / S;
-            while (s_armed[slot] <= use) __nanosleep(20);
-            mbar_wait(&bar[slot], (uint32_t)(use & 1));
-            raw = ring + (size_t)slot * mini;
-        } else {  // an odd number of odd-length rows (the batch's last mini-tile): not a whole number of 16-byte units.
-            raw = prm.X + (size_t)mt * mini;  // Its slot was never armed; the rows are read straight from global memory.
-        }
         bool ok = true;
-        if (lane < rows) {
-            const double* xr = raw + (size_t)lane * n;
+        auto transpose = [&](const double* __restrict__ xr) {  // this lane's row -> its column of xT, with the root bounds check
             double* col = xT + lane;
-            if ((n & 1) == 0) {
+            if (prm.rotate) {  // lanes with (lane & rotate) walk their row one column pair ahead (bank stagger, see the launcher)
+                const int h = n >> 1;
+                const bool ahead = (lane & prm.rotate) != 0;
+                double cl0 = prm.lo[0], cl1 = prm.lo[1], cu0 = prm.hi[0], cu1 = prm.hi[1];
+                for (int i = 0; i < h; ++i) {
+                    const int j0 = 2 * i, j1 = i + 1 == h ? 0 : 2 * (i + 1);
+                    const double nl0 = prm.lo[j1], nl1 = prm.lo[j1 + 1], nu0 = prm.hi[j1], nu1 = prm.hi[j1 + 1];
+                    const int j = ahead ? j1 : j0;
+                    const double2 v = *(const double2*)(xr + j);
+                    col[(size_t)j * 32] = v.x;
+                    col[(size_t)(j + 1) * 32] = v.y;
+                    ok &= (v.x >= (ahead ? nl0 : cl0)) & (v.x <= (ahead ? nu0 : cu0)) & (v.y >= (ahead ? nl1 : cl1)) & (v.y <= (ahead ? nu1 : cu1));
+                    cl0 = nl0; cl1 = nl1; cu0 = nu0; cu1 = nu1;
+                }
+            } else if ((n & 1) == 0) {
                 for (int i = 0; i < n; i += 2) {
                     const double2 v = *(const double2*)(xr + i);
                     col[(size_t)i * 32] = v.x;
@@ -542,6 +544,17 @@ __global__ void __launch_bounds__(1024, 1) k_locate_ring(const __grid_constant__
                     else ok &= (v >= s_lower[i]) & (v <= s_upper[i]);
                 }
             }
+        };
+        if (bulk_ok(mt)) {
+            // Claims run ahead of the data (32 warps, S slots): the parity wait below is only meaningful once the fill of THIS
+            // use has been issued (a parity wait on a barrier that is still one phase behind returns at once), which the
+            // consumer of the slot's previous use announces in s_armed.
+            const int use = k / S;
+            while (s_armed[slot] <= use) __nanosleep(20);
+            mbar_wait(&bar[slot], (uint32_t)(use & 1));
+            if (lane < rows) transpose(ring + (size_t)slot * mini + (size_t)lane * n);  // shared-memory loads (LDS)
+        } else {  // an odd number of odd-length rows (the batch's last mini-tile): not a whole number of 16-byte units.
+            if (lane < rows) transpose(prm.X + (size_t)mt * mini + (size_t)lane * n);  // never armed: straight from global memory
         }
         __syncwarp();  // every row of the slot has been consumed: hand it to the mini-tile S claims ahead
         if (lane == 0) {
@@ -812,6 +825,13 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
     prm.bounds_in_params = n <= CSP_BOUNDS_PARAM;
     if (prm.bounds_in_params)
         for (int i = 0; i < n; ++i) { prm.lo[i] = t->h_lower[i]; prm.hi[i] = t->h_upper[i]; }
+    {
+        const char* renv = getenv("CSP_RING_ROTATE");
+        // n/2 = 2 mod 4 (n = 12, 20, 28): rows are n/2 16-byte units apart, so lanes t and t+4 of a quarter-warp hit the same bank
+        // group in the 128-bit row reads; lanes with bit 2 set walk their row one column pair ahead.  C3: 5.46 -> 5.37 ms per 1e8
+        // queries (masks 8 and 16, i.e. other lane groupings: 5.51 / 5.52).
+        prm.rotate = (prm.bounds_in_params && (n & 1) == 0 && ((n >> 1) & 3) == 2) ? (renv ? atoi(renv) : 4) : 0;
+    }
     const long long nmini = (prm.m + 31) / 32;
     const long long grid = std::min<long long>(nmini, (long long)std::max(1, csp_grid_sms(t->n_sm) / g_csp_grid_div));
     {
