@@ -468,7 +468,9 @@ int csp_dense_eval(const csp_models* mo, int n_sm, const double* dX, const int2*
         // after the compute warps.  tools/ubench/slab_peak.cu times the block alone: 24.5 TFLOP/s issued as used here, 30.0 with
         // z resident and no tile barrier, against 36-37 for an unstructured register-blocked DMMA loop (fp64_peaks.cu): the
         // short triangular k-loop (13 k-blocks at n = 100) with its per-slab prologue, row-dot epilogue and barrier is what
-        // keeps the pipe at 0.57; a tile pipeline per row group (no CTA-wide barrier) is the next step.
+        // keeps the pipe at 0.57.  Also measured and not kept: one free-running tile pipeline per row group (the four warps that
+        // share 16 rows, own Z slices / mbarriers / 128-thread named barrier, CTA barriers only on tiles with a leaf change):
+        // 11.3-11.5 ms at n = 100 and 7.2-7.4 against 6.8 at n = 64, 14.7 against 15.9 at n = 126.
         const size_t smem = ((size_t)dmma_ubase(nt, prm.LD) + (size_t)2 * TR * prm.LD + prm.NP + 2 * JS * TR) * 8 + (size_t)(2 * TR) * 4 + 16;
         const char* lenv = getenv("CSP_DMMA_LAYOUT");
         const int layout = lenv ? atoi(lenv) : 16;
