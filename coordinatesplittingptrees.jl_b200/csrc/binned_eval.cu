@@ -686,7 +686,7 @@ int csp_binned_eval(const csp_models* mo, int n_sm, const double* dX, long long 
             int warps = 8;
             while (warps > 2 && 2 * (warps * (per_warp + 16) + 1024) > 226 * 1024) warps -= 2;
             const size_t smem = warps * (per_warp + 16);
-            const long long mblocks = std::min<long long>((m + 32 * warps - 1) / (32 * warps), (long long)std::max(n_sm, 1) * 2);
+            const long long mblocks = std::min<long long>((m + 32 * warps - 1) / (32 * warps), (long long)std::max(n_sm, 1) * std::max(1, 2 / g_csp_grid_div));
             auto launch_mma = [&](auto kern) {
                 cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 CspTimed tm(CSP_K_EVAL_BINNED, st);

@@ -12,6 +12,7 @@
 //             dimensions; one 256-bit record load per level -- from shared memory for the BFS-first `top` records (the top
 //             levels of the tree), from L1/L2 below that.
 //   evaluate: warp-cooperative; the 32 lanes of a warp read each located leaf's model record with coalesced loads.
+#include <atomic>
 #include <cstring>
 #include <mutex>
 
@@ -765,9 +766,13 @@ template <int P>
 static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStream_t st) {
     auto kern = k_locate_ring<P>;
     const int n = t->v.n;
+    // Two chunks in flight on two streams (CSP_BIN_STREAMS=2): the L1-bound descent of one chunk is meant to share every SM with
+    // the DRAM-bound evaluation of the other, so the kernel keeps its full grid and takes half an SM's shared memory instead.
+    const bool shared_sm = g_csp_grid_div > 1;
+    const void* key = (const char*)(const void*)kern + (shared_sm ? 1 : 0);
     const csp_tree::Geo* g = nullptr;
     for (auto& e : t->geo)
-        if (e.first == (const void*)kern) g = &e.second;
+        if (e.first == key) g = &e.second;
     if (!g) {
         csp_tree::Geo ng{};
         const size_t rec = P == 2 ? sizeof(DRec2) : sizeof(DRec1);
@@ -775,13 +780,13 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         const char* wenv = getenv("CSP_RING_WARPS");
         const char* tenv = getenv("CSP_TOP_RECORDS");
         const char* senv = getenv("CSP_RING_SLOTS");
-        int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : 32;
-        const size_t budget = 227 * 1024;
+        int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : (shared_sm ? 16 : 32);
+        const size_t budget = shared_sm ? 100 * 1024 : 227 * 1024;  // (the tensor-core evaluation CTA takes 114 KB + 1 KB reserved each)
         auto fixed = [&](int w, int tp) {
             return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)w * mini + (size_t)2 * n * 8 + 64 * 8 + 65 * 4 + (P == 2 ? (size_t)tp * 4 : 0) + 16;
         };
         // landing zone: ~48 KB in flight per SM (the HBM latency x the SM's share of the bandwidth), at least 4 slots
-        int slots = senv ? atoi(senv) : (int)std::max<size_t>(4, (48 * 1024 + mini - 1) / mini);
+        int slots = senv ? atoi(senv) : (int)std::max<size_t>(4, ((shared_sm ? 24 : 48) * 1024 + mini - 1) / mini);
         // Tree top in shared memory: a level there costs ~0.4 L1 wavefronts per query against 1.0 from L1/L2, so one more level
         // (1365 records of a CS2 tree, 44 KB) is worth giving up warps for as long as 20 remain.  Measured on C3 (n = 20, ms per
         // 1e8 queries): 32 warps + 85 records 6.17, 32 + 341 5.86, 28 + 341 5.94, 24 + 1365 5.74 (the tiled kernel: 6.28).
@@ -790,7 +795,7 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
             const int big = P == 2 ? 1365 : 1023;
             int w = warps;
             while (w > 4 && fixed(w, big) + (size_t)slots * mini > budget) --w;
-            if (w >= 20) top = big;
+            if (w >= 20 && !shared_sm) top = big;
         }
         if (tenv) top = atoi(tenv);
         top = std::max(0, std::min(top, t->v.n_internal));
@@ -799,7 +804,6 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         if (fixed(warps, top) + (size_t)slots * mini > budget) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the ring descent kernel", n);
         slots = std::min(slots, 64);
         ng.tile = warps * 32; ng.stages = slots; ng.top = top; ng.smem = fixed(warps, top) + (size_t)slots * mini;
-        CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ng.smem));
         // complete levels at the top of the tree (every child internal): read the staged records back once per tree
         ng.occ = 0;  // (re-used as topc for this kernel: one CTA per SM always)
         const char* cenv = getenv("CSP_RING_COMPACT");  // 0: plain records on every level (A/B)
@@ -816,7 +820,7 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
             }
             ng.occ = topc;
         }
-        t->geo.emplace_back((const void*)kern, ng);
+        t->geo.emplace_back(key, ng);
         g = &t->geo.back().second;
     }
     LocateRingParams prm{};
@@ -833,8 +837,15 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         prm.rotate = (prm.bounds_in_params && (n & 1) == 0 && ((n >> 1) & 3) == 2) ? (renv ? atoi(renv) : 4) : 0;
     }
     const long long nmini = (prm.m + 31) / 32;
-    const long long grid = std::min<long long>(nmini, (long long)std::max(1, csp_grid_sms(t->n_sm) / g_csp_grid_div));
+    const long long grid = std::min<long long>(nmini, (long long)csp_grid_sms(t->n_sm));
     {
+        // two geometries (whole SM / shared SM) of one kernel function: the opt-in limit must cover the one launched now
+        static std::atomic<size_t> optin[2][64];
+        const int dev = std::min(63, std::max(0, csp_current_device()));
+        if (optin[P - 1][dev].load(std::memory_order_relaxed) < g->smem) {
+            CSP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+            optin[P - 1][dev].store(227 * 1024, std::memory_order_relaxed);
+        }
         CspTimed tm(CSP_K_LOCATE, st);
         kern<<<(unsigned)grid, g->tile, g->smem, st>>>(prm);
     }
@@ -980,9 +991,14 @@ static int launch_locate(const csp_tree* t, const csp_models* mo, const double* 
         if (preset) chunk = std::min(chunk, preset_cap);
         const long long nchunks = (m + chunk - 1) / chunk;
         const char* senv = getenv("CSP_BIN_STREAMS");
-        // Two internal streams were measured (B200, C2): no gain -- every kernel of the pipeline already fills the GPU, so
-        // concurrent chunks only time-slice (4M chunks: 11.1 ms on one stream, 12.7 ms on two).  Kept as an option.
-        const int ns = !preset && nchunks > 1 && senv && atoi(senv) == 2 ? 2 : 1;
+        // Two chunks in flight on two internal streams: the L1-bound descent of one chunk shares every SM with the DRAM-bound
+        // evaluation of the other (the ring descent kernel then takes half an SM's shared memory, the grids of the other kernels
+        // halve).  Measured on B200 per 1e8 queries: C2 (n = 10, FMA evaluation kernel) 10.44 -> 9.70 ms; C3 (n = 20, tensor-core
+        // evaluation kernel with 114 KB of staged rows per CTA) 13.3 -> 16.5 ms -- both kernels slow down by more than 2x there.
+        // (Round 1, with spatially split grids instead of co-resident CTAs: C2 11.1 -> 12.7 ms.)  Default: two streams where the
+        // FMA evaluation kernel and the ring descent kernel are used (8 <= n <= 12), one otherwise; CSP_BIN_STREAMS=1|2 overrides.
+        const bool two_default = mo->degree == 2 && t->v.n >= CSP_RING_FROM && t->v.n <= 12 && prm.bulk;
+        const int ns = !preset && nchunks > 1 && (senv ? atoi(senv) == 2 : two_default) ? 2 : 1;
         cudaStream_t ss[2] = {st, st};
         if (ns == 2) {
             if (!t->pipe_st[0]) {

@@ -330,6 +330,37 @@ def test_locate_eval_parity(n, p, npoints, mode, monkeypatch):
     assert (np.abs(v2[fin[ok]] - oval[ok][fin[ok]]) <= EVAL_RTOL * np.maximum(scale, 1e-300)).all()
 
 
+@pytest.mark.parametrize("n", [10, 12, 20])
+def test_binned_pipeline_one_and_two_streams_agree(n, monkeypatch):
+    """The chunked binned pipeline with one chunk in flight and with two (two internal streams, the descent of one chunk sharing
+    the SMs with the evaluation of the other: the default for 8 <= n <= 12): same leaf ids, status and value bits, several
+    chunks with a ragged last one, against the oracle's leaf ids."""
+    import torch
+    root, oroot, _ = grow_both(n, 2, 150, seed=900 + n)
+    dt = cb.device_tree(root)
+    models = dt.fit_models()
+    rng = np.random.default_rng(n + 1)
+    X = edge_queries(root, oroot, rng, 300000)
+    oleaf, ostatus, _ = O.find_leaf_batch(oroot, X, nthreads=O.max_threads())
+    Xd = torch.from_numpy(X).cuda()
+    monkeypatch.setenv("CSP_EVAL_MODE", "binned")
+    monkeypatch.setenv("CSP_BIN_CHUNK", "70000")  # 5 chunks, the last one ragged
+    out = {}
+    for streams in ("1", "2"):
+        monkeypatch.setenv("CSP_BIN_STREAMS", streams)
+        for rep in range(2):  # the second call re-uses the streams and the pooled workspaces
+            leaf, val, status = dt.locate_eval(models, Xd)
+            torch.cuda.synchronize()
+        out[streams] = (leaf.cpu().numpy(), val.cpu().numpy(), status.cpu().numpy())
+    assert same(out["1"][0], oleaf) and same(out["1"][2], ostatus)
+    for a, b in zip(out["1"], out["2"]):
+        assert same(a, b)
+    monkeypatch.delenv("CSP_BIN_STREAMS")  # the default choice for this n
+    leaf, val, status = dt.locate_eval(models, Xd)
+    torch.cuda.synchronize()
+    assert same(leaf.cpu().numpy(), oleaf) and same(val.cpu().numpy(), out["1"][1])
+
+
 def test_models_upload_roundtrip_and_supplied_eval():
     """Config-C4 style: models (c, g, Q, b) supplied per leaf; only the evaluation arithmetic is pinned."""
     rng = np.random.default_rng(3)
