@@ -243,7 +243,7 @@ void csp_dev_free(void* p);
 // Optional per-kernel timing with CUDA events on the launching stream (csp_timing_enable / csp_timing_read).
 enum { CSP_K_LOCATE = 0, CSP_K_LOCATE_EVAL, CSP_K_SCAN, CSP_K_SCATTER, CSP_K_EVAL_BINNED, CSP_K_EVAL, CSP_K_FIT, CSP_K_CLASSES };
 extern bool g_csp_timing;
-extern int g_csp_grid_div;  // >1 while two chunks are in flight on two streams: persistent grids shrink so that both fit on the SMs
+extern thread_local int g_csp_grid_div;  // >1 while two chunks are in flight on two streams: persistent grids shrink so that both fit on the SMs
 extern int g_csp_sm_reserve;  // SMs' worth of CTAs the persistent grids leave free while NCCL kernels run beside them (comm.cu)
 inline int csp_grid_sms(int n_sm) { return std::max(1, std::max(n_sm, 1) - g_csp_sm_reserve); }
 void csp_timing_begin(int cls, cudaStream_t st);

@@ -74,7 +74,7 @@ int csp_require_device() {
 }
 
 bool g_csp_timing = false;
-int g_csp_grid_div = 1;
+thread_local int g_csp_grid_div = 1;  // per calling thread: one host thread per GPU launches its own pipeline (comm.cu)
 int g_csp_sm_reserve = 0;
 thread_local bool g_csp_alloc_nosync = false;
 namespace {
