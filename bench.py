@@ -363,10 +363,18 @@ def run_single_gpu_config(cb, torch, name, m, steps, local, with_parity=True):
     ms = evs[0][0].elapsed_time(end) / steps
     fit_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
     loc_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    # per-kernel times: one chunk in flight, so that every kernel is timed alone (for 8 <= n <= 12 the timed pass above keeps two
+    # chunks in flight on two internal streams: the descent of one shares the SMs with the evaluation of the other)
+    prev_streams = os.environ.get("CSP_BIN_STREAMS")
+    os.environ["CSP_BIN_STREAMS"] = "1"
     cdev.timing_read(); cdev.timing_enable(True)
     for k in range(steps):
         step()
     KT = cdev.timing_read(); cdev.timing_enable(False)
+    if prev_streams is None:
+        os.environ.pop("CSP_BIN_STREAMS")
+    else:
+        os.environ["CSP_BIN_STREAMS"] = prev_streams
     touched = int(torch.unique(leaf[: min(m, 20_000_000)]).numel())
     peak, _ = peaks()
     V = mean_visited(tree, flat["leaf_nodes"], n)
@@ -376,6 +384,9 @@ def run_single_gpu_config(cb, torch, name, m, steps, local, with_parity=True):
            "fits": {"value": nl / (fit_ms * 1e-3), "unit": "leaf fits/s", "ms": fit_ms, "kernel_ms": KT["fit"][0] / steps,
                     "mean_splits_examined": V, "algorithmic_bytes_per_leaf": fit_bytes(n, V) if V else None,
                     "frac": nl * fit_bytes(n, V) / (max(KT["fit"][0] / steps, 1e-9) * 1e-3) / 1e9 / peak if V else None}}
+    if out["roofline"] and 8 <= n <= 12:
+        out["roofline"]["note"] += ("; per-kernel times with one chunk in flight (CSP_BIN_STREAMS=1): their sum exceeds locate_eval_ms, "
+                                    "which overlaps two chunks")
     if with_parity:
         try:
             out["parity"], out["cpu_baseline"] = parity_and_cpu(cb, name, tree, models, nq=2_000_000, nfit=nl)
@@ -679,6 +690,8 @@ def main():
         lj = vj = None
 
     # ---- instrumented pass: per-kernel device times (rank-local)
+    prev_streams = os.environ.get("CSP_BIN_STREAMS")
+    os.environ["CSP_BIN_STREAMS"] = "1"  # every kernel timed alone (the default overlaps two chunks for 8 <= n <= 12)
     cdev.timing_read()
     cdev.timing_enable(True)
     ni = max(1, min(args.steps, 3))
@@ -686,6 +699,10 @@ def main():
         step(with_gather=False)
     KT = cdev.timing_read()
     cdev.timing_enable(False)
+    if prev_streams is None:
+        os.environ.pop("CSP_BIN_STREAMS")
+    else:
+        os.environ["CSP_BIN_STREAMS"] = prev_streams
     barrier()
 
     l0, v0 = out_slices(0)

@@ -12,7 +12,7 @@ UNITS = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "
 # config -> kernel class -> [(capture, queries in the profiled launch)]
 CAPS = {"C3": {"locate": [("r2_k_locate_ring_C3", 25_000_000)], "eval_binned": [("r2_k_eval_binned_mma_C3", 25_000_000)],
                "scatter": [("r2_k_scatter_C3", 25_000_000), ("r2_k_unpermute_C3", 25_000_000)]},
-        "C2": {"locate": [("r2_k_locate_only_C2", 4_194_304)], "eval_binned": [("r2_k_eval_binned_exact_C2", 4_194_304)],
+        "C2": {"locate": [("r2_k_locate_ring_C2", 4_194_304)], "eval_binned": [("r2_k_eval_binned_exact_C2", 4_194_304)],
                "scatter": [("r2_k_scatter_C2", 4_194_304), ("r2_k_unpermute_C2", 4_194_304)]}}
 
 
