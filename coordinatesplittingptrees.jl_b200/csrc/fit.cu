@@ -58,6 +58,9 @@ struct FitParams {
     unsigned long long* work_counter;  // optional (zeroed before the launch): warps claim units dynamically instead of striding
     const int4* units; long long n_units;  // all-leaf fits: the real leaves (output rows, -1 padded) under each split that has any
     int warp_smem_bytes;
+    // small n: the per-leaf phases of `multi` sibling leaves run side by side on lane groups of n lanes (multi * n <= 32);
+    // their private arrays (b, y, g, Q / step, dkey, did per slot) start multi_off bytes into the warp's slice
+    int multi, multi_off;
 };
 
 __device__ __forceinline__ double dnan() { return __longlong_as_double(0x7ff8000000000000LL); }
@@ -105,6 +108,15 @@ struct WarpCtx {
     int* plist;  // global-scratch mode only: the slots filled so far, so that nothing has to sweep all n(n-1)/2 of them
     unsigned long long* pk64;  // global-scratch mode: (scan position << 32 | split id) per slot, all ones = empty: one atomic per hit
     int *g_lo1, *g_n1, *g_lo2, *g_lo3, *g_pre;  // one window of up to 32 range groups (g_pre has 33 entries)
+    // Several sibling leaves at once (small n, k_fit's multi-member path): slot m of the diagonal scan works on
+    // sb/sy = mD(m), mD(m) + n and dkey/did = mI(m) + n, mI(m) + 2n; mmask = the slots taking part.  mmask == 0: the single
+    // member of the fields above.
+    double* mD0;
+    int* mI0;
+    int mSD;
+    unsigned mmask;
+    __device__ __forceinline__ double* mD(int m) const { return mD0 + (size_t)m * mSD; }
+    __device__ __forceinline__ int* mI(int m) const { return mI0 + (size_t)m * 3 * n; }
 };
 #define FIT_WINDOW_INTS (4 * 32 + 33 + 3)  // keeps the following doubles 8-byte aligned
 #define FIT_TKB 16                        // k-block width of the staging tiles (rows padded to FIT_TKB + 1 doubles)
@@ -242,7 +254,7 @@ __global__ void __launch_bounds__(256) k_coef_table(const TreeView t, double* __
 // (group, offset) by bisection -- the many one-split groups next to a leaf share a chunk instead of taking one each.
 // DIAG == false: first occurrence per off-diagonal pair slot (coefficients_p).  DIAG == true: first qualifying split per
 // diagonal entry (fit_poly2_diag!).  Returns through tpos the number of positions walked and through found the slots filled.
-template <int P, bool DIAG, bool BIG>
+template <int P, bool DIAG, bool BIG, bool MULTI = false>
 __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w, int box, int nslots, int& tpos, int& found, int& sw_cnt, int& sw_total) {
     const TreeView& t = prm.t;
     const int lane = w.lane, n = w.n, skip = prm.skip;
@@ -456,6 +468,40 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
                 const unsigned nb = __ballot_sync(FULL, newp);
                 if (BIG && w.plist && newp) w.plist[found + __popc(nb & ((1u << lane) - 1))] = pidx;
                 found += __popc(nb);
+            } else if (MULTI) {
+                // the same test against every member slot: the candidates (split, dimension) are common to the sibling leaves,
+                // what counts as new information depends on each leaf's own b and y
+                int dd0 = 0, dd1 = 0, newcnt = 0;
+                unsigned hit0 = 0, hit1 = 0;
+                if (act) {
+                    const int2 dd = __ldg((const int2*)t.idims + id);
+                    dd0 = dd.x; dd1 = dd.y;
+                    const double2 xs = __ldg((const double2*)t.ixs + id);
+                    const double2 xf = __ldg((const double2*)t.ixself + id);
+#pragma unroll
+                    for (int m = 0; m < 4; ++m) {
+                        if (!((w.mmask >> m) & 1u)) continue;
+                        const double *sbm = w.mD(m), *sym = w.mD(m) + n;
+                        int* dkm = w.mI(m) + n;
+                        if (dd0 <= n && dkm[dd0 - 1] > 2 * pos &&
+                            (newinfo(xs.x, sbm[dd0 - 1], sym[dd0 - 1]) || newinfo(xf.x, sbm[dd0 - 1], sym[dd0 - 1]))) {
+                            hit0 |= 1u << m;
+                            newcnt += atomicMin(&dkm[dd0 - 1], 2 * pos) == INT_MAX;
+                        }
+                        if (dd1 <= n && dkm[dd1 - 1] > 2 * pos + 1 &&
+                            (newinfo(xs.y, sbm[dd1 - 1], sym[dd1 - 1]) || newinfo(xf.y, sbm[dd1 - 1], sym[dd1 - 1]))) {
+                            hit1 |= 1u << m;
+                            newcnt += atomicMin(&dkm[dd1 - 1], 2 * pos + 1) == INT_MAX;
+                        }
+                    }
+                }
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    if ((hit0 >> m) & 1u) { int* dkm = w.mI(m) + n; if (dkm[dd0 - 1] == 2 * pos) dkm[n + dd0 - 1] = 2 * id; }
+                    if ((hit1 >> m) & 1u) { int* dkm = w.mI(m) + n; if (dkm[dd1 - 1] == 2 * pos + 1) dkm[n + dd1 - 1] = 2 * id + 1; }
+                }
+                found += __reduce_add_sync(FULL, newcnt);
             } else {
                 int dk0 = -1, dk1 = -1, dd0 = 0, dd1 = 0;
                 bool newd0 = false, newd1 = false;
@@ -493,8 +539,8 @@ __device__ __forceinline__ void fit_scan(const FitParams& prm, const WarpCtx& w,
 // children of one split: their splits() traversals are identical (each leaf child has an empty subtree, so the two sibling
 // ranges of the parent's group always join to the parent's whole subtree), hence so are their off-diagonal coefficients;
 // the pair scan and the coefficient values are computed once and only fit_poly1 / fit_poly2_diag! / canonicalize run per leaf.
-template <int P, bool BIG>  // BIG: pair tables in global scratch and/or Q in global memory (large n)
-__global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
+template <int P, bool BIG, bool MULTI = false>  // BIG: pair tables in global scratch and/or Q in global memory (large n); MULTI: prm.multi > 1
+__global__ void __launch_bounds__(256, BIG ? 2 : (MULTI ? 3 : 4)) k_fit(const FitParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const TreeView& t = prm.t;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, W = blockDim.x >> 5;
@@ -513,6 +559,7 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
     if (prm.pairs_in_smem) { w.pkey = w.did + n; w.pid = w.pkey + npairs; }
     else { w.pkey = prm.scratch + ((size_t)blockIdx.x * W + wib) * 3 * (size_t)((npairs + 1) & ~1); w.pid = w.pkey + npairs; }
     w.plist = (!BIG || prm.pairs_in_smem) ? nullptr : w.pkey + 2 * (size_t)((npairs + 1) & ~1);
+    w.mmask = 0; w.mD0 = nullptr; w.mI0 = nullptr; w.mSD = 0;
     w.pk64 = (unsigned long long*)w.pkey;  // (8-byte aligned: the per-warp slice is a multiple of 8 bytes)
     if (w.plist) {  // the table is cleared once; afterwards every unit resets just the slots it filled
         for (int e = lane; e < npairs; e += 32) w.pk64[e] = ~0ull;
@@ -706,9 +753,155 @@ __global__ void __launch_bounds__(256, BIG ? 2 : 4) k_fit(const FitParams prm) {
             __syncwarp();
         }
 
-        // ---- per member box: fit_poly1 results, fit_poly2_diag!, canonicalize, outputs
+        // ---- small n, all-leaf model fits: the per-leaf phases of up to `multi` sibling leaves side by side.  Lane l works for
+        // slot l / n on entry l % n; every slot has private b, y, g, step, dkey, did and its own copy of the record, started
+        // from the shared off-diagonals in Qo.  The arithmetic per entry is the single-member code below, unchanged.
+        if constexpr (MULTI) {
+            {
+                const int G = prm.multi;
+                const int SD = 3 * n + (int)qlen;  // doubles per slot: b | y | g | record
+                double* xD = (double*)(wbase + prm.multi_off);
+                int* xI = (int*)(xD + (size_t)G * SD);  // ints per slot: step | dkey | did
+                w.mD0 = xD; w.mI0 = xI; w.mSD = SD;
+                const int slot = lane / n, e = lane - slot * n;  // this lane's slot and entry
 #pragma unroll 1
-        for (int mi = 0; mi < 4; ++mi) {
+                for (int m0 = 0; m0 < 4; m0 += G) {
+                    const long long bfirst = m0 == 0 ? members.x : m0 == 1 ? members.y : m0 == 2 ? members.z : members.w;
+                    if (bfirst < 0) break;
+                    long long bis[4];
+                    int gm = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int mi = m0 + u;
+                        bis[u] = (u < G && mi < 4) ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : -1;
+                        if (bis[u] >= 0 && gm == u) gm = u + 1;  // members are packed in front
+                    }
+                    const bool mine = slot < gm && lane < G * n;
+                    long long bi = -1;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) if (slot == u) bi = bis[u];
+                    double* Dm = xD + (size_t)(mine ? slot : 0) * SD;
+                    int* Im = xI + (size_t)(mine ? slot : 0) * 3 * n;
+                    double *sbm = Dm, *sym = Dm + n, *sgm = Dm + 2 * n, *Qm = Dm + 3 * n;
+                    int *stm = Im, *dkm = Im + n, *dim_ = Im + 2 * n;
+                    // every slot's record starts as the unit's shared off-diagonals (diagonal, g column and c still NaN)
+                    for (int u = 0; u < gm; ++u)
+                        for (long long q = lane; q < qlen; q += 32) xD[(size_t)u * SD + 3 * n + q] = Qo[q];
+                    int status = CSP_FIT_OK;
+                    double cval = dnan();
+                    if (mine) {
+                        dkm[e] = INT_MAX; stm[e] = 0;
+                        status = prm.ch_status[bi];
+                        if (status == CSP_FIT_OK) {
+                            const int Itop = prm.ch_itop[bi];
+                            cval = prm.ch_c[bi];
+                            sbm[e] = t.ipos[(size_t)Itop * n + e];
+                            sym[e] = prm.ch_y[bi * n + e];
+                            sgm[e] = prm.ch_g[bi * n + e];
+                            stm[e] = prm.ch_step[bi * n + e];
+                        }
+                    }
+                    const bool ok = mine && status == CSP_FIT_OK;
+                    unsigned okslots = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) okslots |= (__ballot_sync(FULL, ok && slot == u) != 0u ? 1u : 0u) << u;
+                    __syncwarp();
+                    if (okslots) {
+                        w.mmask = okslots;
+                        int dpos, foundd;
+                        fit_scan<P, true, BIG, true>(prm, w, box, n * __popc(okslots), dpos, foundd, sw_cnt, sw_total);
+                        w.mmask = 0;
+                    }
+                    // ---- fit_poly2_diag! (src/cs2.jl:208-274): one lane per (slot, diagonal entry), sequential over k
+                    if (ok && dkm[e] != INT_MAX) {
+                        const int d = e;
+                        const int code = dim_[d];
+                        const int id = code >> 1, dimidx = code & 1;
+                        const double* xpos = t.ipos + (size_t)id * n;
+                        const double bd = sbm[d], yd = sym[d];
+                        const double xsd = t.ixs[2 * id + dimidx];
+                        const int d2 = t.idims[2 * id + (1 - dimidx)] - 1;
+                        const double xs2 = t.ixs[2 * id + (1 - dimidx)];
+                        double xnew, xd, fchild, fref;
+                        bool swapped;
+                        if (newinfo(xsd, bd, yd)) {
+                            swapped = false;
+                            xnew = xsd; xd = xpos[d];
+                            fchild = t.icval[4 * id + (1 + dimidx)];
+                            fref = t.icval[4 * id];
+                        } else {
+                            swapped = true;
+                            xnew = xpos[d]; xd = xsd;
+                            fchild = t.icval[4 * id + (2 - dimidx)];
+                            fref = t.icval[4 * id + 3];
+                        }
+                        const double dxi = xnew - xd;
+                        const double coef = qcoef_lineq(true, dxi, xd, bd, yd, true);
+                        double consts = -sgm[d];
+                        const int sd = stm[d];
+                        QWalk qw(d, n, prm.q_packed);
+#pragma unroll 4
+                        for (int k = 0; k < n; ++k) {
+                            double xk = __ldg(xpos + k);
+                            if (swapped && k == d2) xk = xs2;
+                            const bool precdk = sd <= stm[k];
+                            const double xc = qcoef_lineq(false, dxi, xk, sbm[k], sym[k], precdk);
+                            const double term = Qm[qw.idx] * xc;
+                            qw.step(k);
+                            if (k != d) consts = consts - term;
+                        }
+                        Qm[qi(d, d)] = (consts + (fchild - fref) / (xnew - xd)) / coef;
+                    }
+                    __syncwarp();
+                    // ---- canonicalize (src/cs2.jl:132-140) and outputs
+                    if (mine) {
+                        const int i = e;
+                        double gc = dnan(), bb = dnan();
+                        if (ok) {
+                            gc = sgm[i];
+                            const int si = stm[i];
+                            QWalk qw(i, n, prm.q_packed);
+                            for (int j = 0; j < n; ++j) {
+                                const double chi = (i == j) ? sym[j] : (si <= stm[j] ? sbm[j] : 2 * sym[j] - sbm[j]);
+                                gc = gc + (sbm[j] - chi) * Qm[qw.idx] / 2;
+                                qw.step(j);
+                            }
+                            bb = sbm[i];
+                        }
+                        if (prm.q_packed) {
+                            Qm[qi(i, n)] = gc;
+                            if (ok) Qm[qi(i, i)] = Qm[qi(i, i)] * 0.5;
+                        } else if (prm.g) {
+                            prm.g[bi * prm.g_stride + i] = gc;
+                        }
+                        if (prm.b) prm.b[bi * prm.b_stride + i] = bb;
+                        if (prm.gnat) prm.gnat[bi * n + i] = ok ? sgm[i] : dnan();
+                        if (prm.y) prm.y[bi * n + i] = ok ? sym[i] : dnan();
+                        if (prm.firstmatch) prm.firstmatch[bi * n + i] = ok ? prm.ch_fm[bi * n + i] : 0;
+                        if (e == 0) {
+                            if (prm.q_packed) Qm[qi(n, n)] = ok ? cval : dnan();
+                            else if (prm.c) prm.c[bi * prm.c_stride] = ok ? cval : dnan();
+                            if (prm.status) prm.status[bi] = (uint8_t)status;
+                            if (prm.visited) prm.visited[bi] = nvisited;
+                            if (prm.used) prm.used[bi] = nused;
+                        }
+                    }
+                    __syncwarp();
+                    // records out, coalesced, one slot after the other (a failed chain leaves an all-NaN record)
+                    for (int u = 0; u < gm; ++u) {
+                        const bool uok = (okslots >> u) & 1u;
+                        double* Qg = prm.Q + bis[u] * prm.Q_stride;
+                        const double* Qs = xD + (size_t)u * SD + 3 * n;
+                        for (long long q = lane; q < qlen; q += 32) Qg[q] = uok ? Qs[q] : dnan();
+                    }
+                    __syncwarp();
+                }
+                FIT_TICK(4);
+            }
+        }
+        // ---- per member box: fit_poly1 results, fit_poly2_diag!, canonicalize, outputs (not in the MULTI instantiation)
+#pragma unroll 1
+        for (int mi = 0; mi < (MULTI ? 0 : 4); ++mi) {
             const long long bi = prm.units ? (mi == 0 ? members.x : mi == 1 ? members.y : mi == 2 ? members.z : members.w) : (mi == 0 ? bi0 : -1);
             if (bi < 0) break;
             double* Qg = prm.Q + bi * prm.Q_stride;
@@ -1191,15 +1384,28 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
     per_warp = (per_warp + 15) & ~size_t(15);
     prm.tiles = (!prm.q_in_smem && prm.mode == FIT_MODE_FULL) ? 1 : 0;
     if (prm.tiles) per_warp += FIT_TILE_BYTES;  // multiple of 16
-    int W = (int)std::min<size_t>(8, std::max<size_t>(1, ((prm.tiles ? 110 : 64) * 1024) / per_warp));
-    if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
-    prm.warp_smem_bytes = (int)per_warp;
-    size_t smem = per_warp * W;
     if (prm.mode == FIT_MODE_FULL && P == 2 && !prm.node_ids && prm.nb == t->v.n_leaves && t->fit_units &&
         !(getenv("CSP_FIT_SHARED") && atoi(getenv("CSP_FIT_SHARED")) == 0)) {
         prm.units = t->fit_units;  // all leaves: sibling leaves share the off-diagonal work
         prm.n_units = t->n_fit_units;
     }
+    // Small n: at n = 10 only 10 of a warp's 32 lanes work in the per-leaf phases (diagonal scan, diagonal solve, canonicalize:
+    // 82 % of a unit's time on C2), and a unit has about three leaves: run 32 / n of them side by side (CSP_FIT_MULTI=0: one by one).
+    prm.multi = 1; prm.multi_off = 0;
+    if (P == 2 && prm.units && prm.q_in_smem && prm.pairs_in_smem && !prm.tiles && !prm.prec && !prm.slotmap && n <= 16 &&
+        !(getenv("CSP_FIT_MULTI") && atoi(getenv("CSP_FIT_MULTI")) == 0)) {
+        const int G = std::min(4, 32 / n);
+        if (G > 1) {
+            prm.multi = G;
+            prm.multi_off = (int)per_warp;
+            per_warp += (size_t)G * (((size_t)3 * n + (size_t)qlen) * 8 + (size_t)3 * n * 4);
+            per_warp = (per_warp + 15) & ~size_t(15);
+        }
+    }
+    int W = (int)std::min<size_t>(8, std::max<size_t>(1, ((prm.tiles ? 110 : 64) * 1024) / per_warp));
+    if (per_warp * W > 220 * 1024) return csp_set_error(CSP_ERR_UNSUPPORTED, "n=%d is too large for the fit kernel", n);
+    prm.warp_smem_bytes = (int)per_warp;
+    size_t smem = per_warp * W;
     // the per-split coefficient table is built with the tree (csp_fit_build_coef, called by the device builder): no lazy
     // initialisation here, so concurrent fits on different streams only ever read it
     if (t->fit_coef && !(getenv("CSP_FIT_COEF_TABLE") && atoi(getenv("CSP_FIT_COEF_TABLE")) == 0)) prm.coef = t->fit_coef;
@@ -1268,6 +1474,7 @@ static int launch_fit(const csp_tree* t, FitParams& prm, cudaStream_t st, void**
         return CSP_OK;
     };
     const bool big = !prm.pairs_in_smem || prm.tiles;
+    if (P == 2 && prm.multi > 1 && !big) return launch(k_fit<2, false, true>);
     if (P == 2) return big ? launch(k_fit<2, true>) : launch(k_fit<2, false>);
     return big ? launch(k_fit<1, true>) : launch(k_fit<1, false>);
 }
