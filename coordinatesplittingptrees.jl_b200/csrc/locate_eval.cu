@@ -780,8 +780,11 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
         const char* wenv = getenv("CSP_RING_WARPS");
         const char* tenv = getenv("CSP_TOP_RECORDS");
         const char* senv = getenv("CSP_RING_SLOTS");
-        int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : (shared_sm ? 16 : 32);
-        const size_t budget = shared_sm ? 100 * 1024 : 227 * 1024;  // (the tensor-core evaluation CTA takes 114 KB + 1 KB reserved each)
+        int warps = wenv ? std::max(1, std::min(32, atoi(wenv))) : (shared_sm ? (n <= 12 ? 24 : 16) : 32);
+        // sharing the SM: the tensor-core evaluation CTA takes 114 KB (+ 1 KB reserved each), the FMA evaluation kernel (n <= 12)
+        // 10 KB per CTA, four of them.  C2, two chunks in flight, ms per 1e8 queries: 100 KB 9.82, 150 KB 9.36, 180 KB 9.36.
+        const char* benv = getenv("CSP_RING_SHARED_KB");
+        const size_t budget = shared_sm ? (size_t)(benv ? atoi(benv) : (n <= 12 ? 150 : 100)) * 1024 : 227 * 1024;
         auto fixed = [&](int w, int tp) {
             return (((size_t)tp * rec + 127) & ~(size_t)127) + (size_t)w * mini + (size_t)2 * n * 8 + 64 * 8 + 65 * 4 + (P == 2 ? (size_t)tp * 4 : 0) + 16;
         };
@@ -795,7 +798,7 @@ static int launch_locate_ring(const csp_tree* t, const LocateParams& lp, cudaStr
             const int big = P == 2 ? 1365 : 1023;
             int w = warps;
             while (w > 4 && fixed(w, big) + (size_t)slots * mini > budget) --w;
-            if (w >= 20 && !shared_sm) top = big;
+            if (w >= (shared_sm ? 16 : 20)) top = big;
         }
         if (tenv) top = atoi(tenv);
         top = std::max(0, std::min(top, t->v.n_internal));
