@@ -5,9 +5,13 @@
 // K3a adds modelvalue(c, g, Q, b, x) (reference src/cs2.jl:155-159) of the located leaf's model.
 //
 // Shape of the work: an HBM stream of queries (8n B each) against a tree that lives in L2 / L1 / shared memory
-// (32 B per split).  One CTA processes tiles of `tile` queries; a tile is ONE contiguous block of tile*n doubles in HBM
-// and is brought into shared memory by a single TMA bulk copy (cp.async.bulk + mbarrier), double buffered so the next
-// tile streams in while the current one is being processed.
+// (32 B per split).  Queries are brought into shared memory in contiguous blocks by TMA bulk copies (cp.async.bulk +
+// mbarrier) while earlier blocks are being processed.  Three descent kernels, chosen by n:
+//   k_locate_ring  (8 <= n <= 32)  one persistent CTA per SM: a ring of 32-row landing slots + one transposed tile per warp,
+//                                  warps claim mini-tiles from a shared counter, no CTA barrier in steady state;
+//   k_locate_only  (n < 8)         CTA tiles: raw tile + transposed tile per CTA, one barrier per tile;
+//   k_locate_wide  (n > 32)        no staging: a warp streams its 32 rows once for the bounds check, lanes descend from L1/L2;
+// and the fused k_locate (descent + per-query model fetch and evaluation) for small batches.
 //   locate:   one thread owns one query; its coordinates are read from shared memory at the data-dependent split
 //             dimensions; one 256-bit record load per level -- from shared memory for the BFS-first `top` records (the top
 //             levels of the tree), from L1/L2 below that.
